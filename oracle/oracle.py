@@ -102,3 +102,132 @@ def lab_tables():
     u16 = lambda a: _p(a, C.c_uint16)
     lib().orc_lab_tables(u16(g), u16(c), u16(ly), u16(lf), u8p(ig))
     return dict(gamma=g, cbrt=c, ly=ly, lf=lf, invgamma=ig)
+
+
+# ------------------------------------------------------------------------------------------- APRILTAG path
+class AtParams(C.Structure):
+    _fields_ = [("min_cluster_pixels", C.c_int), ("max_nmaxima", C.c_int), ("critical_rad", C.c_float),
+                ("max_line_fit_mse", C.c_float), ("min_white_black_diff", C.c_int)]
+
+    @classmethod
+    def from_cv(cls, p):
+        return cls(int(p.aprilTagMinClusterPixels), int(p.aprilTagMaxNmaxima), float(p.aprilTagCriticalRad),
+                   float(p.aprilTagMaxLineFitMse), int(p.aprilTagMinWhiteBlackDiff))
+
+
+def fast_atan2(y, x):
+    f = lib().orc_fast_atan2
+    f.restype = C.c_float
+    f.argtypes = [C.c_float, C.c_float]
+    return f(y, x)
+
+
+def at_threshold(gray, min_wb_diff):
+    gray = np.ascontiguousarray(gray)
+    out = np.empty_like(gray)
+    lib().orc_at_threshold(u8p(gray), gray.shape[1], gray.shape[0], int(min_wb_diff), u8p(out))
+    return out
+
+
+def at_unionfind(thresh):
+    thresh = np.ascontiguousarray(thresh)
+    rep = np.empty(thresh.shape, np.uint32)
+    lib().orc_at_unionfind(u8p(thresh), thresh.shape[1], thresh.shape[0], u32p(rep))
+    return rep
+
+
+def at_quads(gray, params, max_quads=4096, dumps=False):
+    """Raw quads of the AprilTag-style detector, (n,4,2) float32, dependency candidate order."""
+    gray = np.ascontiguousarray(gray)
+    h, w = gray.shape
+    P = params if isinstance(params, AtParams) else AtParams.from_cv(params)
+    q = np.zeros((max_quads, 8), np.float32)
+    stats = np.zeros(3, np.int64)
+    t = np.empty((h, w), np.uint8) if dumps else None
+    r = np.empty((h, w), np.uint32) if dumps else None
+    n = lib().orc_at_quads(u8p(gray), w, h, C.byref(P), f32p(q), max_quads, _p(stats, C.c_int64),
+                           u8p(t) if dumps else None, u32p(r) if dumps else None)
+    if n > max_quads:
+        raise RuntimeError("oracle quad capacity exceeded")
+    res = q[:n].reshape(n, 4, 2).copy()
+    if dumps:
+        return res, dict(points=int(stats[0]), clusters=int(stats[1]), fitted=int(stats[2]), thresh=t, rep=r)
+    return res
+
+
+# --------------------------------------------------------------------------- candidate filter + decoding
+class DecParams(C.Structure):
+    _fields_ = [("marker_size", C.c_int), ("border_bits", C.c_int), ("cell_size", C.c_int),
+                ("cell_margin_rate", C.c_double), ("min_otsu_stddev", C.c_double),
+                ("max_border_err_rate", C.c_double), ("error_correction_rate", C.c_double),
+                ("max_correction_bits", C.c_int), ("min_distance_to_border", C.c_int),
+                ("min_marker_distance_rate", C.c_double), ("min_group_distance", C.c_float),
+                ("detect_inverted", C.c_int), ("skip_decoded_parents", C.c_int)]
+
+    @classmethod
+    def from_cv(cls, p, marker_size=4, max_correction_bits=1, skip_decoded_parents=1):
+        return cls(marker_size, int(p.markerBorderBits), int(p.perspectiveRemovePixelPerCell),
+                   float(p.perspectiveRemoveIgnoredMarginPerCell), float(p.minOtsuStdDev),
+                   float(p.maxErroneousBitsInBorderRate), float(p.errorCorrectionRate), max_correction_bits,
+                   int(p.minDistanceToBorder), float(p.minMarkerDistanceRate), float(p.minGroupDistance),
+                   int(bool(p.detectInvertedMarker)), skip_decoded_parents)
+
+
+def perspective_transform(src, dst):
+    M = np.empty(9, np.float64)
+    lib().orc_perspective_transform(f32p(np.ascontiguousarray(src, np.float32)),
+                                    f32p(np.ascontiguousarray(dst, np.float32)), f64p(M))
+    return M.reshape(3, 3)
+
+
+def warp_nearest(gray, corners, S):
+    gray = np.ascontiguousarray(gray)
+    out = np.empty((S, S), np.uint8)
+    lib().orc_warp_nearest(u8p(gray), gray.shape[1], gray.shape[0],
+                           f32p(np.ascontiguousarray(corners, np.float32)), S, u8p(out))
+    return out
+
+
+def otsu(px):
+    px = np.ascontiguousarray(px, np.uint8)
+    return lib().orc_otsu(u8p(px), px.size)
+
+
+def extract_bits(gray, corners, dp):
+    gray = np.ascontiguousarray(gray)
+    n = dp.marker_size + 2 * dp.border_bits
+    bits = np.empty((n, n), np.uint8)
+    thr = C.c_int(0)
+    lib().orc_extract_bits(u8p(gray), gray.shape[1], gray.shape[0], f32p(np.ascontiguousarray(corners, np.float32)),
+                           C.byref(dp), u8p(bits), None, C.byref(thr))
+    return bits, thr.value
+
+
+def identify(inner_bits, bytes_list, max_corr_bits, rate):
+    inner_bits = np.ascontiguousarray(inner_bits, np.uint8)
+    bl = np.ascontiguousarray(bytes_list, np.uint8)
+    idx, rot = C.c_int(-1), C.c_int(0)
+    ok = lib().orc_identify(u8p(inner_bits), inner_bits.shape[0], u8p(bl), bl.shape[0], int(max_corr_bits),
+                            C.c_double(rate), C.byref(idx), C.byref(rot))
+    return bool(ok), idx.value, rot.value
+
+
+def identify_candidates(gray, quads, dp, bytes_list, max_out=4096):
+    gray = np.ascontiguousarray(gray)
+    quads = np.ascontiguousarray(quads, np.float32).reshape(-1, 8)
+    bl = np.ascontiguousarray(bytes_list, np.uint8)
+    corners = np.zeros((max_out, 8), np.float32)
+    rejected = np.zeros((max_out, 8), np.float32)
+    ids = np.zeros(max_out, np.int32)
+    nrej = C.c_int(0)
+    na = lib().orc_identify_candidates(u8p(gray), gray.shape[1], gray.shape[0], f32p(quads), len(quads),
+                                       C.byref(dp), u8p(bl), bl.shape[0], f32p(corners), i32p(ids),
+                                       f32p(rejected), max_out, C.byref(nrej))
+    return corners[:na].reshape(na, 4, 2).copy(), ids[:na].copy(), rejected[:nrej.value].reshape(-1, 4, 2).copy()
+
+
+def detect_markers_apriltag(gray, bytes_list, cvparams, marker_size=4, max_correction_bits=1):
+    """aruco_detect.py:267 (APRILTAG mode) -> (corners (n,4,2) f32, ids (n,) i32, rejected (m,4,2) f32)."""
+    quads = at_quads(gray, cvparams)
+    dp = DecParams.from_cv(cvparams, marker_size, max_correction_bits)
+    return identify_candidates(gray, quads, dp, bytes_list)
