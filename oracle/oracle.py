@@ -231,3 +231,60 @@ def detect_markers_apriltag(gray, bytes_list, cvparams, marker_size=4, max_corre
     quads = at_quads(gray, cvparams)
     dp = DecParams.from_cv(cvparams, marker_size, max_correction_bits)
     return identify_candidates(gray, quads, dp, bytes_list)
+
+
+# ------------------------------------------------------------------------------------------------- pose
+def _k14(D):
+    k = np.zeros(14, np.float64)
+    k[:np.size(D)] = np.asarray(D, np.float64).ravel()
+    return k
+
+
+def project_points(obj, rvec, tvec, K, D, jacobian=False):
+    obj = np.ascontiguousarray(np.asarray(obj, np.float64).reshape(-1, 3))
+    n = len(obj)
+    img = np.empty((n, 2), np.float64)
+    K = np.ascontiguousarray(K, np.float64).ravel()
+    k = _k14(D)
+    r = np.ascontiguousarray(np.asarray(rvec, np.float64).ravel())
+    t = np.ascontiguousarray(np.asarray(tvec, np.float64).ravel())
+    if jacobian:
+        dr = np.empty((2 * n, 3), np.float64)
+        dt = np.empty((2 * n, 3), np.float64)
+        lib().orc_project_points(f64p(obj), n, f64p(r), f64p(t), f64p(K), f64p(k), f64p(img), f64p(dr), f64p(dt))
+        return img, dr, dt
+    lib().orc_project_points(f64p(obj), n, f64p(r), f64p(t), f64p(K), f64p(k), f64p(img), None, None)
+    return img
+
+
+def undistort_points(pts, K, D):
+    pts = np.ascontiguousarray(np.asarray(pts, np.float64).reshape(-1, 2))
+    out = np.empty_like(pts)
+    lib().orc_undistort_points(f64p(pts), len(pts), f64p(np.ascontiguousarray(K, np.float64).ravel()),
+                               f64p(_k14(D)), f64p(out))
+    return out
+
+
+def rodrigues(r):
+    R = np.empty(9, np.float64)
+    J = np.empty(27, np.float64)
+    lib().orc_rodrigues(f64p(np.ascontiguousarray(r, np.float64).ravel()), f64p(R), f64p(J))
+    return R.reshape(3, 3), J.reshape(3, 9)
+
+
+def rodrigues_inv(R):
+    r = np.empty(3, np.float64)
+    lib().orc_rodrigues_inv(f64p(np.ascontiguousarray(R, np.float64).ravel()), f64p(r))
+    return r
+
+
+def estimate_pose_single_markers(corners, marker_length, K, D):
+    """aruco_detect.py:601 -> (rvecs (n,1,3) f64, tvecs (n,1,3) f64)."""
+    c = np.ascontiguousarray(np.asarray(corners, np.float32).reshape(-1, 8))
+    n = len(c)
+    rv = np.zeros((n, 1, 3), np.float64)
+    tv = np.zeros((n, 1, 3), np.float64)
+    lib().orc_estimate_pose_single_markers(f32p(c), n, C.c_float(marker_length),
+                                           f64p(np.ascontiguousarray(K, np.float64).ravel()), f64p(_k14(D)),
+                                           f64p(rv), f64p(tv))
+    return rv, tv
