@@ -1,0 +1,112 @@
+"""ctypes binding of libapse_b200.so (include/apse_b200.h).  There is NO CPU fallback: if the CUDA library
+is missing or no B200 is visible, every hot call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libapse_b200.so")
+
+
+class ApseError(RuntimeError):
+    """Raised for every non-zero apse_status (mirrors cv2.error in the drop-in API)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"apse_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """POD mirror of apse_params == cv2.aruco.DetectorParameters (aruco_detect.py:190-236)."""
+    _fields_ = [
+        ("adaptiveThreshWinSizeMin", C.c_int), ("adaptiveThreshWinSizeMax", C.c_int),
+        ("adaptiveThreshWinSizeStep", C.c_int), ("adaptiveThreshConstant", C.c_double),
+        ("minMarkerPerimeterRate", C.c_double), ("maxMarkerPerimeterRate", C.c_double),
+        ("polygonalApproxAccuracyRate", C.c_double), ("minCornerDistanceRate", C.c_double),
+        ("minDistanceToBorder", C.c_int), ("minMarkerDistanceRate", C.c_double), ("minGroupDistance", C.c_float),
+        ("cornerRefinementMethod", C.c_int), ("cornerRefinementWinSize", C.c_int),
+        ("relativeCornerRefinmentWinSize", C.c_float), ("cornerRefinementMaxIterations", C.c_int),
+        ("cornerRefinementMinAccuracy", C.c_double), ("markerBorderBits", C.c_int),
+        ("perspectiveRemovePixelPerCell", C.c_int), ("perspectiveRemoveIgnoredMarginPerCell", C.c_double),
+        ("maxErroneousBitsInBorderRate", C.c_double), ("minOtsuStdDev", C.c_double),
+        ("errorCorrectionRate", C.c_double), ("aprilTagQuadDecimate", C.c_float), ("aprilTagQuadSigma", C.c_float),
+        ("aprilTagMinClusterPixels", C.c_int), ("aprilTagMaxNmaxima", C.c_int), ("aprilTagCriticalRad", C.c_float),
+        ("aprilTagMaxLineFitMse", C.c_float), ("aprilTagMinWhiteBlackDiff", C.c_int), ("aprilTagDeglitch", C.c_int),
+        ("detectInvertedMarker", C.c_int), ("useAruco3Detection", C.c_int), ("minSideLengthCanonicalImg", C.c_int),
+        ("minMarkerLengthRatioOriginalImg", C.c_float),
+    ]
+
+
+class Detections(C.Structure):
+    _fields_ = [("max_markers", C.c_int), ("corners", C.c_void_p), ("ids", C.c_void_p), ("n_markers", C.c_void_p),
+                ("rejected", C.c_void_p), ("n_rejected", C.c_void_p), ("status", C.c_void_p)]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); must list every symbol of include/apse_b200.h
+SIGNATURES = {
+    "apse_abi_version": [],
+    "apse_params_default": [C.POINTER(Params)],
+    "apse_create": [C.POINTER(_vp), _i, _i, _i, _i],
+    "apse_destroy": [_vp],
+    "apse_last_error": [_vp],
+    "apse_set_camera": [_vp, _dp, _dp, _i, _i, _vp],
+    "apse_set_lut": [_vp, _u8p, _vp],
+    "apse_set_dictionary": [_vp, _u8p, _i, _i, _i, _vp],
+    "apse_set_params": [_vp, C.POINTER(Params)],
+    "apse_init_undistort_map": [_vp, _dp, _dp, _i, _i, _vp, _vp, _vp],
+    "apse_remap": [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "apse_cvt_rgb2lab": [_vp, _vp, _i64, _vp, _vp],
+    "apse_cvt_lab2rgb": [_vp, _vp, _i64, _vp, _vp],
+    "apse_cvt_bgr2gray": [_vp, _vp, _i64, _vp, _vp],
+    "apse_lut": [_vp, _vp, _i64, _i, _vp, _vp, _i, _vp],
+    "apse_preprocess": [_vp, _vp, _vp, _vp, _i, _vp],
+    "apse_detect": [_vp, _vp, _i, _i, _i, C.POINTER(Detections), _vp],
+    "apse_pose": [_vp, _vp, _i, _vp, _f, _dp, _dp, _vp, _vp, _vp],
+    "apse_pose_frames": [_vp, _vp, _vp, _i, _i, _vp, _f, _dp, _dp, _vp, _vp, _vp],
+    "apse_project_points": [_vp, _vp, _i, _vp, _vp, _dp, _dp, _vp, _vp],
+    "apse_project_points_multi": [_vp, _vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp],
+    "apse_debug_apriltag": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, C.POINTER(C.c_int64), _vp],
+    "apse_launch_count": [_vp],
+}
+_RESTYPES = {"apse_destroy": None, "apse_params_default": None, "apse_last_error": C.c_char_p,
+             "apse_launch_count": C.c_int64}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no CUDA call is made here)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ApseError(-2, f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                                "g.build()'` (nvcc, sm_100a); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = lib
+    return _lib
+
+
+def darr(a):
+    import numpy as np
+    a = np.ascontiguousarray(a, np.float64).ravel()
+    return a, a.ctypes.data_as(_dp)
+
+
+def dist14(D):
+    import numpy as np
+    k = np.zeros(14, np.float64)
+    if D is not None:
+        d = np.asarray(D, np.float64).ravel()
+        if d.size not in (4, 5, 8, 12, 14):
+            raise ApseError(-1, f"distortion vector must have 4, 5, 8, 12 or 14 coefficients, got {d.size}")
+        k[:d.size] = d
+    return k

@@ -1,0 +1,219 @@
+// api.cu -- C ABI of libapse_b200.so (include/apse_b200.h): context life cycle, configuration, and the
+// batched detectMarkers entry point that chains the candidate (detect_apriltag.cu) and decode (decode.cu) stages.
+#include "common.cuh"
+#include <math.h>
+#include <string.h>
+#include <new>
+
+int apse_upload_tables(apse_ctx *ctx, const uint8_t *lut, LabTables **dev, cudaStream_t st);  // preprocess.cu
+
+extern "C" {
+
+int apse_abi_version(void) { return APSE_ABI_VERSION; }
+
+void apse_params_default(apse_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->adaptiveThreshWinSizeMin = 3; p->adaptiveThreshWinSizeMax = 23; p->adaptiveThreshWinSizeStep = 10;
+    p->adaptiveThreshConstant = 7;
+    p->minMarkerPerimeterRate = 0.03; p->maxMarkerPerimeterRate = 4.;
+    p->polygonalApproxAccuracyRate = 0.03; p->minCornerDistanceRate = 0.05;
+    p->minDistanceToBorder = 3;
+    p->minMarkerDistanceRate = 0.125;
+    p->minGroupDistance = 0.21f;
+    p->cornerRefinementMethod = 0;
+    p->cornerRefinementWinSize = 5;
+    p->relativeCornerRefinmentWinSize = 0.3f;
+    p->cornerRefinementMaxIterations = 30;
+    p->cornerRefinementMinAccuracy = 0.1;
+    p->markerBorderBits = 1;
+    p->perspectiveRemovePixelPerCell = 4;
+    p->perspectiveRemoveIgnoredMarginPerCell = 0.13;
+    p->maxErroneousBitsInBorderRate = 0.35;
+    p->minOtsuStdDev = 5.0;
+    p->errorCorrectionRate = 0.6;
+    p->aprilTagQuadDecimate = 0.f; p->aprilTagQuadSigma = 0.f;
+    p->aprilTagMinClusterPixels = 5; p->aprilTagMaxNmaxima = 10;
+    p->aprilTagCriticalRad = (float)(10 * M_PI / 180);
+    p->aprilTagMaxLineFitMse = 10.f;
+    p->aprilTagMinWhiteBlackDiff = 5; p->aprilTagDeglitch = 0;
+    p->detectInvertedMarker = 0; p->useAruco3Detection = 0;
+    p->minSideLengthCanonicalImg = 32;
+    p->minMarkerLengthRatioOriginalImg = 0.f;
+}
+
+int apse_create(apse_ctx **out, int device, int max_w, int max_h, int max_batch)
+{
+    if (!out || max_w < 8 || max_h < 8 || max_batch < 1 || max_batch > 64) return APSE_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return APSE_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return APSE_ERR_CUDA;
+    apse_ctx *ctx = new (std::nothrow) apse_ctx();
+    if (!ctx) return APSE_ERR_CUDA;
+    ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
+    apse_params_default(&ctx->params);
+    int rc = apse_detect_alloc(ctx);
+    if (rc == APSE_OK) rc = apse_decode_alloc(ctx);
+    if (rc == APSE_OK) rc = apse_upload_tables(ctx, nullptr, &ctx->tables_id, 0);
+    if (rc != APSE_OK) {
+        fprintf(stderr, "apse_create: %s\n", ctx->err.c_str());
+        apse_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return APSE_OK;
+}
+
+void apse_destroy(apse_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    apse_detect_free(ctx);
+    apse_decode_free(ctx);
+    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->dict);
+    delete ctx;
+}
+
+const char *apse_last_error(apse_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t apse_launch_count(apse_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int apse_set_camera(apse_ctx *ctx, const double K[9], const double D[14], int w, int h, void *stream)
+{
+    if (!ctx || !K || !D) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_camera: bad argument");
+    if (w > ctx->max_w || h > ctx->max_h || w < 8 || h < 8)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_camera: %dx%d outside the context capacity %dx%d", w, h, ctx->max_w, ctx->max_h);
+    if (!ctx->mapx) {
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->mapx, (size_t)ctx->max_w * ctx->max_h * sizeof(float)));
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->mapy, (size_t)ctx->max_w * ctx->max_h * sizeof(float)));
+    }
+    int rc = apse_init_undistort_map(ctx, K, D, w, h, ctx->mapx, ctx->mapy, stream);
+    if (rc) return rc;
+    memcpy(ctx->K, K, sizeof ctx->K);
+    memcpy(ctx->D, D, sizeof ctx->D);
+    ctx->w = w; ctx->h = h;
+    ctx->has_camera = true;
+    return APSE_OK;
+}
+
+int apse_set_lut(apse_ctx *ctx, const uint8_t lut[256], void *stream)
+{
+    if (!ctx || !lut) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_lut: bad argument");
+    memcpy(ctx->lut, lut, 256);
+    int rc = apse_upload_tables(ctx, lut, &ctx->tables, (cudaStream_t)stream);
+    if (rc) return rc;
+    ctx->has_lut = true;
+    return APSE_OK;
+}
+
+int apse_set_dictionary(apse_ctx *ctx, const uint8_t *bytes, int n_markers, int marker_size, int max_corr_bits, void *stream)
+{
+    if (!ctx || !bytes || n_markers <= 0 || marker_size < 3 || marker_size > 7 || max_corr_bits < 0)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_dictionary: bad argument");
+    int nbytes = (marker_size * marker_size + 7) / 8;
+    size_t sz = (size_t)n_markers * 4 * nbytes;
+    cudaFree(ctx->dict);
+    ctx->dict = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->dict, sz));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dict, bytes, sz, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    ctx->n_markers = n_markers; ctx->marker_size = marker_size; ctx->max_corr_bits = max_corr_bits; ctx->nbytes = nbytes;
+    ctx->has_dict = true;
+    return APSE_OK;
+}
+
+int apse_set_params(apse_ctx *ctx, const apse_params *p)
+{
+    if (!ctx || !p) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: bad argument");
+    // asserts the dependency enforces on DetectorParameters
+    if (p->adaptiveThreshWinSizeMin < 3 || p->adaptiveThreshWinSizeMax < 3 ||
+        p->adaptiveThreshWinSizeMax < p->adaptiveThreshWinSizeMin || p->adaptiveThreshWinSizeStep <= 0)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: adaptiveThreshWinSize{Min,Max,Step} invalid");
+    if (p->markerBorderBits <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: markerBorderBits must be > 0");
+    if (p->minMarkerDistanceRate < 0 || p->minDistanceToBorder < 0)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: minMarkerDistanceRate / minDistanceToBorder must be >= 0");
+    if (p->perspectiveRemovePixelPerCell <= 0 || p->perspectiveRemoveIgnoredMarginPerCell < 0 ||
+        p->perspectiveRemoveIgnoredMarginPerCell > 0.5)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: perspectiveRemove* invalid");
+    if (p->aprilTagQuadDecimate > 1 || p->aprilTagQuadSigma != 0 || p->aprilTagDeglitch != 0)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagQuadDecimate / QuadSigma / Deglitch are not supported");
+    if (p->detectInvertedMarker || p->useAruco3Detection)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: detectInvertedMarker / useAruco3Detection are not supported");
+    if (p->cornerRefinementMethod == 2) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: CORNER_REFINE_CONTOUR is not supported");
+    if (p->aprilTagMaxNmaxima < 4 || p->aprilTagMaxNmaxima > 16)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagMaxNmaxima must be in [4,16]");
+    ctx->params = *p;
+    ctx->has_params = true;
+    return APSE_OK;
+}
+
+}  // extern "C"
+
+int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h)
+{
+    const apse_params &p = ctx->params;
+    dp->min_cluster_pixels = p.aprilTagMinClusterPixels;
+    dp->max_nmaxima = p.aprilTagMaxNmaxima;
+    dp->min_white_black_diff = p.aprilTagMinWhiteBlackDiff;
+    dp->critical_rad = p.aprilTagCriticalRad;
+    dp->max_line_fit_mse = p.aprilTagMaxLineFitMse;
+    dp->max_dot = cos((double)p.aprilTagCriticalRad);
+    dp->max_cluster_points = 3 * (2 * w + 2 * h);
+    dp->marker_size = ctx->marker_size;
+    dp->border_bits = p.markerBorderBits;
+    dp->cell_size = p.perspectiveRemovePixelPerCell;
+    dp->cell_margin_px = (int)(p.perspectiveRemoveIgnoredMarginPerCell * p.perspectiveRemovePixelPerCell);
+    dp->max_border_errors = (int)(ctx->marker_size * ctx->marker_size * p.maxErroneousBitsInBorderRate);
+    dp->max_correction = (int)((double)ctx->max_corr_bits * p.errorCorrectionRate);
+    dp->min_otsu_stddev = p.minOtsuStdDev;
+    dp->min_distance_to_border = p.minDistanceToBorder;
+    dp->min_marker_distance_rate = (float)p.minMarkerDistanceRate;
+    dp->min_group_distance = p.minGroupDistance;
+    dp->n_markers = ctx->n_markers;
+    dp->nbytes = ctx->nbytes;
+    return APSE_OK;
+}
+
+extern "C" {
+
+int apse_detect(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, void *stream)
+{
+    if (!ctx || !gray || !out || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: bad argument");
+    if (!ctx->has_dict) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "detect: set_dictionary first");
+    if (ctx->params.cornerRefinementMethod != 3)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: only CORNER_REFINE_APRILTAG candidates are implemented in this build");
+    DeviceParams dp;
+    apse_fill_device_params(ctx, &dp, w, h);
+    int rc = apse_apriltag_quads(ctx, gray, w, h, batch, dp, (cudaStream_t)stream);
+    if (rc) return rc;
+    return apse_decode_candidates(ctx, gray, w, h, batch, dp, out, (cudaStream_t)stream);
+}
+
+int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_t *thresh, uint32_t *labels, float *quads,
+                        int max_quads, int64_t *stats_host, void *stream)
+{
+    if (!ctx || !gray) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "debug_apriltag: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceParams dp;
+    apse_fill_device_params(ctx, &dp, w, h);
+    int rc = apse_apriltag_quads(ctx, gray, w, h, 1, dp, st);
+    if (rc) return rc;
+    size_t npx = (size_t)w * h;
+    if (thresh) CUDA_TRY(ctx, cudaMemcpyAsync(thresh, ctx->thresh, npx, cudaMemcpyDeviceToDevice, st));
+    if (labels) CUDA_TRY(ctx, cudaMemcpyAsync(labels, ctx->labels, npx * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    int32_t cnt[APSE_COUNTERS];
+    CUDA_TRY(ctx, cudaMemcpyAsync(cnt, ctx->counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (cnt[3] != 0) CTX_FAIL(ctx, cnt[3], "debug_apriltag: work buffer capacity exceeded (points %d, clusters %d, quads %d)", cnt[0], cnt[4], cnt[2]);
+    int nq = cnt[2] < max_quads ? cnt[2] : max_quads;
+    if (quads && nq > 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(quads, ctx->quads, (size_t)nq * 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    if (stats_host) { stats_host[0] = cnt[0]; stats_host[1] = cnt[4]; stats_host[2] = cnt[1]; stats_host[3] = cnt[2]; }
+    return APSE_OK;
+}
+
+}  // extern "C"

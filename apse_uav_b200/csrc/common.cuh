@@ -1,0 +1,121 @@
+// common.cuh -- context, error plumbing and launch helpers shared by the libapse_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/apse_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------
+// capacities of the per-frame work buffers of the APRILTAG candidate path (overflow => APSE_ERR_CAPACITY)
+#define APSE_MAX_POINTS (1 << 20)       // boundary points per frame
+#define APSE_HASH_SLOTS (1 << 17)       // cluster hash slots per frame (power of two)
+#define APSE_MAX_CLUSTERS (1 << 14)     // clusters passing the size filter per frame
+#define APSE_MAX_QUADS 512              // fitted quads per frame
+#define APSE_MAX_MAXIMA 512             // local maxima of the line-fit error curve kept per cluster
+#define APSE_SORT_SMEM 4096             // points sorted in shared memory; larger clusters sort in global
+
+struct LabTables {  // integer sRGB<->Lab tables; ly/lf already composed with the gamma LUT
+    uint16_t gamma[256];
+    uint16_t cbrt[3072];
+    uint16_t ly[256];
+    uint16_t lf[256];
+    uint8_t invgamma[4096];
+};
+
+struct ClusterDesc {
+    uint32_t offset;  // into the frame's sorted point array
+    uint32_t count;
+    uint32_t key_lo, key_hi;
+};
+
+struct DeviceParams {  // what the detection kernels need of apse_params (+ derived values computed on host)
+    int min_cluster_pixels, max_nmaxima, min_white_black_diff;
+    float critical_rad, max_line_fit_mse;
+    double max_dot;  // cos(critical_rad), evaluated on the host in double like the dependency does
+    int max_cluster_points;
+    // decode
+    int marker_size, border_bits, cell_size, cell_margin_px, max_border_errors, max_correction;
+    double min_otsu_stddev;
+    int min_distance_to_border;
+    float min_marker_distance_rate, min_group_distance;
+    int n_markers, nbytes;
+};
+
+struct FrameScratch;  // opaque per-batch scratch owned by the context (detect_apriltag.cu)
+
+struct apse_ctx {
+    int device = 0, max_w = 0, max_h = 0, max_batch = 0;
+    std::string err;
+    int64_t launches = 0;
+    // camera
+    bool has_camera = false;
+    int w = 0, h = 0;
+    double K[9], D[14];
+    float *mapx = nullptr, *mapy = nullptr;
+    // colour tables
+    bool has_lut = false;
+    uint8_t lut[256];
+    LabTables *tables = nullptr;      // device, composed with lut (fused preprocess)
+    LabTables *tables_id = nullptr;   // device, identity lut (stand-alone cvtColor)
+    // dictionary
+    bool has_dict = false;
+    uint8_t *dict = nullptr;          // device [n_markers][4][nbytes]
+    int n_markers = 0, marker_size = 0, max_corr_bits = 0, nbytes = 0;
+    // parameters
+    bool has_params = false;
+    apse_params params;
+    // APRILTAG scratch (sized for max_batch frames of max_w x max_h)
+    uint8_t *thresh = nullptr, *tmin = nullptr, *tmax = nullptr;
+    uint32_t *labels = nullptr;
+    uint4 *points = nullptr;          // {key_lo, key_hi, xy, slot|g}
+    uint32_t *point_rank = nullptr;
+    unsigned long long *hash_keys = nullptr;
+    uint32_t *hash_count = nullptr, *hash_offset = nullptr;
+    uint2 *sorted_pts = nullptr;      // {x | y<<16, gx | gy<<16} per kept point, grouped by cluster
+    unsigned long long *sort_keys = nullptr;
+    double *lfps = nullptr;           // [P][6]
+    double *errs = nullptr;           // [P][2]
+    ClusterDesc *clusters = nullptr;
+    int32_t *counters = nullptr;      // per frame: {n_points, n_clusters_kept, n_quads, status, n_clusters_total, n_kept_points}
+    float *quads = nullptr;           // [batch][APSE_MAX_QUADS][8]
+    uint32_t *quad_order = nullptr;   // cluster index of each quad (for deterministic ordering)
+    // decode scratch
+    void *decode_scratch = nullptr;
+};
+
+#define APSE_COUNTERS 8
+
+#define CTX_FAIL(ctx, code, ...)                                   \
+    do {                                                           \
+        char _b[512];                                              \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                      \
+        if (ctx) (ctx)->err = _b;                                  \
+        return (code);                                             \
+    } while (0)
+
+#define CUDA_TRY(ctx, expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            CTX_FAIL(ctx, APSE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                       \
+    do {                                        \
+        (ctx)->launches++;                      \
+        CUDA_TRY(ctx, cudaGetLastError());      \
+    } while (0)
+
+static __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// internal entry points implemented per translation unit
+int apse_detect_alloc(apse_ctx *ctx);
+void apse_detect_free(apse_ctx *ctx);
+int apse_decode_alloc(apse_ctx *ctx);
+void apse_decode_free(apse_ctx *ctx);
+int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h);
+int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
+                        cudaStream_t st);
+int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
+                           apse_detections *out, cudaStream_t st);

@@ -1,0 +1,493 @@
+// decode.cu -- candidate post-filter, perspective bit sampling and dictionary matching of
+// aruco.detectMarkers (aruco_detect.py:267, dictionary aruco_detect.py:263); SURVEY.md rows a6.A5-a6.A7,
+// cv2 4.13 semantics.  One CTA per frame:
+//   * quads ordered deterministically, border filter, stable sort by perimeter (descending)
+//   * "too close" predicate for all pairs in parallel (bit matrix), sequential grouping walk on one thread
+//   * every candidate decoded by one warp: FP64 homography, 48x48 nearest-neighbour gather, Otsu on a
+//     shared-memory histogram, per-cell majority, border check, Hamming match against the dictionary
+//   * nesting hierarchy + depth-ordered acceptance, corner rotation, output
+// Compiled with -fmad=false (homography / Otsu arithmetic follows the dependency's evaluation order).
+#include "common.cuh"
+#include <math.h>
+#include <float.h>
+
+#define DEC_THREADS 256
+#define DEC_WARPS (DEC_THREADS / 32)
+#define DEC_MAX_S 64                      // canonical image side limit ((markerSize + 2*border) * cellSize)
+#define DEC_MAXC APSE_MAX_QUADS           // candidates per frame
+
+struct DecodeSmem {
+    float c[DEC_MAXC][8];                 // candidate corners, sorted by perimeter (descending, stable)
+    float perim[DEC_MAXC];
+    uint32_t key[DEC_MAXC];               // ordering key (cluster index) / scratch
+    uint32_t close_bits[DEC_MAXC][DEC_MAXC / 32];
+    short group_id[DEC_MAXC], next_in_group[DEC_MAXC], close_next[DEC_MAXC], parent[DEC_MAXC], depth[DEC_MAXC];
+    short sel[DEC_MAXC], sel_of[DEC_MAXC];
+    short dec_id[DEC_MAXC];
+    uint8_t dec_valid[DEC_MAXC], dec_rot[DEC_MAXC], selected[DEC_MAXC], was[DEC_MAXC], valid[DEC_MAXC];
+    short use_c[DEC_MAXC];                // candidate whose corners / id are reported for selected v
+    short group_head[DEC_MAXC], group_tail[DEC_MAXC];
+    uint8_t warp_img[DEC_WARPS][DEC_MAX_S * DEC_MAX_S];
+    int hist[DEC_WARPS][256];
+    uint8_t bits[DEC_WARPS][16 * 16];
+    int n, ns, ngroups;
+};
+
+__device__ __forceinline__ float sqf(float v) { return v * v; }
+
+__device__ float perimeter_of(const float *c)
+{
+    float p = 0.f;
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) % 4;
+        p += sqrtf(sqf(c[2 * i] - c[2 * j]) + sqf(c[2 * i + 1] - c[2 * j + 1]));
+    }
+    return p;
+}
+
+__device__ float average_distance(const float *m1, const float *m2)
+{
+    float best = FLT_MAX;
+    for (int fc = 0; fc < 4; fc++) {
+        float d = 0;
+        for (int c = 0; c < 4; c++) {
+            int mc = (c + fc) % 4;
+            float dx = m1[2 * mc] - m2[2 * c], dy = m1[2 * mc + 1] - m2[2 * c + 1];
+            d += dx * dx + dy * dy;
+        }
+        d /= 4.f;
+        best = fminf(best, d);
+    }
+    return sqrtf(best);
+}
+
+__device__ float average_module_size(const float *c, int ms, int bb)
+{
+    float a = 0.f;
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) % 4;
+        float dx = c[2 * i] - c[2 * j], dy = c[2 * i + 1] - c[2 * j + 1];
+        a += sqrtf(dx * dx + dy * dy);
+    }
+    return a / (4.f * (ms + bb * 2));
+}
+
+// pointPolygonTest(poly, pt, false) > 0 for a 4-gon of float points
+__device__ bool strictly_inside(const float *poly, float px, float py)
+{
+    int counter = 0;
+    float vx = poly[6], vy = poly[7];
+    for (int i = 0; i < 4; i++) {
+        float v0x = vx, v0y = vy;
+        vx = poly[2 * i]; vy = poly[2 * i + 1];
+        if ((v0y <= py && vy <= py) || (v0y > py && vy > py) || (v0x < px && vx < px)) {
+            if (py == vy && (px == vx || (py == v0y && ((v0x <= px && px <= vx) || (vx <= px && px <= v0x))))) return false;
+            continue;
+        }
+        double dist = (double)(py - v0y) * (vx - v0x) - (double)(px - v0x) * (vy - v0y);
+        if (dist == 0) return false;
+        if (vy < v0y) dist = -dist;
+        counter += dist > 0;
+    }
+    return (counter % 2) != 0;
+}
+
+// getPerspectiveTransform(corners -> canonical square) followed by the 3x3 inverse used by warpPerspective
+__device__ void inverse_homography(const float *src, int S, double *Mi)
+{
+    double a[64], b[8];
+    const float dstc[8] = {0.f, 0.f, (float)S - 1, 0.f, (float)S - 1, (float)S - 1, 0.f, (float)S - 1};
+    for (int i = 0; i < 64; i++) a[i] = 0;
+    for (int i = 0; i < 4; i++) {
+        double sx = src[2 * i], sy = src[2 * i + 1], dx = dstc[2 * i], dy = dstc[2 * i + 1];
+        a[i * 8 + 0] = a[(i + 4) * 8 + 3] = sx;
+        a[i * 8 + 1] = a[(i + 4) * 8 + 4] = sy;
+        a[i * 8 + 2] = a[(i + 4) * 8 + 5] = 1;
+        a[i * 8 + 6] = -sx * dx;
+        a[i * 8 + 7] = -sy * dx;
+        a[(i + 4) * 8 + 6] = -sx * dy;
+        a[(i + 4) * 8 + 7] = -sy * dy;
+        b[i] = dx;
+        b[i + 4] = dy;
+    }
+    bool ok = true;
+    for (int i = 0; i < 8 && ok; i++) {  // LU, partial pivoting
+        int k = i;
+        for (int j = i + 1; j < 8; j++)
+            if (fabs(a[j * 8 + i]) > fabs(a[k * 8 + i])) k = j;
+        if (fabs(a[k * 8 + i]) < DBL_EPSILON) { ok = false; break; }
+        if (k != i) {
+            for (int j = i; j < 8; j++) { double t = a[i * 8 + j]; a[i * 8 + j] = a[k * 8 + j]; a[k * 8 + j] = t; }
+            double t = b[i]; b[i] = b[k]; b[k] = t;
+        }
+        double d = -1 / a[i * 8 + i];
+        for (int j = i + 1; j < 8; j++) {
+            double alpha = a[j * 8 + i] * d;
+            for (k = i + 1; k < 8; k++) a[j * 8 + k] += alpha * a[i * 8 + k];
+            b[j] += alpha * b[i];
+        }
+    }
+    if (ok)
+        for (int i = 7; i >= 0; i--) {
+            double s = b[i];
+            for (int k = i + 1; k < 8; k++) s -= a[i * 8 + k] * b[k];
+            b[i] = s / a[i * 8 + i];
+        }
+    else
+        for (int i = 0; i < 8; i++) b[i] = 0;
+    double m[9] = {b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.};
+    double d = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    if (d == 0) { for (int i = 0; i < 9; i++) Mi[i] = 0; return; }
+    d = 1. / d;
+    Mi[0] = (m[4] * m[8] - m[5] * m[7]) * d; Mi[1] = (m[2] * m[7] - m[1] * m[8]) * d; Mi[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+    Mi[3] = (m[5] * m[6] - m[3] * m[8]) * d; Mi[4] = (m[0] * m[8] - m[2] * m[6]) * d; Mi[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+    Mi[6] = (m[3] * m[7] - m[4] * m[6]) * d; Mi[7] = (m[1] * m[6] - m[0] * m[7]) * d; Mi[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+}
+
+// one warp: _identifyOneCandidate.  Returns (valid, id, rot) on every lane.
+__device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, const float *corners, const DeviceParams &P,
+                                 const uint8_t *__restrict__ dict, uint8_t *img, int *hist, uint8_t *bits, bool &valid,
+                                 int &id, int &rot)
+{
+    const int lane = threadIdx.x & 31;
+    const int nb = P.marker_size + 2 * P.border_bits, cs = P.cell_size, S = nb * cs;
+    double Mi[9];
+    if (lane == 0) inverse_homography(corners, S, Mi);
+    for (int i = 0; i < 9; i++) Mi[i] = __shfl_sync(0xffffffffu, Mi[i], 0);
+    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+    __syncwarp();
+    // nearest-neighbour warp (rint of the FP64 source coordinate, border 0) + histogram + inner-region moments
+    const int c0 = cs / 2, c1 = S - cs / 2;
+    long long s1 = 0, s2 = 0;
+    for (int p = lane; p < S * S; p += 32) {
+        int y = p / S, x = p - y * S;
+        double X0 = Mi[1] * y + Mi[2], Y0 = Mi[4] * y + Mi[5], W0 = Mi[7] * y + Mi[8];
+        double W = W0 + Mi[6] * x;
+        W = W ? 1. / W : 0;
+        double fX = (X0 + Mi[0] * x) * W, fY = (Y0 + Mi[3] * x) * W;
+        fX = fmin(fmax(fX, (double)INT32_MIN), (double)INT32_MAX);
+        fY = fmin(fmax(fY, (double)INT32_MIN), (double)INT32_MAX);
+        long long X = __double2ll_rn(fX), Y = __double2ll_rn(fY);
+        int v = (X >= 0 && X < w && Y >= 0 && Y < h) ? im[(size_t)Y * w + X] : 0;
+        img[p] = (uint8_t)v;
+        atomicAdd(&hist[v], 1);
+        if (x >= c0 && x < c1 && y >= c0 && y < c1) { s1 += v; s2 += v * v; }
+    }
+    for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d); }
+    __syncwarp();
+    const int cnt = (c1 - c0) * (c1 - c0);
+    double mean = (double)s1 / cnt, var = (double)s2 / cnt - mean * mean;
+    double sd = sqrt(var > 0 ? var : 0);
+    if (sd < P.min_otsu_stddev) {
+        for (int i = lane; i < nb * nb; i += 32) bits[i] = mean > 127 ? 1 : 0;
+    } else {
+        int thr = 0;
+        if (lane == 0) {  // Otsu, sequential over the 256 bins in the dependency's order
+            double mu = 0, scale = 1. / (S * S);
+            for (int i = 0; i < 256; i++) mu += i * (double)hist[i];
+            mu *= scale;
+            double mu1 = 0, q1 = 0, max_sigma = 0;
+            for (int i = 0; i < 256; i++) {
+                double p_i = hist[i] * scale, q2, mu2, sigma;
+                mu1 *= q1;
+                q1 += p_i;
+                q2 = 1. - q1;
+                if (fmin(q1, q2) < FLT_EPSILON || fmax(q1, q2) > 1. - FLT_EPSILON) continue;
+                mu1 = (mu1 + i * p_i) / q1;
+                mu2 = (mu - q1 * mu1) / q2;
+                sigma = q1 * q2 * (mu1 - mu2) * (mu1 - mu2);
+                if (sigma > max_sigma) { max_sigma = sigma; thr = i; }
+            }
+        }
+        thr = __shfl_sync(0xffffffffu, thr, 0);
+        const int margin = P.cell_margin_px, inner = cs - 2 * margin;
+        for (int cell = lane; cell < nb * nb; cell += 32) {
+            int cy = cell / nb, cx = cell - cy * nb, nz = 0;
+            for (int yy = 0; yy < inner; yy++)
+                for (int xx = 0; xx < inner; xx++) nz += img[(cy * cs + margin + yy) * S + cx * cs + margin + xx] > thr;
+            bits[cell] = nz > (inner * inner) / 2;
+        }
+    }
+    __syncwarp();
+    // border errors
+    int e = 0;
+    for (int cell = lane; cell < nb * nb; cell += 32) {
+        int cy = cell / nb, cx = cell - cy * nb;
+        bool border = cy < P.border_bits || cy >= nb - P.border_bits || cx < P.border_bits || cx >= nb - P.border_bits;
+        e += (border && bits[cell]) ? 1 : 0;
+    }
+    for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
+    valid = false; id = -1; rot = 0;
+    if (e > P.max_border_errors) return;
+    // candidate bytes (MSB first, rows of inner bits)
+    const int ms = P.marker_size, nbits = ms * ms, nbytes = P.nbytes;
+    uint8_t cand[8];
+    for (int b = 0; b < nbytes; b++) cand[b] = 0;
+    {
+        int cur_bit = 0, cur_byte = 0;
+        for (int i = 0; i < nbits; i++) {
+            int y = i / ms, x = i - y * ms;
+            cand[cur_byte] = (uint8_t)(cand[cur_byte] << 1);
+            if (bits[(y + P.border_bits) * nb + x + P.border_bits]) cand[cur_byte]++;
+            if (++cur_bit == 8) { cur_bit = 0; cur_byte++; }
+        }
+    }
+    // first marker (lowest index) whose best rotation is within the correction budget
+    int best_m = 0x7fffffff, best_r = 0;
+    for (int m = lane; m < P.n_markers; m += 32) {
+        int bd = nbits + 1, br = -1;
+        for (int r = 0; r < 4; r++) {
+            int hd = 0;
+            for (int b = 0; b < nbytes; b++) hd += __popc((unsigned)(dict[(m * 4 + r) * nbytes + b] ^ cand[b]));
+            if (hd < bd) { bd = hd; br = r; }
+        }
+        if (bd <= P.max_correction && m < best_m) { best_m = m; best_r = br; }
+    }
+    int packed = best_m == 0x7fffffff ? 0x7fffffff : (best_m << 2) | best_r;
+    for (int d = 16; d > 0; d >>= 1) packed = min(packed, __shfl_xor_sync(0xffffffffu, packed, d));
+    if (packed != 0x7fffffff) { valid = true; id = packed >> 2; rot = packed & 3; }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
+                                                        const uint32_t *__restrict__ quad_order, int32_t *__restrict__ counters,
+                                                        DeviceParams P, const uint8_t *__restrict__ dict, int skip_decoded_parents,
+                                                        apse_detections out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint8_t *im = gray + (size_t)f * w * h;
+    int32_t *cnt = counters + f * APSE_COUNTERS;
+    const int nq = min(cnt[2], APSE_MAX_QUADS);
+    const float *q = quads + (size_t)f * APSE_MAX_QUADS * 8;
+    const uint32_t *qo = quad_order + (size_t)f * APSE_MAX_QUADS;
+
+    // ---- deterministic order (cluster index), border filter, perimeter, stable sort (descending)
+    if (tid == 0) S.n = 0;
+    __syncthreads();
+    const float d = (float)P.min_distance_to_border;
+    for (int i = tid; i < nq; i += DEC_THREADS) {
+        const float *c = q + 8 * i;
+        bool near = false;
+        for (int j = 0; j < 4; j++) near |= c[2 * j] < d || c[2 * j + 1] < d || c[2 * j] > w - 1 - d || c[2 * j + 1] > h - 1 - d;
+        S.key[i] = near ? 0xffffffffu : qo[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < nq; i += DEC_THREADS) {
+        uint32_t k = S.key[i];
+        if (k == 0xffffffffu) { S.sel[i] = -1; continue; }
+        int r = 0;
+        for (int j = 0; j < nq; j++) r += S.key[j] < k;
+        S.sel[i] = (short)r;  // rank among kept quads in cluster order
+        atomicAdd(&S.n, 1);
+    }
+    __syncthreads();
+    const int n = S.n;
+    // c[] temporarily in cluster order, perimeters alongside
+    for (int i = tid; i < nq; i += DEC_THREADS) {
+        int r = S.sel[i];
+        if (r < 0) continue;
+        for (int k = 0; k < 8; k++) S.c[r][k] = q[8 * i + k];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += DEC_THREADS) S.perim[i] = perimeter_of(S.c[i]);
+    __syncthreads();
+    // stable descending rank; permute through registers (each thread owns indices tid, tid+T, ...)
+    {
+        float cc[(DEC_MAXC + DEC_THREADS - 1) / DEC_THREADS][9];
+        int rr[(DEC_MAXC + DEC_THREADS - 1) / DEC_THREADS];
+        int u = 0;
+        for (int i = tid; i < n; i += DEC_THREADS, u++) {
+            float p = S.perim[i];
+            int r = 0;
+            for (int j = 0; j < n; j++) { float pj = S.perim[j]; r += (pj > p) || (pj == p && j < i); }
+            rr[u] = r;
+            for (int k = 0; k < 8; k++) cc[u][k] = S.c[i][k];
+            cc[u][8] = p;
+        }
+        __syncthreads();
+        u = 0;
+        for (int i = tid; i < n; i += DEC_THREADS, u++) {
+            for (int k = 0; k < 8; k++) S.c[rr[u]][k] = cc[u][k];
+            S.perim[rr[u]] = cc[u][8];
+        }
+    }
+    __syncthreads();
+
+    // ---- decode every candidate (one warp each)
+    for (int i = wid; i < n; i += DEC_WARPS) {
+        bool v; int id, rot;
+        decode_candidate(im, w, h, S.c[i], P, dict, S.warp_img[wid], S.hist[wid], S.bits[wid], v, id, rot);
+        if (lane == 0) { S.dec_valid[i] = v; S.dec_id[i] = (short)id; S.dec_rot[i] = (uint8_t)rot; }
+        __syncwarp();
+    }
+
+    // ---- too-close predicate matrix: bit (i,j), i < j, set when avgDist(i,j) < perimeter[j] * rate
+    const int words = (n + 31) / 32;
+    for (int p = tid; p < n * words; p += DEC_THREADS) {
+        int i = p / words, wj = p - i * words;
+        uint32_t bitsw = 0;
+        for (int b = 0; b < 32; b++) {
+            int j = wj * 32 + b;
+            if (j > i && j < n) {
+                float md = average_distance(S.c[i], S.c[j]);
+                if (md < S.perim[j] * P.min_marker_distance_rate) bitsw |= 1u << b;
+            }
+        }
+        S.close_bits[i][wj] = bitsw;
+    }
+    for (int i = tid; i < n; i += DEC_THREADS) {
+        S.group_id[i] = -1; S.selected[i] = 1; S.next_in_group[i] = -1; S.close_next[i] = -1;
+        S.parent[i] = -1; S.depth[i] = 0; S.was[i] = 0; S.valid[i] = 0; S.use_c[i] = (short)i;
+    }
+    __syncthreads();
+
+    // ---- sequential grouping walk (order-dependent by definition)
+    if (tid == 0) {
+        int ngroups = 0;
+        for (int i = 0; i < n; i++)
+            for (int wj = i / 32; wj < words; wj++) {
+                uint32_t m = S.close_bits[i][wj];
+                while (m) {
+                    int j = wj * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    S.selected[i] = 0; S.selected[j] = 0;
+                    if (S.group_id[i] < 0 && S.group_id[j] < 0) { S.group_id[i] = S.group_id[j] = (short)ngroups++; }
+                    else if (S.group_id[i] > -1 && S.group_id[j] == -1) S.group_id[j] = S.group_id[i];
+                    else if (S.group_id[j] > -1 && S.group_id[i] == -1) S.group_id[i] = S.group_id[j];
+                }
+            }
+        // members of each group in ascending index order (= largest perimeter first)
+        for (int g = 0; g < ngroups; g++) { S.group_head[g] = -1; S.group_tail[g] = -1; }
+        for (int i = 0; i < n; i++) {
+            int g = S.group_id[i];
+            if (g < 0) continue;
+            if (S.group_head[g] < 0) S.group_head[g] = (short)i; else S.next_in_group[S.group_tail[g]] = (short)i;
+            S.group_tail[g] = (short)i;
+        }
+        for (int g = 0; g < ngroups; g++) {
+            int head = S.group_head[g], cur = head, tail_close = -1;
+            S.selected[head] = 1;
+            for (int id = S.next_in_group[head]; id >= 0; id = S.next_in_group[id]) {
+                float dist = average_distance(S.c[id], S.c[cur]);
+                float msz = average_module_size(S.c[id], P.marker_size, P.border_bits);
+                if (dist > P.min_group_distance * msz) {
+                    cur = id;
+                    if (tail_close < 0) S.close_next[head] = (short)id; else S.close_next[tail_close] = (short)id;
+                    tail_close = id;
+                }
+            }
+        }
+        // NB close_next chains start at the group's head; members never head a chain themselves
+        int ns = 0;
+        for (int i = 0; i < n; i++) if (S.selected[i]) { S.sel[ns] = (short)i; S.sel_of[i] = (short)ns; ns++; }
+        S.ns = ns;
+        S.ngroups = ngroups;
+    }
+    __syncthreads();
+    const int ns = S.ns;
+
+    // ---- nesting hierarchy among the selected candidates: parent = nearest smaller index that contains all 4 corners
+    for (int v = tid; v < ns; v += DEC_THREADS) {
+        const float *a = S.c[S.sel[v]];
+        int par = -1;
+        for (int j = v - 1; j >= 0; j--) {
+            const float *b = S.c[S.sel[j]];
+            if (strictly_inside(b, a[0], a[1]) && strictly_inside(b, a[2], a[3]) && strictly_inside(b, a[4], a[5]) &&
+                strictly_inside(b, a[6], a[7])) { par = j; break; }
+        }
+        S.parent[v] = (short)par;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int max_depth = 0;
+        for (int v = ns - 1; v >= 0; v--) {
+            int p = S.parent[v];
+            if (p >= 0 && S.depth[v] + 1 > S.depth[p]) S.depth[p] = (short)(S.depth[v] + 1);
+        }
+        for (int v = 0; v < ns; v++) max_depth = max(max_depth, (int)S.depth[v]);
+        int counter = 0;
+        for (int dep = 0; dep <= max_depth && counter < ns; dep++) {
+            for (int v = 0; v < ns; v++) {
+                if (S.depth[v] != dep) continue;
+                if (skip_decoded_parents && S.was[v]) continue;
+                S.was[v] = 1;
+                int head = S.sel[v];
+                int use = -1;
+                if (S.dec_valid[head]) use = head;
+                else
+                    for (int c = S.close_next[head]; c >= 0; c = S.close_next[c])
+                        if (S.dec_valid[c]) { use = c; break; }
+                if (use >= 0) { S.valid[v] = 1; S.use_c[v] = (short)use; }
+            }
+            for (int v = 0; v < ns; v++) {
+                if (S.depth[v] != dep) continue;
+                if (S.valid[v]) {
+                    int p = S.parent[v];
+                    while (p != -1) {
+                        if (!S.was[p]) { S.was[p] = 1; counter++; }
+                        p = S.parent[p];
+                    }
+                }
+                counter++;
+            }
+        }
+        // ---- output
+        int na = 0, nr = 0;
+        const int cap = out.max_markers;
+        float *oc = out.corners + (size_t)f * cap * 8;
+        int32_t *oi = out.ids + (size_t)f * cap;
+        float *orj = out.rejected ? out.rejected + (size_t)f * cap * 8 : nullptr;
+        int status = cnt[3];
+        for (int v = 0; v < ns; v++) {
+            if (S.valid[v]) {
+                int u = S.use_c[v];
+                const float *c = S.c[u];
+                if (na < cap) {
+                    int r = S.dec_rot[u];
+                    for (int k = 0; k < 4; k++) {
+                        int s = (k + 4 - r) % 4;
+                        oc[8 * na + 2 * k] = c[2 * s];
+                        oc[8 * na + 2 * k + 1] = c[2 * s + 1];
+                    }
+                    oi[na] = S.dec_id[u];
+                } else status = APSE_ERR_CAPACITY;
+                na++;
+            } else {
+                const float *c = S.c[S.sel[v]];
+                if (orj) {
+                    if (nr < cap) for (int k = 0; k < 8; k++) orj[8 * nr + k] = c[k];
+                    else status = APSE_ERR_CAPACITY;
+                }
+                nr++;
+            }
+        }
+        out.n_markers[f] = min(na, cap);
+        if (out.n_rejected) out.n_rejected[f] = min(nr, cap);
+        out.status[f] = status;
+    }
+}
+
+int apse_decode_alloc(apse_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
+    return APSE_OK;
+}
+void apse_decode_free(apse_ctx *) {}
+
+int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
+                           apse_detections *out, cudaStream_t st)
+{
+    if (!out || !out->corners || !out->ids || !out->n_markers || !out->status || out->max_markers <= 0)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: incomplete apse_detections");
+    if (out->rejected && !out->n_rejected) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: rejected without n_rejected");
+    int nb = dp.marker_size + 2 * dp.border_bits;
+    if (nb * dp.cell_size > DEC_MAX_S || nb > 16 || dp.nbytes > 8)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: canonical marker image %d px exceeds the %d px limit", nb * dp.cell_size, DEC_MAX_S);
+    const char *env = getenv("APSE_IDENTIFY_DECODED_PARENTS");
+    int skip = (env && env[0] == '1') ? 0 : 1;
+    k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem), st>>>(gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, ctx->dict,
+                                                           skip, *out);
+    LAUNCH_CHECK(ctx);
+    return APSE_OK;
+}

@@ -1,0 +1,946 @@
+// detect_apriltag.cu -- candidate stage of aruco.detectMarkers in CORNER_REFINE_APRILTAG mode
+// (aruco_detect.py:266-267), batched over frames, sm_100a.
+//
+//   K2  k_tile_minmax / k_threshold       4x4-tile min/max, 3x3 tile dilation, ternary {0,127,255} image
+//   K3  k_ccl_local / merge / flatten     union-find components (white 8-conn, black 4-conn, 127 skipped);
+//                                         block-local union-find in shared memory + boundary merge
+//   K4  k_emit_points / k_cluster_scan / k_scatter_points
+//                                         black/white boundary points grouped by component pair through a
+//                                         per-frame hash table (counting sort by cluster, no global sort)
+//   K5  k_fit_quads                       persistent kernel, one CTA per cluster: theta sort, dedup, FP64
+//                                         prefix moments, error curve, maxima, 4-subset search, corners
+//
+// Parity notes: this file is compiled with -fmad=false.  All FP64/FP32 expressions are written in the
+// evaluation order of the dependency (OpenCV's apriltag_quad_thresh) so that results are bit-identical:
+// fastAtan2 polynomial, sequential (not tree) prefix sums of the moments, and cosf/sinf evaluated with the
+// same double-precision polynomial the host libm uses.
+#include "common.cuh"
+#include <math.h>
+#include <float.h>
+
+#define CCL_TW 32
+#define CCL_TH 16
+#define FQ_THREADS 128
+#define MAXIMA_CAP 16  // aprilTagMaxNmaxima supported up to this value
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: threshold
+__global__ void k_tile_minmax(const uint8_t *__restrict__ gray, int w, int h, int tw, int th, uint8_t *__restrict__ tmin,
+                              uint8_t *__restrict__ tmax)
+{
+    int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (tx >= tw || ty >= th) return;
+    const uint8_t *g = gray + (size_t)f * w * h;
+    unsigned mn = 255, mx = 0;
+    if ((w & 3) == 0) {
+#pragma unroll
+        for (int dy = 0; dy < 4; dy++) {
+            uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(g + (size_t)(ty * 4 + dy) * w + tx * 4));
+            unsigned a = v & 255, b = (v >> 8) & 255, c = (v >> 16) & 255, d = v >> 24;
+            mn = min(mn, min(min(a, b), min(c, d)));
+            mx = max(mx, max(max(a, b), max(c, d)));
+        }
+    } else {
+        for (int dy = 0; dy < 4; dy++)
+            for (int dx = 0; dx < 4; dx++) {
+                unsigned v = g[(size_t)(ty * 4 + dy) * w + tx * 4 + dx];
+                mn = min(mn, v);
+                mx = max(mx, v);
+            }
+    }
+    size_t o = (size_t)f * tw * th + (size_t)ty * tw + tx;
+    tmin[o] = (uint8_t)mn;
+    tmax[o] = (uint8_t)mx;
+}
+
+__device__ __forceinline__ void dilated_minmax(const uint8_t *tmin, const uint8_t *tmax, int tw, int th, int tx, int ty,
+                                               int &mn, int &mx)
+{
+    mn = 255; mx = 0;
+    for (int dy = -1; dy <= 1; dy++) {
+        int yy = ty + dy;
+        if (yy < 0 || yy >= th) continue;
+        for (int dx = -1; dx <= 1; dx++) {
+            int xx = tx + dx;
+            if (xx < 0 || xx >= tw) continue;
+            mn = min(mn, (int)__ldg(tmin + (size_t)yy * tw + xx));
+            mx = max(mx, (int)__ldg(tmax + (size_t)yy * tw + xx));
+        }
+    }
+}
+
+__global__ void k_threshold(const uint8_t *__restrict__ gray, int w, int h, int tw, int th, const uint8_t *__restrict__ tmin,
+                            const uint8_t *__restrict__ tmax, int min_wb_diff, uint8_t *__restrict__ out)
+{
+    int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (tx >= tw || ty >= th) return;
+    const uint8_t *g = gray + (size_t)f * w * h;
+    uint8_t *o = out + (size_t)f * w * h;
+    int mn, mx;
+    dilated_minmax(tmin + (size_t)f * tw * th, tmax + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
+    bool low = (mx - mn) < min_wb_diff;
+    unsigned thr = mn + (mx - mn) / 2;
+    if ((w & 3) == 0) {
+#pragma unroll
+        for (int dy = 0; dy < 4; dy++) {
+            size_t p = (size_t)(ty * 4 + dy) * w + tx * 4;
+            uint32_t r = 0x7f7f7f7fu;
+            if (!low) {
+                uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(g + p));
+                r = ((v & 255) > thr ? 0xffu : 0u) | (((v >> 8) & 255) > thr ? 0xff00u : 0u) |
+                    (((v >> 16) & 255) > thr ? 0xff0000u : 0u) | ((v >> 24) > thr ? 0xff000000u : 0u);
+            }
+            *reinterpret_cast<uint32_t *>(o + p) = r;
+        }
+    } else {
+        for (int dy = 0; dy < 4; dy++)
+            for (int dx = 0; dx < 4; dx++) {
+                size_t p = (size_t)(ty * 4 + dy) * w + tx * 4 + dx;
+                o[p] = low ? 127 : (g[p] > thr ? 255 : 0);
+            }
+    }
+}
+
+// right / bottom partial tiles: nearest full tile's dilated threshold, never marked 127
+__global__ void k_threshold_edges(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
+                                  const uint8_t *__restrict__ tmin, const uint8_t *__restrict__ tmax,
+                                  uint8_t *__restrict__ out)
+{
+    int f = blockIdx.z;
+    int nright = w - tw * 4, nbottom = h - th * 4;
+    int total = nright * (th * 4) + nbottom * w;
+    const uint8_t *g = gray + (size_t)f * w * h;
+    uint8_t *o = out + (size_t)f * w * h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int x, y;
+        if (i < nright * (th * 4)) { y = i / nright; x = tw * 4 + i % nright; }
+        else { int j = i - nright * (th * 4); y = th * 4 + j / w; x = j % w; }
+        int ty = min(y / 4, th - 1), tx = min(x / 4, tw - 1), mn, mx;
+        dilated_minmax(tmin + (size_t)f * tw * th, tmax + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
+        int thr = mn + (mx - mn) / 2;
+        o[(size_t)y * w + x] = g[(size_t)y * w + x] > thr ? 255 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: connected components.  Union rule of the dependency: for x in [1,w-2], y in [0,h-2], v != 127:
+// join (x+1,y), (x,y+1) when equal; for v == 255 also (x-1,y+1), (x+1,y+1).  Root = smallest pixel index.
+template <typename T>
+__device__ __forceinline__ T uf_find(const volatile T *L, T x)
+{
+    T p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union_smem(int *L, int a, int b)
+{
+    for (;;) {
+        a = uf_find<int>(L, a);
+        b = uf_find<int>(L, b);
+        if (a == b) return;
+        if (a > b) { int t = a; a = b; b = t; }
+        int old = atomicMin(&L[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+__device__ __forceinline__ void uf_union_gmem(uint32_t *L, uint32_t a, uint32_t b)
+{
+    for (;;) {
+        a = uf_find<uint32_t>(L, a);
+        b = uf_find<uint32_t>(L, b);
+        if (a == b) return;
+        if (a > b) { uint32_t t = a; a = b; b = t; }
+        uint32_t old = atomicMin(&L[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_local(const uint8_t *__restrict__ thresh, int w, int h,
+                                                              uint32_t *__restrict__ labels, uint8_t *__restrict__ tile_active)
+{
+    __shared__ int L[CCL_TW * CCL_TH];
+    __shared__ uint8_t V[CCL_TH][CCL_TW + 1];
+    int lx = threadIdx.x, ly = threadIdx.y, li = ly * CCL_TW + lx;
+    int x = blockIdx.x * CCL_TW + lx, y = blockIdx.y * CCL_TH + ly, f = blockIdx.z;
+    const uint8_t *t = thresh + (size_t)f * w * h;
+    bool in = x < w && y < h;
+    int v = in ? t[(size_t)y * w + x] : 127;
+    int any = __syncthreads_or(v != 127);
+    if (li == 0) tile_active[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = any ? 1 : 0;
+    if (!any) return;
+    V[ly][lx] = (uint8_t)v;
+    L[li] = li;
+    __syncthreads();
+    bool src = v != 127 && x >= 1 && x <= w - 2 && y <= h - 2;
+    if (src) {
+        if (lx + 1 < CCL_TW && V[ly][lx + 1] == v) uf_union_smem(L, li, li + 1);
+        if (ly + 1 < CCL_TH) {
+            if (V[ly + 1][lx] == v) uf_union_smem(L, li, li + CCL_TW);
+            if (v == 255) {
+                if (lx > 0 && V[ly + 1][lx - 1] == v) uf_union_smem(L, li, li + CCL_TW - 1);
+                if (lx + 1 < CCL_TW && V[ly + 1][lx + 1] == v) uf_union_smem(L, li, li + CCL_TW + 1);
+            }
+        }
+    }
+    __syncthreads();
+    if (in && v != 127) {
+        int r = uf_find<int>(L, li);
+        int ry = blockIdx.y * CCL_TH + r / CCL_TW, rx = blockIdx.x * CCL_TW + r % CCL_TW;
+        labels[(size_t)f * w * h + (size_t)y * w + x] = (uint32_t)(ry * w + rx);
+    }
+}
+
+// unions across tile boundaries.  kind 0: sources on the last row of a tile (S, SW, SE cross);
+// kind 1: sources on the last / first column of a tile (E, SE / SW cross).
+__global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, uint32_t *__restrict__ labels)
+{
+    int f = blockIdx.z;
+    const uint8_t *t = thresh + (size_t)f * w * h;
+    uint32_t *L = labels + (size_t)f * w * h;
+    int nrows = h / CCL_TH;                 // tile rows with a successor row inside the image
+    if (nrows * CCL_TH == h) nrows--;       // last tile row ends at the image border
+    int ncols = div_up(w, CCL_TW);
+    long long n0 = (long long)max(nrows, 0) * w, n1 = (long long)ncols * 2 * h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (long long)gridDim.x * blockDim.x) {
+        int x, y, kind;
+        if (i < n0) { kind = 0; y = (int)(i / w) * CCL_TH + CCL_TH - 1; x = (int)(i % w); }
+        else {
+            long long j = i - n0;
+            kind = 1;
+            int c = (int)(j / h);
+            y = (int)(j % h);
+            x = (c >> 1) * CCL_TW + ((c & 1) ? CCL_TW - 1 : 0);
+        }
+        if (x < 1 || x > w - 2 || y > h - 2) continue;
+        int v = t[(size_t)y * w + x];
+        if (v == 127) continue;
+        uint32_t o = (uint32_t)(y * w + x);
+        if (kind == 0) {
+            if (t[o + w] == v) uf_union_gmem(L, o, o + w);
+            if (v == 255) {
+                if (t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
+                if (t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
+            }
+        } else if ((x % CCL_TW) == CCL_TW - 1) {
+            if (t[o + 1] == v) uf_union_gmem(L, o, o + 1);
+            if (v == 255 && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
+        } else {
+            if (v == 255 && t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_flatten(const uint8_t *__restrict__ thresh, int w, int h,
+                                                                uint32_t *__restrict__ labels,
+                                                                const uint8_t *__restrict__ tile_active)
+{
+    int f = blockIdx.z;
+    if (!tile_active[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
+    int x = blockIdx.x * CCL_TW + threadIdx.x, y = blockIdx.y * CCL_TH + threadIdx.y;
+    if (x >= w || y >= h) return;
+    size_t o = (size_t)f * w * h + (size_t)y * w + x;
+    if (thresh[o] == 127) return;
+    uint32_t *L = labels + (size_t)f * w * h;
+    uint32_t r = uf_find<uint32_t>(L, L[(size_t)y * w + x]);
+    L[(size_t)y * w + x] = r;  // racing writers store roots of the same tree; finds stay correct
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: boundary points -> clusters
+__device__ __forceinline__ uint32_t hash64(unsigned long long k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (uint32_t)k;
+}
+#define HASH_EMPTY 0xffffffffffffffffULL
+
+__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_emit_points(const uint8_t *__restrict__ thresh, int w, int h,
+                                                                const uint32_t *__restrict__ labels,
+                                                                const uint8_t *__restrict__ tile_active,
+                                                                unsigned long long *__restrict__ hash_keys,
+                                                                uint32_t *__restrict__ hash_count, uint4 *__restrict__ points,
+                                                                int32_t *__restrict__ counters)
+{
+    int f = blockIdx.z;
+    if (!tile_active[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
+    int x = blockIdx.x * CCL_TW + threadIdx.x, y = blockIdx.y * CCL_TH + threadIdx.y;
+    const uint8_t *t = thresh + (size_t)f * w * h;
+    const uint32_t *L = labels + (size_t)f * w * h;
+    bool src = x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2;
+    int v0 = src ? t[(size_t)y * w + x] : 127;
+    src = src && v0 != 127;
+    unsigned long long rep0 = src ? L[(size_t)y * w + x] : 0;
+    unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
+    uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
+    uint4 *pts = points + (size_t)f * APSE_MAX_POINTS;
+    int32_t *cnt = counters + f * APSE_COUNTERS;
+    const int DX[4] = {1, 0, -1, 1}, DY[4] = {0, 1, 1, 1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int dx = DX[k], dy = DY[k];
+        int v1 = src ? t[(size_t)(y + dy) * w + x + dx] : 127;
+        bool emit = src && (v0 + v1 == 255);
+        uint32_t slot = 0, rank = 0;
+        if (emit) {
+            unsigned long long rep1 = L[(size_t)(y + dy) * w + x + dx];
+            unsigned long long key = rep0 < rep1 ? (rep1 << 32) + rep0 : (rep0 << 32) + rep1;
+            slot = hash64(key) & (APSE_HASH_SLOTS - 1);
+            int probes = 0;
+            for (;;) {
+                unsigned long long prev = atomicCAS(&hk[slot], HASH_EMPTY, key);
+                if (prev == HASH_EMPTY || prev == key) break;
+                slot = (slot + 1) & (APSE_HASH_SLOTS - 1);
+                if (++probes >= APSE_HASH_SLOTS) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); emit = false; break; }
+            }
+            if (emit) rank = atomicAdd(&hc[slot], 1u);
+        }
+        // warp-aggregated append
+        unsigned m = __ballot_sync(0xffffffffu, emit);
+        if (m) {
+            int lane = (threadIdx.y * CCL_TW + threadIdx.x) & 31, leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cnt[0], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (emit) {
+                int idx = base + __popc(m & ((1u << lane) - 1));
+                if (idx < APSE_MAX_POINTS) {
+                    int gx = dx * (v1 - v0), gy = dy * (v1 - v0);
+                    pts[idx] = make_uint4(slot, rank, (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 16),
+                                          ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16));
+                } else {
+                    atomicExch(&cnt[3], APSE_ERR_CAPACITY);
+                }
+            }
+        }
+    }
+}
+
+// one block per frame: size filter + exclusive scan of the kept clusters' counts over the hash slots
+__global__ void __launch_bounds__(1024) k_cluster_scan(const unsigned long long *__restrict__ hash_keys,
+                                                       const uint32_t *__restrict__ hash_count,
+                                                       uint32_t *__restrict__ hash_offset, ClusterDesc *__restrict__ clusters,
+                                                       int32_t *__restrict__ counters, int min_px, int max_px)
+{
+    int f = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
+    const uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
+    uint32_t *ho = hash_offset + (size_t)f * APSE_HASH_SLOTS;
+    ClusterDesc *cl = clusters + (size_t)f * APSE_MAX_CLUSTERS;
+    const int per = APSE_HASH_SLOTS / 1024;
+    __shared__ uint32_t s_pts[1024], s_cl[1024], s_all[1024];
+    uint32_t npts = 0, ncl = 0, nall = 0;
+    for (int i = 0; i < per; i++) {
+        uint32_t c = hc[tid * per + i];
+        nall += c != 0;
+        if ((int)c >= min_px && (int)c <= max_px) { npts += c; ncl++; }
+    }
+    s_pts[tid] = npts; s_cl[tid] = ncl; s_all[tid] = nall;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
+        uint32_t a = 0, b = 0, c = 0;
+        if (tid >= d) { a = s_pts[tid - d]; b = s_cl[tid - d]; c = s_all[tid - d]; }
+        __syncthreads();
+        s_pts[tid] += a; s_cl[tid] += b; s_all[tid] += c;
+        __syncthreads();
+    }
+    uint32_t off = s_pts[tid] - npts, ci = s_cl[tid] - ncl;
+    for (int i = 0; i < per; i++) {
+        int s = tid * per + i;
+        uint32_t c = hc[s];
+        if ((int)c >= min_px && (int)c <= max_px) {
+            ho[s] = off;
+            if (ci < APSE_MAX_CLUSTERS) {
+                unsigned long long k = hk[s];
+                cl[ci] = ClusterDesc{off, c, (uint32_t)k, (uint32_t)(k >> 32)};
+            }
+            off += c; ci++;
+        } else {
+            ho[s] = 0xffffffffu;
+        }
+    }
+    if (tid == 1023) {
+        int32_t *cnt = counters + f * APSE_COUNTERS;
+        if (s_cl[1023] > APSE_MAX_CLUSTERS) cnt[3] = APSE_ERR_CAPACITY;
+        cnt[1] = (int32_t)min(s_cl[1023], (uint32_t)APSE_MAX_CLUSTERS);
+        cnt[4] = (int32_t)s_all[1023];
+        cnt[5] = (int32_t)s_pts[1023];
+    }
+}
+
+__global__ void k_scatter_points(const uint4 *__restrict__ points, const uint32_t *__restrict__ hash_offset,
+                                 const int32_t *__restrict__ counters, uint2 *__restrict__ sorted_pts, int batch)
+{
+    for (int f = blockIdx.y; f < batch; f += gridDim.y) {
+        int n = min(counters[f * APSE_COUNTERS], APSE_MAX_POINTS);
+        const uint4 *pts = points + (size_t)f * APSE_MAX_POINTS;
+        const uint32_t *ho = hash_offset + (size_t)f * APSE_HASH_SLOTS;
+        uint2 *sp = sorted_pts + (size_t)f * APSE_MAX_POINTS;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            uint4 p = pts[i];
+            uint32_t off = ho[p.x];
+            if (off != 0xffffffffu) sp[off + p.y] = make_uint2(p.z, p.w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: quad fit
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    // OpenCV's fastAtan2 (scalar path), float32, no FMA
+    const float k = (float)(180 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * k, p3 = -0.3258083974640975f * k;
+    const float p5 = 0.1555786518463281f * k, p7 = -0.04432655554792128f * k;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// cosf / sinf evaluated with the double-precision polynomials of the host libm (glibc >= 2.28 sincosf), so
+// that the float results are bit-identical to the CPU reference.  Valid for |y| < 120 (here y in [0, pi]).
+__device__ __forceinline__ float libm_poly(double x, double x2, bool flip, int n)
+{
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+                 C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    if ((n & 1) == 0) {
+        double x3 = x * x2, s1 = S2 + x2 * S3, x7 = x3 * x2, s = x + x3 * S1;
+        return (float)(s + x7 * s1);
+    }
+    const double f = flip ? -1.0 : 1.0;  // second table of the libm: cosine coefficients negated
+    double x4 = x2 * x2, c2 = (f * C3) + x2 * (f * C4), c1 = (f * C0) + x2 * (f * C1), x6 = x4 * x2;
+    double c = c1 + x4 * (f * C2);
+    return (float)(c + x6 * c2);
+}
+
+__device__ __forceinline__ void libm_sincosf(float y, float *sp, float *cp)
+{
+    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    double x = y;
+    unsigned top = (__float_as_uint(y) >> 20) & 0x7ff;
+    if (top < ((__float_as_uint(0x1.921FB6p-1f) >> 20) & 0x7ff)) {
+        if (top < ((__float_as_uint(0x1p-12f) >> 20) & 0x7ff)) { *sp = y; *cp = 1.0f; return; }
+        double x2 = x * x;
+        *sp = libm_poly(x, x2, false, 0);
+        *cp = libm_poly(x, x2, false, 1);
+        return;
+    }
+    double r = x * hpi_inv;
+    int n = ((int)r + 0x800000) >> 24;
+    x = x - n * hpi;
+    double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+    bool flip = (n & 2) != 0;
+    double x2 = x * x;
+    *sp = libm_poly(x * s, x2, flip, n);
+    *cp = libm_poly(x * s, x2, flip, n ^ 1);
+}
+
+struct LineFit { double Ex, Ey, nx, ny, err, mse; };
+
+// lfps: inclusive prefix sums [sz][6] = {Mx, My, Mxx, Mxy, Myy, W}
+__device__ void fit_line(const double *__restrict__ l, int sz, int i0, int i1, LineFit &o)
+{
+    double Mx, My, Mxx, Mxy, Myy, W;
+    int N;
+    const double *a = l + (size_t)i1 * 6;
+    if (i0 < i1) {
+        N = i1 - i0 + 1;
+        Mx = a[0]; My = a[1]; Mxx = a[2]; Mxy = a[3]; Myy = a[4]; W = a[5];
+        if (i0 > 0) {
+            const double *b = l + (size_t)(i0 - 1) * 6;
+            Mx -= b[0]; My -= b[1]; Mxx -= b[2]; Mxy -= b[3]; Myy -= b[4]; W -= b[5];
+        }
+    } else {
+        const double *e = l + (size_t)(sz - 1) * 6, *b = l + (size_t)(i0 - 1) * 6;
+        Mx = e[0] - b[0]; My = e[1] - b[1]; Mxx = e[2] - b[2]; Mxy = e[3] - b[3]; Myy = e[4] - b[4]; W = e[5] - b[5];
+        Mx += a[0]; My += a[1]; Mxx += a[2]; Mxy += a[3]; Myy += a[4]; W += a[5];
+        N = sz - i0 + i1 + 1;
+    }
+    double Ex = Mx / W, Ey = My / W;
+    double Cxx = Mxx / W - Ex * Ex, Cxy = Mxy / W - Ex * Ey, Cyy = Myy / W - Ey * Ey;
+    float normal_theta = (float)(.5f * (3.14159265358979323846 / 180)) * fast_atan2_deg((float)(-2 * Cxy), (float)(Cyy - Cxx));
+    float sn, cs;
+    libm_sincosf(normal_theta, &sn, &cs);
+    double nx = cs, ny = sn;
+    o.Ex = Ex; o.Ey = Ey; o.nx = nx; o.ny = ny;
+    o.err = nx * nx * N * Cxx + 2 * nx * ny * N * Cxy + ny * ny * N * Cyy;
+    o.mse = nx * nx * Cxx + 2 * nx * ny * Cxy + ny * ny * Cyy;
+}
+
+__device__ __forceinline__ double sq(double v) { return v * v; }
+
+// block-wide helpers (FQ_THREADS threads)
+__device__ __forceinline__ int block_scan_excl(int v, int *s_warp, int &total)
+{
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int i = 0; i < FQ_THREADS / 32; i++) { int t = s_warp[i]; if (i < wid) base += t; tot += t; }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+}
+
+struct FitArgs {
+    const uint8_t *gray;
+    int w, h, batch;
+    const ClusterDesc *clusters;
+    uint2 *sorted_pts;
+    unsigned long long *sort_keys;
+    double *lfps, *errs;
+    int32_t *counters;
+    float *quads;
+    uint32_t *quad_order;
+    int *work_counter;
+    int max_nmaxima;
+    float critical_rad, max_line_fit_mse;
+    double max_dot;
+};
+
+__device__ void bitonic_sort_u64(unsigned long long *keys, int npow2)
+{
+    for (int k = 2; k <= npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += FQ_THREADS) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], b = keys[ixj];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
+{
+    __shared__ unsigned long long s_keys[APSE_SORT_SMEM];
+    __shared__ int s_prefix[65];       // cluster count prefix over frames (batch <= 64 per launch)
+    __shared__ int s_item;
+    __shared__ int s_warp[FQ_THREADS / 32];
+    __shared__ int s_i4[8];
+    __shared__ double s_d[FQ_THREADS / 32];
+    __shared__ int s_max_idx[MAXIMA_CAP + 1];
+    __shared__ double s_max_err[MAXIMA_CAP + 1];
+    __shared__ LineFit s_pair[MAXIMA_CAP][MAXIMA_CAP];
+    __shared__ double s_best_err[FQ_THREADS];
+    __shared__ unsigned s_best_combo[FQ_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) {
+        int acc = 0;
+        for (int f = 0; f < A.batch; f++) { s_prefix[f] = acc; acc += A.counters[f * APSE_COUNTERS + 1]; }
+        s_prefix[A.batch] = acc;
+    }
+    __syncthreads();
+    const int total_items = s_prefix[A.batch];
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(A.work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= total_items) break;
+        int f = 0;
+        while (s_prefix[f + 1] <= item) f++;
+        const int ci = item - s_prefix[f];
+        const ClusterDesc cd = A.clusters[(size_t)f * APSE_MAX_CLUSTERS + ci];
+        const int n = (int)cd.count;
+        uint2 *pts = A.sorted_pts + (size_t)f * APSE_MAX_POINTS + cd.offset;
+        const uint8_t *im = A.gray + (size_t)f * A.w * A.h;
+        double *lf = A.lfps + ((size_t)f * APSE_MAX_POINTS + cd.offset) * 6;
+        double *e0 = A.errs + ((size_t)f * APSE_MAX_POINTS + cd.offset) * 2, *e1 = e0 + n;
+
+        // ---- bounding box
+        int xmin = INT32_MAX, xmax = 0, ymin = INT32_MAX, ymax = 0;
+        for (int i = tid; i < n; i += FQ_THREADS) {
+            uint32_t xy = pts[i].x;
+            int x = xy & 0xffff, y = xy >> 16;
+            xmin = min(xmin, x); xmax = max(xmax, x); ymin = min(ymin, y); ymax = max(ymax, y);
+        }
+        for (int d = 16; d > 0; d >>= 1) {
+            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, d)); xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, d));
+            ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, d)); ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, d));
+        }
+        if (tid == 0) { s_i4[0] = INT32_MAX; s_i4[1] = 0; s_i4[2] = INT32_MAX; s_i4[3] = 0; }
+        __syncthreads();
+        if (lane == 0) { atomicMin(&s_i4[0], xmin); atomicMax(&s_i4[1], xmax); atomicMin(&s_i4[2], ymin); atomicMax(&s_i4[3], ymax); }
+        __syncthreads();
+        const double cx = (s_i4[0] + s_i4[1]) * 0.5 + 0.05118, cy = (s_i4[2] + s_i4[3]) * 0.5 + -0.028581;
+
+        // ---- theta keys + orientation test (black inside white)
+        int npow2 = 1;
+        while (npow2 < n) npow2 <<= 1;
+        unsigned long long *keys = npow2 <= APSE_SORT_SMEM ? s_keys : A.sort_keys + (size_t)f * APSE_MAX_POINTS * 2 + 2 * (size_t)cd.offset;
+        double dot = 0;
+        for (int i = tid; i < npow2; i += FQ_THREADS) {
+            unsigned long long key = 0xffffffffffffffffULL;
+            if (i < n) {
+                uint2 p = pts[i];
+                int x = p.x & 0xffff, y = p.x >> 16;
+                int gx = (int)(short)(p.y & 0xffff), gy = (int)(short)(p.y >> 16);
+                double dx = x - cx, dy = y - cy;
+                float theta = fast_atan2_deg((float)dy, (float)dx) * (float)(3.14159265358979323846 / 180);
+                dot += dx * gx + dy * gy;
+                key = ((unsigned long long)__float_as_uint(theta) << 32) | p.x;
+            }
+            keys[i] = key;
+        }
+        for (int d = 16; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d);
+        if (lane == 0) s_d[wid] = dot;
+        __syncthreads();
+        dot = 0;
+        for (int i = 0; i < FQ_THREADS / 32; i++) dot += s_d[i];
+        if (dot < 0) continue;
+
+        // ---- sort by theta (ties: packed y,x), drop adjacent duplicates
+        bitonic_sort_u64(keys, npow2);
+        uint32_t *uniq = reinterpret_cast<uint32_t *>(pts);  // reuse the cluster's point segment (n uint2 = 2n u32)
+        int sz = 0;
+        for (int base = 0; base < n; base += FQ_THREADS) {
+            int i = base + tid;
+            uint32_t xy = 0;
+            int flag = 0;
+            if (i < n) {
+                xy = (uint32_t)keys[i];
+                flag = (i == 0) || ((uint32_t)keys[i - 1] != xy);
+            }
+            int tot;
+            int pos = block_scan_excl(flag, s_warp, tot);
+            if (flag) uniq[sz + pos] = xy;
+            sz += tot;
+        }
+        __syncthreads();
+        if (sz < 4) continue;
+        const int ksz = min(20, sz / 12);
+        if (ksz < 2) continue;
+
+        // ---- weighted moments: terms in parallel, then exact sequential prefix sums (one thread per moment)
+        for (int i = tid; i < sz; i += FQ_THREADS) {
+            uint32_t xy = uniq[i];
+            double x = (xy & 0xffff) * .5 + 0.5, y = (xy >> 16) * .5 + 0.5;
+            int ix = (int)x, iy = (int)y;
+            double W = 1;
+            if (ix > 0 && ix + 1 < A.w && iy > 0 && iy + 1 < A.h) {
+                int gx = (int)im[(size_t)iy * A.w + ix + 1] - (int)im[(size_t)iy * A.w + ix - 1];
+                int gy = (int)im[(size_t)(iy + 1) * A.w + ix] - (int)im[(size_t)(iy - 1) * A.w + ix];
+                W = sqrt((double)(gx * gx + gy * gy)) + 1;
+            }
+            double *t = lf + (size_t)i * 6;
+            t[0] = W * x; t[1] = W * y; t[2] = W * x * x; t[3] = W * x * y; t[4] = W * y * y; t[5] = W;
+        }
+        __syncthreads();
+        if (tid < 6) {
+            double acc = lf[tid];
+            for (int i = 1; i < sz; i++) {
+                acc = acc + lf[(size_t)i * 6 + tid];
+                lf[(size_t)i * 6 + tid] = acc;
+            }
+        }
+        __syncthreads();
+
+        // ---- line-fit error curve, 7-tap Gaussian (sigma 1) low-pass
+        for (int i = tid; i < sz; i += FQ_THREADS) {
+            LineFit lfit;
+            fit_line(lf, sz, (i + sz - ksz) % sz, (i + ksz) % sz, lfit);
+            e0[i] = lfit.err;
+        }
+        __syncthreads();
+        {
+            // f[j] = (float)exp(-j*j/2) for j = -3..3
+            const float fw[7] = {0.011108996f, 0.13533528f, 0.60653067f, 1.0f, 0.60653067f, 0.13533528f, 0.011108996f};
+            for (int i = tid; i < sz; i += FQ_THREADS) {
+                double acc = 0;
+#pragma unroll
+                for (int t = 0; t < 7; t++) acc += e0[(i + t - 3 + sz) % sz] * fw[t];
+                e1[i] = acc;
+            }
+        }
+        __syncthreads();
+
+        // ---- strict local maxima
+        int nloc = 0;
+        for (int i = tid; i < sz; i += FQ_THREADS) {
+            double e = e1[i];
+            nloc += (e > e1[(i + 1) % sz] && e > e1[(i + sz - 1) % sz]) ? 1 : 0;
+        }
+        int nmaxima;
+        (void)block_scan_excl(nloc, s_warp, nmaxima);
+        if (nmaxima < 4) continue;
+        double thresh = -HUGE_VAL;  // keep maxima with err > thresh
+        if (nmaxima > A.max_nmaxima) {
+            // (max_nmaxima+1)-th largest maximum, duplicates counted: remove one instance per round
+            for (int r = 0; r <= A.max_nmaxima; r++) {
+                double best = -HUGE_VAL;
+                int bi = -1;
+                for (int i = tid; i < sz; i += FQ_THREADS) {
+                    double e = e1[i];
+                    if (!(e > e1[(i + 1) % sz] && e > e1[(i + sz - 1) % sz])) continue;
+                    bool removed = false;
+                    for (int q = 0; q < r; q++) removed |= (s_max_idx[q] == i);
+                    if (removed) continue;
+                    if (e > best || (e == best && i < bi)) { best = e; bi = i; }
+                }
+                s_best_err[tid] = best;
+                s_best_combo[tid] = (unsigned)bi;
+                __syncthreads();
+                if (tid == 0) {
+                    double b = -HUGE_VAL; int idx = -1;
+                    for (int t = 0; t < FQ_THREADS; t++) {
+                        int ti = (int)s_best_combo[t];
+                        if (ti < 0) continue;
+                        if (s_best_err[t] > b || (s_best_err[t] == b && ti < idx)) { b = s_best_err[t]; idx = ti; }
+                    }
+                    s_max_idx[r] = idx;
+                    s_max_err[r] = b;
+                }
+                __syncthreads();
+            }
+            thresh = s_max_err[A.max_nmaxima];
+            __syncthreads();
+        }
+        // gather kept maxima in index order (at most MAXIMA_CAP)
+        if (tid == 0) s_i4[4] = 0;
+        __syncthreads();
+        for (int base = 0; base < sz; base += FQ_THREADS) {
+            int i = base + tid;
+            int flag = 0;
+            if (i < sz) {
+                double e = e1[i];
+                flag = (e > e1[(i + 1) % sz] && e > e1[(i + sz - 1) % sz] && e > thresh) ? 1 : 0;
+            }
+            int tot;
+            int pos = block_scan_excl(flag, s_warp, tot);
+            int start = s_i4[4];
+            if (flag && start + pos < MAXIMA_CAP) s_max_idx[start + pos] = i;
+            __syncthreads();
+            if (tid == 0) s_i4[4] = start + tot;
+            __syncthreads();
+        }
+        const int m = min(s_i4[4], MAXIMA_CAP);
+        if (m < 4) continue;
+
+        // ---- line fits between all ordered pairs of maxima, then the 4-subset search
+        for (int p = tid; p < m * m; p += FQ_THREADS) {
+            int a = p / m, b = p % m;
+            if (a != b) fit_line(lf, sz, s_max_idx[a], s_max_idx[b], s_pair[a][b]);
+        }
+        __syncthreads();
+        double best_err = HUGE_VAL;
+        unsigned best_combo = 0xffffffffu;
+        const double mse_max = A.max_line_fit_mse;
+        for (int p = tid; p < m * m; p += FQ_THREADS) {
+            int m0 = p / m, m1 = p % m;
+            if (m1 <= m0) continue;
+            const LineFit &l01 = s_pair[m0][m1];
+            if (l01.mse > mse_max) continue;
+            for (int m2 = m1 + 1; m2 < m - 1; m2++) {
+                const LineFit &l12 = s_pair[m1][m2];
+                if (l12.mse > mse_max) continue;
+                double dt = l01.nx * l12.nx + l01.ny * l12.ny;
+                if (fabs(dt) > A.max_dot) continue;
+                for (int m3 = m2 + 1; m3 < m; m3++) {
+                    const LineFit &l23 = s_pair[m2][m3];
+                    if (l23.mse > mse_max) continue;
+                    const LineFit &l30 = s_pair[m3][m0];
+                    if (l30.mse > mse_max) continue;
+                    double err = l01.err + l12.err + l23.err + l30.err;
+                    unsigned combo = ((unsigned)m0 << 24) | ((unsigned)m1 << 16) | ((unsigned)m2 << 8) | (unsigned)m3;
+                    if (err < best_err || (err == best_err && combo < best_combo)) { best_err = err; best_combo = combo; }
+                }
+            }
+        }
+        s_best_err[tid] = best_err;
+        s_best_combo[tid] = best_combo;
+        __syncthreads();
+        if (tid == 0) {
+            double be = HUGE_VAL;
+            unsigned bc = 0xffffffffu;
+            for (int t = 0; t < FQ_THREADS; t++)
+                if (s_best_combo[t] != 0xffffffffu && (s_best_err[t] < be || (s_best_err[t] == be && s_best_combo[t] < bc))) {
+                    be = s_best_err[t]; bc = s_best_combo[t];
+                }
+            bool ok = bc != 0xffffffffu && (be / sz < (double)A.max_line_fit_mse);
+            float quad[4][2];
+            if (ok) {
+                int idx[4] = {s_max_idx[bc >> 24], s_max_idx[(bc >> 16) & 255], s_max_idx[(bc >> 8) & 255], s_max_idx[bc & 255]};
+                LineFit L[4];
+                for (int i = 0; i < 4 && ok; i++) {
+                    fit_line(lf, sz, idx[i], idx[(i + 1) & 3], L[i]);
+                    if (L[i].mse > (double)A.max_line_fit_mse) ok = false;
+                }
+                for (int i = 0; i < 4 && ok; i++) {
+                    int j = (i + 1) & 3;
+                    double A00 = L[i].ny, A01 = -L[j].ny, A10 = -L[i].nx, A11 = L[j].nx;
+                    double B0 = -L[i].Ex + L[j].Ex, B1 = -L[i].Ey + L[j].Ey;
+                    double det = A00 * A11 - A10 * A01;
+                    if (fabs(det) < 0.001) { ok = false; break; }
+                    double det_inv = 1.0 / det;
+                    double W00 = A11 * det_inv, W01 = -A01 * det_inv;
+                    double L0 = W00 * B0 + W01 * B1;
+                    quad[i][0] = (float)(L[i].Ex + L0 * A00);
+                    quad[i][1] = (float)(L[i].Ey + L0 * A10);
+                }
+            }
+            if (ok) {
+                double area = 0, len[3], p;
+                for (int i = 0; i < 3; i++) {
+                    int a = i, b = (i + 1) % 3;
+                    len[i] = sqrt(sq(quad[b][0] - quad[a][0]) + sq(quad[b][1] - quad[a][1]));
+                }
+                p = (len[0] + len[1] + len[2]) / 2;
+                area += sqrt(p * (p - len[0]) * (p - len[1]) * (p - len[2]));
+                const int idxs[4] = {2, 3, 0, 2};
+                for (int i = 0; i < 3; i++) {
+                    int a = idxs[i], b = idxs[i + 1];
+                    len[i] = sqrt(sq(quad[b][0] - quad[a][0]) + sq(quad[b][1] - quad[a][1]));
+                }
+                p = (len[0] + len[1] + len[2]) / 2;
+                area += sqrt(p * (p - len[0]) * (p - len[1]) * (p - len[2]));
+                if (area < 64) ok = false;
+            }
+            if (ok) {
+                double total = 0;
+                bool res = true;
+                for (int i = 0; i < 4; i++) {
+                    int i0 = i, i1 = (i + 1) & 3, i2 = (i + 2) & 3;
+                    double t0 = atan2f(quad[i0][1] - quad[i1][1], quad[i0][0] - quad[i1][0]);
+                    double t1 = atan2f(quad[i2][1] - quad[i1][1], quad[i2][0] - quad[i1][0]);
+                    double dth = t0 - t1;
+                    if (dth < 0) dth += 2 * 3.14159265358979323846;
+                    if (dth < A.critical_rad || dth > (3.14159265358979323846 - A.critical_rad)) res = false;
+                    total += dth;
+                }
+                if (total < 6.2 || total > 6.4) res = false;
+                ok = res;
+            }
+            if (ok) {
+                int32_t *cnt = A.counters + f * APSE_COUNTERS;
+                int qi = atomicAdd(&cnt[2], 1);
+                if (qi < APSE_MAX_QUADS) {
+                    float *q = A.quads + ((size_t)f * APSE_MAX_QUADS + qi) * 8;
+                    const int order[4] = {3, 0, 1, 2};
+                    for (int k = 0; k < 4; k++) { q[2 * k] = quad[order[k]][0]; q[2 * k + 1] = quad[order[k]][1]; }
+                    A.quad_order[(size_t)f * APSE_MAX_QUADS + qi] = (uint32_t)ci;
+                } else {
+                    atomicExch(&cnt[3], APSE_ERR_CAPACITY);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+struct DetectExtra {
+    uint8_t *tile_active;
+    int *work_counter;
+};
+
+int apse_detect_alloc(apse_ctx *ctx)
+{
+    size_t B = ctx->max_batch, npx = (size_t)ctx->max_w * ctx->max_h;
+    size_t ntiles = (size_t)div_up(ctx->max_w, 4) * div_up(ctx->max_h, 4);
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->thresh, B * npx));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmin, B * ntiles));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmax, B * ntiles));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->labels, B * npx * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->points, B * APSE_MAX_POINTS * sizeof(uint4)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->hash_keys, B * APSE_HASH_SLOTS * sizeof(unsigned long long)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->hash_count, B * APSE_HASH_SLOTS * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->hash_offset, B * APSE_HASH_SLOTS * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->sorted_pts, B * APSE_MAX_POINTS * sizeof(uint2)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->sort_keys, B * APSE_MAX_POINTS * 2 * sizeof(unsigned long long)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->lfps, B * APSE_MAX_POINTS * 6 * sizeof(double)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->errs, B * APSE_MAX_POINTS * 2 * sizeof(double)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->clusters, B * APSE_MAX_CLUSTERS * sizeof(ClusterDesc)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->counters, B * APSE_COUNTERS * sizeof(int32_t)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->quads, B * APSE_MAX_QUADS * 8 * sizeof(float)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->quad_order, B * APSE_MAX_QUADS * sizeof(uint32_t)));
+    DetectExtra *ex = new DetectExtra();
+    size_t nct = (size_t)div_up(ctx->max_w, CCL_TW) * div_up(ctx->max_h, CCL_TH);
+    CUDA_TRY(ctx, cudaMalloc((void **)&ex->tile_active, B * nct));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ex->work_counter, sizeof(int)));
+    ctx->point_rank = reinterpret_cast<uint32_t *>(ex);  // opaque slot reused to carry the extra pointers
+    return APSE_OK;
+}
+
+void apse_detect_free(apse_ctx *ctx)
+{
+    cudaFree(ctx->thresh); cudaFree(ctx->tmin); cudaFree(ctx->tmax); cudaFree(ctx->labels); cudaFree(ctx->points);
+    cudaFree(ctx->hash_keys); cudaFree(ctx->hash_count); cudaFree(ctx->hash_offset); cudaFree(ctx->sorted_pts);
+    cudaFree(ctx->sort_keys); cudaFree(ctx->lfps); cudaFree(ctx->errs); cudaFree(ctx->clusters); cudaFree(ctx->counters);
+    cudaFree(ctx->quads); cudaFree(ctx->quad_order);
+    DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
+    if (ex) { cudaFree(ex->tile_active); cudaFree(ex->work_counter); delete ex; }
+    ctx->point_rank = nullptr;
+}
+
+// runs K2..K5 for `batch` gray frames; leaves quads / counters in the context scratch
+int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp, cudaStream_t st)
+{
+    if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch || batch > 64)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: frame %dx%d x%d exceeds the context capacity %dx%d x%d (64 max)", w, h,
+                 batch, ctx->max_w, ctx->max_h, ctx->max_batch);
+    if (w < 8 || h < 8 || w > 32767 || h > 32767) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
+    DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
+    int tw = w / 4, th = h / 4;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hash_keys, 0xff, (size_t)batch * APSE_HASH_SLOTS * sizeof(unsigned long long), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hash_count, 0, (size_t)batch * APSE_HASH_SLOTS * sizeof(uint32_t), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, sizeof(int), st));
+    {
+        dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
+        k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax);
+        LAUNCH_CHECK(ctx);
+        k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, dp.min_white_black_diff, ctx->thresh);
+        LAUNCH_CHECK(ctx);
+        if (tw * 4 != w || th * 4 != h) {
+            k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, ctx->thresh);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    {
+        dim3 block(CCL_TW, CCL_TH), grid(div_up(w, CCL_TW), div_up(h, CCL_TH), batch);
+        k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active);
+        LAUNCH_CHECK(ctx);
+        k_ccl_merge<<<dim3(148 * 4, 1, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels);
+        LAUNCH_CHECK(ctx);
+        k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active);
+        LAUNCH_CHECK(ctx);
+        k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active, ctx->hash_keys, ctx->hash_count,
+                                              ctx->points, ctx->counters);
+        LAUNCH_CHECK(ctx);
+    }
+    k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ctx->clusters, ctx->counters,
+                                           dp.min_cluster_pixels, dp.max_cluster_points);
+    LAUNCH_CHECK(ctx);
+    k_scatter_points<<<dim3(148, min(batch, 8)), 256, 0, st>>>(ctx->points, ctx->hash_offset, ctx->counters, ctx->sorted_pts, batch);
+    LAUNCH_CHECK(ctx);
+    FitArgs A;
+    A.gray = gray; A.w = w; A.h = h; A.batch = batch; A.clusters = ctx->clusters; A.sorted_pts = ctx->sorted_pts;
+    A.sort_keys = ctx->sort_keys; A.lfps = ctx->lfps; A.errs = ctx->errs; A.counters = ctx->counters; A.quads = ctx->quads;
+    A.quad_order = ctx->quad_order; A.work_counter = ex->work_counter; A.max_nmaxima = dp.max_nmaxima;
+    A.critical_rad = dp.critical_rad; A.max_line_fit_mse = dp.max_line_fit_mse; A.max_dot = dp.max_dot;
+    k_fit_quads<<<148 * 4, FQ_THREADS, 0, st>>>(A);
+    LAUNCH_CHECK(ctx);
+    return APSE_OK;
+}

@@ -1,0 +1,156 @@
+/* apse_b200.h -- C ABI of libapse_b200.so: B200 (sm_100a) CUDA implementation of the per-frame ArUco marker
+ * pipeline of vision-agh/apse_uav's aruco_detect.py.
+ *
+ * The reference has no FFI of its own: its only language boundary is Python -> OpenCV C++ at each cv2.*
+ * call.  Every entry point below replaces one of those calls; the citation gives the
+ * aruco_detect.py line of the call it stands in for.  All image / result pointers are DEVICE pointers unless
+ * the parameter name ends in _host; all work is enqueued on the caller's stream (cudaStream_t passed as
+ * void*, NULL = legacy default stream) and is asynchronous until the caller synchronises.
+ *
+ * Every function returns 0 on success or a negative apse_status; apse_last_error() returns the message.
+ * Plain C types only (no torch / C++ types) so it can be bound from ctypes, cgo, JNI, ...
+ */
+#ifndef APSE_B200_H
+#define APSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APSE_ABI_VERSION 1
+
+typedef enum {
+    APSE_OK = 0,
+    APSE_ERR_INVALID_ARG = -1,   /* NULL pointer, bad size, unsupported parameter value        */
+    APSE_ERR_CUDA = -2,          /* a CUDA runtime call failed (message has the CUDA error)     */
+    APSE_ERR_NOT_CONFIGURED = -3,/* camera / lut / dictionary / params not set before use       */
+    APSE_ERR_CAPACITY = -4,      /* a fixed-capacity work buffer overflowed (never truncates silently) */
+    APSE_ERR_UNSUPPORTED = -5    /* parameter combination outside the implemented hot path      */
+} apse_status;
+
+typedef struct apse_ctx apse_ctx;
+
+/* POD mirror of cv2.aruco.DetectorParameters (aruco_detect.py:190-236; field names follow OpenCV).
+ * apse_params_default() fills the cv2 4.13 defaults. */
+typedef struct apse_params {
+    int adaptiveThreshWinSizeMin, adaptiveThreshWinSizeMax, adaptiveThreshWinSizeStep;
+    double adaptiveThreshConstant;
+    double minMarkerPerimeterRate, maxMarkerPerimeterRate;
+    double polygonalApproxAccuracyRate, minCornerDistanceRate;
+    int minDistanceToBorder;
+    double minMarkerDistanceRate;
+    float minGroupDistance;
+    int cornerRefinementMethod;       /* 0 NONE, 1 SUBPIX, 2 CONTOUR (unsupported), 3 APRILTAG */
+    int cornerRefinementWinSize;
+    float relativeCornerRefinmentWinSize;
+    int cornerRefinementMaxIterations;
+    double cornerRefinementMinAccuracy;
+    int markerBorderBits;
+    int perspectiveRemovePixelPerCell;
+    double perspectiveRemoveIgnoredMarginPerCell;
+    double maxErroneousBitsInBorderRate;
+    double minOtsuStdDev;
+    double errorCorrectionRate;
+    float aprilTagQuadDecimate, aprilTagQuadSigma;   /* must be 0 (reference leaves them disabled) */
+    int aprilTagMinClusterPixels, aprilTagMaxNmaxima;
+    float aprilTagCriticalRad, aprilTagMaxLineFitMse;
+    int aprilTagMinWhiteBlackDiff, aprilTagDeglitch; /* deglitch must be 0 */
+    int detectInvertedMarker;                        /* must be 0 */
+    int useAruco3Detection;                          /* must be 0 */
+    int minSideLengthCanonicalImg;
+    float minMarkerLengthRatioOriginalImg;
+} apse_params;
+
+/* Per-batch detection output (caller-owned DEVICE arrays, capacity max_markers per frame).
+ * corners/rejected: [batch][max_markers][4][2] float32; ids: [batch][max_markers] int32;
+ * n_markers / n_rejected / status: [batch] int32 (status != 0 -> capacity overflow code for that frame). */
+typedef struct apse_detections {
+    int max_markers;
+    float *corners;
+    int32_t *ids;
+    int32_t *n_markers;
+    float *rejected;      /* nullable */
+    int32_t *n_rejected;  /* nullable iff rejected is NULL */
+    int32_t *status;
+} apse_detections;
+
+int apse_abi_version(void);
+void apse_params_default(apse_params *p);
+
+/* Context: owns all scratch (labels, point lists, tables) sized here; no allocation on the hot path. */
+int apse_create(apse_ctx **out, int device, int max_w, int max_h, int max_batch);
+void apse_destroy(apse_ctx *ctx);
+const char *apse_last_error(apse_ctx *ctx);
+
+/* aruco_detect.py:92-103,568 -- camera model; builds the undistort maps on the device (initUndistortRectifyMap) */
+int apse_set_camera(apse_ctx *ctx, const double K_host[9], const double D_host[14], int w, int h, void *stream);
+/* aruco_detect.py:537-540 -- gamma look-up table applied to the Lab L channel */
+int apse_set_lut(apse_ctx *ctx, const uint8_t lut_host[256], void *stream);
+/* aruco_detect.py:263 -- dictionary bytesList [n_markers][4 rotations][nbytes] */
+int apse_set_dictionary(apse_ctx *ctx, const uint8_t *bytes_host, int n_markers, int marker_size, int max_corr_bits,
+                        void *stream);
+/* aruco_detect.py:190-236,266 */
+int apse_set_params(apse_ctx *ctx, const apse_params *p);
+
+/* ---- stage entry points (device pointers) --------------------------------------------------------------- */
+/* aruco_detect.py:568  cv2.initUndistortRectifyMap(K, D, None, K, (w,h), CV_32FC1) */
+int apse_init_undistort_map(apse_ctx *ctx, const double K_host[9], const double D_host[14], int w, int h,
+                            float *mapx, float *mapy, void *stream);
+/* aruco_detect.py:252  cv2.remap(src, mapx, mapy, INTER_LINEAR), BORDER_CONSTANT 0; cn = 1 or 3 */
+int apse_remap(apse_ctx *ctx, const uint8_t *src, int sw, int sh, int cn, const float *mapx, const float *mapy,
+               int dw, int dh, uint8_t *dst, void *stream);
+/* aruco_detect.py:255  cv2.cvtColor(.., COLOR_RGB2LAB) on 8-bit 3-channel pixels */
+int apse_cvt_rgb2lab(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream);
+/* aruco_detect.py:257  cv2.cvtColor(.., COLOR_LAB2RGB) */
+int apse_cvt_lab2rgb(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream);
+/* aruco_detect.py:592  cv2.cvtColor(.., COLOR_BGR2GRAY) */
+int apse_cvt_bgr2gray(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream);
+/* aruco_detect.py:256  cv2.LUT(src, lut) on a channel of an interleaved image: src/dst element stride in bytes */
+int apse_lut(apse_ctx *ctx, const uint8_t *src, int64_t n, int src_stride, const uint8_t *lut_dev, uint8_t *dst,
+             int dst_stride, void *stream);
+
+/* aruco_detect.py:250-259 + :592 fused: remap + Lab gamma + gray for a batch of frames
+ * bgr: [batch][h][w][3]; bgr_out (nullable): same shape; gray: [batch][h][w] */
+int apse_preprocess(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, int batch, void *stream);
+
+/* aruco_detect.py:267  aruco.detectMarkers(gray, dict, parameters=...) for a batch of gray frames [batch][h][w] */
+int apse_detect(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, void *stream);
+
+/* aruco_detect.py:601  aruco.estimatePoseSingleMarkers(corners, markerLength, K, D)
+ * corners: [n][4][2] float32 (device); marker_len: [n] float32 (device) or NULL to use marker_len_all;
+ * rvec/tvec: [n][3] float64 (device) */
+int apse_pose(apse_ctx *ctx, const float *corners, int n, const float *marker_len, float marker_len_all,
+              const double K_host[9], const double D_host[14], double *rvec, double *tvec, void *stream);
+
+/* Batched form of apse_pose over the output of apse_detect: corners [batch][max_markers][4][2], n_markers [batch];
+ * marker_len: [batch] float32 (device, one length per frame -- aruco_detect.py:601 uses the global markerLength of
+ * that frame) or NULL for marker_len_all; rvec/tvec: [batch][max_markers][3] float64; slots >= n_markers untouched */
+int apse_pose_frames(apse_ctx *ctx, const float *corners, const int32_t *n_markers, int batch, int max_markers,
+                     const float *marker_len, float marker_len_all, const double K_host[9], const double D_host[14],
+                     double *rvec, double *tvec, void *stream);
+
+/* aruco_detect.py:344,377,424,468  cv2.projectPoints(obj, rvec, tvec, K, D)
+ * obj: [n][3] float64, rvec/tvec: [3] float64, img: [n][2] float64 -- all device pointers */
+int apse_project_points(apse_ctx *ctx, const double *obj, int n, const double *rvec, const double *tvec,
+                        const double K_host[9], const double D_host[14], double *img, void *stream);
+
+/* Many projectPoints calls in one launch: point i uses pose pose_idx[i] of rvecs/tvecs [m][3] (all device) */
+int apse_project_points_multi(apse_ctx *ctx, const double *obj, int n, const int32_t *pose_idx, const double *rvecs,
+                              const double *tvecs, const double K_host[9], const double D_host[14], double *img,
+                              void *stream);
+
+/* Debug / parity taps of the APRILTAG candidate path for ONE frame (device pointers, nullable):
+ * thresh [h][w] u8 ternary image, labels [h][w] u32 component representative (valid where thresh != 127),
+ * quads [max_quads][8] float32 raw quads (cluster-key order), stats[4] int64 {points, clusters, fitted, quads} */
+int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_t *thresh, uint32_t *labels,
+                        float *quads, int max_quads, int64_t *stats_host, void *stream);
+
+/* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
+int64_t apse_launch_count(apse_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APSE_B200_H */
