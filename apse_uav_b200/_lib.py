@@ -72,9 +72,13 @@ SIGNATURES = {
     "apse_project_points_multi": [_vp, _vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp],
     "apse_debug_apriltag": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, C.POINTER(C.c_int64), _vp],
     "apse_launch_count": [_vp],
+    "apse_kernel_count": [],
+    "apse_kernel_name": [_i],
+    "apse_timing_enable": [_vp, _i],
+    "apse_timing_collect": [_vp, _dp, C.POINTER(C.c_int64), _i],
 }
 _RESTYPES = {"apse_destroy": None, "apse_params_default": None, "apse_last_error": C.c_char_p,
-             "apse_launch_count": C.c_int64}
+             "apse_launch_count": C.c_int64, "apse_kernel_name": C.c_char_p}
 
 _lib = None
 

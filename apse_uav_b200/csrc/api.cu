@@ -72,6 +72,7 @@ void apse_destroy(apse_ctx *ctx)
     cudaSetDevice(ctx->device);
     apse_detect_free(ctx);
     apse_decode_free(ctx);
+    for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
     cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->dict);
     delete ctx;
 }
@@ -79,6 +80,32 @@ void apse_destroy(apse_ctx *ctx)
 const char *apse_last_error(apse_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int64_t apse_launch_count(apse_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static const char *KERNEL_NAMES[KID_COUNT] = {
+    "k_build_undistort_map", "k_preprocess_fused", "k_remap", "k_cvt", "k_lut", "k_tile_minmax", "k_threshold",
+    "k_ccl_local", "k_ccl_merge", "k_ccl_flatten", "k_emit_points", "k_cluster_scan", "k_scatter_points", "k_fit_quads",
+    "k_decode", "k_pose", "k_project_points", "k_classic"};
+
+int apse_kernel_count(void) { return KID_COUNT; }
+const char *apse_kernel_name(int kid) { return kid >= 0 && kid < KID_COUNT ? KERNEL_NAMES[kid] : ""; }
+
+int apse_timing_enable(apse_ctx *ctx, int on)
+{
+    if (!ctx) return APSE_ERR_INVALID_ARG;
+    if (!on && ctx->timing) { int rc = apse_timing_flush(ctx); if (rc) return rc; }
+    ctx->timing = on != 0;
+    return APSE_OK;
+}
+
+int apse_timing_collect(apse_ctx *ctx, double *ms, int64_t *launches, int reset)
+{
+    if (!ctx || !ms || !launches) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "timing_collect: bad argument");
+    int rc = apse_timing_flush(ctx);
+    if (rc) return rc;
+    for (int i = 0; i < KID_COUNT; i++) { ms[i] = ctx->kernel_ms[i]; launches[i] = ctx->kernel_launches[i]; }
+    if (reset) for (int i = 0; i < KID_COUNT; i++) { ctx->kernel_ms[i] = 0; ctx->kernel_launches[i] = 0; }
+    return APSE_OK;
+}
 
 int apse_set_camera(apse_ctx *ctx, const double K[9], const double D[14], int w, int h, void *stream)
 {
@@ -150,6 +177,20 @@ int apse_set_params(apse_ctx *ctx, const apse_params *p)
 }
 
 }  // extern "C"
+
+// waits for the recorded events and accumulates their durations per kernel id
+int apse_timing_flush(apse_ctx *ctx)
+{
+    for (int i = 0; i < ctx->ev_used; i++) {
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stop[i]));
+        float ms = 0;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_start[i], ctx->ev_stop[i]));
+        ctx->kernel_ms[ctx->ev_kid[i]] += ms;
+        ctx->kernel_launches[ctx->ev_kid[i]]++;
+    }
+    ctx->ev_used = 0;
+    return APSE_OK;
+}
 
 int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h)
 {

@@ -42,12 +42,24 @@ struct DeviceParams {  // what the detection kernels need of apse_params (+ deri
     int n_markers, nbytes;
 };
 
-struct FrameScratch;  // opaque per-batch scratch owned by the context (detect_apriltag.cu)
+enum KernelId {
+    KID_BUILD_MAP = 0, KID_PREPROCESS, KID_REMAP, KID_CVT, KID_LUT, KID_TILE_MINMAX, KID_THRESHOLD, KID_CCL_LOCAL,
+    KID_CCL_MERGE, KID_CCL_FLATTEN, KID_EMIT, KID_CLUSTER_SCAN, KID_SCATTER, KID_FIT_QUADS, KID_DECODE, KID_POSE,
+    KID_PROJECT, KID_CLASSIC, KID_COUNT
+};
+#define APSE_EVENT_POOL 2048
 
 struct apse_ctx {
     int device = 0, max_w = 0, max_h = 0, max_batch = 0;
     std::string err;
     int64_t launches = 0;
+    // optional per-kernel CUDA-event timing (bench.py roofline): event pairs recorded around each launch
+    bool timing = false;
+    cudaEvent_t ev_start[APSE_EVENT_POOL], ev_stop[APSE_EVENT_POOL];
+    int ev_kid[APSE_EVENT_POOL];
+    int ev_used = 0, ev_created = 0;
+    double kernel_ms[KID_COUNT] = {0};
+    int64_t kernel_launches[KID_COUNT] = {0};
     // camera
     bool has_camera = false;
     int w = 0, h = 0;
@@ -101,10 +113,28 @@ struct apse_ctx {
             CTX_FAIL(ctx, APSE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-#define LAUNCH_CHECK(ctx)                       \
-    do {                                        \
-        (ctx)->launches++;                      \
-        CUDA_TRY(ctx, cudaGetLastError());      \
+int apse_timing_flush(apse_ctx *ctx);
+
+// KLAUNCH(ctx, kernel id, stream, kernel<<<...>>>(...)): counts the launch, checks it, and -- when timing is
+// enabled -- brackets it with CUDA events on the launching stream.
+#define KLAUNCH(ctx, kid, st, ...)                                                          \
+    do {                                                                                    \
+        int _slot = -1;                                                                     \
+        if ((ctx)->timing) {                                                                \
+            if ((ctx)->ev_used == APSE_EVENT_POOL) { int _r = apse_timing_flush(ctx); if (_r) return _r; } \
+            _slot = (ctx)->ev_used++;                                                       \
+            if (_slot >= (ctx)->ev_created) {                                               \
+                CUDA_TRY(ctx, cudaEventCreate(&(ctx)->ev_start[_slot]));                    \
+                CUDA_TRY(ctx, cudaEventCreate(&(ctx)->ev_stop[_slot]));                     \
+                (ctx)->ev_created = _slot + 1;                                              \
+            }                                                                               \
+            (ctx)->ev_kid[_slot] = (kid);                                                   \
+            CUDA_TRY(ctx, cudaEventRecord((ctx)->ev_start[_slot], (st)));                   \
+        }                                                                                   \
+        __VA_ARGS__;                                                                        \
+        if (_slot >= 0) CUDA_TRY(ctx, cudaEventRecord((ctx)->ev_stop[_slot], (st)));        \
+        (ctx)->launches++;                                                                  \
+        CUDA_TRY(ctx, cudaGetLastError());                                                  \
     } while (0)
 
 static __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }

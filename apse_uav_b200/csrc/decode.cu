@@ -99,14 +99,15 @@ __device__ void inverse_homography(const float *src, int S, double *Mi)
     const float dstc[8] = {0.f, 0.f, (float)S - 1, 0.f, (float)S - 1, (float)S - 1, 0.f, (float)S - 1};
     for (int i = 0; i < 64; i++) a[i] = 0;
     for (int i = 0; i < 4; i++) {
-        double sx = src[2 * i], sy = src[2 * i + 1], dx = dstc[2 * i], dy = dstc[2 * i + 1];
+        float sx = src[2 * i], sy = src[2 * i + 1], dx = dstc[2 * i], dy = dstc[2 * i + 1];
         a[i * 8 + 0] = a[(i + 4) * 8 + 3] = sx;
         a[i * 8 + 1] = a[(i + 4) * 8 + 4] = sy;
         a[i * 8 + 2] = a[(i + 4) * 8 + 5] = 1;
-        a[i * 8 + 6] = -sx * dx;
-        a[i * 8 + 7] = -sy * dx;
-        a[(i + 4) * 8 + 6] = -sx * dy;
-        a[(i + 4) * 8 + 7] = -sy * dy;
+        // the dependency forms these products on float32 point members before widening to double
+        a[i * 8 + 6] = __fmul_rn(-sx, dx);
+        a[i * 8 + 7] = __fmul_rn(-sy, dx);
+        a[(i + 4) * 8 + 6] = __fmul_rn(-sx, dy);
+        a[(i + 4) * 8 + 7] = __fmul_rn(-sy, dy);
         b[i] = dx;
         b[i + 4] = dy;
     }
@@ -486,8 +487,7 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: canonical marker image %d px exceeds the %d px limit", nb * dp.cell_size, DEC_MAX_S);
     const char *env = getenv("APSE_IDENTIFY_DECODED_PARENTS");
     int skip = (env && env[0] == '1') ? 0 : 1;
-    k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem), st>>>(gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, ctx->dict,
-                                                           skip, *out);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem), st>>>(gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, ctx->dict,
+                                                           skip, *out));
     return APSE_OK;
 }

@@ -909,38 +909,28 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, sizeof(int), st));
     {
         dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
-        k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax);
-        LAUNCH_CHECK(ctx);
-        k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, dp.min_white_black_diff, ctx->thresh);
-        LAUNCH_CHECK(ctx);
+        KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax));
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, dp.min_white_black_diff, ctx->thresh));
         if (tw * 4 != w || th * 4 != h) {
-            k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, ctx->thresh);
-            LAUNCH_CHECK(ctx);
+            KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, ctx->thresh));
         }
     }
     {
         dim3 block(CCL_TW, CCL_TH), grid(div_up(w, CCL_TW), div_up(h, CCL_TH), batch);
-        k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active);
-        LAUNCH_CHECK(ctx);
-        k_ccl_merge<<<dim3(148 * 4, 1, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels);
-        LAUNCH_CHECK(ctx);
-        k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active);
-        LAUNCH_CHECK(ctx);
-        k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active, ctx->hash_keys, ctx->hash_count,
-                                              ctx->points, ctx->counters);
-        LAUNCH_CHECK(ctx);
+        KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active));
+        KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<dim3(148 * 4, 1, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels));
+        KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active));
+        KLAUNCH(ctx, KID_EMIT, st, k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active, ctx->hash_keys, ctx->hash_count,
+                                              ctx->points, ctx->counters));
     }
-    k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ctx->clusters, ctx->counters,
-                                           dp.min_cluster_pixels, dp.max_cluster_points);
-    LAUNCH_CHECK(ctx);
-    k_scatter_points<<<dim3(148, min(batch, 8)), 256, 0, st>>>(ctx->points, ctx->hash_offset, ctx->counters, ctx->sorted_pts, batch);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_CLUSTER_SCAN, st, k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ctx->clusters, ctx->counters,
+                                           dp.min_cluster_pixels, dp.max_cluster_points));
+    KLAUNCH(ctx, KID_SCATTER, st, k_scatter_points<<<dim3(148, min(batch, 8)), 256, 0, st>>>(ctx->points, ctx->hash_offset, ctx->counters, ctx->sorted_pts, batch));
     FitArgs A;
     A.gray = gray; A.w = w; A.h = h; A.batch = batch; A.clusters = ctx->clusters; A.sorted_pts = ctx->sorted_pts;
     A.sort_keys = ctx->sort_keys; A.lfps = ctx->lfps; A.errs = ctx->errs; A.counters = ctx->counters; A.quads = ctx->quads;
     A.quad_order = ctx->quad_order; A.work_counter = ex->work_counter; A.max_nmaxima = dp.max_nmaxima;
     A.critical_rad = dp.critical_rad; A.max_line_fit_mse = dp.max_line_fit_mse; A.max_dot = dp.max_dot;
-    k_fit_quads<<<148 * 4, FQ_THREADS, 0, st>>>(A);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<148 * 4, FQ_THREADS, 0, st>>>(A));
     return APSE_OK;
 }

@@ -178,6 +178,40 @@ __device__ bool lu_solve8(double *A, double *b)
 __device__ void sym_solve6(const double *Ain, const double *b, double *x)
 {
     const int n = 6;
+    {
+        // Fast path: the damped normal matrix is symmetric positive definite in every well-posed solve, where
+        // a Cholesky solve equals the pseudo-inverse solution to rounding (1e-16 * cond).  Rank-deficient
+        // systems fall through to the eigen-decomposition below, which reproduces the SVD's truncation.
+        double Lm[36], tr = 0;
+        bool ok = true;
+        for (int i = 0; i < n; i++) tr += Ain[i * n + i];
+        for (int j = 0; j < n && ok; j++) {
+            double d = Ain[j * n + j];
+            for (int k = 0; k < j; k++) d -= Lm[j * n + k] * Lm[j * n + k];
+            if (!(d > tr * 1e-13)) { ok = false; break; }
+            d = sqrt(d);
+            Lm[j * n + j] = d;
+            for (int i = j + 1; i < n; i++) {
+                double s = Ain[i * n + j];
+                for (int k = 0; k < j; k++) s -= Lm[i * n + k] * Lm[j * n + k];
+                Lm[i * n + j] = s / d;
+            }
+        }
+        if (ok) {
+            double y[6];
+            for (int i = 0; i < n; i++) {
+                double s = b[i];
+                for (int k = 0; k < i; k++) s -= Lm[i * n + k] * y[k];
+                y[i] = s / Lm[i * n + i];
+            }
+            for (int i = n - 1; i >= 0; i--) {
+                double s = y[i];
+                for (int k = i + 1; k < n; k++) s -= Lm[k * n + i] * x[k];
+                x[i] = s / Lm[i * n + i];
+            }
+            return;
+        }
+    }
     double A[36], V[36];
     for (int i = 0; i < 36; i++) { A[i] = Ain[i]; V[i] = 0; }
     for (int i = 0; i < n; i++) V[i * n + i] = 1;
@@ -386,8 +420,7 @@ int apse_pose(apse_ctx *ctx, const float *corners, int n, const float *marker_le
     CamModel C;
     int rc = make_cam(ctx, K, D, &C);
     if (rc) return rc;
-    k_pose<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(corners, n, marker_len, marker_len_all, C, rvec, tvec);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_POSE, (cudaStream_t)stream, k_pose<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(corners, n, marker_len, marker_len_all, C, rvec, tvec));
     return APSE_OK;
 }
 
@@ -398,8 +431,7 @@ int apse_project_points(apse_ctx *ctx, const double *obj, int n, const double *r
     CamModel C;
     int rc = make_cam(ctx, K, D, &C);
     if (rc) return rc;
-    k_project_points<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(obj, n, rvec, tvec, C, img);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_PROJECT, (cudaStream_t)stream, k_project_points<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(obj, n, rvec, tvec, C, img));
     return APSE_OK;
 }
 
@@ -412,9 +444,8 @@ int apse_pose_frames(apse_ctx *ctx, const float *corners, const int32_t *n_marke
     CamModel C;
     int rc = make_cam(ctx, K, D, &C);
     if (rc) return rc;
-    k_pose_frames<<<div_up(batch * max_markers, 64), 64, 0, (cudaStream_t)stream>>>(corners, n_markers, batch, max_markers, marker_len,
-                                                                               marker_len_all, C, rvec, tvec);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_POSE, (cudaStream_t)stream, k_pose_frames<<<div_up(batch * max_markers, 64), 64, 0, (cudaStream_t)stream>>>(corners, n_markers, batch, max_markers, marker_len,
+                                                                               marker_len_all, C, rvec, tvec));
     return APSE_OK;
 }
 
@@ -425,7 +456,6 @@ int apse_project_points_multi(apse_ctx *ctx, const double *obj, int n, const int
     CamModel C;
     int rc = make_cam(ctx, K, D, &C);
     if (rc) return rc;
-    k_project_points_multi<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(obj, n, pose_idx, rvecs, tvecs, C, img);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_PROJECT, (cudaStream_t)stream, k_project_points_multi<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(obj, n, pose_idx, rvecs, tvecs, C, img));
     return APSE_OK;
 }

@@ -153,10 +153,9 @@ int apse_init_undistort_map(apse_ctx *ctx, const double K[9], const double D[14]
     if (!ctx || !K || !D || !mapx || !mapy || w <= 0 || h <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "init_undistort_map: bad argument");
     if (D[12] != 0 || D[13] != 0) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "tilted sensor model (tauX/tauY) is not supported");
     dim3 block(256), grid(div_up(w, 256), h);
-    k_build_undistort_map<<<grid, block, 0, (cudaStream_t)stream>>>(w, h, K[0], K[4], K[2], K[5], D[0], D[1], D[2], D[3],
+    KLAUNCH(ctx, KID_BUILD_MAP, (cudaStream_t)stream, k_build_undistort_map<<<grid, block, 0, (cudaStream_t)stream>>>(w, h, K[0], K[4], K[2], K[5], D[0], D[1], D[2], D[3],
                                                                     D[4], D[5], D[6], D[7], D[8], D[9], D[10], D[11],
-                                                                    mapx, mapy);
-    LAUNCH_CHECK(ctx);
+                                                                    mapx, mapy));
     return APSE_OK;
 }
 
@@ -266,9 +265,8 @@ int apse_preprocess(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t
     int w = ctx->w, h = ctx->h;
     int fpb = batch >= 8 ? 8 : batch;
     dim3 grid(div_up(w, 32 * K1_PX), div_up(h, 8), div_up(batch, fpb));
-    k_preprocess_fused<<<grid, 256, 0, (cudaStream_t)stream>>>(bgr, bgr_out, gray, ctx->mapx, ctx->mapy, ctx->tables, w, h,
-                                                              batch, fpb);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_PREPROCESS, (cudaStream_t)stream, k_preprocess_fused<<<grid, 256, 0, (cudaStream_t)stream>>>(bgr, bgr_out, gray, ctx->mapx, ctx->mapy, ctx->tables, w, h,
+                                                              batch, fpb));
     return APSE_OK;
 }
 
@@ -292,8 +290,7 @@ int apse_remap(apse_ctx *ctx, const uint8_t *src, int sw, int sh, int cn, const 
     if (cn != 1 && cn != 3) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "remap: only 1- or 3-channel 8-bit images");
     if ((int64_t)sw * sh * cn >= (1ll << 31)) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "remap: source image too large");
     dim3 grid(div_up(dw, 256), dh);
-    k_remap<<<grid, 256, 0, (cudaStream_t)stream>>>(src, sw, sh, cn, mapx, mapy, dw, dh, dst);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_REMAP, (cudaStream_t)stream, k_remap<<<grid, 256, 0, (cudaStream_t)stream>>>(src, sw, sh, cn, mapx, mapy, dw, dh, dst));
     return APSE_OK;
 }
 
@@ -348,22 +345,19 @@ static int grid_for(int64_t n) { return (int)((n + 255) / 256 < 148 * 16 ? (n + 
 int apse_cvt_rgb2lab(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream)
 {
     if (!ctx || !src || !dst || npx <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "cvt_rgb2lab: bad argument");
-    k_rgb2lab<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_rgb2lab<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id));
     return APSE_OK;
 }
 int apse_cvt_lab2rgb(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream)
 {
     if (!ctx || !src || !dst || npx <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "cvt_lab2rgb: bad argument");
-    k_lab2rgb<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_lab2rgb<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id));
     return APSE_OK;
 }
 int apse_cvt_bgr2gray(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream)
 {
     if (!ctx || !src || !dst || npx <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "cvt_bgr2gray: bad argument");
-    k_bgr2gray<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_bgr2gray<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst));
     return APSE_OK;
 }
 int apse_lut(apse_ctx *ctx, const uint8_t *src, int64_t n, int src_stride, const uint8_t *lut_dev, uint8_t *dst,
@@ -371,7 +365,6 @@ int apse_lut(apse_ctx *ctx, const uint8_t *src, int64_t n, int src_stride, const
 {
     if (!ctx || !src || !dst || !lut_dev || n <= 0 || src_stride <= 0 || dst_stride <= 0)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "lut: bad argument");
-    k_lut<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(src, n, src_stride, lut_dev, dst, dst_stride);
-    LAUNCH_CHECK(ctx);
+    KLAUNCH(ctx, KID_LUT, (cudaStream_t)stream, k_lut<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(src, n, src_stride, lut_dev, dst, dst_stride));
     return APSE_OK;
 }

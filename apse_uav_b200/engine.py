@@ -81,6 +81,17 @@ class Engine:
     def launches(self):
         return int(self.lib.apse_launch_count(self.h))
 
+    def timing(self, on: bool):
+        self._check(self.lib.apse_timing_enable(self.h, 1 if on else 0))
+
+    def timing_collect(self, reset=True):
+        """{kernel name: (total ms, launches)} accumulated since the last reset (synchronises)."""
+        n = self.lib.apse_kernel_count()
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._check(self.lib.apse_timing_collect(self.h, ms, cnt, 1 if reset else 0))
+        return {self.lib.apse_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
+
     # ------------------------------------------------------------------------------------ configuration
     def set_camera(self, K, D, w, h):
         self.K = np.ascontiguousarray(K, np.float64).reshape(3, 3)

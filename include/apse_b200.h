@@ -150,6 +150,13 @@ int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_
 /* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
 int64_t apse_launch_count(apse_ctx *ctx);
 
+/* Optional per-kernel device timing: while enabled every launch is bracketed by CUDA events on the launching
+ * stream; collect() synchronises and returns accumulated milliseconds / launch counts per kernel id. */
+int apse_kernel_count(void);
+const char *apse_kernel_name(int kid);
+int apse_timing_enable(apse_ctx *ctx, int on);
+int apse_timing_collect(apse_ctx *ctx, double *ms_host, int64_t *launches_host, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,14 +60,15 @@ void orc_perspective_transform(const float *src, const float *dst, double *M)
     double a[64], b[8];
     memset(a, 0, sizeof a);
     for (int i = 0; i < 4; i++) {
-        double sx = src[2 * i], sy = src[2 * i + 1], dx = dst[2 * i], dy = dst[2 * i + 1];
+        float sx = src[2 * i], sy = src[2 * i + 1], dx = dst[2 * i], dy = dst[2 * i + 1];
         a[i * 8 + 0] = a[(i + 4) * 8 + 3] = sx;
         a[i * 8 + 1] = a[(i + 4) * 8 + 4] = sy;
         a[i * 8 + 2] = a[(i + 4) * 8 + 5] = 1;
-        a[i * 8 + 6] = -sx * dx;
-        a[i * 8 + 7] = -sy * dx;
-        a[(i + 4) * 8 + 6] = -sx * dy;
-        a[(i + 4) * 8 + 7] = -sy * dy;
+        /* the dependency forms these products on float32 point members before widening to double */
+        a[i * 8 + 6] = (float)(-sx * dx);
+        a[i * 8 + 7] = (float)(-sy * dx);
+        a[(i + 4) * 8 + 6] = (float)(-sx * dy);
+        a[(i + 4) * 8 + 7] = (float)(-sy * dy);
         b[i] = dx;
         b[i + 4] = dy;
     }

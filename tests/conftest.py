@@ -1,0 +1,81 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def has_cv2():
+    try:
+        import cv2  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+needs_cv2 = pytest.mark.skipif(not has_cv2(), reason="cv2 (the reference's dependency) not importable")
+
+
+@pytest.fixture(scope="session")
+def camera():
+    cam = json.load(open(os.path.join(GOLDEN, "cam_params.json")))
+    return np.array(cam["mtx"]), np.array(cam["dist"]).ravel()
+
+
+@pytest.fixture(scope="session")
+def lut():
+    import __graft_entry__ as G
+    return G.gamma_lut()
+
+
+@pytest.fixture(scope="session")
+def dictionary():
+    from apse_uav_b200 import aruco
+    return aruco.getPredefinedDictionary(aruco.DICT_4X4_50)
+
+
+@pytest.fixture(scope="session")
+def ref_params():
+    from apse_uav_b200 import aruco
+    import __graft_entry__ as G
+    return G.reference_parameters(aruco)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O
+
+
+def golden_cases():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+@pytest.fixture(scope="session")
+def frames4k(dictionary):
+    """One sparse and one dense synthetic 4K frame (seeded)."""
+    from tools import synth
+    return {"sparse": synth.make_frame(dictionary.bytesList, 3), "dense": synth.make_dense_frame(dictionary.bytesList, 11)}
+
+
+def cv2_params(p):
+    import cv2
+    q = cv2.aruco.DetectorParameters()
+    for k, v in vars(p).items():
+        setattr(q, k, v)
+    return q

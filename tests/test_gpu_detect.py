@@ -1,0 +1,135 @@
+"""GPU parity: aruco.detectMarkers in CORNER_REFINE_APRILTAG mode (aruco_detect.py:266-267) through the C ABI.
+Bars (BASELINE.json): ids / candidate counts bit-exact, sub-pixel corners <= 1e-3 px (observed: bit-identical)."""
+import numpy as np
+import pytest
+from conftest import golden_cases, load_golden, has_cv2, cv2_params
+
+pytestmark = pytest.mark.gpu
+CORNER_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def eng(dictionary, ref_params):
+    from apse_uav_b200.engine import Engine
+    e = Engine(0, 3840, 2160, 4)
+    e.set_dictionary(dictionary.raw, dictionary.markerSize, dictionary.maxCorrectionBits)
+    e.set_params(ref_params)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def grays4k(oracle, camera, lut, frames4k):
+    K, D = camera
+    ox, oy = oracle.init_undistort_map(K, D, 3840, 2160)
+    return {k: oracle.preprocess(v, ox, oy, lut)[1] for k, v in frames4k.items()}
+
+
+@pytest.mark.parametrize("kind", ["sparse", "dense"])
+def test_apriltag_stages_4k(eng, oracle, ref_params, grays4k, kind):
+    """every intermediate of the candidate path: ternary image, component labels, point / cluster counts, raw quads."""
+    import torch
+    gray = grays4k[kind]
+    oq, st = oracle.at_quads(gray, ref_params, dumps=True)
+    dbg = eng.debug_apriltag(torch.from_numpy(gray).cuda())
+    th = dbg["thresh"].cpu().numpy()
+    assert np.array_equal(th, st["thresh"])
+    lab = dbg["labels"].cpu().numpy().view(np.uint32)
+    m = th != 127
+    assert np.array_equal(lab[m], st["rep"][m])          # same representative (smallest pixel index) everywhere
+    assert (dbg["points"], dbg["clusters"], dbg["fitted"], dbg["n_quads"]) == (st["points"], st["clusters"], st["fitted"], len(oq))
+    gq = dbg["quads"].cpu().numpy().reshape(-1, 8)
+    dist = np.abs(gq[:, None, :] - oq.reshape(-1, 8)[None, :, :]).max(-1)
+    assert (dist.min(1) == 0).all() and (dist.min(0) == 0).all()   # bit-identical quad set
+
+
+@pytest.mark.parametrize("kind", ["sparse", "dense"])
+def test_detect_markers_4k(oracle, dictionary, ref_params, grays4k, kind):
+    from apse_uav_b200 import aruco
+    gray = grays4k[kind]
+    c, ids, rej = aruco.detectMarkers(gray, dictionary, parameters=ref_params)
+    oc, oi, orj = oracle.detect_markers_apriltag(gray, dictionary.raw, ref_params)
+    assert ids.dtype == np.int32 and ids.shape == (len(oi), 1) and c[0].shape == (1, 4, 2) and c[0].dtype == np.float32
+    assert np.array_equal(ids.ravel(), oi)
+    assert np.abs(np.array(c).reshape(-1, 4, 2) - oc).max() <= CORNER_TOL
+    assert len(rej) == len(orj) and (len(orj) == 0 or np.abs(np.array(rej).reshape(-1, 4, 2) - orj).max() <= CORNER_TOL)
+    if has_cv2():
+        import cv2
+        det = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(ref_params))
+        rc, ri, rr = det.detectMarkers(gray)
+        assert np.array_equal(ids.ravel(), ri.ravel()) and len(rr) == len(rej)
+        assert np.abs(np.array(c) - np.array(rc)).max() <= CORNER_TOL
+
+
+def test_empty_frame_returns_none_ids(dictionary, ref_params):
+    from apse_uav_b200 import aruco
+    flat = np.full((480, 640), 128, np.uint8)
+    c, ids, rej = aruco.detectMarkers(flat, dictionary, parameters=ref_params)
+    assert ids is None and c == () and rej == ()    # aruco_detect.py:599 relies on ids being None
+    noise = np.random.default_rng(0).integers(100, 140, (480, 640), dtype=np.uint8)
+    c, ids, rej = aruco.detectMarkers(noise, dictionary, parameters=ref_params)
+    assert ids is None
+
+
+def test_ragged_sizes_borders_and_bgr_input(oracle, dictionary, ref_params):
+    """sizes not divisible by the 4x4 threshold tiles / the CCL tiles, markers cut by the image border, BGR input."""
+    from apse_uav_b200 import aruco
+    from tools import synth
+    for seed, (w, h) in enumerate([(1280, 720), (1283, 721), (1001, 750), (333, 251)]):
+        f = synth.make_frame(dictionary.bytesList, 40 + seed, w, h, ids=[i % 50 for i in range(30)], side_range=(40, 120),
+                             jitter=0.15, occlude_frac=0.15, margin=0, noise_sigma=3)
+        gray = oracle.bgr2gray(f)
+        oc, oi, orj = oracle.detect_markers_apriltag(gray, dictionary.raw, ref_params)
+        for img in (gray, f):
+            c, ids, rej = aruco.detectMarkers(img, dictionary, parameters=ref_params)
+            got = ids.ravel() if ids is not None else np.zeros(0, np.int32)
+            assert np.array_equal(got, oi), (w, h)
+            assert len(oi) == 0 or np.abs(np.array(c).reshape(-1, 4, 2) - oc).max() <= CORNER_TOL
+            assert len(rej) == len(orj)
+
+
+def test_batch_equals_single_frames(eng, grays4k):
+    import torch
+    batch = torch.from_numpy(np.stack([grays4k["sparse"], grays4k["dense"], grays4k["sparse"], grays4k["dense"]])).cuda()
+    r = eng.detect(batch, max_markers=256)
+    n = r["n"].cpu().numpy()
+    assert (r["status"].cpu().numpy() == 0).all() and n[0] == n[2] and n[1] == n[3] and n[0] >= 4 and n[1] >= 150
+    for a, b in ((0, 2), (1, 3)):
+        assert torch.equal(r["ids"][a], r["ids"][b]) and torch.equal(r["corners"][a], r["corners"][b])
+    single = eng.detect(batch[1:2], max_markers=256)
+    assert torch.equal(single["ids"][0], r["ids"][1]) and torch.equal(single["corners"][0], r["corners"][1])
+
+
+def test_capacity_overflow_is_reported_not_truncated(eng, grays4k):
+    import torch
+    r = eng.detect(torch.from_numpy(grays4k["dense"]).cuda(), max_markers=16)
+    assert int(r["status"][0]) == -4 and int(r["n"][0]) == 16
+
+
+def test_parameter_validation_mirrors_opencv_asserts(dictionary):
+    from apse_uav_b200 import aruco, ApseError
+    img = np.zeros((64, 64), np.uint8)
+    p = aruco.DetectorParameters(); p.cornerRefinementMethod = aruco.CORNER_REFINE_APRILTAG; p.markerBorderBits = 0
+    with pytest.raises(ApseError):
+        aruco.detectMarkers(img, dictionary, parameters=p)
+    p = aruco.DetectorParameters(); p.cornerRefinementMethod = aruco.CORNER_REFINE_APRILTAG; p.aprilTagQuadDecimate = 2.0
+    with pytest.raises(ApseError):
+        aruco.detectMarkers(img, dictionary, parameters=p)
+    with pytest.raises(ApseError):
+        aruco.detectMarkers(np.zeros((0, 0), np.uint8), dictionary)
+    with pytest.raises(ApseError):
+        aruco.detectMarkers(img.astype(np.float32), dictionary)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_detect_golden(dictionary, ref_params, oracle, name):
+    from apse_uav_b200 import aruco
+    g = load_golden(name)
+    h, w = g["frame"].shape[:2]
+    ox, oy = oracle.init_undistort_map(g["K"], g["D"], w, h)
+    _, gray = oracle.preprocess(g["frame"], ox, oy, g["lut"])
+    c, ids, rej = aruco.detectMarkers(gray, dictionary, parameters=ref_params)
+    got = ids.ravel() if ids is not None else np.zeros(0, np.int32)
+    assert np.array_equal(got, g["ids"])
+    assert len(got) == 0 or np.abs(np.array(c).reshape(-1, 4, 2) - g["corners"]).max() <= CORNER_TOL
+    assert len(rej) == len(g["rejected"])

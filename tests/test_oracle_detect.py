@@ -1,0 +1,92 @@
+"""CPU: the oracle's detectMarkers (APRILTAG mode) against cv2 and the golden vectors."""
+import numpy as np
+import pytest
+from conftest import needs_cv2, golden_cases, load_golden, cv2_params
+
+
+@needs_cv2
+def test_fast_atan2_bit_exact(oracle):
+    import cv2
+    rng = np.random.default_rng(1)
+    y = rng.normal(0, 100, 20000).astype(np.float32)
+    x = rng.normal(0, 100, 20000).astype(np.float32)
+    y[:5] = 0; x[5:10] = 0
+    for a, b in zip(y, x):
+        assert np.float32(cv2.fastAtan2(float(a), float(b))) == np.float32(oracle.fast_atan2(float(a), float(b)))
+
+
+def _check(oracle, gray, dictionary, p, ref_c, ref_i, ref_r):
+    oc, oi, orj = oracle.detect_markers_apriltag(gray, dictionary.raw, p)
+    assert np.array_equal(oi, ref_i)
+    assert oc.shape == ref_c.shape and (len(oc) == 0 or np.abs(oc - ref_c).max() <= 1e-3)
+    assert orj.shape == ref_r.shape and (len(orj) == 0 or np.abs(orj - ref_r).max() <= 1e-3)
+    return oc, oi
+
+
+@needs_cv2
+@pytest.mark.parametrize("kind", ["sparse", "dense"])
+def test_detect_4k_vs_cv2(oracle, camera, lut, dictionary, ref_params, frames4k, kind):
+    import cv2
+    K, D = camera
+    mx, my = oracle.init_undistort_map(K, D, 3840, 2160)
+    _, gray = oracle.preprocess(frames4k[kind], mx, my, lut)
+    det = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(ref_params))
+    c, i, r = det.detectMarkers(gray)
+    oc, oi = _check(oracle, gray, dictionary, ref_params, np.array(c, np.float32).reshape(-1, 4, 2), i.ravel(),
+                    np.array(r, np.float32).reshape(-1, 4, 2))
+    assert len(oi) >= (4 if kind == "sparse" else 150)
+    assert np.array_equal(oc, np.array(c, np.float32).reshape(-1, 4, 2))  # bit-identical on these frames
+
+
+@needs_cv2
+def test_detect_border_and_partial_tiles_vs_cv2(oracle, dictionary, ref_params):
+    """markers crossing the image border, image sizes not divisible by the 4x4 threshold tiles."""
+    import cv2
+    from tools import synth
+    det = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(ref_params))
+    for seed, (w, h) in enumerate([(1280, 720), (1283, 721), (1001, 750)]):
+        f = synth.make_frame(dictionary.bytesList, 40 + seed, w, h, ids=[i % 50 for i in range(30)], side_range=(40, 120),
+                             jitter=0.15, occlude_frac=0.15, margin=0, noise_sigma=3)
+        gray = cv2.cvtColor(f, cv2.COLOR_BGR2GRAY)
+        c, i, r = det.detectMarkers(gray)
+        _check(oracle, gray, dictionary, ref_params, np.array(c, np.float32).reshape(-1, 4, 2),
+               i.ravel() if i is not None else np.zeros(0, np.int32), np.array(r, np.float32).reshape(-1, 4, 2))
+
+
+@needs_cv2
+def test_decode_units_vs_cv2(oracle, dictionary):
+    import cv2
+    rng = np.random.default_rng(5)
+    gray = cv2.GaussianBlur(rng.integers(0, 256, (300, 400), dtype=np.uint8), (7, 7), 2)
+    for _ in range(20):
+        q = (np.float32([[80, 60], [300, 70], [310, 240], [70, 230]]) + rng.uniform(-25, 25, (4, 2))).astype(np.float32)
+        S = 48
+        dst = np.float32([[0, 0], [S - 1, 0], [S - 1, S - 1], [0, S - 1]])
+        M = cv2.getPerspectiveTransform(q, dst)
+        assert np.allclose(M, oracle.perspective_transform(q, dst), rtol=1e-9, atol=1e-12)
+        ref = cv2.warpPerspective(gray, M, (S, S), flags=cv2.INTER_NEAREST)
+        mine = oracle.warp_nearest(gray, q, S)
+        assert np.array_equal(ref, mine)
+        t, _ = cv2.threshold(ref, 125, 255, cv2.THRESH_BINARY | cv2.THRESH_OTSU)
+        assert int(t) == oracle.otsu(ref)
+    cvd = cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50)
+    for _ in range(3000):
+        bits = rng.integers(0, 2, (4, 4), dtype=np.uint8)
+        if rng.uniform() < 0.5:  # near a real marker
+            m = rng.integers(0, 50)
+            bits = cv2.aruco.Dictionary_getBitsFromByteList(cvd.bytesList[m:m + 1], 4)
+            bits = np.rot90(bits, rng.integers(0, 4)).copy()
+            for _k in range(rng.integers(0, 4)):
+                bits[rng.integers(0, 4), rng.integers(0, 4)] ^= 1
+        ok, idx, rot = cvd.identify(bits, 2.0)
+        ok2, idx2, rot2 = oracle.identify(bits, dictionary.raw, 1, 2.0)
+        assert (ok, idx, rot) == (ok2, idx2, rot2) if ok else not ok2
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_detect_vs_golden(oracle, dictionary, ref_params, name):
+    g = load_golden(name)
+    h, w = g["frame"].shape[:2]
+    mx, my = oracle.init_undistort_map(g["K"], g["D"], w, h)
+    _, gray = oracle.preprocess(g["frame"], mx, my, g["lut"])
+    _check(oracle, gray, dictionary, ref_params, g["corners"], g["ids"], g["rejected"])

@@ -1,0 +1,57 @@
+"""CPU: the oracle's preprocess stage against the reference's dependency (cv2) and the golden vectors."""
+import zlib
+import numpy as np
+import pytest
+from conftest import needs_cv2, golden_cases, load_golden
+
+
+@needs_cv2
+def test_undistort_map_vs_cv2(oracle, camera):
+    import cv2
+    K, D = camera
+    mx, my = cv2.initUndistortRectifyMap(K, D, None, K, (3840, 2160), 5)
+    ox, oy = oracle.init_undistort_map(K, D, 3840, 2160)
+    bad = (ox != mx) | (oy != my)
+    assert bad.sum() <= 4  # cv2 accumulates along the row; <= 1 float32 ulp on a handful of pixels
+    assert np.abs(ox - mx).max() <= 5e-4 and np.abs(oy - my).max() <= 5e-4
+    # and those pixels map to the same Q5 fixed-point coordinate, i.e. remap output is unaffected
+    assert np.array_equal(np.rint(ox[bad] * np.float32(32)), np.rint(mx[bad] * np.float32(32)))
+
+
+@needs_cv2
+def test_remap_bit_exact(oracle, camera):
+    import cv2
+    K, D = camera
+    K = K.copy(); K[:2] *= 0.5
+    mx, my = cv2.initUndistortRectifyMap(K, D, None, K, (1920, 1080), 5)
+    img = np.random.default_rng(0).integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    assert np.array_equal(cv2.remap(img, mx, my, cv2.INTER_LINEAR), oracle.remap(img, mx, my))
+    g = img[..., 0].copy()
+    assert np.array_equal(cv2.remap(g, mx, my, cv2.INTER_LINEAR), oracle.remap(g, mx, my))
+
+
+@needs_cv2
+def test_colour_chain_all_colours(oracle, lut):
+    import cv2
+    c = np.arange(1 << 24, dtype=np.uint32)
+    cols = np.stack([(c >> 16) & 255, (c >> 8) & 255, c & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    lab = cv2.cvtColor(cols, cv2.COLOR_RGB2LAB)
+    assert np.array_equal(lab, oracle.rgb2lab(cols))
+    assert np.array_equal(cv2.cvtColor(cols, cv2.COLOR_LAB2RGB), oracle.lab2rgb(cols))
+    assert np.array_equal(cv2.cvtColor(cols, cv2.COLOR_BGR2GRAY), oracle.bgr2gray(cols))
+    lab[..., 0] = cv2.LUT(lab[..., 0], lut.reshape(1, 256))
+    ref = cv2.cvtColor(lab, cv2.COLOR_LAB2RGB)
+    olab = oracle.rgb2lab(cols)
+    olab[..., 0] = lut[olab[..., 0]]
+    assert np.array_equal(ref, oracle.lab2rgb(olab))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_preprocess_vs_golden(oracle, name):
+    g = load_golden(name)
+    h, w = g["frame"].shape[:2]
+    mx, my = oracle.init_undistort_map(g["K"], g["D"], w, h)
+    out, gray = oracle.preprocess(g["frame"], mx, my, g["lut"])
+    assert zlib.crc32(out.tobytes()) == int(g["corrected_crc"])
+    assert zlib.crc32(gray.tobytes()) == int(g["gray_crc"])
+    assert np.array_equal(gray[::37], g["gray_rows"])
