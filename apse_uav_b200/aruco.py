@@ -134,6 +134,8 @@ def estimatePoseSingleMarkers(corners, markerLength, cameraMatrix, distCoeffs, r
         c = corners.reshape(-1, 4, 2)
     else:
         c = np.asarray([np.asarray(x, np.float32).reshape(4, 2) for x in corners], np.float32).reshape(-1, 4, 2)
+        if c.shape[0] == 0:
+            c = np.zeros((0, 4, 2), np.float32)
     n = c.shape[0]
     rv, tv = e.pose(c, float(markerLength), np.asarray(cameraMatrix, np.float64), distCoeffs)
     h = np.float32(np.float32(markerLength) / np.float32(2.0))

@@ -253,6 +253,8 @@ class Engine:
         n = c.shape[0]
         rv = torch.zeros((n, 3), dtype=torch.float64, device=self.tdev)
         tv = torch.zeros((n, 3), dtype=torch.float64, device=self.tdev)
+        if n == 0:
+            return rv, tv
         (ka, kp), (da, dp) = self._cam(K, D)
         ml = None
         if isinstance(marker_length, torch.Tensor) or np.ndim(marker_length) > 0:

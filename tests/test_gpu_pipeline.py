@@ -61,3 +61,24 @@ def test_sequence_properties_full_size(pipe, dictionary, frames4k):
             assert np.abs(d).max() < 2.0
     # pose sanity: tvec_z within the 15-60 m band the synthetic marker sizes imply
     assert ((res["tvec"][0, :n0, 2] > 10) & (res["tvec"][0, :n0, 2] < 80)).all()
+
+
+def test_sequence_csv_matches_reference_script(pipe, dictionary):
+    """End to end on the GPU: frames -> Pipeline -> two-pass post-pass -> CSV rows of aruco_detect.py:146-185, compared
+    with the rows the reference script itself wrote for the same seeded frames (tests/golden/sequence_4k.json)."""
+    import json, os, torch
+    pytest.importorskip("cv2")   # tools.synth renders the frames with cv2.warpPerspective / resize
+    from conftest import GOLDEN
+    from tools import synth
+    from apse_uav_b200 import shard
+    from apse_uav_b200.postpass import CSV_FIELDS
+    g = json.load(open(os.path.join(GOLDEN, "sequence_4k.json")))
+    ref = np.array([[float(v) for v in line.split(",")] for line in g["csv"][1:]])
+    frames = torch.from_numpy(np.stack(list(synth.make_sequence(dictionary.bytesList, g["base_seed"], g["n_frames"])))).cuda()
+    rows = shard.run_sequence(pipe, frames)
+    got = np.array([[float(r[f]) for f in CSV_FIELDS] for r in rows])
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, [0, 1, 3, 7, 10, 13]], ref[:, [0, 1, 3, 7, 10, 13]])
+    num = [2, 4, 5, 6, 8, 9, 11, 12, 14, 15]
+    assert np.all(np.abs(got[:, num] - ref[:, num]) <= 1e-4 * np.abs(ref[:, num]) + 0.0101)
+    assert np.abs(got[:, 2] - ref[:, 2]).max() <= 1.01e-5
