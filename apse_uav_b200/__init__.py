@@ -22,6 +22,7 @@ from . import engine as _engine
 from .engine import Engine, default_engine  # noqa: F401
 from . import aruco  # noqa: F401
 from .pipeline import Pipeline  # noqa: F401
+from . import postpass, shard  # noqa: F401
 
 error = ApseError
 

@@ -18,8 +18,6 @@
 #include <math.h>
 #include <float.h>
 
-#define CCL_TW 32
-#define CCL_TH 16
 #define FQ_THREADS 128
 #define MAXIMA_CAP 16  // aprilTagMaxNmaxima supported up to this value
 
@@ -69,8 +67,13 @@ __device__ __forceinline__ void dilated_minmax(const uint8_t *tmin, const uint8_
     }
 }
 
+// CCL tiles (CCL_TW x CCL_TH px) that contain at least one non-127 pixel are flagged here and compacted into a work
+// list, so that the component / boundary kernels only ever touch the ~1-20 % of the image that has contrast.
+#define CCL_TW 32
+#define CCL_TH 16
 __global__ void k_threshold(const uint8_t *__restrict__ gray, int w, int h, int tw, int th, const uint8_t *__restrict__ tmin,
-                            const uint8_t *__restrict__ tmax, int min_wb_diff, uint8_t *__restrict__ out)
+                            const uint8_t *__restrict__ tmax, int min_wb_diff, uint8_t *__restrict__ out,
+                            uint8_t *__restrict__ tile_active, int ctw, int cth)
 {
     int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
     if (tx >= tw || ty >= th) return;
@@ -80,6 +83,7 @@ __global__ void k_threshold(const uint8_t *__restrict__ gray, int w, int h, int 
     dilated_minmax(tmin + (size_t)f * tw * th, tmax + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
     bool low = (mx - mn) < min_wb_diff;
     unsigned thr = mn + (mx - mn) / 2;
+    if (!low) tile_active[((size_t)f * cth + (ty * 4) / CCL_TH) * ctw + (tx * 4) / CCL_TW] = 1;
     if ((w & 3) == 0) {
 #pragma unroll
         for (int dy = 0; dy < 4; dy++) {
@@ -104,7 +108,7 @@ __global__ void k_threshold(const uint8_t *__restrict__ gray, int w, int h, int 
 // right / bottom partial tiles: nearest full tile's dilated threshold, never marked 127
 __global__ void k_threshold_edges(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
                                   const uint8_t *__restrict__ tmin, const uint8_t *__restrict__ tmax,
-                                  uint8_t *__restrict__ out)
+                                  uint8_t *__restrict__ out, uint8_t *__restrict__ tile_active, int ctw, int cth)
 {
     int f = blockIdx.z;
     int nright = w - tw * 4, nbottom = h - th * 4;
@@ -119,7 +123,22 @@ __global__ void k_threshold_edges(const uint8_t *__restrict__ gray, int w, int h
         dilated_minmax(tmin + (size_t)f * tw * th, tmax + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
         int thr = mn + (mx - mn) / 2;
         o[(size_t)y * w + x] = g[(size_t)y * w + x] > thr ? 255 : 0;
+        tile_active[((size_t)f * cth + y / CCL_TH) * ctw + x / CCL_TW] = 1;
     }
+}
+
+// compaction of the flagged tiles of the whole batch into list[] = frame << 20 | tile index (warp-aggregated append)
+__global__ void k_compact_tiles(const uint8_t *__restrict__ tile_active, int ntiles_total, int tiles_per_frame,
+                                uint32_t *__restrict__ list, int *__restrict__ n_active)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool on = i < ntiles_total && tile_active[i];
+    unsigned m = __ballot_sync(0xffffffffu, on);
+    if (!m) return;
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+    if (lane == leader) base = atomicAdd(n_active, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (on) list[base + __popc(m & ((1u << lane) - 1))] = ((uint32_t)(i / tiles_per_frame) << 20) | (uint32_t)(i % tiles_per_frame);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -160,72 +179,72 @@ __device__ __forceinline__ void uf_union_gmem(uint32_t *L, uint32_t a, uint32_t 
 }
 
 __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_local(const uint8_t *__restrict__ thresh, int w, int h,
-                                                              uint32_t *__restrict__ labels, uint8_t *__restrict__ tile_active)
+                                                              uint32_t *__restrict__ labels,
+                                                              const uint32_t *__restrict__ list, const int *__restrict__ n_active,
+                                                              int ctw)
 {
     __shared__ int L[CCL_TW * CCL_TH];
     __shared__ uint8_t V[CCL_TH][CCL_TW + 1];
-    int lx = threadIdx.x, ly = threadIdx.y, li = ly * CCL_TW + lx;
-    int x = blockIdx.x * CCL_TW + lx, y = blockIdx.y * CCL_TH + ly, f = blockIdx.z;
-    const uint8_t *t = thresh + (size_t)f * w * h;
-    bool in = x < w && y < h;
-    int v = in ? t[(size_t)y * w + x] : 127;
-    int any = __syncthreads_or(v != 127);
-    if (li == 0) tile_active[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = any ? 1 : 0;
-    if (!any) return;
-    V[ly][lx] = (uint8_t)v;
-    L[li] = li;
-    __syncthreads();
-    bool src = v != 127 && x >= 1 && x <= w - 2 && y <= h - 2;
-    if (src) {
-        if (lx + 1 < CCL_TW && V[ly][lx + 1] == v) uf_union_smem(L, li, li + 1);
-        if (ly + 1 < CCL_TH) {
-            if (V[ly + 1][lx] == v) uf_union_smem(L, li, li + CCL_TW);
-            if (v == 255) {
-                if (lx > 0 && V[ly + 1][lx - 1] == v) uf_union_smem(L, li, li + CCL_TW - 1);
-                if (lx + 1 < CCL_TW && V[ly + 1][lx + 1] == v) uf_union_smem(L, li, li + CCL_TW + 1);
+    const int lx = threadIdx.x, ly = threadIdx.y, li = ly * CCL_TW + lx;
+    const int n = *n_active;
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint32_t e = list[it];
+        const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
+        const int x = txb * CCL_TW + lx, y = tyb * CCL_TH + ly;
+        const uint8_t *t = thresh + (size_t)f * w * h;
+        const bool in = x < w && y < h;
+        const int v = in ? t[(size_t)y * w + x] : 127;
+        V[ly][lx] = (uint8_t)v;
+        L[li] = li;
+        __syncthreads();
+        const bool src = v != 127 && x >= 1 && x <= w - 2 && y <= h - 2;
+        if (src) {
+            if (lx + 1 < CCL_TW && V[ly][lx + 1] == v) uf_union_smem(L, li, li + 1);
+            if (ly + 1 < CCL_TH) {
+                if (V[ly + 1][lx] == v) uf_union_smem(L, li, li + CCL_TW);
+                if (v == 255) {
+                    if (lx > 0 && V[ly + 1][lx - 1] == v) uf_union_smem(L, li, li + CCL_TW - 1);
+                    if (lx + 1 < CCL_TW && V[ly + 1][lx + 1] == v) uf_union_smem(L, li, li + CCL_TW + 1);
+                }
             }
         }
-    }
-    __syncthreads();
-    if (in && v != 127) {
-        int r = uf_find<int>(L, li);
-        int ry = blockIdx.y * CCL_TH + r / CCL_TW, rx = blockIdx.x * CCL_TW + r % CCL_TW;
-        labels[(size_t)f * w * h + (size_t)y * w + x] = (uint32_t)(ry * w + rx);
+        __syncthreads();
+        if (in && v != 127) {
+            int r = uf_find<int>(L, li);
+            int ry = tyb * CCL_TH + r / CCL_TW, rx = txb * CCL_TW + r % CCL_TW;
+            labels[(size_t)f * w * h + (size_t)y * w + x] = (uint32_t)(ry * w + rx);
+        }
+        __syncthreads();
     }
 }
 
-// unions across tile boundaries.  kind 0: sources on the last row of a tile (S, SW, SE cross);
-// kind 1: sources on the last / first column of a tile (E, SE / SW cross).
-__global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, uint32_t *__restrict__ labels)
+// unions across tile boundaries, per active tile: sources on its last row (S, SW, SE cross), on its last
+// column (E, SE cross) and on its first column (SW crosses).  64 threads per tile.
+__global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, uint32_t *__restrict__ labels,
+                            const uint32_t *__restrict__ list, const int *__restrict__ n_active, int ctw)
 {
-    int f = blockIdx.z;
-    const uint8_t *t = thresh + (size_t)f * w * h;
-    uint32_t *L = labels + (size_t)f * w * h;
-    int nrows = h / CCL_TH;                 // tile rows with a successor row inside the image
-    if (nrows * CCL_TH == h) nrows--;       // last tile row ends at the image border
-    int ncols = div_up(w, CCL_TW);
-    long long n0 = (long long)max(nrows, 0) * w, n1 = (long long)ncols * 2 * h;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n0 + n1; i += (long long)gridDim.x * blockDim.x) {
+    const int n = *n_active;
+    const int per_block = blockDim.x / 64, sub = threadIdx.x / 64, k = threadIdx.x % 64;
+    for (int it = blockIdx.x * per_block + sub; it < n; it += gridDim.x * per_block) {
+        const uint32_t e = list[it];
+        const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
+        const uint8_t *t = thresh + (size_t)f * w * h;
+        uint32_t *L = labels + (size_t)f * w * h;
         int x, y, kind;
-        if (i < n0) { kind = 0; y = (int)(i / w) * CCL_TH + CCL_TH - 1; x = (int)(i % w); }
-        else {
-            long long j = i - n0;
-            kind = 1;
-            int c = (int)(j / h);
-            y = (int)(j % h);
-            x = (c >> 1) * CCL_TW + ((c & 1) ? CCL_TW - 1 : 0);
-        }
+        if (k < 32) { kind = 0; x = txb * CCL_TW + k; y = tyb * CCL_TH + CCL_TH - 1; }
+        else if (k < 48) { kind = 1; x = txb * CCL_TW + CCL_TW - 1; y = tyb * CCL_TH + (k - 32); }
+        else { kind = 2; x = txb * CCL_TW; y = tyb * CCL_TH + (k - 48); }
         if (x < 1 || x > w - 2 || y > h - 2) continue;
-        int v = t[(size_t)y * w + x];
+        const int v = t[(size_t)y * w + x];
         if (v == 127) continue;
-        uint32_t o = (uint32_t)(y * w + x);
+        const uint32_t o = (uint32_t)(y * w + x);
         if (kind == 0) {
             if (t[o + w] == v) uf_union_gmem(L, o, o + w);
             if (v == 255) {
                 if (t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
                 if (t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
             }
-        } else if ((x % CCL_TW) == CCL_TW - 1) {
+        } else if (kind == 1) {
             if (t[o + 1] == v) uf_union_gmem(L, o, o + 1);
             if (v == 255 && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
         } else {
@@ -236,17 +255,21 @@ __global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, ui
 
 __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_flatten(const uint8_t *__restrict__ thresh, int w, int h,
                                                                 uint32_t *__restrict__ labels,
-                                                                const uint8_t *__restrict__ tile_active)
+                                                                const uint32_t *__restrict__ list,
+                                                                const int *__restrict__ n_active, int ctw)
 {
-    int f = blockIdx.z;
-    if (!tile_active[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
-    int x = blockIdx.x * CCL_TW + threadIdx.x, y = blockIdx.y * CCL_TH + threadIdx.y;
-    if (x >= w || y >= h) return;
-    size_t o = (size_t)f * w * h + (size_t)y * w + x;
-    if (thresh[o] == 127) return;
-    uint32_t *L = labels + (size_t)f * w * h;
-    uint32_t r = uf_find<uint32_t>(L, L[(size_t)y * w + x]);
-    L[(size_t)y * w + x] = r;  // racing writers store roots of the same tree; finds stay correct
+    const int n = *n_active;
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint32_t e = list[it];
+        const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
+        const int x = txb * CCL_TW + threadIdx.x, y = tyb * CCL_TH + threadIdx.y;
+        if (x >= w || y >= h) continue;
+        const size_t o = (size_t)f * w * h + (size_t)y * w + x;
+        if (thresh[o] == 127) continue;
+        uint32_t *L = labels + (size_t)f * w * h;
+        uint32_t r = uf_find<uint32_t>(L, L[(size_t)y * w + x]);
+        L[(size_t)y * w + x] = r;  // racing writers store roots of the same tree; finds stay correct
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -260,14 +283,17 @@ __device__ __forceinline__ uint32_t hash64(unsigned long long k)
 
 __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_emit_points(const uint8_t *__restrict__ thresh, int w, int h,
                                                                 const uint32_t *__restrict__ labels,
-                                                                const uint8_t *__restrict__ tile_active,
+                                                                const uint32_t *__restrict__ list,
+                                                                const int *__restrict__ n_active, int ctw,
                                                                 unsigned long long *__restrict__ hash_keys,
                                                                 uint32_t *__restrict__ hash_count, uint4 *__restrict__ points,
                                                                 int32_t *__restrict__ counters)
 {
-    int f = blockIdx.z;
-    if (!tile_active[((size_t)f * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x]) return;
-    int x = blockIdx.x * CCL_TW + threadIdx.x, y = blockIdx.y * CCL_TH + threadIdx.y;
+  const int n_act = *n_active;
+  for (int it = blockIdx.x; it < n_act; it += gridDim.x) {
+    const uint32_t e = list[it];
+    const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
+    int x = txb * CCL_TW + threadIdx.x, y = tyb * CCL_TH + threadIdx.y;
     const uint8_t *t = thresh + (size_t)f * w * h;
     const uint32_t *L = labels + (size_t)f * w * h;
     bool src = x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2;
@@ -317,6 +343,7 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_emit_points(const uint8_t *_
             }
         }
     }
+  }
 }
 
 // one block per frame: size filter + exclusive scan of the kept clusters' counts over the hash slots
@@ -852,7 +879,8 @@ __global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
 // host side
 struct DetectExtra {
     uint8_t *tile_active;
-    int *work_counter;
+    uint32_t *tile_list;
+    int *work_counter;   // [0] quad-fit work counter, [1] number of active tiles
 };
 
 int apse_detect_alloc(apse_ctx *ctx)
@@ -878,7 +906,8 @@ int apse_detect_alloc(apse_ctx *ctx)
     DetectExtra *ex = new DetectExtra();
     size_t nct = (size_t)div_up(ctx->max_w, CCL_TW) * div_up(ctx->max_h, CCL_TH);
     CUDA_TRY(ctx, cudaMalloc((void **)&ex->tile_active, B * nct));
-    CUDA_TRY(ctx, cudaMalloc((void **)&ex->work_counter, sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ex->tile_list, B * nct * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ex->work_counter, 2 * sizeof(int)));
     ctx->point_rank = reinterpret_cast<uint32_t *>(ex);  // opaque slot reused to carry the extra pointers
     return APSE_OK;
 }
@@ -890,7 +919,7 @@ void apse_detect_free(apse_ctx *ctx)
     cudaFree(ctx->sort_keys); cudaFree(ctx->lfps); cudaFree(ctx->errs); cudaFree(ctx->clusters); cudaFree(ctx->counters);
     cudaFree(ctx->quads); cudaFree(ctx->quad_order);
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
-    if (ex) { cudaFree(ex->tile_active); cudaFree(ex->work_counter); delete ex; }
+    if (ex) { cudaFree(ex->tile_active); cudaFree(ex->tile_list); cudaFree(ex->work_counter); delete ex; }
     ctx->point_rank = nullptr;
 }
 
@@ -900,28 +929,36 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch || batch > 64)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: frame %dx%d x%d exceeds the context capacity %dx%d x%d (64 max)", w, h,
                  batch, ctx->max_w, ctx->max_h, ctx->max_batch);
-    if (w < 8 || h < 8 || w > 32767 || h > 32767) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
+    if (w < 8 || h < 8 || w > 32767 || h > 32767 || (long long)div_up(w, CCL_TW) * div_up(h, CCL_TH) >= (1 << 20))
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
     int tw = w / 4, th = h / 4;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->hash_keys, 0xff, (size_t)batch * APSE_HASH_SLOTS * sizeof(unsigned long long), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->hash_count, 0, (size_t)batch * APSE_HASH_SLOTS * sizeof(uint32_t), st));
-    CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, sizeof(int), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, 2 * sizeof(int), st));
+    const int ctw = div_up(w, CCL_TW), cth = div_up(h, CCL_TH), nct = ctw * cth;
+    CUDA_TRY(ctx, cudaMemsetAsync(ex->tile_active, 0, (size_t)batch * nct, st));
     {
         dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
         KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax));
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, dp.min_white_black_diff, ctx->thresh));
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, dp.min_white_black_diff, ctx->thresh,
+                                                                           ex->tile_active, ctw, cth));
         if (tw * 4 != w || th * 4 != h) {
-            KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, ctx->thresh));
+            KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, ctx->thresh,
+                                                                                     ex->tile_active, ctw, cth));
         }
     }
     {
-        dim3 block(CCL_TW, CCL_TH), grid(div_up(w, CCL_TW), div_up(h, CCL_TH), batch);
-        KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active));
-        KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<dim3(148 * 4, 1, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels));
-        KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active));
-        KLAUNCH(ctx, KID_EMIT, st, k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_active, ctx->hash_keys, ctx->hash_count,
-                                              ctx->points, ctx->counters));
+        int *n_active = ex->work_counter + 1;
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_compact_tiles<<<div_up(batch * nct, 256), 256, 0, st>>>(ex->tile_active, batch * nct, nct, ex->tile_list, n_active));
+        dim3 block(CCL_TW, CCL_TH);
+        const int grid = 148 * 4;   // persistent: 4 CTAs of 512 threads per SM, tiles taken round-robin from the list
+        KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
+        KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<148 * 4, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
+        KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
+        KLAUNCH(ctx, KID_EMIT, st, k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, ctx->hash_keys,
+                                                                          ctx->hash_count, ctx->points, ctx->counters));
     }
     KLAUNCH(ctx, KID_CLUSTER_SCAN, st, k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ctx->clusters, ctx->counters,
                                            dp.min_cluster_pixels, dp.max_cluster_points));
