@@ -56,32 +56,55 @@ def base_frames(n, seed=1000):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle reasons DURING the timed region, read in-process through NVML (nvidia-ml-py); spawning
+    nvidia-smi inside the timed region stalls CUDA launches, so it is only the fallback for a single sample."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.nv, self.handle = index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _reasons(self):
+        nv = self.nv
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        out = []
+        for name, attr in (("hw_slowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksThrottleReasonSwPowerCap")):
+            bit = getattr(nv, attr, None)
+            if bit is not None and mask & bit:
+                out.append(name)
+        return out
 
     def run(self):
+        if self.nv is None:
+            return
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                self.samples.append((float(self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)), self._reasons()))
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvml unavailable"}
+        sm = [s[0] for s in self.samples]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": self.max_sm, "reasons": sorted({r for s in self.samples for r in s[1]}),
+                "samples": len(sm), "source": "nvml, 20 ms period, during the timed region"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
