@@ -299,8 +299,8 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_emit_points(const uint8_t *_
                                                                 const uint32_t *__restrict__ list,
                                                                 const int *__restrict__ n_active, int ctw,
                                                                 unsigned long long *__restrict__ hash_keys,
-                                                                uint32_t *__restrict__ hash_count, uint4 *__restrict__ points,
-                                                                int32_t *__restrict__ counters)
+                                                                uint32_t *__restrict__ hash_count, uint32_t *__restrict__ used_slots,
+                                                                uint4 *__restrict__ points, int32_t *__restrict__ counters)
 {
   const int n_act = *n_active;
   for (int it = blockIdx.x; it < n_act; it += gridDim.x) {
@@ -331,7 +331,11 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_emit_points(const uint8_t *_
             int probes = 0;
             for (;;) {
                 unsigned long long prev = atomicCAS(&hk[slot], HASH_EMPTY, key);
-                if (prev == HASH_EMPTY || prev == key) break;
+                if (prev == HASH_EMPTY) {  // this thread created the cluster: list the slot for the scan kernel
+                    used_slots[(size_t)f * APSE_HASH_SLOTS + atomicAdd(&cnt[6], 1)] = slot;
+                    break;
+                }
+                if (prev == key) break;
                 slot = (slot + 1) & (APSE_HASH_SLOTS - 1);
                 if (++probes >= APSE_HASH_SLOTS) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); emit = false; break; }
             }
@@ -359,54 +363,56 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_emit_points(const uint8_t *_
   }
 }
 
-// one block per frame: size filter + exclusive scan of the kept clusters' counts over the hash slots
-__global__ void __launch_bounds__(1024) k_cluster_scan(const unsigned long long *__restrict__ hash_keys,
-                                                       const uint32_t *__restrict__ hash_count,
-                                                       uint32_t *__restrict__ hash_offset, ClusterDesc *__restrict__ clusters,
-                                                       int32_t *__restrict__ counters, int min_px, int max_px)
+// one block per frame: size filter + exclusive scan of the kept clusters' counts over the list of used hash slots;
+// the slots are reset here (their last reader), so the tables never need a memset between batches
+__global__ void __launch_bounds__(1024) k_cluster_scan(unsigned long long *__restrict__ hash_keys, uint32_t *__restrict__ hash_count,
+                                                       uint32_t *__restrict__ hash_offset, const uint32_t *__restrict__ used_slots,
+                                                       ClusterDesc *__restrict__ clusters, int32_t *__restrict__ counters,
+                                                       int min_px, int max_px)
 {
-    int f = blockIdx.x, tid = threadIdx.x;
-    const unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
-    const uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
+    uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
     uint32_t *ho = hash_offset + (size_t)f * APSE_HASH_SLOTS;
+    const uint32_t *us = used_slots + (size_t)f * APSE_HASH_SLOTS;
     ClusterDesc *cl = clusters + (size_t)f * APSE_MAX_CLUSTERS;
-    const int per = APSE_HASH_SLOTS / 1024;
-    __shared__ uint32_t s_pts[1024], s_cl[1024], s_all[1024];
-    uint32_t npts = 0, ncl = 0, nall = 0;
-    for (int i = 0; i < per; i++) {
-        uint32_t c = hc[tid * per + i];
-        nall += c != 0;
+    int32_t *cnt = counters + f * APSE_COUNTERS;
+    const int n_used = cnt[6];
+    __shared__ uint32_t s_pts[1024], s_cl[1024];
+    uint32_t npts = 0, ncl = 0;
+    for (int i = tid; i < n_used; i += 1024) {
+        uint32_t c = hc[us[i]];
         if ((int)c >= min_px && (int)c <= max_px) { npts += c; ncl++; }
     }
-    s_pts[tid] = npts; s_cl[tid] = ncl; s_all[tid] = nall;
+    s_pts[tid] = npts; s_cl[tid] = ncl;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan
-        uint32_t a = 0, b = 0, c = 0;
-        if (tid >= d) { a = s_pts[tid - d]; b = s_cl[tid - d]; c = s_all[tid - d]; }
+        uint32_t a = 0, b = 0;
+        if (tid >= d) { a = s_pts[tid - d]; b = s_cl[tid - d]; }
         __syncthreads();
-        s_pts[tid] += a; s_cl[tid] += b; s_all[tid] += c;
+        s_pts[tid] += a; s_cl[tid] += b;
         __syncthreads();
     }
     uint32_t off = s_pts[tid] - npts, ci = s_cl[tid] - ncl;
-    for (int i = 0; i < per; i++) {
-        int s = tid * per + i;
-        uint32_t c = hc[s];
+    for (int i = tid; i < n_used; i += 1024) {
+        const uint32_t sl = us[i], c = hc[sl];
         if ((int)c >= min_px && (int)c <= max_px) {
-            ho[s] = off;
+            ho[sl] = off;
             if (ci < APSE_MAX_CLUSTERS) {
-                unsigned long long k = hk[s];
+                unsigned long long k = hk[sl];
                 cl[ci] = ClusterDesc{off, c, (uint32_t)k, (uint32_t)(k >> 32)};
             }
             off += c; ci++;
         } else {
-            ho[s] = 0xffffffffu;
+            ho[sl] = 0xffffffffu;
         }
+        hk[sl] = HASH_EMPTY;
+        hc[sl] = 0;
     }
     if (tid == 1023) {
-        int32_t *cnt = counters + f * APSE_COUNTERS;
         if (s_cl[1023] > APSE_MAX_CLUSTERS) cnt[3] = APSE_ERR_CAPACITY;
         cnt[1] = (int32_t)min(s_cl[1023], (uint32_t)APSE_MAX_CLUSTERS);
-        cnt[4] = (int32_t)s_all[1023];
+        cnt[4] = n_used;
         cnt[5] = (int32_t)s_pts[1023];
     }
 }
@@ -893,6 +899,7 @@ __global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
 struct DetectExtra {
     uint8_t *tile_active;
     uint32_t *tile_list;
+    uint32_t *used_slots;
     int *work_counter;   // [0] quad-fit work counter, [1] number of active tiles
 };
 
@@ -921,6 +928,10 @@ int apse_detect_alloc(apse_ctx *ctx)
     CUDA_TRY(ctx, cudaMalloc((void **)&ex->tile_active, B * nct));
     CUDA_TRY(ctx, cudaMalloc((void **)&ex->tile_list, B * nct * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ex->work_counter, 2 * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ex->used_slots, B * APSE_HASH_SLOTS * sizeof(uint32_t)));
+    // the hash tables are cleared once; k_cluster_scan resets exactly the slots a batch used
+    CUDA_TRY(ctx, cudaMemset(ctx->hash_keys, 0xff, B * APSE_HASH_SLOTS * sizeof(unsigned long long)));
+    CUDA_TRY(ctx, cudaMemset(ctx->hash_count, 0, B * APSE_HASH_SLOTS * sizeof(uint32_t)));
     ctx->point_rank = reinterpret_cast<uint32_t *>(ex);  // opaque slot reused to carry the extra pointers
     return APSE_OK;
 }
@@ -932,7 +943,7 @@ void apse_detect_free(apse_ctx *ctx)
     cudaFree(ctx->sort_keys); cudaFree(ctx->lfps); cudaFree(ctx->errs); cudaFree(ctx->clusters); cudaFree(ctx->counters);
     cudaFree(ctx->quads); cudaFree(ctx->quad_order);
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
-    if (ex) { cudaFree(ex->tile_active); cudaFree(ex->tile_list); cudaFree(ex->work_counter); delete ex; }
+    if (ex) { cudaFree(ex->tile_active); cudaFree(ex->tile_list); cudaFree(ex->used_slots); cudaFree(ex->work_counter); delete ex; }
     ctx->point_rank = nullptr;
 }
 
@@ -947,8 +958,6 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
     int tw = w / 4, th = h / 4;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hash_keys, 0xff, (size_t)batch * APSE_HASH_SLOTS * sizeof(unsigned long long), st));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->hash_count, 0, (size_t)batch * APSE_HASH_SLOTS * sizeof(uint32_t), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, 2 * sizeof(int), st));
     const int ctw = div_up(w, CCL_TW), cth = div_up(h, CCL_TH), nct = ctw * cth;
     CUDA_TRY(ctx, cudaMemsetAsync(ex->tile_active, 0, (size_t)batch * nct, st));
@@ -971,9 +980,9 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<148 * 4, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
         KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
         KLAUNCH(ctx, KID_EMIT, st, k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, ctx->hash_keys,
-                                                                          ctx->hash_count, ctx->points, ctx->counters));
+                                                                          ctx->hash_count, ex->used_slots, ctx->points, ctx->counters));
     }
-    KLAUNCH(ctx, KID_CLUSTER_SCAN, st, k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ctx->clusters, ctx->counters,
+    KLAUNCH(ctx, KID_CLUSTER_SCAN, st, k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ex->used_slots, ctx->clusters, ctx->counters,
                                            dp.min_cluster_pixels, dp.max_cluster_points));
     KLAUNCH(ctx, KID_SCATTER, st, k_scatter_points<<<dim3(148, min(batch, 8)), 256, 0, st>>>(ctx->points, ctx->hash_offset, ctx->counters, ctx->sorted_pts, batch));
     FitArgs A;

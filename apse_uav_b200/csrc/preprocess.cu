@@ -202,7 +202,7 @@ __device__ __forceinline__ int sample(const uint8_t *__restrict__ src, const Tap
 // The map of the tile is read once and kept in registers while the block walks `fpb` frames of the batch, so
 // map traffic is amortised over the batch; gray is written as one 32-bit word per lane (128 B per warp).
 #define K1_PX 4
-__global__ void __launch_bounds__(256) k_preprocess_fused(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
+__global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
                                                           uint8_t *__restrict__ gray, const float *__restrict__ mapx,
                                                           const float *__restrict__ mapy, const LabTables *__restrict__ tables,
                                                           int w, int h, int batch, int fpb)

@@ -204,14 +204,10 @@ class Engine:
         return out, gray
 
     # -------------------------------------------------------------------------------------------- detect
-    def detect(self, gray, max_markers=256, want_rejected=True):
-        """aruco_detect.py:267 for a batch: gray [B,H,W] u8 -> dict of device tensors."""
-        torch = self.torch
-        gray = self._u8(gray, "detectMarkers")
-        if gray.dim() == 2:
-            gray = gray[None]
-        B, H, W = gray.shape
-        dev = self.tdev
+    def alloc_detections(self, B, max_markers, want_rejected=True, pose=False):
+        """Output buffers of detect() (and pose_frames()) for B frames; slices along dim 0 can be handed to several
+        engines / streams."""
+        torch, dev = self.torch, self.tdev
         res = dict(corners=torch.zeros((B, max_markers, 4, 2), dtype=torch.float32, device=dev),
                    ids=torch.full((B, max_markers), -1, dtype=torch.int32, device=dev),
                    n=torch.zeros(B, dtype=torch.int32, device=dev),
@@ -219,6 +215,20 @@ class Engine:
         if want_rejected:
             res["rejected"] = torch.zeros((B, max_markers, 4, 2), dtype=torch.float32, device=dev)
             res["n_rejected"] = torch.zeros(B, dtype=torch.int32, device=dev)
+        if pose:
+            res["rvec"] = torch.zeros((B, max_markers, 3), dtype=torch.float64, device=dev)
+            res["tvec"] = torch.zeros((B, max_markers, 3), dtype=torch.float64, device=dev)
+        return res
+
+    def detect(self, gray, max_markers=256, want_rejected=True, out=None):
+        """aruco_detect.py:267 for a batch: gray [B,H,W] u8 -> dict of device tensors (written into `out` if given)."""
+        gray = self._u8(gray, "detectMarkers")
+        if gray.dim() == 2:
+            gray = gray[None]
+        B, H, W = gray.shape
+        res = out if out is not None else self.alloc_detections(B, max_markers, want_rejected)
+        want_rejected = "rejected" in res
+        max_markers = res["corners"].shape[1]
         d = Detections(max_markers, res["corners"].data_ptr(), res["ids"].data_ptr(), res["n"].data_ptr(),
                        res["rejected"].data_ptr() if want_rejected else None,
                        res["n_rejected"].data_ptr() if want_rejected else None, res["status"].data_ptr())
@@ -264,11 +274,11 @@ class Engine:
                                        self._stream()))
         return rv, tv
 
-    def pose_frames(self, corners, n_markers, marker_length, K=None, D=None):
+    def pose_frames(self, corners, n_markers, marker_length, K=None, D=None, out=None):
         torch = self.torch
         B, M = corners.shape[:2]
-        rv = torch.zeros((B, M, 3), dtype=torch.float64, device=self.tdev)
-        tv = torch.zeros((B, M, 3), dtype=torch.float64, device=self.tdev)
+        rv = out[0] if out is not None else torch.zeros((B, M, 3), dtype=torch.float64, device=self.tdev)
+        tv = out[1] if out is not None else torch.zeros((B, M, 3), dtype=torch.float64, device=self.tdev)
         (ka, kp), (da, dp) = self._cam(K, D)
         ml = None
         if isinstance(marker_length, torch.Tensor) or np.ndim(marker_length) > 0:

@@ -14,31 +14,70 @@ from ._lib import ApseError
 
 
 class Pipeline:
+    """`streams` > 1 splits every batch over that many CUDA streams, each with its own context (scratch), so that the
+    latency-bound tail of one sub-batch (cluster scan, quad fit, decode, pose) overlaps the bandwidth/issue-bound
+    preprocess of the next one."""
+
     def __init__(self, camera_matrix, dist_coeffs, size, lut, dictionary, params, max_batch=16, device=0,
-                 max_markers=64, marker_length=0.55):
+                 max_markers=64, marker_length=0.55, streams=1):
         w, h = int(size[0]), int(size[1])
-        self.engine = Engine(device, w, h, max_batch)
-        self.engine.set_camera(camera_matrix, dist_coeffs, w, h)
-        self.engine.set_lut(lut)
+        streams = max(1, min(int(streams), max_batch))
+        self.sub_batch = (max_batch + streams - 1) // streams
         bl = np.ascontiguousarray(dictionary.bytesList, np.uint8)
-        self.engine.set_dictionary(bl.reshape(bl.shape[0], -1), dictionary.markerSize, dictionary.maxCorrectionBits)
-        self.engine.set_params(params)
+        self.engines = []
+        for _ in range(streams):
+            e = Engine(device, w, h, self.sub_batch)
+            e.set_camera(camera_matrix, dist_coeffs, w, h)
+            e.set_lut(lut)
+            e.set_dictionary(bl.reshape(bl.shape[0], -1), dictionary.markerSize, dictionary.maxCorrectionBits)
+            e.set_params(params)
+            self.engines.append(e)
+        self.engine = self.engines[0]
+        torch = self.engine.torch
+        self.streams = [torch.cuda.Stream(device=self.engine.tdev) for _ in range(streams)] if streams > 1 else []
         self.max_batch, self.max_markers, self.marker_length = max_batch, max_markers, float(marker_length)
         self.size = (w, h)
 
     @property
     def launches(self):
-        return self.engine.launches
+        return sum(e.launches for e in self.engines)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def _run_on(self, e, frames, out, want_gray, marker_length):
+        _, gray = e.preprocess(frames, want_bgr=False)
+        e.detect(gray, out=out)
+        e.pose_frames(out["corners"], out["n"], marker_length, out=(out["rvec"], out["tvec"]))
+        return gray if want_gray else None
 
     def run_batch(self, frames, want_gray=False, want_rejected=False, marker_length=None):
         """frames: [B,H,W,3] uint8 CUDA tensor, B <= max_batch.  Returns dict of device tensors."""
         e = self.engine
-        if frames.shape[0] > self.max_batch:
-            raise ApseError(-1, f"batch {frames.shape[0]} exceeds max_batch {self.max_batch}")
-        _, gray = e.preprocess(frames, want_bgr=False)
-        det = e.detect(gray, max_markers=self.max_markers, want_rejected=want_rejected)
+        torch = e.torch
+        B = frames.shape[0]
+        if B > self.max_batch:
+            raise ApseError(-1, f"batch {B} exceeds max_batch {self.max_batch}")
         ml = self.marker_length if marker_length is None else marker_length
-        det["rvec"], det["tvec"] = e.pose_frames(det["corners"], det["n"], ml)
+        det = e.alloc_detections(B, self.max_markers, want_rejected, pose=True)
+        if not self.streams or B <= 1:
+            gray = self._run_on(e, frames, det, want_gray, ml)
+        else:
+            cur = torch.cuda.current_stream(e.tdev)
+            ready = cur.record_event()
+            grays = []
+            for s, (eng, st) in enumerate(zip(self.engines, self.streams)):
+                lo, hi = s * self.sub_batch, min(B, (s + 1) * self.sub_batch)
+                if lo >= hi:
+                    break
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    sl = {k: v[lo:hi] for k, v in det.items()}
+                    mls = ml[lo:hi] if isinstance(ml, torch.Tensor) else ml
+                    grays.append(self._run_on(eng, frames[lo:hi], sl, want_gray, mls))
+                cur.wait_stream(st)
+            gray = torch.cat(grays, 0) if want_gray else None
         if want_gray:
             det["gray"] = gray
         return det
@@ -47,6 +86,8 @@ class Pipeline:
         """Any number of frames, processed in batches of max_batch; results concatenated on the device."""
         torch = self.engine.torch
         outs = [self.run_batch(frames[i:i + self.max_batch], **kw) for i in range(0, frames.shape[0], self.max_batch)]
+        if len(outs) == 1:
+            return outs[0]
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
 
     @staticmethod

@@ -82,3 +82,17 @@ def test_sequence_csv_matches_reference_script(pipe, dictionary):
     num = [2, 4, 5, 6, 8, 9, 11, 12, 14, 15]
     assert np.all(np.abs(got[:, num] - ref[:, num]) <= 1e-4 * np.abs(ref[:, num]) + 0.0101)
     assert np.abs(got[:, 2] - ref[:, 2]).max() <= 1.01e-5
+
+
+def test_multi_stream_equals_single_stream(pipe, camera, lut, dictionary, ref_params, frames4k):
+    """sub-batches in flight on several streams / contexts give bit-identical results."""
+    import torch
+    import apse_uav_b200 as A
+    K, D = camera
+    p3 = A.Pipeline(K, D, (3840, 2160), lut, dictionary, ref_params, max_batch=5, max_markers=256, streams=3)
+    frames = torch.from_numpy(np.stack([frames4k["sparse"], frames4k["dense"], frames4k["sparse"], frames4k["dense"], frames4k["sparse"]])).cuda()
+    a = A.Pipeline.to_host(p3.run_batch(frames, want_rejected=True))
+    b = A.Pipeline.to_host(pipe.run_batch(frames, want_rejected=True))
+    for k in ("n", "ids", "corners", "n_rejected", "rejected", "rvec", "tvec"):
+        assert np.array_equal(a[k], b[k]), k
+    p3.close()

@@ -13,6 +13,9 @@ K, D = bench.load_camera()
 d = aruco.getPredefinedDictionary(aruco.DICT_4X4_50)
 pipe = A.Pipeline(K, D, (3840, 2160), G.gamma_lut(), d, G.reference_parameters(aruco), max_batch=B, max_markers=256 if dense else 64)
 e = pipe.engine
+S = int(os.environ.get("STREAMS", "1"))
+if S > 1:
+    pipe2 = A.Pipeline(K, D, (3840, 2160), G.gamma_lut(), d, G.reference_parameters(aruco), max_batch=B, max_markers=256 if dense else 64, streams=S)
 from tools import synth
 base = [synth.make_dense_frame(d.bytesList, 11 + i) if dense else synth.make_frame(d.bytesList, 1000 + i) for i in range(3)]
 frames = torch.from_numpy(np.stack([base[i % 3] for i in range(B)])).cuda()
@@ -41,4 +44,12 @@ for timing in (False, True):
     if kt:
         print("   kernels (ms/step):", {k: round(v[0] / N, 3) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])}, "sum", round(sum(v[0] for v in kt.values()) / N, 3))
 e.timing(False)
+if S > 1:
+    for _ in range(3): pipe2.run_batch(frames)
+    torch.cuda.synchronize()
+    a, b = ev(), ev(); a.record()
+    for i in range(6): out2 = pipe2.run_batch(frames if i % 2 == 0 else frames2)
+    b.record(); torch.cuda.synchronize()
+    print(f"streams={S}: step {a.elapsed_time(b) / 6:.3f} ms -> {1e3 * B * 6 / a.elapsed_time(b):.0f} frames/s; equal to 1-stream result:",
+          torch.equal(out2["ids"], pipe.run_batch(frames2)["ids"]))
 print("markers per frame:", det["n"][:6].tolist(), " -> frames/s", 1e3 * B / tot)
