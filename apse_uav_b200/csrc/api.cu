@@ -6,6 +6,7 @@
 #include <new>
 
 int apse_upload_tables(apse_ctx *ctx, const uint8_t *lut, LabTables **dev, cudaStream_t st);  // preprocess.cu
+int apse_upload_p2_tables(apse_ctx *ctx, const uint8_t *lut, P2Tables **dev, cudaStream_t st);
 
 extern "C" {
 
@@ -73,7 +74,7 @@ void apse_destroy(apse_ctx *ctx)
     apse_detect_free(ctx);
     apse_decode_free(ctx);
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
-    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->dict);
+    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict);
     delete ctx;
 }
 
@@ -130,6 +131,8 @@ int apse_set_lut(apse_ctx *ctx, const uint8_t lut[256], void *stream)
     if (!ctx || !lut) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_lut: bad argument");
     memcpy(ctx->lut, lut, 256);
     int rc = apse_upload_tables(ctx, lut, &ctx->tables, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = apse_upload_p2_tables(ctx, lut, &ctx->tables2, (cudaStream_t)stream);
     if (rc) return rc;
     ctx->has_lut = true;
     return APSE_OK;

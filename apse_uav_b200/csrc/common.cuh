@@ -23,6 +23,15 @@ struct LabTables {  // integer sRGB<->Lab tables; ly/lf already 
     uint8_t invgamma[4096];
 };
 
+struct P2Tables {   // composed tables of the TMA-staged preprocess kernel (preprocess.cu, K1t)
+    uint16_t gamma[256];     // 8-bit sRGB -> linear * 2040
+    int16_t at[1008];        // (500 (fX - fY) + c) >> 15, offset 372 -> X-axis shift of Lab2RGB (clip to 8 bit folded in)
+    int16_t bt[408];         // (200 (fY - fZ) + c) >> 15, offset 72  -> Z-axis shift
+    uint16_t cb[2048];       // cube-root table on the 0..2040 index range
+    uint2 yt[2048];          // idxY -> {cbrt | y << 16, f}: L, the gamma LUT on L and LabToYF composed
+    uint8_t invgamma[4096];
+};
+
 struct ClusterDesc {
     uint32_t offset;  // into the frame's sorted point array
     uint32_t count;
@@ -70,6 +79,7 @@ struct apse_ctx {
     uint8_t lut[256];
     LabTables *tables = nullptr;      // device, composed with lut (fused preprocess)
     LabTables *tables_id = nullptr;   // device, identity lut (stand-alone cvtColor)
+    P2Tables *tables2 = nullptr;      // device, composed tables of the TMA-staged fused kernel
     // dictionary
     bool has_dict = false;
     uint8_t *dict = nullptr;          // device [n_markers][4][nbytes]
@@ -140,6 +150,8 @@ int apse_timing_flush(apse_ctx *ctx);
 static __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // internal entry points implemented per translation unit
+int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, uint8_t *tmin, uint8_t *tmax, int batch,
+                       cudaStream_t st);   // returns 1 when the tile extrema were not produced (generic path)
 int apse_detect_alloc(apse_ctx *ctx);
 void apse_detect_free(apse_ctx *ctx);
 int apse_decode_alloc(apse_ctx *ctx);

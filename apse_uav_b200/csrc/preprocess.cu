@@ -5,8 +5,10 @@
 // Integer pipeline, bit-exact with the dependency's 8-bit paths.  HBM-bound by design:
 // one pass over the BGR frame (24.9 MB read) producing gray (8.3 MB) and optionally the corrected BGR frame.
 #include "common.cuh"
+#include <cuda.h>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------------------------------
 // host: integer colour tables (values are what OpenCV's RGB2Lab_b / Lab2RGBinteger tables hold)
@@ -258,16 +260,328 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K1t: TMA-staged fused preprocess (the hot-path variant; k_preprocess_fused above stays as the generic path).
+//
+// One CTA (512 threads) owns a 64x32 output tile and walks `fpb` frames of the batch.  The bilinear taps of the
+// tile (smem offset + two packed Q10 weight pairs per pixel) are computed once from the undistort map and stay in
+// registers.  Per frame the bounding box of the tile's source pixels (<= 74 x 40 px for this camera; the map is
+// smooth) is fetched by ONE bulk tensor copy (TMA, 3-D map over [batch][h][w*3/4] u32 words, out-of-image words
+// zero-filled = BORDER_CONSTANT 0), expanded in shared memory to one 32-bit BGRx word per pixel, and sampled with
+// conflict-free 32-bit LDS + PRMT + IDP.2A (16-bit weight x 8-bit pixel dot products).  The next frame's box is in
+// flight while the current one is being processed.  The colour chain uses tables composed on the host
+// (P2Tables): idxY -> {cbrt, y, f}, (fX-fY) -> a-contribution, (fY-fZ) -> b-contribution, so the 8-bit Lab
+// round trip costs 11 shared-memory look-ups per pixel and no clip / divide instructions.
+// Tiles whose source box does not fit (folded corners of the rational model) take the direct-gather path.
+// The kernel also emits the 4x4-tile min / max of gray that the APRILTAG threshold needs (a6.A1), so the
+// candidate stage does not have to re-read gray for it.
+#define P2_TW 64
+#define P2_TH 32
+#define P2_THREADS 512
+#define P2_NPX 4
+#define P2_BOX_WORDS 64                       // 256 B = 85 px + 1 B per box row
+#define P2_BOX_H 40
+#define P2_BOX_PX 85
+#define P2_PITCH 96                           // BGRx words per staged row (multiple of 32: lanes map to distinct banks)
+#define P2_RAW_BYTES (P2_BOX_WORDS * 4 * P2_BOX_H)
+#define P2_OFF_BGRX (P2_RAW_BYTES + 128)
+#define P2_OFF_TABLES (P2_OFF_BGRX + P2_PITCH * P2_BOX_H * 4)
+#define P2_OFF_MISC (P2_OFF_TABLES + (int)sizeof(P2Tables))
+#define P2_SMEM_BYTES (P2_OFF_MISC + 32)
+#define XZ_MAGIC 551553470                    // ceil(108 * 2^32 / 841)
+
+static void build_p2_tables_host(P2Tables &P, const LabTables &T)
+{
+    memcpy(P.gamma, T.gamma, sizeof P.gamma);
+    memcpy(P.invgamma, T.invgamma, sizeof P.invgamma);
+    memset(P.cb, 0, sizeof P.cb);
+    memset(P.yt, 0, sizeof P.yt);
+    for (int i = 0; i <= 2040; i++) {
+        int fY = T.cbrt[i];
+        int L = (296 * fY - 1336934 + 16384) >> 15;
+        L = L < 0 ? 0 : L > 255 ? 255 : L;
+        P.cb[i] = (uint16_t)fY;
+        P.yt[i].x = (uint32_t)fY | ((uint32_t)T.ly[L] << 16);
+        P.yt[i].y = T.lf[L];
+    }
+    for (int i = 0; i < 1008; i++) {
+        int a = i - 372;
+        a = a < 0 ? 0 : a > 255 ? 255 : a;
+        P.at[i] = (int16_t)(((5 * a * 53687 + 128) >> 13) - 4194);
+    }
+    for (int i = 0; i < 408; i++) {
+        int b = i - 72;
+        b = b < 0 ? 0 : b > 255 ? 255 : b;
+        P.bt[i] = (int16_t)(((b * 41943 + 16) >> 9) - 10485 + 1);
+    }
+}
+
+int apse_upload_p2_tables(apse_ctx *ctx, const uint8_t *lut, P2Tables **dev, cudaStream_t st)
+{
+    LabTables T;
+    build_lab_tables_host(T, lut);
+    P2Tables *P = new P2Tables();
+    build_p2_tables_host(*P, T);
+    cudaError_t e = cudaSuccess;
+    if (!*dev) e = cudaMalloc((void **)dev, sizeof(P2Tables));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(*dev, P, sizeof(P2Tables), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    delete P;
+    CUDA_TRY(ctx, e);
+    return APSE_OK;
+}
+
+__device__ __forceinline__ int xz_px(int v)
+{
+    // v <= 3390: trunc(v*108/841) - 290 (signed high product + 1 for negative v); else floor(floor(v^2/2^14) v / 2^14)
+    int lo = __mulhi(v, XZ_MAGIC) + (int)((unsigned)v >> 31) - 290;
+    int hi = (((v * v) >> 14) * v) >> 14;
+    return v <= 3390 ? lo : hi;
+}
+
+// colour chain of one pixel on the composed tables: (c0,c1,c2) -> corrected (o0,o1,o2) and gray
+__device__ __forceinline__ int chain_px(const P2Tables *T, int c0, int c1, int c2, int &o0, int &o1, int &o2)
+{
+    int R = T->gamma[c0], G = T->gamma[c1], B = T->gamma[c2];
+    int iX = (R * 1777 + G * 1541 + B * 778 + 2048) >> 12;
+    int iY = (R * 871 + G * 2929 + B * 296 + 2048) >> 12;
+    int iZ = (R * 73 + G * 448 + B * 3575 + 2048) >> 12;
+    uint2 yv = T->yt[iY];
+    int fX = T->cb[iX], fZ = T->cb[iZ];
+    int fY = yv.x & 0xffff, y = yv.x >> 16, f = (int)yv.y;
+    int ia = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
+    int ib = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
+    int X = xz_px(f + T->at[ia + 372]), Z = xz_px(f - T->bt[ib + 72]);
+    int r0 = (12615 * X - 6296 * y - 2223 * Z + 8192) >> 14;
+    int r1 = (-3773 * X + 7684 * y + 185 * Z + 8192) >> 14;
+    int r2 = (217 * X - 836 * y + 4715 * Z + 8192) >> 14;
+    o0 = T->invgamma[min(max(r0, 0), 4095)];
+    o1 = T->invgamma[min(max(r1, 0), 4095)];
+    o2 = T->invgamma[min(max(r2, 0), 4095)];
+    return gray_px(o0, o1, o2);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra D_%=;\n"
+        "bra W_%=;\n"
+        "D_%=:\n"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, int c2, uint32_t mbar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"((uint32_t)P2_RAW_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(mbar)
+        : "memory");
+}
+
+template <bool WANT_BGR>
+__global__ void __launch_bounds__(P2_THREADS, 2)
+k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
+                 uint8_t *__restrict__ gray, uint8_t *__restrict__ tmin, uint8_t *__restrict__ tmax,
+                 const float *__restrict__ mapx, const float *__restrict__ mapy, const P2Tables *__restrict__ tables, int w, int h,
+                 int batch, int fpb)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *raw = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *bgrx = reinterpret_cast<uint32_t *>(smem + P2_OFF_BGRX);
+    P2Tables *T = reinterpret_cast<P2Tables *>(smem + P2_OFF_TABLES);
+    unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);
+    int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 8);   // xmin, xmax, ymin, ymax
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mbar = smem_u32(mbar_p);
+
+    {   // tables -> shared memory
+        const uint4 *src = reinterpret_cast<const uint4 *>(tables);
+        uint4 *dst = reinterpret_cast<uint4 *>(T);
+        for (int i = tid; i < (int)(sizeof(P2Tables) / 16); i += P2_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        box[0] = INT32_MAX; box[1] = INT32_MIN; box[2] = INT32_MAX; box[3] = INT32_MIN;
+    }
+    __syncthreads();
+
+    // ---- taps of this thread's 4 pixels: column x, rows y0..y0+3
+    const int x = blockIdx.x * P2_TW + (warp & 1) * 32 + lane;
+    const int y0 = blockIdx.y * P2_TH + (warp >> 1) * 4;
+    const bool valid = x < w && y0 < h;           // h % 4 == 0: a 4-row group is inside or outside as a whole
+    int ixs[P2_NPX], iys[P2_NPX];
+    uint32_t wA[P2_NPX], wB[P2_NPX];
+    int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
+#pragma unroll
+    for (int k = 0; k < P2_NPX; k++) {
+        ixs[k] = iys[k] = 0; wA[k] = wB[k] = 0;
+        if (valid) {
+            size_t o = (size_t)(y0 + k) * w + x;
+            int sx = q5(__ldg(mapx + o)), sy = q5(__ldg(mapy + o));
+            int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+            // taps completely outside the image contribute 0: clamp them next to the image so that the box stays small
+            ix = min(max(ix, -2), w + 1); iy = min(max(iy, -2), h + 1);
+            ixs[k] = ix; iys[k] = iy;
+            wA[k] = (uint32_t)((32 - fy) * (32 - fx)) | ((uint32_t)((32 - fy) * fx) << 16);
+            wB[k] = (uint32_t)(fy * (32 - fx)) | ((uint32_t)(fy * fx) << 16);
+            xmin = min(xmin, ix); xmax = max(xmax, ix + 1); ymin = min(ymin, iy); ymax = max(ymax, iy + 1);
+        }
+    }
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+    if (lane == 0 && xmin != INT32_MAX) { atomicMin(&box[0], xmin); atomicMax(&box[1], xmax); atomicMin(&box[2], ymin); atomicMax(&box[3], ymax); }
+    __syncthreads();
+    const int bx0 = box[0] & ~15, by0 = box[2];   // TMA: the innermost start coordinate must be 16-byte aligned (16 px = 48 B)
+    const int bw = box[1] - bx0 + 1, bh = box[3] - by0 + 1;
+    const bool fast = bw <= P2_BOX_PX && bh <= P2_BOX_H;   // CTA-uniform
+    int off[P2_NPX];
+#pragma unroll
+    for (int k = 0; k < P2_NPX; k++) off[k] = valid ? (iys[k] - by0) * P2_PITCH + (ixs[k] - bx0) : 0;
+
+    const size_t frame_px = (size_t)w * h;
+    const int f0 = blockIdx.z * fpb, f1 = min(batch, f0 + fpb);
+    const int tw4 = w >> 2;
+    uint32_t phase = 0;
+    if (fast && tid == 0) tma_load_box(smem_u32(raw), &tmap, (bx0 * 3) >> 2, by0, f0, mbar);
+
+    for (int f = f0; f < f1; f++) {
+        int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
+        if (fast) {
+            mbar_wait(mbar, phase);
+            phase ^= 1;
+            // raw BGR bytes -> one BGRx word per pixel (4 px = 3 words in, 4 words out per item)
+            const int ngroups = (bw + 3) >> 2;
+            for (int i = tid; i < ngroups * bh; i += P2_THREADS) {
+                int r = i / ngroups, gq = i - r * ngroups;
+                const uint32_t *s = raw + r * P2_BOX_WORDS + gq * 3;
+                uint32_t a = s[0], b = s[1], c = s[2];
+                uint4 v = make_uint4(a, __funnelshift_r(a, b, 24), __funnelshift_r(b, c, 16), c >> 8);
+                *reinterpret_cast<uint4 *>(bgrx + r * P2_PITCH + gq * 4) = v;
+            }
+            __syncthreads();
+            if (tid == 0 && f + 1 < f1) tma_load_box(smem_u32(raw), &tmap, (bx0 * 3) >> 2, by0, f + 1, mbar);
+            if (valid) {
+#pragma unroll
+                for (int k = 0; k < P2_NPX; k++) {
+                    const uint32_t *s = bgrx + off[k];
+                    uint32_t W00 = s[0], W01 = s[1], W10 = s[P2_PITCH], W11 = s[P2_PITCH + 1];
+                    uint32_t T0 = __byte_perm(W00, W01, 0x5140), T1 = __byte_perm(W10, W11, 0x5140);
+                    uint32_t U0 = __byte_perm(W00, W01, 0x6262), U1 = __byte_perm(W10, W11, 0x6262);
+                    int c0 = (int)(__dp2a_lo(wA[k], T0, __dp2a_lo(wB[k], T1, 512u)) >> 10);
+                    int c1 = (int)(__dp2a_hi(wA[k], T0, __dp2a_hi(wB[k], T1, 512u)) >> 10);
+                    int c2 = (int)(__dp2a_lo(wA[k], U0, __dp2a_lo(wB[k], U1, 512u)) >> 10);
+                    g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
+                }
+            }
+        } else if (valid) {
+            // direct-gather path (source box larger than the staging buffer)
+            const uint8_t *src = bgr + (size_t)f * frame_px * 3;
+#pragma unroll
+            for (int k = 0; k < P2_NPX; k++) {
+                size_t o = (size_t)(y0 + k) * w + x;
+                Taps t = make_taps(__ldg(mapx + o), __ldg(mapy + o), w, h, 3);
+                int c0 = sample(src, t, w * 3, 3, 0), c1 = sample(src, t, w * 3, 3, 1), c2 = sample(src, t, w * 3, 3, 2);
+                g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
+            }
+        }
+        if (valid) {
+            size_t o = (size_t)f * frame_px + (size_t)y0 * w + x;
+#pragma unroll
+            for (int k = 0; k < P2_NPX; k++) {
+                gray[o + (size_t)k * w] = (uint8_t)g[k];
+                if (WANT_BGR) {
+                    uint8_t *d = bgr_out + (o + (size_t)k * w) * 3;
+                    d[0] = (uint8_t)o0[k]; d[1] = (uint8_t)o1[k]; d[2] = (uint8_t)o2[k];
+                }
+            }
+        }
+        if (tmin) {
+            // 4x4-tile min / max: this thread holds one column of the tile, 4 lanes hold its columns
+            int mn = 255, mx = 0;
+            if (valid) {
+                mn = min(min(g[0], g[1]), min(g[2], g[3]));
+                mx = max(max(g[0], g[1]), max(g[2], g[3]));
+            }
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            if (valid && (lane & 3) == 0) {
+                size_t to = ((size_t)f * (h >> 2) + (y0 >> 2)) * tw4 + (x >> 2);
+                tmin[to] = (uint8_t)mn;
+                tmax[to] = (uint8_t)mx;
+            }
+        }
+        if (fast) __syncthreads();   // all reads of bgrx done before the next frame's expansion overwrites it
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_tmap_encoder()
+{
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+// fused preprocess of a batch; tmin/tmax (nullable) receive the 4x4-tile extrema of gray: [batch][h/4][w/4]
+int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, uint8_t *tmin, uint8_t *tmax, int batch,
+                       cudaStream_t st)
+{
+    int w = ctx->w, h = ctx->h;
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    static const bool force_generic = getenv("APSE_K1_GENERIC") != nullptr;   // development switch: generic kernel only
+    bool tma_ok = !force_generic && enc && (w % 4) == 0 && (h % 4) == 0 && w >= P2_TW && h >= P2_TH && ((uintptr_t)bgr % 16) == 0 && ctx->tables2;
+    if (!tma_ok) {
+        int fpb = batch >= 8 ? 8 : batch;
+        dim3 grid(div_up(w, 32 * K1_PX), div_up(h, 8), div_up(batch, fpb));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_fused<<<grid, 256, 0, st>>>(bgr, bgr_out, gray, ctx->mapx, ctx->mapy, ctx->tables, w, h, batch, fpb));
+        return 1;   // tile extrema not produced
+    }
+    CUtensorMap tmap;
+    cuuint64_t dims[3] = {(cuuint64_t)(w * 3 / 4), (cuuint64_t)h, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * 3 * h};
+    cuuint32_t boxd[3] = {P2_BOX_WORDS, P2_BOX_H, 1}, estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)bgr, dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) CTX_FAIL(ctx, APSE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        attr_set = true;
+    }
+    int fpb = batch >= 8 ? 8 : batch;
+    dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), div_up(batch, fpb));
+    if (bgr_out)
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmin, tmax, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
+    else
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmin, tmax, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
+    return APSE_OK;
+}
+
 int apse_preprocess(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, int batch, void *stream)
 {
     if (!ctx || !bgr || !gray || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "preprocess: bad argument");
     if (!ctx->has_camera || !ctx->has_lut) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "preprocess: set_camera and set_lut first");
-    int w = ctx->w, h = ctx->h;
-    int fpb = batch >= 8 ? 8 : batch;
-    dim3 grid(div_up(w, 32 * K1_PX), div_up(h, 8), div_up(batch, fpb));
-    KLAUNCH(ctx, KID_PREPROCESS, (cudaStream_t)stream, k_preprocess_fused<<<grid, 256, 0, (cudaStream_t)stream>>>(bgr, bgr_out, gray, ctx->mapx, ctx->mapy, ctx->tables, w, h,
-                                                              batch, fpb));
-    return APSE_OK;
+    int rc = apse_preprocess_ex(ctx, bgr, bgr_out, gray, nullptr, nullptr, batch, (cudaStream_t)stream);
+    return rc < 0 ? rc : APSE_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
