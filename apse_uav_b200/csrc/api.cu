@@ -74,7 +74,7 @@ void apse_destroy(apse_ctx *ctx)
     apse_detect_free(ctx);
     apse_decode_free(ctx);
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
-    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict);
+    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch);
     delete ctx;
 }
 
@@ -233,6 +233,36 @@ int apse_detect(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, aps
     int rc = apse_apriltag_quads(ctx, gray, w, h, batch, dp, (cudaStream_t)stream);
     if (rc) return rc;
     return apse_decode_candidates(ctx, gray, w, h, batch, dp, out, (cudaStream_t)stream);
+}
+
+int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, apse_detections *out, const float *marker_len,
+                        float marker_len_all, double *rvec, double *tvec, void *stream)
+{
+    if (!ctx || !bgr || !out || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "process_frames: bad argument");
+    if (!ctx->has_camera || !ctx->has_lut || !ctx->has_dict)
+        CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "process_frames: set_camera, set_lut and set_dictionary first");
+    if (ctx->params.cornerRefinementMethod != 3)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "process_frames: only CORNER_REFINE_APRILTAG candidates are implemented in this build");
+    if (batch > ctx->max_batch) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "process_frames: batch %d exceeds the context capacity %d", batch, ctx->max_batch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int w = ctx->w, h = ctx->h;
+    if (!gray) {
+        if (!ctx->gray_scratch) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->gray_scratch, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h));
+        gray = ctx->gray_scratch;
+    }
+    // K1 writes the 4x4-tile extrema of gray straight into the candidate stage's tile arrays
+    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmin, ctx->tmax, batch, st);
+    if (rc < 0) return rc;
+    const bool have_minmax = rc == APSE_OK;
+    DeviceParams dp;
+    apse_fill_device_params(ctx, &dp, w, h);
+    rc = apse_apriltag_quads(ctx, gray, w, h, batch, dp, st, have_minmax);
+    if (rc) return rc;
+    rc = apse_decode_candidates(ctx, gray, w, h, batch, dp, out, st);
+    if (rc) return rc;
+    if (rvec && tvec)
+        rc = apse_pose_frames(ctx, out->corners, out->n_markers, batch, out->max_markers, marker_len, marker_len_all, ctx->K, ctx->D, rvec, tvec, stream);
+    return rc;
 }
 
 int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_t *thresh, uint32_t *labels, float *quads,

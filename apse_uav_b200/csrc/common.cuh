@@ -104,6 +104,7 @@ struct apse_ctx {
     uint32_t *quad_order = nullptr;   // cluster index of each quad (for deterministic ordering)
     // decode scratch
     void *decode_scratch = nullptr;
+    uint8_t *gray_scratch = nullptr;  // [max_batch][h][w], allocated on first use by apse_process_frames(gray = NULL)
 };
 
 #define APSE_COUNTERS 8
@@ -158,6 +159,6 @@ int apse_decode_alloc(apse_ctx *ctx);
 void apse_decode_free(apse_ctx *ctx);
 int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h);
 int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
-                        cudaStream_t st);
+                        cudaStream_t st, bool have_tile_minmax = false);   // true: ctx->tmin/tmax already hold this batch's extrema
 int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
                            apse_detections *out, cudaStream_t st);

@@ -948,7 +948,8 @@ void apse_detect_free(apse_ctx *ctx)
 }
 
 // runs K2..K5 for `batch` gray frames; leaves quads / counters in the context scratch
-int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp, cudaStream_t st)
+int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp, cudaStream_t st,
+                        bool have_tile_minmax)
 {
     if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch || batch > 64)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: frame %dx%d x%d exceeds the context capacity %dx%d x%d (64 max)", w, h,
@@ -963,7 +964,8 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     CUDA_TRY(ctx, cudaMemsetAsync(ex->tile_active, 0, (size_t)batch * nct, st));
     {
         dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
-        KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax));
+        if (!have_tile_minmax)
+            KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax));
         KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, dp.min_white_black_diff, ctx->thresh,
                                                                            ex->tile_active, ctw, cth));
         if (tw * 4 != w || th * 4 != h) {

@@ -567,8 +567,9 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         attr_set = true;
     }
-    int fpb = batch >= 8 ? 8 : batch;
-    dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), div_up(batch, fpb));
+    // frames per CTA: the tap set-up (map reads, box reduction, table load) is amortised over up to 20 frames
+    const int nz = div_up(batch, 20), fpb = div_up(batch, nz);
+    dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), nz);
     if (bgr_out)
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmin, tmax, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
     else

@@ -235,6 +235,27 @@ class Engine:
         self._check(self.lib.apse_detect(self.h, gray.data_ptr(), W, H, B, C.byref(d), self._stream()))
         return res
 
+    def process_frames(self, bgr, out, marker_length, gray=None):
+        """aruco_detect.py:589-601 for a batch in ONE library call (apse_process_frames): preprocess -> detect -> pose.
+        `out` is a dict from alloc_detections(..., pose=True); gray [B,H,W] is written if given, else context scratch."""
+        torch = self.torch
+        bgr = self._u8(bgr, "process_frames")
+        B, H, W, _ = bgr.shape
+        if self.size != (W, H):
+            raise ApseError(-3, f"process_frames: frames are {W}x{H} but the camera was set for {self.size}")
+        want_rejected = "rejected" in out
+        d = Detections(out["corners"].shape[1], out["corners"].data_ptr(), out["ids"].data_ptr(), out["n"].data_ptr(),
+                       out["rejected"].data_ptr() if want_rejected else None,
+                       out["n_rejected"].data_ptr() if want_rejected else None, out["status"].data_ptr())
+        ml = None
+        if isinstance(marker_length, torch.Tensor) or np.ndim(marker_length) > 0:
+            ml = torch.as_tensor(marker_length, dtype=torch.float32, device=self.tdev).contiguous()
+        self._check(self.lib.apse_process_frames(self.h, bgr.data_ptr(), gray.data_ptr() if gray is not None else None, B,
+                                                 C.byref(d), ml.data_ptr() if ml is not None else None,
+                                                 float(marker_length) if ml is None else 0.0, out["rvec"].data_ptr(),
+                                                 out["tvec"].data_ptr(), self._stream()))
+        return out
+
     def debug_apriltag(self, gray, max_quads=512):
         torch = self.torch
         gray = self._u8(gray, "debug_apriltag")

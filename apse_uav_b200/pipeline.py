@@ -47,10 +47,11 @@ class Pipeline:
             e.close()
 
     def _run_on(self, e, frames, out, want_gray, marker_length):
-        _, gray = e.preprocess(frames, want_bgr=False)
-        e.detect(gray, out=out)
-        e.pose_frames(out["corners"], out["n"], marker_length, out=(out["rvec"], out["tvec"]))
-        return gray if want_gray else None
+        gray = None
+        if want_gray:
+            gray = e.torch.empty(frames.shape[:3], dtype=e.torch.uint8, device=e.tdev)
+        e.process_frames(frames, out, marker_length, gray=gray)   # one library call: K1t -> candidates -> decode -> pose
+        return gray
 
     def run_batch(self, frames, want_gray=False, want_rejected=False, marker_length=None):
         """frames: [B,H,W,3] uint8 CUDA tensor, B <= max_batch.  Returns dict of device tensors."""

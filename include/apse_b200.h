@@ -131,6 +131,13 @@ int apse_pose_frames(apse_ctx *ctx, const float *corners, const int32_t *n_marke
                      const float *marker_len, float marker_len_all, const double K_host[9], const double D_host[14],
                      double *rvec, double *tvec, void *stream);
 
+/* aruco_detect.py:589-601 in one call for a batch of raw frames: preprocessFrame + BGR2GRAY + detectMarkers +
+ * estimatePoseSingleMarkers (camera of apse_set_camera).  Same results as apse_preprocess -> apse_detect ->
+ * apse_pose_frames; the fused kernel hands the 4x4-tile extrema of gray to the candidate stage directly.
+ * bgr: [batch][h][w][3]; gray: [batch][h][w] or NULL (context scratch); rvec/tvec nullable (no pose) */
+int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, apse_detections *out,
+                        const float *marker_len, float marker_len_all, double *rvec, double *tvec, void *stream);
+
 /* aruco_detect.py:344,377,424,468  cv2.projectPoints(obj, rvec, tvec, K, D)
  * obj: [n][3] float64, rvec/tvec: [3] float64, img: [n][2] float64 -- all device pointers */
 int apse_project_points(apse_ctx *ctx, const double *obj, int n, const double *rvec, const double *tvec,
