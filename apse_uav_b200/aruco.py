@@ -111,7 +111,7 @@ def detectMarkers(image, dictionary, corners=None, ids=None, parameters=None, re
     raw, ms, mc = _dict_fields(dictionary)
     e.set_dictionary(raw, ms, mc)
     e.set_params(parameters if parameters is not None else DetectorParameters())
-    res = e.detect(img, max_markers=512, want_rejected=True)
+    res = e.detect(img, max_markers=1024, want_rejected=True)
     status = int(res["status"][0])
     if status != 0:
         raise ApseError(status, "detectMarkers: work-buffer capacity exceeded for this frame")

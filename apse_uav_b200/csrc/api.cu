@@ -220,19 +220,34 @@ int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h)
     return APSE_OK;
 }
 
+// candidates (APRILTAG quad detector or the classic threshold / contour path) -> grouping + decoding -> SUBPIX
+static int apse_detect_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, cudaStream_t st,
+                            bool have_tile_minmax)
+{
+    DeviceParams dp;
+    apse_fill_device_params(ctx, &dp, w, h);
+    const int mode = ctx->params.cornerRefinementMethod;
+    int rc;
+    if (mode == 3) {
+        rc = apse_apriltag_quads(ctx, gray, w, h, batch, dp, st, have_tile_minmax);
+    } else {
+        rc = apse_decode_big_scratch(ctx);
+        if (!rc) rc = apse_classic_quads(ctx, gray, w, h, batch, st);
+    }
+    if (rc) return rc;
+    rc = apse_decode_candidates(ctx, gray, w, h, batch, dp, out, st);
+    if (rc) return rc;
+    if (mode == 1) rc = apse_corner_subpix(ctx, gray, w, h, batch, out, st);
+    return rc;
+}
+
 extern "C" {
 
 int apse_detect(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, void *stream)
 {
     if (!ctx || !gray || !out || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: bad argument");
     if (!ctx->has_dict) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "detect: set_dictionary first");
-    if (ctx->params.cornerRefinementMethod != 3)
-        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: only CORNER_REFINE_APRILTAG candidates are implemented in this build");
-    DeviceParams dp;
-    apse_fill_device_params(ctx, &dp, w, h);
-    int rc = apse_apriltag_quads(ctx, gray, w, h, batch, dp, (cudaStream_t)stream);
-    if (rc) return rc;
-    return apse_decode_candidates(ctx, gray, w, h, batch, dp, out, (cudaStream_t)stream);
+    return apse_detect_impl(ctx, gray, w, h, batch, out, (cudaStream_t)stream, false);
 }
 
 int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, apse_detections *out, const float *marker_len,
@@ -241,8 +256,6 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
     if (!ctx || !bgr || !out || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "process_frames: bad argument");
     if (!ctx->has_camera || !ctx->has_lut || !ctx->has_dict)
         CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "process_frames: set_camera, set_lut and set_dictionary first");
-    if (ctx->params.cornerRefinementMethod != 3)
-        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "process_frames: only CORNER_REFINE_APRILTAG candidates are implemented in this build");
     if (batch > ctx->max_batch) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "process_frames: batch %d exceeds the context capacity %d", batch, ctx->max_batch);
     cudaStream_t st = (cudaStream_t)stream;
     const int w = ctx->w, h = ctx->h;
@@ -254,15 +267,38 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
     int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmin, ctx->tmax, batch, st);
     if (rc < 0) return rc;
     const bool have_minmax = rc == APSE_OK;
-    DeviceParams dp;
-    apse_fill_device_params(ctx, &dp, w, h);
-    rc = apse_apriltag_quads(ctx, gray, w, h, batch, dp, st, have_minmax);
-    if (rc) return rc;
-    rc = apse_decode_candidates(ctx, gray, w, h, batch, dp, out, st);
+    rc = apse_detect_impl(ctx, gray, w, h, batch, out, st, have_minmax);
     if (rc) return rc;
     if (rvec && tvec)
         rc = apse_pose_frames(ctx, out->corners, out->n_markers, batch, out->max_markers, marker_len, marker_len_all, ctx->K, ctx->D, rvec, tvec, stream);
     return rc;
+}
+
+int apse_adaptive_threshold(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out, void *stream)
+{
+    if (!ctx || !gray || !out || batch <= 0 || w <= 0 || h <= 0 || win < 3) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "adaptive_threshold: bad argument");
+    return apse_adaptive_threshold_impl(ctx, gray, w, h, batch, win, c, out, (cudaStream_t)stream);
+}
+
+int apse_debug_classic(apse_ctx *ctx, const uint8_t *gray, int w, int h, float *quads, uint32_t *order, int max_quads,
+                       int64_t *stats_host, void *stream)
+{
+    if (!ctx || !gray) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "debug_classic: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = apse_classic_quads(ctx, gray, w, h, 1, st);
+    if (rc) return rc;
+    int32_t cnt[APSE_COUNTERS];
+    CUDA_TRY(ctx, cudaMemcpyAsync(cnt, ctx->counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (cnt[3] != 0) CTX_FAIL(ctx, cnt[3], "debug_classic: work buffer capacity exceeded (quads %d)", cnt[2]);
+    int nq = cnt[2] < max_quads ? cnt[2] : max_quads;
+    if (quads && order && nq > 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(quads, ctx->quads, (size_t)nq * 8 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(order, ctx->quad_order, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    if (stats_host) { stats_host[0] = cnt[2]; stats_host[1] = 0; stats_host[2] = 0; stats_host[3] = 0; }
+    return APSE_OK;
 }
 
 int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_t *thresh, uint32_t *labels, float *quads,

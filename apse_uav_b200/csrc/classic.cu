@@ -1,0 +1,599 @@
+// classic.cu -- CLASSIC candidate stage of aruco.detectMarkers (aruco_detect.py:267 with cornerRefinementMethod
+// NONE / SUBPIX; north_star stages (2)-(4), BASELINE.json config 5), batched, sm_100a.
+//
+//   C1  k_adaptive_threshold   box-mean threshold (MEAN_C, BINARY_INV) of one window size: gray tile + halo staged in
+//                              shared memory, row prefix sums by warp shuffles, sliding column sums
+//   C2  k_ccl_* (detect_apriltag.cu, full-range mode)  foreground 8-connected / background 4-connected components,
+//                              root = raster-first pixel;  k_mark_outside flags the background components that touch
+//                              the image edge;  k_border_jobs lists one border per foreground component (outer) and
+//                              per enclosed background component (hole) -- exactly the borders Suzuki-Abe border
+//                              following finds, without its sequential raster scan
+//       k_trace_borders        one thread per border: border following with the dependency's start / direction
+//                              conventions; borders inside the perimeter limits are stored
+//   C3  k_approx_quads         one warp per stored border: closed Douglas-Peucker (3 farthest-point rounds,
+//                              explicit stack, point-to-segment distance, clean-up pass), convexity, corner
+//                              distance, clockwise order -> candidate quad + ordering key
+//       k_rank_quads           dependency candidate order: window ascending, then descending raster order of
+//                              the border's trigger pixel
+//   C4  k_corner_subpix        cornerSubPix on the accepted markers (thread per corner, FP64 normal equations)
+//
+// Integer / FP64 arithmetic follows the dependency's evaluation order (-fmad=false); parity: tests/test_gpu_classic.py.
+#include "common.cuh"
+#include <math.h>
+#include <float.h>
+
+// ---------------------------------------------------------------------------------------------------------
+// C1: adaptive threshold.  Tile 64 x 32 outputs, 256 threads; halo r = win / 2 (win <= 65).
+#define AT_TW 64
+#define AT_TH 32
+#define AT_RMAX 32
+#define AT_SW (AT_TW + 2 * AT_RMAX)   // 128
+#define AT_SH (AT_TH + 2 * AT_RMAX)   // 96
+
+__global__ void __launch_bounds__(256) k_adaptive_threshold(const uint8_t *__restrict__ gray, int w, int h, int win, int idelta,
+                                                            uint8_t *__restrict__ out)
+{
+    __shared__ uint16_t P[AT_SH][AT_SW + 2];   // inclusive row prefix sums of the staged tile (<= 128 * 255 fits 16 bits)
+    const int r = win >> 1, sw = AT_TW + 2 * r, sh = AT_TH + 2 * r;
+    const int f = blockIdx.z, x0 = blockIdx.x * AT_TW, y0 = blockIdx.y * AT_TH;
+    const uint8_t *g = gray + (size_t)f * w * h;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // stage rows (replicated border) and turn each into prefix sums: one warp per row, 4 columns per lane
+    for (int ry = warp; ry < sh; ry += 8) {
+        const int gy = min(max(y0 - r + ry, 0), h - 1);
+        const uint8_t *row = g + (size_t)gy * w;
+        int v[4], s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int cx = lane * 4 + k;
+            int gx = min(max(x0 - r + cx, 0), w - 1);
+            v[k] = cx < sw ? (int)__ldg(row + gx) : 0;
+            s += v[k];
+        }
+        int inc = s;
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        int run = inc - s;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { run += v[k]; P[ry][lane * 4 + k + 1] = (uint16_t)run; }
+        if (lane == 0) P[ry][0] = 0;
+    }
+    __syncthreads();
+    // column sums of the horizontal box sums: thread = (column, group of 8 output rows), sliding along y
+    const int cx = tid & 63, yg = tid >> 6;
+    const int x = x0 + cx;
+    const int area = win * win;
+    int s = 0;
+    for (int k = 0; k < win; k++) s += (int)P[yg * 8 + k][cx + win] - (int)P[yg * 8 + k][cx];
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+        const int oy = yg * 8 + j, y = y0 + oy;
+        if (j > 0) s += ((int)P[oy + win - 1][cx + win] - (int)P[oy + win - 1][cx]) - ((int)P[oy - 1][cx + win] - (int)P[oy - 1][cx]);
+        if (x < w && y < h) {
+            // mean = round-half-even(s / area); area is odd, so no ties exist and floor((2s + area) / (2 area)) is exact
+            int mean = (2 * s + area) / (2 * area);
+            out[(size_t)f * w * h + (size_t)y * w + x] = ((int)g[(size_t)y * w + x] - mean <= -idelta) ? 255 : 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C2: border jobs
+#define LBL_OUTSIDE 0x80000000u
+
+// background components that touch the image edge are connected to the (virtual) outside: flag their root
+__global__ void k_mark_outside(const uint8_t *__restrict__ bin, int w, int h, uint32_t *__restrict__ labels, int batch)
+{
+    const int per = 2 * (w + h);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per * batch; i += gridDim.x * blockDim.x) {
+        int f = i / per, k = i - f * per, x, y;
+        if (k < w) { x = k; y = 0; }
+        else if (k < 2 * w) { x = k - w; y = h - 1; }
+        else if (k < 2 * w + h) { x = 0; y = k - 2 * w; }
+        else { x = w - 1; y = k - 2 * w - h; }
+        size_t o = (size_t)f * w * h + (size_t)y * w + x;
+        if (bin[o] == 0) {
+            uint32_t root = labels[o] & ~LBL_OUTSIDE;
+            atomicOr(&labels[(size_t)f * w * h + root], LBL_OUTSIDE);
+        }
+    }
+}
+
+// one job per border: trigger pixel index | hole flag (bit 31)
+__global__ void __launch_bounds__(256) k_border_jobs(const uint8_t *__restrict__ bin, int w, int h, const uint32_t *__restrict__ labels,
+                                                     uint32_t *__restrict__ jobs, int job_cap, int32_t *__restrict__ counters)
+{
+    const int f = blockIdx.y;
+    const size_t npx = (size_t)w * h;
+    const uint8_t *b = bin + f * npx;
+    const uint32_t *L = labels + f * npx;
+    uint32_t *J = jobs + (size_t)f * job_cap;
+    int32_t *cnt = counters + f * APSE_COUNTERS;
+    const int lane = threadIdx.x & 31;
+    for (size_t p0 = (size_t)blockIdx.x * blockDim.x; p0 < npx; p0 += (size_t)gridDim.x * blockDim.x) {
+        size_t p = p0 + threadIdx.x;
+        bool job = false;
+        uint32_t enc = 0;
+        if (p < npx) {
+            uint32_t l = L[p];
+            if ((l & ~LBL_OUTSIDE) == (uint32_t)p) {
+                if (b[p]) { job = true; enc = (uint32_t)p; }
+                else if (!(l & LBL_OUTSIDE)) { job = true; enc = (uint32_t)p | 0x80000000u; }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, job);
+        if (m) {
+            int leader = __ffs(m) - 1, base = 0;
+            if (lane == leader) base = atomicAdd(&cnt[0], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (job) {
+                int idx = base + __popc(m & ((1u << lane) - 1));
+                if (idx < job_cap) J[idx] = enc; else atomicExch(&cnt[3], APSE_ERR_CAPACITY);
+            }
+        }
+    }
+}
+
+// Border following (Suzuki-Abe), directions 0..7 = E, NE, N, NW, W, SW, S, SE with y growing downwards.
+struct BinImage {
+    const uint8_t *b;
+    int w, h;
+    __device__ __forceinline__ bool fg(int x, int y) const { return x >= 0 && x < w && y >= 0 && y < h && b[(size_t)y * w + x] != 0; }
+};
+__device__ __constant__ int8_t c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+__device__ __constant__ int8_t c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+
+template <bool STORE>
+__device__ int trace_border(const BinImage &I, int x0, int y0, bool hole, int max_n, uint32_t *out)
+{
+    int s = hole ? 0 : 4;
+    const int s_end = s;
+    bool found = false;
+    do {
+        s = (s - 1) & 7;
+        if (I.fg(x0 + c_dx[s], y0 + c_dy[s])) { found = true; break; }
+    } while (s != s_end);
+    if (!found) {
+        if (STORE) out[0] = (uint32_t)x0 | ((uint32_t)y0 << 16);
+        return 1;
+    }
+    const int x1 = x0 + c_dx[s], y1 = y0 + c_dy[s];
+    int cx = x0, cy = y0, n = 0;
+    for (;;) {
+        int nx, ny;
+        for (;;) {
+            s = (s + 1) & 7;
+            nx = cx + c_dx[s]; ny = cy + c_dy[s];
+            if (I.fg(nx, ny)) break;
+        }
+        if (STORE) out[n] = (uint32_t)cx | ((uint32_t)cy << 16);
+        n++;
+        if (nx == x0 && ny == y0 && cx == x1 && cy == y1) break;
+        if (n > max_n) break;   // longer than the perimeter limit: the caller drops it
+        cx = nx; cy = ny;
+        s = (s + 4) & 7;
+    }
+    return n;
+}
+
+struct ContourDesc { uint32_t offset, count, trigger, hole; };   // same footprint as ClusterDesc (scratch is shared)
+
+__global__ void __launch_bounds__(128) k_trace_borders(const uint8_t *__restrict__ bin, int w, int h, const uint32_t *__restrict__ jobs,
+                                                       int job_cap, int32_t *__restrict__ counters, int min_px, int max_px,
+                                                       uint32_t *__restrict__ pts, int pts_cap, ContourDesc *__restrict__ descs,
+                                                       int desc_cap, int batch)
+{
+    const int f = blockIdx.y;
+    const int32_t *cnt_r = counters + f * APSE_COUNTERS;
+    int32_t *cnt = counters + f * APSE_COUNTERS;
+    const int njobs = min(cnt_r[0], job_cap);
+    BinImage I{bin + (size_t)f * w * h, w, h};
+    const uint32_t *J = jobs + (size_t)f * job_cap;
+    uint32_t *P = pts + (size_t)f * pts_cap;
+    ContourDesc *D = descs + (size_t)f * desc_cap;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < njobs; j += gridDim.x * blockDim.x) {
+        uint32_t e = J[j];
+        bool hole = (e >> 31) != 0;
+        uint32_t trig = e & 0x7fffffffu;
+        int ty = trig / w, tx = trig - ty * w;
+        int x0 = hole ? tx - 1 : tx, y0 = ty;
+        int n = trace_border<false>(I, x0, y0, hole, max_px, nullptr);
+        if (n < min_px || n > max_px) continue;
+        int di = atomicAdd(&cnt[1], 1);
+        int off = atomicAdd(&cnt[5], n);
+        if (di >= desc_cap || off + n > pts_cap) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); continue; }
+        trace_border<true>(I, x0, y0, hole, max_px, P + off);
+        D[di] = ContourDesc{(uint32_t)off, (uint32_t)n, trig, hole ? 1u : 0u};
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C3: polygon approximation + quad filters, one warp per stored border
+#define AQ_WARPS 8
+#define AQ_STACK 96
+#define AQ_MAXV 128
+
+__device__ __forceinline__ int pt_x(uint32_t p) { return (int)(p & 0xffffu); }
+__device__ __forceinline__ int pt_y(uint32_t p) { return (int)(p >> 16); }
+
+// squared point-to-segment distance (FP64, the dependency's expression order)
+__device__ __forceinline__ double seg_dist2(int ax, int ay, int bx, int by, int px_, int py_, double dx, double dy, double len2)
+{
+    double px = px_ - ax, py = py_ - ay;
+    double proj = px * dx + py * dy;
+    if (proj < 0) return px * px + py * py;
+    if (proj > len2) { double qx = px_ - bx, qy = py_ - by; return qx * qx + qy * qy; }
+    double cr = py * dx - px * dy;
+    return cr * cr / len2;
+}
+
+struct ClassicArgs {
+    const uint32_t *pts;
+    int pts_cap;
+    const ContourDesc *descs;
+    int desc_cap;
+    int32_t *counters;
+    float *quads;
+    unsigned long long *quad_keys;
+    int quad_cap;
+    int w, h, window_index;
+    double accuracy_rate, min_corner_rate;
+};
+
+__global__ void __launch_bounds__(AQ_WARPS * 32) k_approx_quads(ClassicArgs A)
+{
+    __shared__ int2 s_stack[AQ_WARPS][AQ_STACK];
+    __shared__ uint32_t s_out[AQ_WARPS][AQ_MAXV];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t *cnt = A.counters + f * APSE_COUNTERS;
+    const int ndesc = min(cnt[1], A.desc_cap);
+    const uint32_t *P = A.pts + (size_t)f * A.pts_cap;
+    const ContourDesc *D = A.descs + (size_t)f * A.desc_cap;
+    int2 *stack = s_stack[wid];
+    uint32_t *outv = s_out[wid];
+    for (int ci = blockIdx.x * AQ_WARPS + wid; ci < ndesc; ci += gridDim.x * AQ_WARPS) {
+        const ContourDesc cd = D[ci];
+        const uint32_t *src = P + cd.offset;
+        const int count = (int)cd.count;
+        const double eps = (double)count * A.accuracy_rate, eps2 = eps * eps;
+        // ---- farthest point from the current start, three rounds (first maximum wins)
+        int pos = 0, right_start = 0, start_idx = 0;
+        bool le_eps = false;
+        for (int it = 0; it < 3; it++) {
+            pos = (pos + right_start) % count;
+            start_idx = pos;
+            const uint32_t sp = src[start_idx];
+            const int sx = pt_x(sp), sy = pt_y(sp);
+            int best = 0, best_j = 0;   // max_dist starts at 0: j is only taken on a strictly larger distance
+            for (int j = 1 + lane; j < count; j += 32) {
+                int q = start_idx + j;
+                if (q >= count) q -= count;
+                const uint32_t pp = src[q];
+                const int dx = pt_x(pp) - sx, dy = pt_y(pp) - sy, d = dx * dx + dy * dy;
+                if (d > best) { best = d; best_j = j; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                int ob = __shfl_xor_sync(0xffffffffu, best, o), oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+                if (ob > best || (ob == best && ob > 0 && oj < best_j)) { best = ob; best_j = oj; }
+            }
+            if (best > 0) right_start = best_j;
+            le_eps = (double)best <= eps2;
+            pos = start_idx;   // the read position is back at the start point after a full round
+        }
+        int nout = 0, top = 0;
+        bool overflow = false;
+        if (!le_eps) {
+            int slice_start = pos % count;
+            int slice_end = (right_start + slice_start) % count;
+            // right slice pushed first, left slice processed first
+            if (lane == 0) { stack[0] = make_int2(slice_end, slice_start); stack[1] = make_int2(slice_start, slice_end); }
+            top = 2;
+        } else {
+            if (lane == 0) outv[0] = src[start_idx];
+            nout = 1;
+        }
+        __syncwarp();
+        while (top > 0) {
+            const int2 sl = stack[--top];
+            __syncwarp();
+            const uint32_t ep = src[sl.y], sp = src[sl.x];
+            const int ex = pt_x(ep), ey = pt_y(ep), sx = pt_x(sp), sy = pt_y(sp);
+            int first = sl.x + 1;
+            if (first >= count) first = 0;
+            bool ok;
+            int split = 0;
+            if (first != sl.y) {
+                const double dx = ex - sx, dy = ey - sy, len2 = dx * dx + dy * dy;
+                int m = sl.y - first;
+                if (m < 0) m += count;            // interior points first .. end-1 (cyclic)
+                double best = 0;
+                int best_k = -1;
+                for (int k = lane; k < m; k += 32) {
+                    int q = first + k;
+                    if (q >= count) q -= count;
+                    const uint32_t pp = src[q];
+                    double d = seg_dist2(sx, sy, ex, ey, pt_x(pp), pt_y(pp), dx, dy, len2);
+                    if (d > best) { best = d; best_k = k; }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    int ok_ = __shfl_xor_sync(0xffffffffu, best_k, o);
+                    if (ob > best || (ob == best && ok_ >= 0 && (best_k < 0 || ok_ < best_k))) { best = ob; best_k = ok_; }
+                }
+                ok = best <= eps2;
+                if (!ok) { split = first + best_k; if (split >= count) split -= count; }
+            } else {
+                ok = true;
+            }
+            if (ok) {
+                if (nout < AQ_MAXV) { if (lane == 0) outv[nout] = sp; } else overflow = true;
+                nout++;
+            } else {
+                if (top + 2 <= AQ_STACK) {
+                    if (lane == 0) { stack[top] = make_int2(split, sl.y); stack[top + 1] = make_int2(sl.x, split); }
+                    top += 2;
+                } else { overflow = true; top = 0; }
+            }
+            __syncwarp();
+        }
+        if (overflow) { if (lane == 0) atomicExch(&cnt[3], APSE_ERR_CAPACITY); continue; }
+        // ---- clean-up pass + filters: sequential, lane 0
+        if (lane == 0) {
+            int cntv = nout, new_count = nout;
+            if (cntv >= 3) {
+                int rp = cntv - 1, wpos;
+                auto rd = [&](int &x, int &y) { uint32_t v = outv[rp]; x = pt_x(v); y = pt_y(v); if (++rp >= cntv) rp = 0; };
+                int sx, sy, px, py, ex, ey;
+                rd(sx, sy);
+                wpos = rp;
+                rd(px, py);
+                for (int i = 0; i < cntv && new_count > 2; i++) {
+                    rd(ex, ey);
+                    double dx = ex - sx, dy = ey - sy;
+                    double dist = fabs((double)(px - sx) * dy - (double)(py - sy) * dx);
+                    double sip = (double)(px - sx) * (ex - px) + (double)(py - sy) * (ey - py);
+                    if (dist * dist <= 0.5 * eps2 * (dx * dx + dy * dy) && dx != 0 && dy != 0 && sip >= 0) {
+                        new_count--;
+                        outv[wpos] = (uint32_t)ex | ((uint32_t)ey << 16);
+                        sx = ex; sy = ey;
+                        if (++wpos >= cntv) wpos = 0;
+                        rd(px, py);
+                        i++;
+                        continue;
+                    }
+                    outv[wpos] = (uint32_t)px | ((uint32_t)py << 16);
+                    sx = px; sy = py;
+                    if (++wpos >= cntv) wpos = 0;
+                    px = ex; py = ey;
+                }
+            }
+            if (new_count == 4) {
+                int qx[4], qy[4];
+                for (int k = 0; k < 4; k++) { qx[k] = pt_x(outv[k]); qy[k] = pt_y(outv[k]); }
+                // convexity (collinear / repeated vertices reject)
+                bool convex = true;
+                {
+                    int prx = qx[2], pry = qy[2], cux = qx[3], cuy = qy[3];
+                    long long dx0 = cux - prx, dy0 = cuy - pry;
+                    int orient = 0;
+                    for (int i = 0; i < 4; i++) {
+                        prx = cux; pry = cuy; cux = qx[i]; cuy = qy[i];
+                        long long dx = cux - prx, dy = cuy - pry;
+                        long long dxdy0 = dx * dy0, dydx0 = dy * dx0;
+                        orient |= (dydx0 > dxdy0) ? 1 : ((dydx0 < dxdy0) ? 2 : 3);
+                        if (orient == 3) { convex = false; break; }
+                        dx0 = dx; dy0 = dy;
+                    }
+                }
+                if (convex) {
+                    const int mx = max(A.w, A.h);
+                    double min_d2 = (double)mx * mx;
+                    for (int j = 0; j < 4; j++) {
+                        int k = (j + 1) & 3;
+                        double d = (double)(qx[j] - qx[k]) * (qx[j] - qx[k]) + (double)(qy[j] - qy[k]) * (qy[j] - qy[k]);
+                        min_d2 = fmin(min_d2, d);
+                    }
+                    double min_corner = (double)count * A.min_corner_rate;
+                    if (!(min_d2 < min_corner * min_corner)) {
+                        int qi = atomicAdd(&cnt[2], 1);
+                        if (qi < A.quad_cap) {
+                            float *q = A.quads + ((size_t)f * A.quad_cap + qi) * 8;
+                            float c[8];
+                            for (int k = 0; k < 4; k++) { c[2 * k] = (float)qx[k]; c[2 * k + 1] = (float)qy[k]; }
+                            double dx1 = c[2] - c[0], dy1 = c[3] - c[1], dx2 = c[4] - c[0], dy2 = c[5] - c[1];
+                            if (dx1 * dy2 - dy1 * dx2 < 0.0) { float tx = c[2], ty = c[3]; c[2] = c[6]; c[3] = c[7]; c[6] = tx; c[7] = ty; }
+                            for (int k = 0; k < 8; k++) q[k] = c[k];
+                            // candidate order of the dependency: window ascending, then descending trigger pixel
+                            A.quad_keys[(size_t)f * A.quad_cap + qi] =
+                                ((unsigned long long)A.window_index << 32) | (unsigned long long)(0xffffffffu - cd.trigger);
+                        } else {
+                            atomicExch(&cnt[3], APSE_ERR_CAPACITY);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// rank of every quad of a frame in key order -> quad_order (consumed by the decode stage)
+__global__ void k_rank_quads(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ counters, int quad_cap,
+                             uint32_t *__restrict__ quad_order)
+{
+    const int f = blockIdx.y;
+    const int n = min(counters[f * APSE_COUNTERS + 2], quad_cap);
+    const unsigned long long *K = keys + (size_t)f * quad_cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned long long k = K[i];
+        int r = 0;
+        for (int j = 0; j < n; j++) r += K[j] < k;
+        quad_order[(size_t)f * quad_cap + i] = (uint32_t)r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C4: cornerSubPix on the accepted markers (thread per corner)
+#define SP_MAXWIN 8
+__device__ __forceinline__ float subpix_sample(const uint8_t *im, int w, int h, int x0, int y0, bool inside, float a11, float a12,
+                                               float a21, float a22)
+{
+    int x1 = x0 + 1, y1 = y0 + 1;
+    if (!inside) {
+        x0 = min(max(x0, 0), w - 1); x1 = min(max(x1, 0), w - 1);
+        y0 = min(max(y0, 0), h - 1); y1 = min(max(y1, 0), h - 1);
+    }
+    // ((p00 a11 + p01 a12) + p10 a21) + p11 a22, float32, no contraction
+    float v = __fmul_rn((float)im[(size_t)y0 * w + x0], a11);
+    v = __fadd_rn(v, __fmul_rn((float)im[(size_t)y0 * w + x1], a12));
+    v = __fadd_rn(v, __fmul_rn((float)im[(size_t)y1 * w + x0], a21));
+    v = __fadd_rn(v, __fmul_rn((float)im[(size_t)y1 * w + x1], a22));
+    return v;
+}
+
+__global__ void __launch_bounds__(64) k_corner_subpix(const uint8_t *__restrict__ gray, int w, int h, float *__restrict__ corners,
+                                                     const int32_t *__restrict__ n_markers, int batch, int max_markers, int marker_cells,
+                                                     float rel_win, int max_win, int max_iter, double eps)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = t < batch * max_markers * 4;
+    const int f = in_range ? t / (max_markers * 4) : 0, r = t - f * max_markers * 4, m = r >> 2, k = r & 3;
+    const bool active = in_range && m < n_markers[f];
+    const uint8_t *im = gray + (size_t)f * w * h;
+    float *c = corners + ((size_t)f * max_markers + m) * 8;
+    // the four corners of a marker are refined by four lanes of one warp: all of them read the unrefined corners
+    // (window size) before any of them writes its result
+    float c0[8];
+    for (int i = 0; i < 8; i++) c0[i] = active ? c[i] : 0.f;
+    __syncwarp();
+    if (!active) return;
+    // window from the marker's average module size (float32, the dependency's order)
+    float side = 0.f;
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        float dx = c0[2 * i] - c0[2 * j], dy = c0[2 * i + 1] - c0[2 * j + 1];
+        side = __fadd_rn(side, sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))));
+    }
+    float module = side / (4.f * (float)marker_cells);
+    int win = max(1, __float2int_rn(__fmul_rn(rel_win, module)));
+    win = min(min(win, max_win), SP_MAXWIN);
+    const int ww = 2 * win + 1, pw = ww + 2;
+    float mk[2 * SP_MAXWIN + 1];
+    for (int i = 0; i < ww; i++) {
+        float x = (float)(i - win) / (float)win;
+        mk[i] = (float)exp((double)(-__fmul_rn(x, x)));
+    }
+    const float ctx = c0[2 * k], cty = c0[2 * k + 1];
+    float cix = ctx, ciy = cty;
+    const double eps2 = eps * eps;
+    int iter = 0;
+    double err = 0;
+    do {
+        float fx = cix - (float)(pw - 1) * 0.5f, fy = ciy - (float)(pw - 1) * 0.5f;
+        int ipx = (int)floorf(fx), ipy = (int)floorf(fy);
+        float a = fx - (float)ipx, b = fy - (float)ipy;
+        float a11 = __fmul_rn(1.f - a, 1.f - b), a12 = __fmul_rn(a, 1.f - b), a21 = __fmul_rn(1.f - a, b), a22 = __fmul_rn(a, b);
+        bool inside = ipx >= 0 && ipx + pw < w && ipy >= 0 && ipy + pw < h;
+        double sa = 0, sb = 0, sc = 0, bb1 = 0, bb2 = 0;
+        for (int i = 0; i < ww; i++) {
+            double py = i - win;
+            // gradient taps of patch row i+1: keep a sliding window of three patch rows' samples per column
+            for (int j = 0; j < ww; j++) {
+                float l = subpix_sample(im, w, h, ipx + j, ipy + i + 1, inside, a11, a12, a21, a22);
+                float rr = subpix_sample(im, w, h, ipx + j + 2, ipy + i + 1, inside, a11, a12, a21, a22);
+                float u = subpix_sample(im, w, h, ipx + j + 1, ipy + i, inside, a11, a12, a21, a22);
+                float d = subpix_sample(im, w, h, ipx + j + 1, ipy + i + 2, inside, a11, a12, a21, a22);
+                double mm = __fmul_rn(mk[j], mk[i]);
+                double tgx = __fsub_rn(rr, l), tgy = __fsub_rn(d, u);
+                double gxx = tgx * tgx * mm, gxy = tgx * tgy * mm, gyy = tgy * tgy * mm;
+                double px = j - win;
+                sa += gxx; sb += gxy; sc += gyy;
+                bb1 += gxx * px + gxy * py;
+                bb2 += gxy * px + gyy * py;
+            }
+        }
+        double det = sa * sc - sb * sb;
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        double scale = 1.0 / det;
+        float nx = (float)(cix + sc * scale * bb1 - sb * scale * bb2);
+        float ny = (float)(ciy - sb * scale * bb1 + sa * scale * bb2);
+        err = (double)(nx - cix) * (nx - cix) + (double)(ny - ciy) * (ny - ciy);
+        cix = nx; ciy = ny;
+        if (cix < 0 || cix >= w || ciy < 0 || ciy >= h) break;
+    } while (++iter < max_iter && err > eps2);
+    if (fabsf(cix - ctx) > win || fabsf(ciy - cty) > win) { cix = ctx; ciy = cty; }
+    c[2 * k] = cix;
+    c[2 * k + 1] = ciy;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+int apse_ccl_binary(apse_ctx *ctx, const uint8_t *bin, int w, int h, int batch, cudaStream_t st);   // detect_apriltag.cu
+
+int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out, cudaStream_t st)
+{
+    if (win % 2 == 0) win++;
+    if (win > 2 * AT_RMAX + 1) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "adaptiveThreshold: block size %d exceeds the supported %d", win, 2 * AT_RMAX + 1);
+    dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), batch);
+    KLAUNCH(ctx, KID_CLASSIC, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, (int)floor(c), out));
+    return APSE_OK;
+}
+
+int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, cudaStream_t st)
+{
+    const apse_params &p = ctx->params;
+    if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: frame %dx%d x%d exceeds the context capacity", w, h, batch);
+    if (w < 8 || h < 8 || w > 32767 || h > 32767) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
+    const int n_scales = (p.adaptiveThreshWinSizeMax - p.adaptiveThreshWinSizeMin) / p.adaptiveThreshWinSizeStep + 1;
+    const int mx = w > h ? w : h;
+    const int min_px = (int)(unsigned)(p.minMarkerPerimeterRate * mx);
+    long long max_px_ll = (long long)(p.maxMarkerPerimeterRate * mx);
+    const int max_px = (int)(max_px_ll > 0x3fffffff ? 0x3fffffff : max_px_ll);
+    const int idelta = (int)floor(p.adaptiveThreshConstant);
+    // scratch shared with the APRILTAG path: thresh = binary image, labels, points = border jobs, sorted_pts = border
+    // points, clusters = border descriptors; counters: [0] jobs, [1] borders kept, [2] quads, [3] status, [5] points
+    const int job_cap = APSE_MAX_POINTS * 4, pts_cap = APSE_MAX_POINTS * 2, desc_cap = APSE_MAX_CLUSTERS;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
+    for (int s = 0; s < n_scales; s++) {
+        int win = p.adaptiveThreshWinSizeMin + s * p.adaptiveThreshWinSizeStep;
+        if (win % 2 == 0) win++;
+        if (win > 2 * AT_RMAX + 1) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: adaptiveThreshWinSize %d exceeds the supported %d", win, 2 * AT_RMAX + 1);
+        dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), batch);
+        KLAUNCH(ctx, KID_CLASSIC, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, idelta, ctx->thresh));
+        int rc = apse_ccl_binary(ctx, ctx->thresh, w, h, batch, st);
+        if (rc) return rc;
+        KLAUNCH(ctx, KID_CLASSIC, st, k_mark_outside<<<div_up(2 * (w + h) * batch, 256), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, batch));
+        // per window: reset the job / border / point counters, keep quads and status
+        KLAUNCH(ctx, KID_CLASSIC, st, k_border_jobs<<<dim3(148 * 2, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters));
+        KLAUNCH(ctx, KID_CLASSIC, st, k_trace_borders<<<dim3(148, batch), 128, 0, st>>>(ctx->thresh, w, h, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, min_px,
+                                                                                max_px, reinterpret_cast<uint32_t *>(ctx->sorted_pts), pts_cap,
+                                                                                reinterpret_cast<ContourDesc *>(ctx->clusters), desc_cap, batch));
+        ClassicArgs A;
+        A.pts = reinterpret_cast<uint32_t *>(ctx->sorted_pts); A.pts_cap = pts_cap;
+        A.descs = reinterpret_cast<ContourDesc *>(ctx->clusters); A.desc_cap = desc_cap;
+        A.counters = ctx->counters; A.quads = ctx->quads; A.quad_keys = ctx->sort_keys; A.quad_cap = APSE_MAX_QUADS;
+        A.w = w; A.h = h; A.window_index = s;
+        A.accuracy_rate = p.polygonalApproxAccuracyRate; A.min_corner_rate = p.minCornerDistanceRate;
+        KLAUNCH(ctx, KID_CLASSIC, st, k_approx_quads<<<dim3(148, batch), AQ_WARPS * 32, 0, st>>>(A));
+        // counters [0] (jobs), [1] (borders), [5] (points) restart for the next window
+        CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters, APSE_COUNTERS * sizeof(int32_t), 0, 2 * sizeof(int32_t), batch, st));
+        CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters + 5, APSE_COUNTERS * sizeof(int32_t), 0, sizeof(int32_t), batch, st));
+    }
+    KLAUNCH(ctx, KID_CLASSIC, st, k_rank_quads<<<dim3(8, batch), 256, 0, st>>>(ctx->sort_keys, ctx->counters, APSE_MAX_QUADS, ctx->quad_order));
+    return APSE_OK;
+}
+
+int apse_corner_subpix(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, cudaStream_t st)
+{
+    const apse_params &p = ctx->params;
+    if (p.cornerRefinementWinSize > SP_MAXWIN)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: cornerRefinementWinSize %d exceeds the supported %d", p.cornerRefinementWinSize, SP_MAXWIN);
+    if (p.cornerRefinementWinSize < 1 || p.cornerRefinementMaxIterations < 1 || p.cornerRefinementMinAccuracy <= 0)
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: cornerRefinement{WinSize,MaxIterations,MinAccuracy} must be positive");
+    const int total = batch * out->max_markers * 4;
+    KLAUNCH(ctx, KID_CLASSIC, st, k_corner_subpix<<<div_up(total, 64), 64, 0, st>>>(gray, w, h, out->corners, out->n_markers, batch, out->max_markers,
+                                                                        ctx->marker_size + 2 * p.markerBorderBits, p.relativeCornerRefinmentWinSize,
+                                                                        p.cornerRefinementWinSize, p.cornerRefinementMaxIterations,
+                                                                        p.cornerRefinementMinAccuracy));
+    return APSE_OK;
+}

@@ -11,7 +11,7 @@
 #define APSE_MAX_POINTS (1 << 20)       // boundary points per frame
 #define APSE_HASH_SLOTS (1 << 17)       // cluster hash slots per frame (power of two)
 #define APSE_MAX_CLUSTERS (1 << 14)     // clusters passing the size filter per frame
-#define APSE_MAX_QUADS 512              // fitted quads per frame
+#define APSE_MAX_QUADS 4096             // candidate quads per frame (classic path, dense frames: ~1000)
 #define APSE_MAX_MAXIMA 512             // local maxima of the line-fit error curve kept per cluster
 #define APSE_SORT_SMEM 4096             // points sorted in shared memory; larger clusters sort in global
 
@@ -160,5 +160,9 @@ void apse_decode_free(apse_ctx *ctx);
 int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h);
 int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
                         cudaStream_t st, bool have_tile_minmax = false);   // true: ctx->tmin/tmax already hold this batch's extrema
+int apse_decode_big_scratch(apse_ctx *ctx);
+int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out, cudaStream_t st);
+int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, cudaStream_t st);
+int apse_corner_subpix(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, cudaStream_t st);
 int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
                            apse_detections *out, cudaStream_t st);

@@ -14,23 +14,49 @@
 #define DEC_THREADS 256
 #define DEC_WARPS (DEC_THREADS / 32)
 #define DEC_MAX_S 64                      // canonical image side limit ((markerSize + 2*border) * cellSize)
-#define DEC_MAXC APSE_MAX_QUADS           // candidates per frame
+#define DEC_SMEMC 512                     // candidates per frame handled entirely in shared memory
+#define DEC_MAXC APSE_MAX_QUADS           // candidates per frame (beyond DEC_SMEMC the arrays live in global scratch)
+
+// per-frame candidate arrays, carved out of shared memory (n <= DEC_SMEMC) or of a global scratch block
+struct DecodeArrays {
+    float (*c)[8];                        // candidate corners, sorted by perimeter (descending, stable)
+    float *perim;
+    uint32_t *key;                        // ordering key (cluster index) / scratch
+    uint32_t *close_bits;                 // [cap][cap / 32] too-close predicate, bit (i, j)
+    uint32_t *row_mask;                   // [cap][4]: which 32-bit words of row i are non-zero (cap / 32 <= 128)
+    short *group_id, *next_in_group, *close_next, *parent, *depth, *sel, *sel_of, *dec_id, *use_c, *group_head, *group_tail;
+    uint8_t *dec_valid, *dec_rot, *selected, *was, *valid;
+    int cap;
+};
+
+__host__ __device__ inline size_t decode_arrays_bytes(int cap)
+{
+    return (size_t)cap * (8 * 4 + 4 + 4 + (cap / 32) * 4 + 4 * 4 + 11 * 2 + 5) + 64;
+}
+
+__device__ inline void decode_arrays_carve(DecodeArrays &A, unsigned char *base, int cap)
+{
+    A.cap = cap;
+    unsigned char *p = base;
+    A.c = reinterpret_cast<float(*)[8]>(p); p += (size_t)cap * 32;
+    A.perim = reinterpret_cast<float *>(p); p += (size_t)cap * 4;
+    A.key = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4;
+    A.close_bits = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * (cap / 32) * 4;
+    A.row_mask = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 16;
+    short **sp[11] = {&A.group_id, &A.next_in_group, &A.close_next, &A.parent, &A.depth, &A.sel, &A.sel_of, &A.dec_id, &A.use_c,
+                      &A.group_head, &A.group_tail};
+    for (int i = 0; i < 11; i++) { *sp[i] = reinterpret_cast<short *>(p); p += (size_t)cap * 2; }
+    uint8_t **bp[5] = {&A.dec_valid, &A.dec_rot, &A.selected, &A.was, &A.valid};
+    for (int i = 0; i < 5; i++) { *bp[i] = p; p += cap; }
+}
 
 struct DecodeSmem {
-    float c[DEC_MAXC][8];                 // candidate corners, sorted by perimeter (descending, stable)
-    float perim[DEC_MAXC];
-    uint32_t key[DEC_MAXC];               // ordering key (cluster index) / scratch
-    uint32_t close_bits[DEC_MAXC][DEC_MAXC / 32];
-    short group_id[DEC_MAXC], next_in_group[DEC_MAXC], close_next[DEC_MAXC], parent[DEC_MAXC], depth[DEC_MAXC];
-    short sel[DEC_MAXC], sel_of[DEC_MAXC];
-    short dec_id[DEC_MAXC];
-    uint8_t dec_valid[DEC_MAXC], dec_rot[DEC_MAXC], selected[DEC_MAXC], was[DEC_MAXC], valid[DEC_MAXC];
-    short use_c[DEC_MAXC];                // candidate whose corners / id are reported for selected v
-    short group_head[DEC_MAXC], group_tail[DEC_MAXC];
     uint8_t warp_img[DEC_WARPS][DEC_MAX_S * DEC_MAX_S];
     int hist[DEC_WARPS][256];
     uint8_t bits[DEC_WARPS][16 * 16];
     int n, ns, ngroups;
+    int pad;
+    // followed by decode_arrays_bytes(DEC_SMEMC) bytes
 };
 
 __device__ __forceinline__ float sqf(float v) { return v * v; }
@@ -252,65 +278,66 @@ __device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, c
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
                                                         const uint32_t *__restrict__ quad_order, int32_t *__restrict__ counters,
                                                         DeviceParams P, const uint8_t *__restrict__ dict, int skip_decoded_parents,
-                                                        apse_detections out)
+                                                        unsigned char *__restrict__ big_scratch, size_t big_stride, apse_detections out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
+    __shared__ DecodeArrays A;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t *im = gray + (size_t)f * w * h;
     int32_t *cnt = counters + f * APSE_COUNTERS;
-    const int nq = min(cnt[2], APSE_MAX_QUADS);
+    const int nq = min(cnt[2], DEC_MAXC);
     const float *q = quads + (size_t)f * APSE_MAX_QUADS * 8;
     const uint32_t *qo = quad_order + (size_t)f * APSE_MAX_QUADS;
+    if (nq > DEC_SMEMC && !big_scratch) {   // host passes the scratch whenever the path can produce this many quads
+        if (tid == 0) { out.n_markers[f] = 0; if (out.n_rejected) out.n_rejected[f] = 0; out.status[f] = APSE_ERR_CAPACITY; }
+        return;
+    }
+    if (tid == 0) {
+        if (nq <= DEC_SMEMC) decode_arrays_carve(A, smem_raw + sizeof(DecodeSmem), DEC_SMEMC);
+        else decode_arrays_carve(A, big_scratch + (size_t)f * big_stride, DEC_MAXC);
+    }
+    __syncthreads();
+    const int rw = A.cap / 32;   // words per close_bits row
 
-    // ---- deterministic order (cluster index), border filter, perimeter, stable sort (descending)
-    if (tid == 0) S.n = 0;
-    __syncthreads();
-    const float d = (float)P.min_distance_to_border;
-    for (int i = tid; i < nq; i += DEC_THREADS) {
-        const float *c = q + 8 * i;
-        bool near = false;
-        for (int j = 0; j < 4; j++) near |= c[2 * j] < d || c[2 * j + 1] < d || c[2 * j] > w - 1 - d || c[2 * j + 1] > h - 1 - d;
-        S.key[i] = near ? 0xffffffffu : qo[i];
-    }
+    // ---- deterministic order (candidate key), perimeter, stable sort (descending).  n = nq: the border-distance test
+    // comes AFTER the grouping (4.13: a border-touching quad still groups and, as a group main, takes its group with it)
+    for (int i = tid; i < nq; i += DEC_THREADS) A.key[i] = qo[i];
     __syncthreads();
     for (int i = tid; i < nq; i += DEC_THREADS) {
-        uint32_t k = S.key[i];
-        if (k == 0xffffffffu) { S.sel[i] = -1; continue; }
+        uint32_t k = A.key[i];
         int r = 0;
-        for (int j = 0; j < nq; j++) r += S.key[j] < k;
-        S.sel[i] = (short)r;  // rank among kept quads in cluster order
-        atomicAdd(&S.n, 1);
+        for (int j = 0; j < nq; j++) r += A.key[j] < k;
+        A.sel[i] = (short)r;  // rank in candidate order
     }
     __syncthreads();
-    const int n = S.n;
-    // c[] temporarily in cluster order, perimeters alongside
+    const int n = nq;
     for (int i = tid; i < nq; i += DEC_THREADS) {
-        int r = S.sel[i];
-        if (r < 0) continue;
-        for (int k = 0; k < 8; k++) S.c[r][k] = q[8 * i + k];
+        int r = A.sel[i];
+        for (int k = 0; k < 8; k++) A.c[r][k] = q[8 * i + k];
     }
     __syncthreads();
-    for (int i = tid; i < n; i += DEC_THREADS) S.perim[i] = perimeter_of(S.c[i]);
+    for (int i = tid; i < n; i += DEC_THREADS) A.perim[i] = perimeter_of(A.c[i]);
     __syncthreads();
-    // stable descending rank; permute through registers (each thread owns indices tid, tid+T, ...)
+    // stable descending rank; permute through the key / close_bits scratch (ranks first, then a copy pass)
+    for (int i = tid; i < n; i += DEC_THREADS) {
+        float p = A.perim[i];
+        int r = 0;
+        for (int j = 0; j < n; j++) { float pj = A.perim[j]; r += (pj > p) || (pj == p && j < i); }
+        A.sel_of[i] = (short)r;
+    }
+    __syncthreads();
     {
-        float cc[(DEC_MAXC + DEC_THREADS - 1) / DEC_THREADS][9];
-        int rr[(DEC_MAXC + DEC_THREADS - 1) / DEC_THREADS];
-        int u = 0;
-        for (int i = tid; i < n; i += DEC_THREADS, u++) {
-            float p = S.perim[i];
-            int r = 0;
-            for (int j = 0; j < n; j++) { float pj = S.perim[j]; r += (pj > p) || (pj == p && j < i); }
-            rr[u] = r;
-            for (int k = 0; k < 8; k++) cc[u][k] = S.c[i][k];
-            cc[u][8] = p;
+        float *tmp = reinterpret_cast<float *>(A.close_bits);   // >= 9 floats per candidate (cap / 32 >= 16 words per row)
+        for (int i = tid; i < n; i += DEC_THREADS) {
+            for (int k = 0; k < 8; k++) tmp[9 * i + k] = A.c[i][k];
+            tmp[9 * i + 8] = A.perim[i];
         }
         __syncthreads();
-        u = 0;
-        for (int i = tid; i < n; i += DEC_THREADS, u++) {
-            for (int k = 0; k < 8; k++) S.c[rr[u]][k] = cc[u][k];
-            S.perim[rr[u]] = cc[u][8];
+        for (int i = tid; i < n; i += DEC_THREADS) {
+            int r = A.sel_of[i];
+            for (int k = 0; k < 8; k++) A.c[r][k] = tmp[9 * i + k];
+            A.perim[r] = tmp[9 * i + 8];
         }
     }
     __syncthreads();
@@ -318,28 +345,32 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
     // ---- decode every candidate (one warp each)
     for (int i = wid; i < n; i += DEC_WARPS) {
         bool v; int id, rot;
-        decode_candidate(im, w, h, S.c[i], P, dict, S.warp_img[wid], S.hist[wid], S.bits[wid], v, id, rot);
-        if (lane == 0) { S.dec_valid[i] = v; S.dec_id[i] = (short)id; S.dec_rot[i] = (uint8_t)rot; }
+        decode_candidate(im, w, h, A.c[i], P, dict, S.warp_img[wid], S.hist[wid], S.bits[wid], v, id, rot);
+        if (lane == 0) { A.dec_valid[i] = v; A.dec_id[i] = (short)id; A.dec_rot[i] = (uint8_t)rot; }
         __syncwarp();
     }
 
     // ---- too-close predicate matrix: bit (i,j), i < j, set when avgDist(i,j) < perimeter[j] * rate
     const int words = (n + 31) / 32;
+    for (int i = tid; i < n; i += DEC_THREADS) { A.row_mask[4 * i] = A.row_mask[4 * i + 1] = A.row_mask[4 * i + 2] = A.row_mask[4 * i + 3] = 0; }
+    __syncthreads();
     for (int p = tid; p < n * words; p += DEC_THREADS) {
         int i = p / words, wj = p - i * words;
         uint32_t bitsw = 0;
-        for (int b = 0; b < 32; b++) {
-            int j = wj * 32 + b;
-            if (j > i && j < n) {
-                float md = average_distance(S.c[i], S.c[j]);
-                if (md < S.perim[j] * P.min_marker_distance_rate) bitsw |= 1u << b;
+        if (wj * 32 + 31 > i)
+            for (int b = 0; b < 32; b++) {
+                int j = wj * 32 + b;
+                if (j > i && j < n) {
+                    float md = average_distance(A.c[i], A.c[j]);
+                    if (md < A.perim[j] * P.min_marker_distance_rate) bitsw |= 1u << b;
+                }
             }
-        }
-        S.close_bits[i][wj] = bitsw;
+        A.close_bits[(size_t)i * rw + wj] = bitsw;
+        if (bitsw) atomicOr(&A.row_mask[4 * i + (wj >> 5)], 1u << (wj & 31));
     }
     for (int i = tid; i < n; i += DEC_THREADS) {
-        S.group_id[i] = -1; S.selected[i] = 1; S.next_in_group[i] = -1; S.close_next[i] = -1;
-        S.parent[i] = -1; S.depth[i] = 0; S.was[i] = 0; S.valid[i] = 0; S.use_c[i] = (short)i;
+        A.group_id[i] = -1; A.selected[i] = 1; A.next_in_group[i] = -1; A.close_next[i] = -1;
+        A.parent[i] = -1; A.depth[i] = 0; A.was[i] = 0; A.valid[i] = 0; A.use_c[i] = (short)i;
     }
     __syncthreads();
 
@@ -347,41 +378,55 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
     if (tid == 0) {
         int ngroups = 0;
         for (int i = 0; i < n; i++)
-            for (int wj = i / 32; wj < words; wj++) {
-                uint32_t m = S.close_bits[i][wj];
-                while (m) {
-                    int j = wj * 32 + __ffs(m) - 1;
-                    m &= m - 1;
-                    S.selected[i] = 0; S.selected[j] = 0;
-                    if (S.group_id[i] < 0 && S.group_id[j] < 0) { S.group_id[i] = S.group_id[j] = (short)ngroups++; }
-                    else if (S.group_id[i] > -1 && S.group_id[j] == -1) S.group_id[j] = S.group_id[i];
-                    else if (S.group_id[j] > -1 && S.group_id[i] == -1) S.group_id[i] = S.group_id[j];
+            for (int mw = 0; mw < 4; mw++) {
+                uint32_t rm = A.row_mask[4 * i + mw];
+                while (rm) {
+                    int wj = mw * 32 + __ffs(rm) - 1;
+                    rm &= rm - 1;
+                    uint32_t m = A.close_bits[(size_t)i * rw + wj];
+                    while (m) {
+                        int j = wj * 32 + __ffs(m) - 1;
+                        m &= m - 1;
+                        A.selected[i] = 0; A.selected[j] = 0;
+                        if (A.group_id[i] < 0 && A.group_id[j] < 0) { A.group_id[i] = A.group_id[j] = (short)ngroups++; }
+                        else if (A.group_id[i] > -1 && A.group_id[j] == -1) A.group_id[j] = A.group_id[i];
+                        else if (A.group_id[j] > -1 && A.group_id[i] == -1) A.group_id[i] = A.group_id[j];
+                    }
                 }
             }
         // members of each group in ascending index order (= largest perimeter first)
-        for (int g = 0; g < ngroups; g++) { S.group_head[g] = -1; S.group_tail[g] = -1; }
+        for (int g = 0; g < ngroups; g++) { A.group_head[g] = -1; A.group_tail[g] = -1; }
         for (int i = 0; i < n; i++) {
-            int g = S.group_id[i];
+            int g = A.group_id[i];
             if (g < 0) continue;
-            if (S.group_head[g] < 0) S.group_head[g] = (short)i; else S.next_in_group[S.group_tail[g]] = (short)i;
-            S.group_tail[g] = (short)i;
+            if (A.group_head[g] < 0) A.group_head[g] = (short)i; else A.next_in_group[A.group_tail[g]] = (short)i;
+            A.group_tail[g] = (short)i;
         }
         for (int g = 0; g < ngroups; g++) {
-            int head = S.group_head[g], cur = head, tail_close = -1;
-            S.selected[head] = 1;
-            for (int id = S.next_in_group[head]; id >= 0; id = S.next_in_group[id]) {
-                float dist = average_distance(S.c[id], S.c[cur]);
-                float msz = average_module_size(S.c[id], P.marker_size, P.border_bits);
+            int head = A.group_head[g], cur = head, tail_close = -1;
+            A.selected[head] = 1;
+            for (int id = A.next_in_group[head]; id >= 0; id = A.next_in_group[id]) {
+                float dist = average_distance(A.c[id], A.c[cur]);
+                float msz = average_module_size(A.c[id], P.marker_size, P.border_bits);
                 if (dist > P.min_group_distance * msz) {
                     cur = id;
-                    if (tail_close < 0) S.close_next[head] = (short)id; else S.close_next[tail_close] = (short)id;
+                    if (tail_close < 0) A.close_next[head] = (short)id; else A.close_next[tail_close] = (short)id;
                     tail_close = id;
                 }
             }
         }
-        // NB close_next chains start at the group's head; members never head a chain themselves
+        // NB close_next chains start at the group's head; members never head a chain themselves.
+        // Border-distance test on the selected (main) candidates only: a main too near the edge is dropped with its group.
+        const float d = (float)P.min_distance_to_border;
         int ns = 0;
-        for (int i = 0; i < n; i++) if (S.selected[i]) { S.sel[ns] = (short)i; S.sel_of[i] = (short)ns; ns++; }
+        for (int i = 0; i < n; i++) {
+            if (!A.selected[i]) continue;
+            const float *c = A.c[i];
+            bool near = false;
+            for (int j = 0; j < 4; j++) near |= c[2 * j] < d || c[2 * j + 1] < d || c[2 * j] > w - 1 - d || c[2 * j + 1] > h - 1 - d;
+            if (near) continue;
+            A.sel[ns] = (short)i; A.sel_of[i] = (short)ns; ns++;
+        }
         S.ns = ns;
         S.ngroups = ngroups;
     }
@@ -390,44 +435,44 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
 
     // ---- nesting hierarchy among the selected candidates: parent = nearest smaller index that contains all 4 corners
     for (int v = tid; v < ns; v += DEC_THREADS) {
-        const float *a = S.c[S.sel[v]];
+        const float *a = A.c[A.sel[v]];
         int par = -1;
         for (int j = v - 1; j >= 0; j--) {
-            const float *b = S.c[S.sel[j]];
+            const float *b = A.c[A.sel[j]];
             if (strictly_inside(b, a[0], a[1]) && strictly_inside(b, a[2], a[3]) && strictly_inside(b, a[4], a[5]) &&
                 strictly_inside(b, a[6], a[7])) { par = j; break; }
         }
-        S.parent[v] = (short)par;
+        A.parent[v] = (short)par;
     }
     __syncthreads();
     if (tid == 0) {
         int max_depth = 0;
         for (int v = ns - 1; v >= 0; v--) {
-            int p = S.parent[v];
-            if (p >= 0 && S.depth[v] + 1 > S.depth[p]) S.depth[p] = (short)(S.depth[v] + 1);
+            int p = A.parent[v];
+            if (p >= 0 && A.depth[v] + 1 > A.depth[p]) A.depth[p] = (short)(A.depth[v] + 1);
         }
-        for (int v = 0; v < ns; v++) max_depth = max(max_depth, (int)S.depth[v]);
+        for (int v = 0; v < ns; v++) max_depth = max(max_depth, (int)A.depth[v]);
         int counter = 0;
         for (int dep = 0; dep <= max_depth && counter < ns; dep++) {
             for (int v = 0; v < ns; v++) {
-                if (S.depth[v] != dep) continue;
-                if (skip_decoded_parents && S.was[v]) continue;
-                S.was[v] = 1;
-                int head = S.sel[v];
+                if (A.depth[v] != dep) continue;
+                if (skip_decoded_parents && A.was[v]) continue;
+                A.was[v] = 1;
+                int head = A.sel[v];
                 int use = -1;
-                if (S.dec_valid[head]) use = head;
+                if (A.dec_valid[head]) use = head;
                 else
-                    for (int c = S.close_next[head]; c >= 0; c = S.close_next[c])
-                        if (S.dec_valid[c]) { use = c; break; }
-                if (use >= 0) { S.valid[v] = 1; S.use_c[v] = (short)use; }
+                    for (int c = A.close_next[head]; c >= 0; c = A.close_next[c])
+                        if (A.dec_valid[c]) { use = c; break; }
+                if (use >= 0) { A.valid[v] = 1; A.use_c[v] = (short)use; }
             }
             for (int v = 0; v < ns; v++) {
-                if (S.depth[v] != dep) continue;
-                if (S.valid[v]) {
-                    int p = S.parent[v];
+                if (A.depth[v] != dep) continue;
+                if (A.valid[v]) {
+                    int p = A.parent[v];
                     while (p != -1) {
-                        if (!S.was[p]) { S.was[p] = 1; counter++; }
-                        p = S.parent[p];
+                        if (!A.was[p]) { A.was[p] = 1; counter++; }
+                        p = A.parent[p];
                     }
                 }
                 counter++;
@@ -441,21 +486,21 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
         float *orj = out.rejected ? out.rejected + (size_t)f * cap * 8 : nullptr;
         int status = cnt[3];
         for (int v = 0; v < ns; v++) {
-            if (S.valid[v]) {
-                int u = S.use_c[v];
-                const float *c = S.c[u];
+            if (A.valid[v]) {
+                int u = A.use_c[v];
+                const float *c = A.c[u];
                 if (na < cap) {
-                    int r = S.dec_rot[u];
+                    int r = A.dec_rot[u];
                     for (int k = 0; k < 4; k++) {
                         int s = (k + 4 - r) % 4;
                         oc[8 * na + 2 * k] = c[2 * s];
                         oc[8 * na + 2 * k + 1] = c[2 * s + 1];
                     }
-                    oi[na] = S.dec_id[u];
+                    oi[na] = A.dec_id[u];
                 } else status = APSE_ERR_CAPACITY;
                 na++;
             } else {
-                const float *c = S.c[S.sel[v]];
+                const float *c = A.c[A.sel[v]];
                 if (orj) {
                     if (nr < cap) for (int k = 0; k < 8; k++) orj[8 * nr + k] = c[k];
                     else status = APSE_ERR_CAPACITY;
@@ -471,10 +516,18 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
 
 int apse_decode_alloc(apse_ctx *ctx)
 {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(DecodeSmem) + decode_arrays_bytes(DEC_SMEMC))));
     return APSE_OK;
 }
-void apse_decode_free(apse_ctx *) {}
+void apse_decode_free(apse_ctx *ctx) { cudaFree(ctx->decode_scratch); ctx->decode_scratch = nullptr; }
+
+// global candidate arrays for frames with more than DEC_SMEMC quads (classic path); allocated on first use
+int apse_decode_big_scratch(apse_ctx *ctx)
+{
+    if (!ctx->decode_scratch) CUDA_TRY(ctx, cudaMalloc(&ctx->decode_scratch, decode_arrays_bytes(DEC_MAXC) * ctx->max_batch));
+    return APSE_OK;
+}
 
 int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
                            apse_detections *out, cudaStream_t st)
@@ -487,7 +540,8 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: canonical marker image %d px exceeds the %d px limit", nb * dp.cell_size, DEC_MAX_S);
     const char *env = getenv("APSE_IDENTIFY_DECODED_PARENTS");
     int skip = (env && env[0] == '1') ? 0 : 1;
-    KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem), st>>>(gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, ctx->dict,
-                                                           skip, *out));
+    KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem) + decode_arrays_bytes(DEC_SMEMC), st>>>(
+                gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, ctx->dict, skip,
+                (unsigned char *)ctx->decode_scratch, decode_arrays_bytes(DEC_MAXC), *out));
     return APSE_OK;
 }

@@ -184,7 +184,7 @@ __device__ __forceinline__ void uf_union_gmem(uint32_t *L, uint32_t a, uint32_t 
 __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_local(const uint8_t *__restrict__ thresh, int w, int h,
                                                               uint32_t *__restrict__ labels,
                                                               const uint32_t *__restrict__ list, const int *__restrict__ n_active,
-                                                              int ctw)
+                                                              int ctw, int full)
 {
     __shared__ int L[CCL_TW * CCL_TH];
     __shared__ uint8_t V[CCL_TH][CCL_TW + 1];
@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_local(const uint8_t *__r
         const uint8_t *t = thresh + (size_t)f * w * h;
         const bool in = x < w && y < h;
         const int v = in ? t[(size_t)y * w + x] : 127;
-        const bool src = v != 127 && x >= 1 && x <= w - 2 && y <= h - 2;   // pixel may initiate joins
+        // pixel may initiate joins (full = classic path: every pixel; otherwise the dependency's AprilTag loop ranges)
+        const bool src = v != 127 && (full || (x >= 1 && x <= w - 2 && y <= h - 2));
         const int vr = __shfl_down_sync(0xffffffffu, v, 1);
         const bool join_r = src && lx + 1 < CCL_TW && vr == v;
         const uint32_t jr = __ballot_sync(0xffffffffu, join_r);
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_local(const uint8_t *__r
 // unions across tile boundaries, per active tile: sources on its last row (S, SW, SE cross), on its last
 // column (E, SE cross) and on its first column (SW crosses).  64 threads per tile.
 __global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, uint32_t *__restrict__ labels,
-                            const uint32_t *__restrict__ list, const int *__restrict__ n_active, int ctw)
+                            const uint32_t *__restrict__ list, const int *__restrict__ n_active, int ctw, int full)
 {
     const int n = *n_active;
     const int per_block = blockDim.x / 64, sub = threadIdx.x / 64, k = threadIdx.x % 64;
@@ -247,21 +248,23 @@ __global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, ui
         if (k < 32) { kind = 0; x = txb * CCL_TW + k; y = tyb * CCL_TH + CCL_TH - 1; }
         else if (k < 48) { kind = 1; x = txb * CCL_TW + CCL_TW - 1; y = tyb * CCL_TH + (k - 32); }
         else { kind = 2; x = txb * CCL_TW; y = tyb * CCL_TH + (k - 48); }
-        if (x < 1 || x > w - 2 || y > h - 2) continue;
+        if (x >= w || y >= h) continue;
+        if (!full && (x < 1 || x > w - 2 || y > h - 2)) continue;
         const int v = t[(size_t)y * w + x];
         if (v == 127) continue;
         const uint32_t o = (uint32_t)(y * w + x);
+        const bool has_s = y + 1 < h, has_e = x + 1 < w, has_w = x >= 1;   // always true inside the AprilTag ranges
         if (kind == 0) {
-            if (t[o + w] == v) uf_union_gmem(L, o, o + w);
-            if (v == 255) {
-                if (t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
-                if (t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
+            if (has_s && t[o + w] == v) uf_union_gmem(L, o, o + w);
+            if (v == 255 && has_s) {
+                if (has_w && t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
+                if (has_e && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
             }
         } else if (kind == 1) {
-            if (t[o + 1] == v) uf_union_gmem(L, o, o + 1);
-            if (v == 255 && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
+            if (has_e && t[o + 1] == v) uf_union_gmem(L, o, o + 1);
+            if (v == 255 && has_e && has_s && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
         } else {
-            if (v == 255 && t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
+            if (v == 255 && has_w && has_s && t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
         }
     }
 }
@@ -978,8 +981,8 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         KLAUNCH(ctx, KID_THRESHOLD, st, k_compact_tiles<<<div_up(batch * nct, 256), 256, 0, st>>>(ex->tile_active, batch * nct, nct, ex->tile_list, n_active));
         dim3 block(CCL_TW, CCL_TH);
         const int grid = 148 * 4;   // persistent: 4 CTAs of 512 threads per SM, tiles taken round-robin from the list
-        KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
-        KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<148 * 4, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
+        KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
+        KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<148 * 4, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
         KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
         KLAUNCH(ctx, KID_EMIT, st, k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, ctx->hash_keys,
                                                                           ctx->hash_count, ex->used_slots, ctx->points, ctx->counters));
@@ -993,5 +996,24 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     A.quad_order = ctx->quad_order; A.work_counter = ex->work_counter; A.max_nmaxima = dp.max_nmaxima;
     A.critical_rad = dp.critical_rad; A.max_line_fit_mse = dp.max_line_fit_mse; A.max_dot = dp.max_dot;
     KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<148 * 4, FQ_THREADS, 0, st>>>(A));
+    return APSE_OK;
+}
+
+// Components of a binary image for the classic path (classic.cu): foreground (255) 8-connected, background (0)
+// 4-connected, every pixel in range, root = raster-first pixel of the component.  Labels go to ctx->labels.
+int apse_ccl_binary(apse_ctx *ctx, const uint8_t *bin, int w, int h, int batch, cudaStream_t st)
+{
+    if ((long long)div_up(w, CCL_TW) * div_up(h, CCL_TH) >= (1 << 20)) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
+    DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
+    const int ctw = div_up(w, CCL_TW), cth = div_up(h, CCL_TH), nct = ctw * cth;
+    int *n_active = ex->work_counter + 1;
+    CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, 2 * sizeof(int), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ex->tile_active, 1, (size_t)batch * nct, st));   // no low-contrast class: all tiles
+    KLAUNCH(ctx, KID_THRESHOLD, st, k_compact_tiles<<<div_up(batch * nct, 256), 256, 0, st>>>(ex->tile_active, batch * nct, nct, ex->tile_list, n_active));
+    dim3 block(CCL_TW, CCL_TH);
+    const int grid = 148 * 4;
+    KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
+    KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<148 * 4, 256, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
+    KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw));
     return APSE_OK;
 }

@@ -270,6 +270,32 @@ class Engine:
         return dict(thresh=thresh, labels=labels, quads=quads[:nq], points=int(stats[0]), clusters=int(stats[1]),
                     fitted=int(stats[2]), n_quads=int(stats[3]))
 
+    def adaptive_threshold(self, gray, win, c):
+        """cv2.adaptiveThreshold(gray, 255, ADAPTIVE_THRESH_MEAN_C, THRESH_BINARY_INV, win, c) on [H,W] or [B,H,W]."""
+        torch = self.torch
+        gray = self._u8(gray, "adaptiveThreshold")
+        single = gray.dim() == 2
+        g = gray[None] if single else gray
+        B, H, W = g.shape
+        out = torch.empty_like(g)
+        self._check(self.lib.apse_adaptive_threshold(self.h, g.data_ptr(), W, H, B, int(win), float(c), out.data_ptr(), self._stream()))
+        return out[0] if single else out
+
+    def debug_classic(self, gray, max_quads=4096):
+        """Raw candidate quads of the classic path for one frame, in the dependency's candidate order."""
+        torch = self.torch
+        gray = self._u8(gray, "debug_classic")
+        H, W = gray.shape
+        quads = torch.zeros((max_quads, 4, 2), dtype=torch.float32, device=self.tdev)
+        order = torch.zeros(max_quads, dtype=torch.int32, device=self.tdev)
+        stats = (C.c_int64 * 4)()
+        self._check(self.lib.apse_debug_classic(self.h, gray.data_ptr(), W, H, quads.data_ptr(), order.data_ptr(), max_quads,
+                                                stats, self._stream()))
+        n = min(int(stats[0]), max_quads)
+        res = torch.empty((n, 4, 2), dtype=torch.float32, device=self.tdev)
+        res[order[:n].long()] = quads[:n]
+        return res
+
     # ---------------------------------------------------------------------------------------------- pose
     def _cam(self, K, D):
         K = self.K if K is None else np.ascontiguousarray(K, np.float64)

@@ -154,6 +154,17 @@ int apse_project_points_multi(apse_ctx *ctx, const double *obj, int n, const int
 int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_t *thresh, uint32_t *labels,
                         float *quads, int max_quads, int64_t *stats_host, void *stream);
 
+/* cv2.adaptiveThreshold(gray, 255, ADAPTIVE_THRESH_MEAN_C, THRESH_BINARY_INV, win, c) for a batch [batch][h][w]: the
+ * threshold step of the classic candidate path inside aruco.detectMarkers (aruco_detect.py:267 with
+ * cornerRefinementMethod NONE / SUBPIX; north_star stage 2).  Even win is bumped to win + 1 as aruco does. */
+int apse_adaptive_threshold(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out,
+                            void *stream);
+
+/* Debug / parity tap of the classic candidate path for ONE frame: quads [max_quads][8] float32 (unordered) and
+ * order [max_quads] = rank of each quad in the dependency's candidate order; stats[0] = number of quads */
+int apse_debug_classic(apse_ctx *ctx, const uint8_t *gray, int w, int h, float *quads, uint32_t *order, int max_quads,
+                       int64_t *stats_host, void *stream);
+
 /* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
 int64_t apse_launch_count(apse_ctx *ctx);
 

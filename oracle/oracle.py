@@ -288,3 +288,92 @@ def estimate_pose_single_markers(corners, marker_length, K, D):
                                            f64p(np.ascontiguousarray(K, np.float64).ravel()), f64p(_k14(D)),
                                            f64p(rv), f64p(tv))
     return rv, tv
+
+
+# -------------------------------------------------------------------------------------------- classic path
+class ClassicParams(C.Structure):
+    _fields_ = [("win_min", C.c_int), ("win_max", C.c_int), ("win_step", C.c_int), ("constant", C.c_double),
+                ("min_perimeter_rate", C.c_double), ("max_perimeter_rate", C.c_double),
+                ("approx_accuracy_rate", C.c_double), ("min_corner_distance_rate", C.c_double),
+                ("min_distance_to_border", C.c_int)]
+
+    @classmethod
+    def from_cv(cls, p):
+        return cls(int(p.adaptiveThreshWinSizeMin), int(p.adaptiveThreshWinSizeMax), int(p.adaptiveThreshWinSizeStep),
+                   float(p.adaptiveThreshConstant), float(p.minMarkerPerimeterRate), float(p.maxMarkerPerimeterRate),
+                   float(p.polygonalApproxAccuracyRate), float(p.minCornerDistanceRate), int(p.minDistanceToBorder))
+
+
+def adaptive_threshold(gray, win, c):
+    """cv2.adaptiveThreshold(gray, 255, ADAPTIVE_THRESH_MEAN_C, THRESH_BINARY_INV, win, c) (even win -> win + 1)."""
+    gray = np.ascontiguousarray(gray)
+    out = np.empty_like(gray)
+    lib().orc_adaptive_threshold(u8p(gray), gray.shape[1], gray.shape[0], int(win), C.c_double(c), u8p(out))
+    return out
+
+
+def find_contours(binary):
+    """cv2.findContours(binary, RETR_LIST, CHAIN_APPROX_NONE) -> list of (n,2) int32 arrays in cv2's order."""
+    b = np.ascontiguousarray(binary, np.uint8)
+    h, w = b.shape
+    max_pts = 2 * w * h + 16
+    max_c = w * h // 2 + 16
+    pts = np.empty((max_pts, 2), np.int32)
+    off = np.empty(max_c + 1, np.int64)
+    n = lib().orc_find_contours(u8p(b), w, h, i32p(pts), C.c_longlong(max_pts), _p(off, C.c_int64), max_c)
+    if n < 0:
+        raise RuntimeError("oracle contour capacity exceeded")
+    return [pts[off[i]:off[i + 1]].copy() for i in range(n)]
+
+
+def approx_poly_dp(contour, eps):
+    c = np.ascontiguousarray(np.asarray(contour, np.int32).reshape(-1, 2))
+    out = np.empty((len(c) + 4, 2), np.int32)
+    n = lib().orc_approx_poly_dp(i32p(c), len(c), C.c_double(eps), i32p(out), len(out))
+    return out[:n].copy()
+
+
+def is_contour_convex(poly):
+    p = np.ascontiguousarray(np.asarray(poly, np.int32).reshape(-1, 2))
+    return bool(lib().orc_is_contour_convex(i32p(p), len(p)))
+
+
+def classic_quads(gray, cvparams, max_quads=1 << 16):
+    """Candidate quads of the classic path, (n,4,2) float32, dependency order (windows ascending, contour order)."""
+    gray = np.ascontiguousarray(gray)
+    P = cvparams if isinstance(cvparams, ClassicParams) else ClassicParams.from_cv(cvparams)
+    q = np.zeros((max_quads, 8), np.float32)
+    n = lib().orc_classic_quads(u8p(gray), gray.shape[1], gray.shape[0], C.byref(P), f32p(q), max_quads)
+    if n > max_quads:
+        raise RuntimeError("oracle quad capacity exceeded")
+    return q[:n].reshape(n, 4, 2).copy()
+
+
+def corner_subpix(gray, corners, win, max_iter, eps):
+    gray = np.ascontiguousarray(gray)
+    c = np.ascontiguousarray(np.asarray(corners, np.float32).reshape(-1, 2)).copy()
+    lib().orc_corner_subpix(u8p(gray), gray.shape[1], gray.shape[0], f32p(c), len(c), int(win), int(max_iter),
+                            C.c_double(eps))
+    return c
+
+
+def detect_markers_classic(gray, bytes_list, cvparams, marker_size=4, max_correction_bits=1):
+    """aruco_detect.py:267 with cornerRefinementMethod NONE (0) or SUBPIX (1) -> (corners, ids, rejected)."""
+    quads = classic_quads(gray, cvparams)
+    dp = DecParams.from_cv(cvparams, marker_size, max_correction_bits)
+    corners, ids, rejected = identify_candidates(gray, quads, dp, bytes_list)
+    if int(cvparams.cornerRefinementMethod) == 1 and len(corners):
+        nb = marker_size + 2 * int(cvparams.markerBorderBits)
+        for i in range(len(corners)):
+            c = corners[i]
+            side = np.float32(0)
+            for a in range(4):
+                b = (a + 1) % 4
+                dx, dy = np.float32(c[a, 0] - c[b, 0]), np.float32(c[a, 1] - c[b, 1])
+                side = np.float32(side + np.sqrt(np.float32(dx * dx + dy * dy)))
+            module = np.float32(side / np.float32(4.0 * nb))
+            win = max(1, int(np.rint(np.float32(cvparams.relativeCornerRefinmentWinSize) * module)))
+            win = min(win, int(cvparams.cornerRefinementWinSize))
+            corners[i] = corner_subpix(gray, c, win, int(cvparams.cornerRefinementMaxIterations),
+                                       float(cvparams.cornerRefinementMinAccuracy))
+    return corners, ids, rejected

@@ -333,10 +333,6 @@ int orc_identify_candidates(const uint8_t *im, int w, int h, const float *quads,
     float d = (float)P->min_distance_to_border;
     for (int i = 0; i < nq; i++) {
         const float *q = quads + 8 * i;
-        int near = 0;
-        for (int j = 0; j < 4; j++)
-            if (q[2 * j] < d || q[2 * j + 1] < d || q[2 * j] > w - 1 - d || q[2 * j + 1] > h - 1 - d) near = 1;
-        if (near) continue;
         memcpy(cand[n].c, q, sizeof(float) * 8);
         cand[n].perimeter = perimeter_of(q);
         cand[n].order = n;
@@ -390,7 +386,18 @@ int orc_identify_candidates(const uint8_t *im, int w, int h, const float *quads,
     /* compact the selected candidates (sorted order kept) */
     int *sel = (int *)malloc(sizeof(int) * (n + 1));
     int ns = 0;
-    for (int i = 0; i < n; i++) if (selected[i]) sel[ns++] = i;
+    /* 4.13: the border-distance test is applied AFTER the grouping, to the group mains only: a main closer than
+     * minDistanceToBorder to the image edge disappears together with its close contours (neither accepted nor
+     * rejected); border-touching quads therefore still take part in the grouping above.  Pinned by
+     * tests/test_oracle_classic.py::test_border_quad_swallows_group. */
+    for (int i = 0; i < n; i++) {
+        if (!selected[i]) continue;
+        const float *q = cand[i].c;
+        int near = 0;
+        for (int j = 0; j < 4; j++)
+            if (q[2 * j] < d || q[2 * j + 1] < d || q[2 * j] > w - 1 - d || q[2 * j + 1] > h - 1 - d) near = 1;
+        if (!near) sel[ns++] = i;
+    }
     int *parent = (int *)malloc(sizeof(int) * (ns + 1)), *depth = (int *)calloc(ns + 1, sizeof(int));
     for (int i = 0; i < ns; i++) parent[i] = -1;
     for (int i = ns - 1; i >= 0; i--)

@@ -59,7 +59,21 @@ def oracle():
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("classic_"))
+
+
+def classic_cases():
+    """fixtures of the classic candidate path (tools/gen_golden_classic.py)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("classic_"))
+
+
+def classic_params(aruco_mod, refine, wins=(3, 23, 10)):
+    """parameters of aruco_detect.py:190-203 with the classic candidate path selected (NONE = 0 / SUBPIX = 1)"""
+    import __graft_entry__ as G
+    p = G.reference_parameters(aruco_mod)
+    p.cornerRefinementMethod = refine
+    p.adaptiveThreshWinSizeMin, p.adaptiveThreshWinSizeMax, p.adaptiveThreshWinSizeStep = wins
+    return p
 
 
 def load_golden(name):

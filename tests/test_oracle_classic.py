@@ -1,0 +1,155 @@
+"""CPU: the oracle's CLASSIC candidate path (adaptive threshold -> border following -> polygon approximation ->
+quad filters -> grouping / decoding -> cornerSubPix) against cv2 4.13 and the golden
+vectors of tools/gen_golden_classic.py."""
+import zlib
+import numpy as np
+import pytest
+from conftest import needs_cv2, classic_cases, load_golden, classic_params, cv2_params
+
+
+@pytest.fixture(scope="module")
+def gray_dense(frames4k):
+    import cv2
+    return cv2.cvtColor(frames4k["dense"], cv2.COLOR_BGR2GRAY)
+
+
+@needs_cv2
+@pytest.mark.parametrize("win,c", [(3, 7), (13, 7), (23, 7), (43, 7), (53, 7), (4, 7), (5, 3.5), (7, -2.5), (23, 0)])
+def test_adaptive_threshold_vs_cv2(oracle, gray_dense, win, c):
+    import cv2
+    g = gray_dense[:1080, :1920]
+    w2 = win + 1 if win % 2 == 0 else win
+    ref = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, w2, c)
+    assert np.array_equal(oracle.adaptive_threshold(g, win, c), ref)
+
+
+@needs_cv2
+def test_adaptive_threshold_small_and_ragged(oracle):
+    import cv2
+    rng = np.random.default_rng(2)
+    for shape in ((5, 7), (31, 17), (64, 64), (101, 203)):
+        g = rng.integers(0, 256, shape, dtype=np.uint8)
+        for win in (3, 9, 23):
+            ref = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, win, 7)
+            assert np.array_equal(oracle.adaptive_threshold(g, win, 7), ref), (shape, win)
+
+
+def _same_contours(ref, mine):
+    assert len(ref) == len(mine)
+    for a, b in zip(ref, mine):
+        assert np.array_equal(np.asarray(a).reshape(-1, 2), b)
+
+
+@needs_cv2
+def test_find_contours_vs_cv2(oracle, gray_dense):
+    import cv2
+    rng = np.random.default_rng(1)
+    imgs = [(rng.random((64, 64)) > 0.5).astype(np.uint8) * 255, (rng.random((300, 500)) > 0.7).astype(np.uint8) * 255,
+            (rng.random((300, 500)) > 0.3).astype(np.uint8) * 255, np.full((20, 30), 255, np.uint8), np.zeros((20, 30), np.uint8)]
+    one = np.zeros((9, 9), np.uint8); one[4, 4] = 255                      # single pixel -> 1-point contour
+    line = np.zeros((9, 12), np.uint8); line[3, 2:9] = 255                 # 1-px stroke: traversed out and back
+    ring = np.zeros((12, 12), np.uint8); ring[2:10, 2:10] = 255; ring[4:8, 4:8] = 0   # outer + hole border
+    edge = np.zeros((10, 10), np.uint8); edge[0:4, 0:5] = 255; edge[6:, 7:] = 255     # foreground touching the edges
+    imgs += [one, line, ring, edge]
+    for win in (3, 13, 23):
+        imgs.append(cv2.adaptiveThreshold(gray_dense[:900, :1200], 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, win, 7))
+    for im in imgs:
+        ref, _ = cv2.findContours(im.copy(), cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+        _same_contours(ref, oracle.find_contours(im))
+
+
+@needs_cv2
+def test_approx_poly_and_convexity_vs_cv2(oracle, gray_dense):
+    import cv2
+    b = cv2.adaptiveThreshold(gray_dense[:1400, :2000], 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY_INV, 13, 7)
+    ref, _ = cv2.findContours(b, cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+    tested = quads = 0
+    for c in ref:
+        m = len(c)
+        if m < 20:
+            continue
+        for rate in (0.03, 0.01, 0.08):
+            a = cv2.approxPolyDP(c, m * rate, True).reshape(-1, 2)
+            assert np.array_equal(a, oracle.approx_poly_dp(c.reshape(-1, 2), m * rate))
+            tested += 1
+            if len(a) == 4:
+                quads += 1
+                assert cv2.isContourConvex(a) == oracle.is_contour_convex(a)
+    assert tested > 3000 and quads > 100
+    rng = np.random.default_rng(3)
+    for _ in range(5000):
+        q = rng.integers(0, 12, (4, 2)).astype(np.int32)
+        assert cv2.isContourConvex(q) == oracle.is_contour_convex(q)
+
+
+def _detect_cv2(gray, p):
+    import cv2
+    c, i, r = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(p)).detectMarkers(gray)
+    return (np.array(c, np.float32).reshape(-1, 4, 2), i.ravel() if i is not None else np.zeros(0, np.int32),
+            np.array(r, np.float32).reshape(-1, 4, 2))
+
+
+@needs_cv2
+@pytest.mark.parametrize("wins", [(3, 23, 10), (3, 53, 10), (3, 23, 4), (5, 5, 1), (13, 13, 1)])   # BASELINE.json config 5 sweep
+@pytest.mark.parametrize("refine", [0, 1])
+def test_detect_classic_dense_4k_vs_cv2(oracle, dictionary, gray_dense, wins, refine):
+    from apse_uav_b200 import aruco
+    p = classic_params(aruco, refine, wins)
+    rc, ri, rr = _detect_cv2(gray_dense, p)
+    oc, oi, orj = oracle.detect_markers_classic(gray_dense, dictionary.raw, p)
+    assert len(ri) >= 150
+    assert np.array_equal(oi, ri)
+    assert np.array_equal(oc, rc)          # integer quads (NONE) and cornerSubPix output (SUBPIX) bit-identical here
+    assert np.array_equal(orj, rr)
+
+
+@needs_cv2
+def test_border_quad_swallows_group(oracle, dictionary, gray_dense):
+    """4.13 applies minDistanceToBorder AFTER the too-close grouping: a border-touching quad that groups with a marker's
+    quiet-zone quad becomes the group's main and the whole group (marker included) disappears -- neither accepted nor
+    rejected.  Found on this crop: cv2 reports nothing although the marker decodes when grouping is disabled."""
+    from apse_uav_b200 import aruco
+    crop = gray_dense[0:260, 860:1140].copy()
+    for rate, expect in ((0.0, [44]), (0.125, [])):
+        p = classic_params(aruco, 0, (23, 23, 1))
+        p.minMarkerPerimeterRate = 38.4 / 280; p.maxMarkerPerimeterRate = 15360.5 / 280
+        p.minMarkerDistanceRate = rate
+        rc, ri, rr = _detect_cv2(crop, p)
+        oc, oi, orj = oracle.detect_markers_classic(crop, dictionary.raw, p)
+        assert ri.tolist() == expect and oi.tolist() == expect
+        assert np.array_equal(oc, rc) and np.array_equal(orj, rr)
+
+
+@needs_cv2
+def test_detect_classic_sparse_defaults_and_ragged_vs_cv2(oracle, dictionary, frames4k):
+    import cv2
+    from apse_uav_b200 import aruco
+    from tools import synth
+    cases = [(cv2.cvtColor(frames4k["sparse"], cv2.COLOR_BGR2GRAY), classic_params(aruco, 0)),
+             (cv2.cvtColor(frames4k["sparse"], cv2.COLOR_BGR2GRAY), aruco.DetectorParameters())]      # library defaults
+    for seed, (w, h) in enumerate([(1283, 721), (1001, 750)]):
+        f = synth.make_frame(dictionary.bytesList, 60 + seed, w, h, ids=[i % 50 for i in range(30)], side_range=(40, 120),
+                             jitter=0.15, occlude_frac=0.15, margin=0, noise_sigma=3)
+        cases.append((cv2.cvtColor(f, cv2.COLOR_BGR2GRAY), classic_params(aruco, 1)))
+    for gray, p in cases:
+        rc, ri, rr = _detect_cv2(gray, p)
+        oc, oi, orj = oracle.detect_markers_classic(gray, dictionary.raw, p)
+        assert np.array_equal(oi, ri) and np.array_equal(orj, rr)
+        assert oc.shape == rc.shape and (len(oc) == 0 or np.abs(oc - rc).max() <= 1e-3)
+
+
+@pytest.mark.parametrize("name", classic_cases())
+def test_classic_golden(oracle, dictionary, name):
+    """no cv2 needed: committed outputs of the reference's dependency"""
+    from apse_uav_b200 import aruco
+    g = load_golden(name)
+    gray, wins = g["gray"], tuple(int(v) for v in g["wins"])
+    for k, win in enumerate(range(wins[0], wins[1] + 1, wins[2])):
+        b = oracle.adaptive_threshold(gray, win, 7)
+        assert zlib.crc32(b.tobytes()) == int(g["thresh_crc"][k])
+        assert len(oracle.find_contours(b)) == int(g["n_contours"][k])
+    for refine, tag in ((0, "none"), (1, "subpix")):
+        oc, oi, orj = oracle.detect_markers_classic(gray, dictionary.raw, classic_params(aruco, refine, wins))
+        assert np.array_equal(oi, g[f"ids_{tag}"])
+        assert np.array_equal(orj, g[f"rejected_{tag}"])
+        assert oc.shape == g[f"corners_{tag}"].shape and (len(oc) == 0 or np.abs(oc - g[f"corners_{tag}"]).max() <= 1e-3)
