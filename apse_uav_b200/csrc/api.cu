@@ -74,7 +74,7 @@ void apse_destroy(apse_ctx *ctx)
     apse_detect_free(ctx);
     apse_decode_free(ctx);
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
-    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch);
+    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask);
     delete ctx;
 }
 
@@ -85,7 +85,8 @@ int64_t apse_launch_count(apse_ctx *ctx) { return ctx ? ctx->launches : 0; }
 static const char *KERNEL_NAMES[KID_COUNT] = {
     "k_build_undistort_map", "k_preprocess_fused", "k_remap", "k_cvt", "k_lut", "k_tile_minmax", "k_threshold",
     "k_ccl_local", "k_ccl_merge", "k_ccl_flatten", "k_emit_points", "k_cluster_scan", "k_scatter_points", "k_fit_quads",
-    "k_decode", "k_pose", "k_project_points", "k_classic"};
+    "k_decode", "k_pose", "k_project_points", "k_classic", "k_adaptive_threshold", "k_border_jobs", "k_trace_borders",
+    "k_approx_quads", "k_corner_subpix", "k_decode_bits"};
 
 int apse_kernel_count(void) { return KID_COUNT; }
 const char *apse_kernel_name(int kid) { return kid >= 0 && kid < KID_COUNT ? KERNEL_NAMES[kid] : ""; }

@@ -99,12 +99,16 @@ __global__ void k_mark_outside(const uint8_t *__restrict__ bin, int w, int h, ui
 }
 
 // one job per border: trigger pixel index | hole flag (bit 31)
+// Also writes, for every foreground pixel, the 8-bit mask of its foreground neighbours (bit s = direction s), so that
+// a border-following step is ONE dependent load instead of up to eight.
 __global__ void __launch_bounds__(256) k_border_jobs(const uint8_t *__restrict__ bin, int w, int h, const uint32_t *__restrict__ labels,
-                                                     uint32_t *__restrict__ jobs, int job_cap, int32_t *__restrict__ counters)
+                                                     uint32_t *__restrict__ jobs, int job_cap, int32_t *__restrict__ counters,
+                                                     uint8_t *__restrict__ nbr_mask)
 {
     const int f = blockIdx.y;
     const size_t npx = (size_t)w * h;
     const uint8_t *b = bin + f * npx;
+    uint8_t *M = nbr_mask + f * npx;
     const uint32_t *L = labels + f * npx;
     uint32_t *J = jobs + (size_t)f * job_cap;
     int32_t *cnt = counters + f * APSE_COUNTERS;
@@ -115,10 +119,20 @@ __global__ void __launch_bounds__(256) k_border_jobs(const uint8_t *__restrict__
         uint32_t enc = 0;
         if (p < npx) {
             uint32_t l = L[p];
+            const bool is_fg = b[p] != 0;
             if ((l & ~LBL_OUTSIDE) == (uint32_t)p) {
-                if (b[p]) { job = true; enc = (uint32_t)p; }
+                if (is_fg) { job = true; enc = (uint32_t)p; }
                 else if (!(l & LBL_OUTSIDE)) { job = true; enc = (uint32_t)p | 0x80000000u; }
             }
+            unsigned m = 0;
+            if (is_fg) {
+                const int y = (int)(p / w), x = (int)(p - (size_t)y * w);
+                const bool n_ = y > 0, s_ = y + 1 < h, w_ = x > 0, e_ = x + 1 < w;
+                m = (e_ && b[p + 1] ? 1u : 0u) | (n_ && e_ && b[p - w + 1] ? 2u : 0u) | (n_ && b[p - w] ? 4u : 0u) |
+                    (n_ && w_ && b[p - w - 1] ? 8u : 0u) | (w_ && b[p - 1] ? 16u : 0u) | (s_ && w_ && b[p + w - 1] ? 32u : 0u) |
+                    (s_ && b[p + w] ? 64u : 0u) | (s_ && e_ && b[p + w + 1] ? 128u : 0u);
+            }
+            M[p] = (uint8_t)m;
         }
         unsigned m = __ballot_sync(0xffffffffu, job);
         if (m) {
@@ -133,43 +147,35 @@ __global__ void __launch_bounds__(256) k_border_jobs(const uint8_t *__restrict__
     }
 }
 
-// Border following (Suzuki-Abe), directions 0..7 = E, NE, N, NW, W, SW, S, SE with y growing downwards.
-struct BinImage {
-    const uint8_t *b;
-    int w, h;
-    __device__ __forceinline__ bool fg(int x, int y) const { return x >= 0 && x < w && y >= 0 && y < h && b[(size_t)y * w + x] != 0; }
-};
+// Border following (Suzuki-Abe) on the neighbour masks; directions 0..7 = E, NE, N, NW, W, SW, S, SE (y downwards).
 __device__ __constant__ int8_t c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 __device__ __constant__ int8_t c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+__device__ __forceinline__ unsigned rotr8(unsigned m, int r) { return ((m >> r) | (m << (8 - r))) & 0xffu; }
 
 template <bool STORE>
-__device__ int trace_border(const BinImage &I, int x0, int y0, bool hole, int max_n, uint32_t *out)
+__device__ int trace_border(const uint8_t *__restrict__ M, int w, int x0, int y0, bool hole, int max_n, uint32_t *out)
 {
-    int s = hole ? 0 : 4;
-    const int s_end = s;
-    bool found = false;
-    do {
-        s = (s - 1) & 7;
-        if (I.fg(x0 + c_dx[s], y0 + c_dy[s])) { found = true; break; }
-    } while (s != s_end);
-    if (!found) {
+    const int s0 = hole ? 0 : 4;
+    unsigned m = M[(size_t)y0 * w + x0];
+    if (m == 0) {   // isolated pixel
         if (STORE) out[0] = (uint32_t)x0 | ((uint32_t)y0 << 16);
         return 1;
     }
+    // first neighbour clockwise from s0 - 1: candidate k <-> direction (s0 - 1 - k) & 7
+    int s = (s0 - 1 - (__ffs(rotr8(__brev(m) >> 24, (8 - s0) & 7)) - 1)) & 7;
     const int x1 = x0 + c_dx[s], y1 = y0 + c_dy[s];
     int cx = x0, cy = y0, n = 0;
     for (;;) {
-        int nx, ny;
-        for (;;) {
-            s = (s + 1) & 7;
-            nx = cx + c_dx[s]; ny = cy + c_dy[s];
-            if (I.fg(nx, ny)) break;
-        }
+        // next neighbour counter-clockwise from s + 1: candidate k <-> direction (s + 1 + k) & 7
+        const int base = (s + 1) & 7;
+        s = (base + __ffs(rotr8(m, base)) - 1) & 7;
+        const int nx = cx + c_dx[s], ny = cy + c_dy[s];
         if (STORE) out[n] = (uint32_t)cx | ((uint32_t)cy << 16);
         n++;
         if (nx == x0 && ny == y0 && cx == x1 && cy == y1) break;
         if (n > max_n) break;   // longer than the perimeter limit: the caller drops it
         cx = nx; cy = ny;
+        m = M[(size_t)cy * w + cx];
         s = (s + 4) & 7;
     }
     return n;
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(128) k_trace_borders(const uint8_t *__restrict
     const int32_t *cnt_r = counters + f * APSE_COUNTERS;
     int32_t *cnt = counters + f * APSE_COUNTERS;
     const int njobs = min(cnt_r[0], job_cap);
-    BinImage I{bin + (size_t)f * w * h, w, h};
+    const uint8_t *I = bin + (size_t)f * w * h;   // neighbour masks
     const uint32_t *J = jobs + (size_t)f * job_cap;
     uint32_t *P = pts + (size_t)f * pts_cap;
     ContourDesc *D = descs + (size_t)f * desc_cap;
@@ -196,12 +202,12 @@ __global__ void __launch_bounds__(128) k_trace_borders(const uint8_t *__restrict
         uint32_t trig = e & 0x7fffffffu;
         int ty = trig / w, tx = trig - ty * w;
         int x0 = hole ? tx - 1 : tx, y0 = ty;
-        int n = trace_border<false>(I, x0, y0, hole, max_px, nullptr);
+        int n = trace_border<false>(I, w, x0, y0, hole, max_px, nullptr);
         if (n < min_px || n > max_px) continue;
         int di = atomicAdd(&cnt[1], 1);
         int off = atomicAdd(&cnt[5], n);
         if (di >= desc_cap || off + n > pts_cap) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); continue; }
-        trace_border<true>(I, x0, y0, hole, max_px, P + off);
+        trace_border<true>(I, w, x0, y0, hole, max_px, P + off);
         D[di] = ContourDesc{(uint32_t)off, (uint32_t)n, trig, hole ? 1u : 0u};
     }
 }
@@ -534,7 +540,7 @@ int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int 
     if (win % 2 == 0) win++;
     if (win > 2 * AT_RMAX + 1) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "adaptiveThreshold: block size %d exceeds the supported %d", win, 2 * AT_RMAX + 1);
     dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), batch);
-    KLAUNCH(ctx, KID_CLASSIC, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, (int)floor(c), out));
+    KLAUNCH(ctx, KID_ADAPTIVE, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, (int)floor(c), out));
     return APSE_OK;
 }
 
@@ -554,18 +560,19 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
     // points, clusters = border descriptors; counters: [0] jobs, [1] borders kept, [2] quads, [3] status, [5] points
     const int job_cap = APSE_MAX_POINTS * 4, pts_cap = APSE_MAX_POINTS * 2, desc_cap = APSE_MAX_CLUSTERS;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
+    if (!ctx->nbr_mask) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->nbr_mask, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h));
     for (int s = 0; s < n_scales; s++) {
         int win = p.adaptiveThreshWinSizeMin + s * p.adaptiveThreshWinSizeStep;
         if (win % 2 == 0) win++;
         if (win > 2 * AT_RMAX + 1) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: adaptiveThreshWinSize %d exceeds the supported %d", win, 2 * AT_RMAX + 1);
         dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), batch);
-        KLAUNCH(ctx, KID_CLASSIC, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, idelta, ctx->thresh));
+        KLAUNCH(ctx, KID_ADAPTIVE, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, idelta, ctx->thresh));
         int rc = apse_ccl_binary(ctx, ctx->thresh, w, h, batch, st);
         if (rc) return rc;
-        KLAUNCH(ctx, KID_CLASSIC, st, k_mark_outside<<<div_up(2 * (w + h) * batch, 256), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, batch));
+        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_mark_outside<<<div_up(2 * (w + h) * batch, 256), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, batch));
         // per window: reset the job / border / point counters, keep quads and status
-        KLAUNCH(ctx, KID_CLASSIC, st, k_border_jobs<<<dim3(148 * 2, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters));
-        KLAUNCH(ctx, KID_CLASSIC, st, k_trace_borders<<<dim3(148, batch), 128, 0, st>>>(ctx->thresh, w, h, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, min_px,
+        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_border_jobs<<<dim3(148 * 2, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, ctx->nbr_mask));
+        KLAUNCH(ctx, KID_TRACE, st, k_trace_borders<<<dim3(148, batch), 128, 0, st>>>(ctx->nbr_mask, w, h, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, min_px,
                                                                                 max_px, reinterpret_cast<uint32_t *>(ctx->sorted_pts), pts_cap,
                                                                                 reinterpret_cast<ContourDesc *>(ctx->clusters), desc_cap, batch));
         ClassicArgs A;
@@ -574,12 +581,12 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
         A.counters = ctx->counters; A.quads = ctx->quads; A.quad_keys = ctx->sort_keys; A.quad_cap = APSE_MAX_QUADS;
         A.w = w; A.h = h; A.window_index = s;
         A.accuracy_rate = p.polygonalApproxAccuracyRate; A.min_corner_rate = p.minCornerDistanceRate;
-        KLAUNCH(ctx, KID_CLASSIC, st, k_approx_quads<<<dim3(148, batch), AQ_WARPS * 32, 0, st>>>(A));
+        KLAUNCH(ctx, KID_APPROX, st, k_approx_quads<<<dim3(148, batch), AQ_WARPS * 32, 0, st>>>(A));
         // counters [0] (jobs), [1] (borders), [5] (points) restart for the next window
         CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters, APSE_COUNTERS * sizeof(int32_t), 0, 2 * sizeof(int32_t), batch, st));
         CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters + 5, APSE_COUNTERS * sizeof(int32_t), 0, sizeof(int32_t), batch, st));
     }
-    KLAUNCH(ctx, KID_CLASSIC, st, k_rank_quads<<<dim3(8, batch), 256, 0, st>>>(ctx->sort_keys, ctx->counters, APSE_MAX_QUADS, ctx->quad_order));
+    KLAUNCH(ctx, KID_APPROX, st, k_rank_quads<<<dim3(8, batch), 256, 0, st>>>(ctx->sort_keys, ctx->counters, APSE_MAX_QUADS, ctx->quad_order));
     return APSE_OK;
 }
 
@@ -591,7 +598,7 @@ int apse_corner_subpix(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
     if (p.cornerRefinementWinSize < 1 || p.cornerRefinementMaxIterations < 1 || p.cornerRefinementMinAccuracy <= 0)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: cornerRefinement{WinSize,MaxIterations,MinAccuracy} must be positive");
     const int total = batch * out->max_markers * 4;
-    KLAUNCH(ctx, KID_CLASSIC, st, k_corner_subpix<<<div_up(total, 64), 64, 0, st>>>(gray, w, h, out->corners, out->n_markers, batch, out->max_markers,
+    KLAUNCH(ctx, KID_SUBPIX, st, k_corner_subpix<<<div_up(total, 64), 64, 0, st>>>(gray, w, h, out->corners, out->n_markers, batch, out->max_markers,
                                                                         ctx->marker_size + 2 * p.markerBorderBits, p.relativeCornerRefinmentWinSize,
                                                                         p.cornerRefinementWinSize, p.cornerRefinementMaxIterations,
                                                                         p.cornerRefinementMinAccuracy));

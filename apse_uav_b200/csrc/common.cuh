@@ -54,7 +54,7 @@ struct DeviceParams {  // what the detection kernels need of apse_params (+ deri
 enum KernelId {
     KID_BUILD_MAP = 0, KID_PREPROCESS, KID_REMAP, KID_CVT, KID_LUT, KID_TILE_MINMAX, KID_THRESHOLD, KID_CCL_LOCAL,
     KID_CCL_MERGE, KID_CCL_FLATTEN, KID_EMIT, KID_CLUSTER_SCAN, KID_SCATTER, KID_FIT_QUADS, KID_DECODE, KID_POSE,
-    KID_PROJECT, KID_CLASSIC, KID_COUNT
+    KID_PROJECT, KID_CLASSIC, KID_ADAPTIVE, KID_BORDER_JOBS, KID_TRACE, KID_APPROX, KID_SUBPIX, KID_DECODE_BITS, KID_COUNT
 };
 #define APSE_EVENT_POOL 2048
 
@@ -104,6 +104,7 @@ struct apse_ctx {
     uint32_t *quad_order = nullptr;   // cluster index of each quad (for deterministic ordering)
     // decode scratch
     void *decode_scratch = nullptr;
+    uint8_t *nbr_mask = nullptr;      // [max_batch][h][w] 8-neighbour foreground masks of the classic path (first use)
     uint8_t *gray_scratch = nullptr;  // [max_batch][h][w], allocated on first use by apse_process_frames(gray = NULL)
 };
 

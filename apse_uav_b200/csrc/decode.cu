@@ -23,7 +23,8 @@ struct DecodeArrays {
     float *perim;
     uint32_t *key;                        // ordering key (cluster index) / scratch
     uint32_t *close_bits;                 // [cap][cap / 32] too-close predicate, bit (i, j)
-    uint32_t *row_mask;                   // [cap][4]: which 32-bit words of row i are non-zero (cap / 32 <= 128)
+    uint32_t *pairs;                      // [cap * 8] too-close pairs (i << 16 | j) in row-major order
+    float *cxy;                           // [cap][2] candidate centroids (cheap rejection in the pair matrix)
     short *group_id, *next_in_group, *close_next, *parent, *depth, *sel, *sel_of, *dec_id, *use_c, *group_head, *group_tail;
     uint8_t *dec_valid, *dec_rot, *selected, *was, *valid;
     int cap;
@@ -31,7 +32,7 @@ struct DecodeArrays {
 
 __host__ __device__ inline size_t decode_arrays_bytes(int cap)
 {
-    return (size_t)cap * (8 * 4 + 4 + 4 + (cap / 32) * 4 + 4 * 4 + 11 * 2 + 5) + 64;
+    return (size_t)cap * (8 * 4 + 4 + 4 + (cap / 32) * 4 + 8 * 4 + 2 * 4 + 11 * 2 + 5) + 64;
 }
 
 __device__ inline void decode_arrays_carve(DecodeArrays &A, unsigned char *base, int cap)
@@ -42,7 +43,8 @@ __device__ inline void decode_arrays_carve(DecodeArrays &A, unsigned char *base,
     A.perim = reinterpret_cast<float *>(p); p += (size_t)cap * 4;
     A.key = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4;
     A.close_bits = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * (cap / 32) * 4;
-    A.row_mask = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 16;
+    A.pairs = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 32;
+    A.cxy = reinterpret_cast<float *>(p); p += (size_t)cap * 8;
     short **sp[11] = {&A.group_id, &A.next_in_group, &A.close_next, &A.parent, &A.depth, &A.sel, &A.sel_of, &A.dec_id, &A.use_c,
                       &A.group_head, &A.group_tail};
     for (int i = 0; i < 11; i++) { *sp[i] = reinterpret_cast<short *>(p); p += (size_t)cap * 2; }
@@ -51,9 +53,6 @@ __device__ inline void decode_arrays_carve(DecodeArrays &A, unsigned char *base,
 }
 
 struct DecodeSmem {
-    uint8_t warp_img[DEC_WARPS][DEC_MAX_S * DEC_MAX_S];
-    int hist[DEC_WARPS][256];
-    uint8_t bits[DEC_WARPS][16 * 16];
     int n, ns, ngroups;
     int pad;
     // followed by decode_arrays_bytes(DEC_SMEMC) bytes
@@ -275,16 +274,35 @@ __device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, c
     if (packed != 0x7fffffff) { valid = true; id = packed >> 2; rot = packed & 3; }
 }
 
+// _identifyOneCandidate for every raw quad of the batch: warp per candidate, grid = (candidate groups, frames).
+// Results (valid | rot << 1 | id << 8) are indexed like the raw quads; k_decode picks them up after its sort.
+__global__ void __launch_bounds__(DEC_THREADS) k_decode_bits(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
+                                                             const int32_t *__restrict__ counters, DeviceParams P,
+                                                             const uint8_t *__restrict__ dict, int32_t *__restrict__ dec_raw)
+{
+    __shared__ uint8_t s_img[DEC_WARPS][DEC_MAX_S * DEC_MAX_S];
+    __shared__ int s_hist[DEC_WARPS][256];
+    __shared__ uint8_t s_bits[DEC_WARPS][16 * 16];
+    const int f = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nq = min(counters[f * APSE_COUNTERS + 2], DEC_MAXC);
+    const uint8_t *im = gray + (size_t)f * w * h;
+    for (int i = blockIdx.x * DEC_WARPS + wid; i < nq; i += gridDim.x * DEC_WARPS) {
+        bool v; int id, rot;
+        decode_candidate(im, w, h, quads + ((size_t)f * APSE_MAX_QUADS + i) * 8, P, dict, s_img[wid], s_hist[wid], s_bits[wid], v, id, rot);
+        if (lane == 0) dec_raw[(size_t)f * APSE_MAX_QUADS + i] = (v ? 1 : 0) | (rot << 1) | (id << 8);
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
                                                         const uint32_t *__restrict__ quad_order, int32_t *__restrict__ counters,
-                                                        DeviceParams P, const uint8_t *__restrict__ dict, int skip_decoded_parents,
+                                                        DeviceParams P, const int32_t *__restrict__ dec_raw, int skip_decoded_parents,
                                                         unsigned char *__restrict__ big_scratch, size_t big_stride, apse_detections out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
     __shared__ DecodeArrays A;
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint8_t *im = gray + (size_t)f * w * h;
+    const int f = blockIdx.x, tid = threadIdx.x;
     int32_t *cnt = counters + f * APSE_COUNTERS;
     const int nq = min(cnt[2], DEC_MAXC);
     const float *q = quads + (size_t)f * APSE_MAX_QUADS * 8;
@@ -312,9 +330,12 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
     }
     __syncthreads();
     const int n = nq;
+    const int32_t *dr = dec_raw + (size_t)f * APSE_MAX_QUADS;
     for (int i = tid; i < nq; i += DEC_THREADS) {
         int r = A.sel[i];
         for (int k = 0; k < 8; k++) A.c[r][k] = q[8 * i + k];
+        A.group_id[r] = (short)(dr[i] & 0xff);      // decode result rides along through the two permutations
+        A.next_in_group[r] = (short)(dr[i] >> 8);
     }
     __syncthreads();
     for (int i = tid; i < n; i += DEC_THREADS) A.perim[i] = perimeter_of(A.c[i]);
@@ -338,35 +359,74 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
             int r = A.sel_of[i];
             for (int k = 0; k < 8; k++) A.c[r][k] = tmp[9 * i + k];
             A.perim[r] = tmp[9 * i + 8];
+            int flags = A.group_id[i];
+            A.dec_valid[r] = (uint8_t)(flags & 1); A.dec_rot[r] = (uint8_t)((flags >> 1) & 3); A.dec_id[r] = A.next_in_group[i];
         }
     }
     __syncthreads();
 
-    // ---- decode every candidate (one warp each)
-    for (int i = wid; i < n; i += DEC_WARPS) {
-        bool v; int id, rot;
-        decode_candidate(im, w, h, A.c[i], P, dict, S.warp_img[wid], S.hist[wid], S.bits[wid], v, id, rot);
-        if (lane == 0) { A.dec_valid[i] = v; A.dec_id[i] = (short)id; A.dec_rot[i] = (uint8_t)rot; }
-        __syncwarp();
-    }
-
-    // ---- too-close predicate matrix: bit (i,j), i < j, set when avgDist(i,j) < perimeter[j] * rate
+    // ---- too-close predicate matrix: bit (i,j), i < j, set when avgDist(i,j) < perimeter[j] * rate.
+    // avgDist^2 is a mean of squared corner distances, so it is never below the squared centroid distance (Jensen):
+    // pairs whose centroids are clearly farther apart than the threshold are skipped without the 4-shift evaluation.
     const int words = (n + 31) / 32;
-    for (int i = tid; i < n; i += DEC_THREADS) { A.row_mask[4 * i] = A.row_mask[4 * i + 1] = A.row_mask[4 * i + 2] = A.row_mask[4 * i + 3] = 0; }
+    for (int i = tid; i < n; i += DEC_THREADS) {
+        const float *c = A.c[i];
+        A.cxy[2 * i] = 0.25f * (c[0] + c[2] + c[4] + c[6]);
+        A.cxy[2 * i + 1] = 0.25f * (c[1] + c[3] + c[5] + c[7]);
+    }
     __syncthreads();
     for (int p = tid; p < n * words; p += DEC_THREADS) {
         int i = p / words, wj = p - i * words;
         uint32_t bitsw = 0;
-        if (wj * 32 + 31 > i)
+        if (wj * 32 + 31 > i) {
+            const float cxi = A.cxy[2 * i], cyi = A.cxy[2 * i + 1];
             for (int b = 0; b < 32; b++) {
                 int j = wj * 32 + b;
                 if (j > i && j < n) {
+                    const float thr = A.perim[j] * P.min_marker_distance_rate;
+                    const float dx = A.cxy[2 * j] - cxi, dy = A.cxy[2 * j + 1] - cyi;
+                    if (dx * dx + dy * dy > thr * thr * 1.02f + 4.f) continue;   // conservative: float rounding of the centroids
                     float md = average_distance(A.c[i], A.c[j]);
-                    if (md < A.perim[j] * P.min_marker_distance_rate) bitsw |= 1u << b;
+                    if (md < thr) bitsw |= 1u << b;
                 }
             }
+        }
         A.close_bits[(size_t)i * rw + wj] = bitsw;
-        if (bitsw) atomicOr(&A.row_mask[4 * i + (wj >> 5)], 1u << (wj & 31));
+    }
+    __syncthreads();
+    // compact the set bits into a row-major pair list: per-row counts, block scan, scatter
+    {
+        __shared__ int s_part[DEC_THREADS];
+        const int chunk = (n + DEC_THREADS - 1) / DEC_THREADS, r0 = tid * chunk, r1 = min(n, r0 + chunk);
+        int local = 0;
+        for (int i = r0; i < r1; i++) {
+            int c = 0;
+            for (int wj = i / 32; wj < words; wj++) c += __popc(A.close_bits[(size_t)i * rw + wj]);
+            A.key[i] = (uint32_t)c;
+            local += c;
+        }
+        s_part[tid] = local;
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int t = 0; t < DEC_THREADS; t++) { int v = s_part[t]; s_part[t] = acc; acc += v; }
+            S.n = acc;   // total number of too-close pairs
+        }
+        __syncthreads();
+        int off = s_part[tid];
+        const int pair_cap = A.cap * 8;
+        for (int i = r0; i < r1; i++) {
+            if (!A.key[i]) continue;
+            for (int wj = i / 32; wj < words; wj++) {
+                uint32_t m = A.close_bits[(size_t)i * rw + wj];
+                while (m) {
+                    int j = wj * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (off < pair_cap) A.pairs[off] = ((uint32_t)i << 16) | (uint32_t)j;
+                    off++;
+                }
+            }
+        }
     }
     for (int i = tid; i < n; i += DEC_THREADS) {
         A.group_id[i] = -1; A.selected[i] = 1; A.next_in_group[i] = -1; A.close_next[i] = -1;
@@ -374,26 +434,19 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
     }
     __syncthreads();
 
-    // ---- sequential grouping walk (order-dependent by definition)
+    // ---- sequential grouping walk over the pair list (order-dependent by definition)
     if (tid == 0) {
         int ngroups = 0;
-        for (int i = 0; i < n; i++)
-            for (int mw = 0; mw < 4; mw++) {
-                uint32_t rm = A.row_mask[4 * i + mw];
-                while (rm) {
-                    int wj = mw * 32 + __ffs(rm) - 1;
-                    rm &= rm - 1;
-                    uint32_t m = A.close_bits[(size_t)i * rw + wj];
-                    while (m) {
-                        int j = wj * 32 + __ffs(m) - 1;
-                        m &= m - 1;
-                        A.selected[i] = 0; A.selected[j] = 0;
-                        if (A.group_id[i] < 0 && A.group_id[j] < 0) { A.group_id[i] = A.group_id[j] = (short)ngroups++; }
-                        else if (A.group_id[i] > -1 && A.group_id[j] == -1) A.group_id[j] = A.group_id[i];
-                        else if (A.group_id[j] > -1 && A.group_id[i] == -1) A.group_id[i] = A.group_id[j];
-                    }
-                }
-            }
+        const int npairs = S.n;
+        if (npairs > A.cap * 8) cnt[3] = APSE_ERR_CAPACITY;   // reported through status; never truncated silently
+        for (int k = 0; k < min(npairs, A.cap * 8); k++) {
+            const uint32_t pr = A.pairs[k];
+            const int i = pr >> 16, j = pr & 0xffff;
+            A.selected[i] = 0; A.selected[j] = 0;
+            if (A.group_id[i] < 0 && A.group_id[j] < 0) { A.group_id[i] = A.group_id[j] = (short)ngroups++; }
+            else if (A.group_id[i] > -1 && A.group_id[j] == -1) A.group_id[j] = A.group_id[i];
+            else if (A.group_id[j] > -1 && A.group_id[i] == -1) A.group_id[i] = A.group_id[j];
+        }
         // members of each group in ascending index order (= largest perimeter first)
         for (int g = 0; g < ngroups; g++) { A.group_head[g] = -1; A.group_tail[g] = -1; }
         for (int i = 0; i < n; i++) {
@@ -540,8 +593,12 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: canonical marker image %d px exceeds the %d px limit", nb * dp.cell_size, DEC_MAX_S);
     const char *env = getenv("APSE_IDENTIFY_DECODED_PARENTS");
     int skip = (env && env[0] == '1') ? 0 : 1;
+    // hierarchy scratch of the quad fit is free at this point: [batch][APSE_MAX_QUADS] decode results
+    int32_t *dec_raw = reinterpret_cast<int32_t *>(ctx->errs);
+    const int cand_blocks = ctx->params.cornerRefinementMethod == 3 ? 4 : 32;   // classic path: hundreds of candidates per frame
+    KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<<<dim3(cand_blocks, batch), DEC_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw));
     KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem) + decode_arrays_bytes(DEC_SMEMC), st>>>(
-                gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, ctx->dict, skip,
+                gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, dec_raw, skip,
                 (unsigned char *)ctx->decode_scratch, decode_arrays_bytes(DEC_MAXC), *out));
     return APSE_OK;
 }
