@@ -267,9 +267,9 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 // tile (smem offset + two packed Q10 weight pairs per pixel) are computed once from the undistort map and stay in
 // registers.  Per frame the bounding box of the tile's source pixels (<= 74 x 40 px for this camera; the map is
 // smooth) is fetched by ONE bulk tensor copy (TMA, 3-D map over [batch][h][w*3/4] u32 words, out-of-image words
-// zero-filled = BORDER_CONSTANT 0), expanded in shared memory to one 32-bit BGRx word per pixel, and sampled with
-// conflict-free 32-bit LDS + PRMT + IDP.2A (16-bit weight x 8-bit pixel dot products).  The next frame's box is in
-// flight while the current one is being processed.  The colour chain uses tables composed on the host
+// zero-filled = BORDER_CONSTANT 0) into one of two staging buffers and sampled in place: three aligned 32-bit LDS per
+// tap row, a funnel shift to the tap's byte offset, PRMT, and IDP.2A (16-bit weight x 8-bit pixel dot products).
+// The next frame's box is in flight while the current one is being processed.  The colour chain uses tables composed on the host
 // (P2Tables): idxY -> {cbrt, y, f}, (fX-fY) -> a-contribution, (fY-fZ) -> b-contribution, so the 8-bit Lab
 // round trip costs 11 shared-memory look-ups per pixel and no clip / divide instructions.
 // Tiles whose source box does not fit (folded corners of the rational model) take the direct-gather path.
@@ -282,10 +282,9 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 #define P2_BOX_WORDS 64                       // 256 B = 85 px + 1 B per box row
 #define P2_BOX_H 40
 #define P2_BOX_PX 85
-#define P2_PITCH 96                           // BGRx words per staged row (multiple of 32: lanes map to distinct banks)
 #define P2_RAW_BYTES (P2_BOX_WORDS * 4 * P2_BOX_H)
-#define P2_OFF_BGRX (P2_RAW_BYTES + 128)
-#define P2_OFF_TABLES (P2_OFF_BGRX + P2_PITCH * P2_BOX_H * 4)
+#define P2_RAW_STRIDE (P2_RAW_BYTES + 128)    // two staging buffers (double-buffered over frames), 128 B slack each
+#define P2_OFF_TABLES (2 * P2_RAW_STRIDE)
 #define P2_OFF_MISC (P2_OFF_TABLES + (int)sizeof(P2Tables))
 #define P2_SMEM_BYTES (P2_OFF_MISC + 32)
 #define XZ_MAGIC 551553470                    // ceil(108 * 2^32 / 841)
@@ -393,13 +392,11 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                  int batch, int fpb)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t *raw = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *bgrx = reinterpret_cast<uint32_t *>(smem + P2_OFF_BGRX);
     P2Tables *T = reinterpret_cast<P2Tables *>(smem + P2_OFF_TABLES);
-    unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);
-    int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 8);   // xmin, xmax, ymin, ymax
+    unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);   // two barriers
+    int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 16);   // xmin, xmax, ymin, ymax
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t mbar = smem_u32(mbar_p);
+    const uint32_t mbar0 = smem_u32(mbar_p), raw0 = smem_u32(smem);
 
     {   // tables -> shared memory
         const uint4 *src = reinterpret_cast<const uint4 *>(tables);
@@ -407,7 +404,8 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         for (int i = tid; i < (int)(sizeof(P2Tables) / 16); i += P2_THREADS) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         box[0] = INT32_MAX; box[1] = INT32_MIN; box[2] = INT32_MAX; box[3] = INT32_MIN;
     }
@@ -442,39 +440,46 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     const int bx0 = box[0] & ~15, by0 = box[2];   // TMA: the innermost start coordinate must be 16-byte aligned (16 px = 48 B)
     const int bw = box[1] - bx0 + 1, bh = box[3] - by0 + 1;
     const bool fast = bw <= P2_BOX_PX && bh <= P2_BOX_H;   // CTA-uniform
-    int off[P2_NPX];
+    // per pixel: shared-memory byte address (buffer 0) of the aligned word holding the first tap byte, and the funnel
+    // shift (0 / 8 / 16 / 24) that brings that byte to bit 0
+    uint32_t addr[P2_NPX], shf[P2_NPX];
 #pragma unroll
-    for (int k = 0; k < P2_NPX; k++) off[k] = valid ? (iys[k] - by0) * P2_PITCH + (ixs[k] - bx0) : 0;
+    for (int k = 0; k < P2_NPX; k++) {
+        int b = valid ? (ixs[k] - bx0) * 3 : 0, r = valid ? iys[k] - by0 : 0;
+        addr[k] = raw0 + (uint32_t)(r * (P2_BOX_WORDS * 4) + (b & ~3));
+        shf[k] = (uint32_t)(b & 3) * 8;
+    }
 
     const size_t frame_px = (size_t)w * h;
     const int f0 = blockIdx.z * fpb, f1 = min(batch, f0 + fpb);
     const int tw4 = w >> 2;
-    uint32_t phase = 0;
-    if (fast && tid == 0) tma_load_box(smem_u32(raw), &tmap, (bx0 * 3) >> 2, by0, f0, mbar);
+    const int c0x = (bx0 * 3) >> 2;
+    if (fast && tid == 0) tma_load_box(raw0, &tmap, c0x, by0, f0, mbar0);
 
     for (int f = f0; f < f1; f++) {
         int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
         if (fast) {
-            mbar_wait(mbar, phase);
-            phase ^= 1;
-            // raw BGR bytes -> one BGRx word per pixel (4 px = 3 words in, 4 words out per item)
-            const int ngroups = (bw + 3) >> 2;
-            for (int i = tid; i < ngroups * bh; i += P2_THREADS) {
-                int r = i / ngroups, gq = i - r * ngroups;
-                const uint32_t *s = raw + r * P2_BOX_WORDS + gq * 3;
-                uint32_t a = s[0], b = s[1], c = s[2];
-                uint4 v = make_uint4(a, __funnelshift_r(a, b, 24), __funnelshift_r(b, c, 16), c >> 8);
-                *reinterpret_cast<uint4 *>(bgrx + r * P2_PITCH + gq * 4) = v;
-            }
-            __syncthreads();
-            if (tid == 0 && f + 1 < f1) tma_load_box(smem_u32(raw), &tmap, (bx0 * 3) >> 2, by0, f + 1, mbar);
+            const int cur = (f - f0) & 1;
+            // the other buffer was last read in the previous iteration (all threads passed its closing barrier)
+            if (tid == 0 && f + 1 < f1) tma_load_box(raw0 + (cur ^ 1) * P2_RAW_STRIDE, &tmap, c0x, by0, f + 1, mbar0 + (cur ^ 1) * 8);
+            mbar_wait(mbar0 + cur * 8, ((f - f0) >> 1) & 1);
             if (valid) {
+                const uint32_t boff = cur * P2_RAW_STRIDE;
 #pragma unroll
                 for (int k = 0; k < P2_NPX; k++) {
-                    const uint32_t *s = bgrx + off[k];
-                    uint32_t W00 = s[0], W01 = s[1], W10 = s[P2_PITCH], W11 = s[P2_PITCH + 1];
-                    uint32_t T0 = __byte_perm(W00, W01, 0x5140), T1 = __byte_perm(W10, W11, 0x5140);
-                    uint32_t U0 = __byte_perm(W00, W01, 0x6262), U1 = __byte_perm(W10, W11, 0x6262);
+                    const uint32_t a = addr[k] + boff;
+                    uint32_t r00, r01, r02, r10, r11, r12;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r00) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r01) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r02) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(r10) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+260];" : "=r"(r11) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+264];" : "=r"(r12) : "r"(a));
+                    // bytes b .. b+5 of each row: (c0 c1 c2 of tap ix, c0 c1 c2 of tap ix+1)
+                    const uint32_t X0 = __funnelshift_r(r00, r01, shf[k]), X1 = __funnelshift_r(r01, r02, shf[k]);
+                    const uint32_t Y0 = __funnelshift_r(r10, r11, shf[k]), Y1 = __funnelshift_r(r11, r12, shf[k]);
+                    const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);   // (c0, c0', c1, c1')
+                    const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);   // (c2, c2', ..)
                     int c0 = (int)(__dp2a_lo(wA[k], T0, __dp2a_lo(wB[k], T1, 512u)) >> 10);
                     int c1 = (int)(__dp2a_hi(wA[k], T0, __dp2a_hi(wB[k], T1, 512u)) >> 10);
                     int c2 = (int)(__dp2a_lo(wA[k], U0, __dp2a_lo(wB[k], U1, 512u)) >> 10);
@@ -518,7 +523,7 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                 tmax[to] = (uint8_t)mx;
             }
         }
-        if (fast) __syncthreads();   // all reads of bgrx done before the next frame's expansion overwrites it
+        if (fast) __syncthreads();   // all reads of this frame's buffer done before it is refilled (frame f + 2)
     }
 }
 
