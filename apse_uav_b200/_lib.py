@@ -69,9 +69,12 @@ SIGNATURES = {
     "apse_pose": [_vp, _vp, _i, _vp, _f, _dp, _dp, _vp, _vp, _vp],
     "apse_pose_frames": [_vp, _vp, _vp, _i, _i, _vp, _f, _dp, _dp, _vp, _vp, _vp],
     "apse_process_frames": [_vp, _vp, _vp, _i, C.POINTER(Detections), _vp, _f, _vp, _vp, _vp],
+    "apse_preprocess_tiles": [_vp, _vp, _vp, _i, _vp],
+    "apse_detect_pose_frames": [_vp, _vp, _i, C.POINTER(Detections), _vp, _f, _vp, _vp, _vp],
     "apse_project_points": [_vp, _vp, _i, _vp, _vp, _dp, _dp, _vp, _vp],
     "apse_project_points_multi": [_vp, _vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp],
     "apse_debug_apriltag": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, C.POINTER(C.c_int64), _vp],
+    "apse_patch_sums": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp],
     "apse_adaptive_threshold": [_vp, _vp, _i, _i, _i, _i, C.c_double, _vp, _vp],
     "apse_debug_classic": [_vp, _vp, _i, _i, _vp, _vp, _i, C.POINTER(C.c_int64), _vp],
     "apse_launch_count": [_vp],

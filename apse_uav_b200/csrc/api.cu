@@ -265,10 +265,36 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
         gray = ctx->gray_scratch;
     }
     // K1 writes the 4x4-tile extrema of gray straight into the candidate stage's tile arrays
-    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmin, ctx->tmax, batch, st);
+    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm, batch, st);
     if (rc < 0) return rc;
     const bool have_minmax = rc == APSE_OK;
     rc = apse_detect_impl(ctx, gray, w, h, batch, out, st, have_minmax);
+    if (rc) return rc;
+    if (rvec && tvec)
+        rc = apse_pose_frames(ctx, out->corners, out->n_markers, batch, out->max_markers, marker_len, marker_len_all, ctx->K, ctx->D, rvec, tvec, stream);
+    return rc;
+}
+
+int apse_preprocess_tiles(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream)
+{
+    if (!ctx || !bgr || !gray || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "preprocess_tiles: bad argument");
+    if (!ctx->has_camera || !ctx->has_lut) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "preprocess_tiles: set_camera and set_lut first");
+    if (batch > ctx->max_batch) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "preprocess_tiles: batch %d exceeds the context capacity %d", batch, ctx->max_batch);
+    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm, batch, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    ctx->tiles_gray = rc == APSE_OK ? gray : nullptr;   // the extrema in ctx->tmm belong to exactly this gray batch
+    ctx->tiles_batch = batch;
+    return APSE_OK;
+}
+
+int apse_detect_pose_frames(apse_ctx *ctx, const uint8_t *gray, int batch, apse_detections *out, const float *marker_len,
+                            float marker_len_all, double *rvec, double *tvec, void *stream)
+{
+    if (!ctx || !gray || !out || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect_pose_frames: bad argument");
+    if (!ctx->has_camera || !ctx->has_dict) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "detect_pose_frames: set_camera and set_dictionary first");
+    const bool have_minmax = ctx->tiles_gray == gray && ctx->tiles_batch == batch;
+    ctx->tiles_gray = nullptr;                            // consumed: a later call on other data recomputes the extrema
+    int rc = apse_detect_impl(ctx, gray, ctx->w, ctx->h, batch, out, (cudaStream_t)stream, have_minmax);
     if (rc) return rc;
     if (rvec && tvec)
         rc = apse_pose_frames(ctx, out->corners, out->n_markers, batch, out->max_markers, marker_len, marker_len_all, ctx->K, ctx->D, rvec, tvec, stream);

@@ -88,7 +88,8 @@ struct apse_ctx {
     bool has_params = false;
     apse_params params;
     // APRILTAG scratch (sized for max_batch frames of max_w x max_h)
-    uint8_t *thresh = nullptr, *tmin = nullptr, *tmax = nullptr;
+    uint8_t *thresh = nullptr;
+    uint16_t *tmm = nullptr;          // 4x4-tile extrema of gray, min | max << 8, [batch][h/4][w/4]
     uint32_t *labels = nullptr;
     uint4 *points = nullptr;          // {key_lo, key_hi, xy, slot|g}
     uint32_t *point_rank = nullptr;
@@ -104,6 +105,8 @@ struct apse_ctx {
     uint32_t *quad_order = nullptr;   // cluster index of each quad (for deterministic ordering)
     // decode scratch
     void *decode_scratch = nullptr;
+    const uint8_t *tiles_gray = nullptr;   // gray batch whose tile extrema are in tmm (apse_preprocess_tiles -> apse_detect_pose_frames)
+    int tiles_batch = 0;
     uint8_t *nbr_mask = nullptr;      // [max_batch][h][w] 8-neighbour foreground masks of the classic path (first use)
     uint8_t *gray_scratch = nullptr;  // [max_batch][h][w], allocated on first use by apse_process_frames(gray = NULL)
 };
@@ -152,7 +155,7 @@ int apse_timing_flush(apse_ctx *ctx);
 static __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // internal entry points implemented per translation unit
-int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, uint8_t *tmin, uint8_t *tmax, int batch,
+int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, uint16_t *tmm, int batch,
                        cudaStream_t st);   // returns 1 when the tile extrema were not produced (generic path)
 int apse_detect_alloc(apse_ctx *ctx);
 void apse_detect_free(apse_ctx *ctx);
@@ -160,7 +163,7 @@ int apse_decode_alloc(apse_ctx *ctx);
 void apse_decode_free(apse_ctx *ctx);
 int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h);
 int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
-                        cudaStream_t st, bool have_tile_minmax = false);   // true: ctx->tmin/tmax already hold this batch's extrema
+                        cudaStream_t st, bool have_tile_minmax = false);   // true: ctx->tmm already holds this batch's tile extrema
 int apse_decode_big_scratch(apse_ctx *ctx);
 int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out, cudaStream_t st);
 int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, cudaStream_t st);

@@ -23,8 +23,7 @@
 
 // ---------------------------------------------------------------------------------------------------------
 // K2: threshold
-__global__ void k_tile_minmax(const uint8_t *__restrict__ gray, int w, int h, int tw, int th, uint8_t *__restrict__ tmin,
-                              uint8_t *__restrict__ tmax)
+__global__ void k_tile_minmax(const uint8_t *__restrict__ gray, int w, int h, int tw, int th, uint16_t *__restrict__ tmm)
 {
     int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
     if (tx >= tw || ty >= th) return;
@@ -46,13 +45,10 @@ __global__ void k_tile_minmax(const uint8_t *__restrict__ gray, int w, int h, in
                 mx = max(mx, v);
             }
     }
-    size_t o = (size_t)f * tw * th + (size_t)ty * tw + tx;
-    tmin[o] = (uint8_t)mn;
-    tmax[o] = (uint8_t)mx;
+    tmm[(size_t)f * tw * th + (size_t)ty * tw + tx] = (uint16_t)(mn | (mx << 8));
 }
 
-__device__ __forceinline__ void dilated_minmax(const uint8_t *tmin, const uint8_t *tmax, int tw, int th, int tx, int ty,
-                                               int &mn, int &mx)
+__device__ __forceinline__ void dilated_minmax(const uint16_t *tmm, int tw, int th, int tx, int ty, int &mn, int &mx)
 {
     mn = 255; mx = 0;
     for (int dy = -1; dy <= 1; dy++) {
@@ -61,8 +57,9 @@ __device__ __forceinline__ void dilated_minmax(const uint8_t *tmin, const uint8_
         for (int dx = -1; dx <= 1; dx++) {
             int xx = tx + dx;
             if (xx < 0 || xx >= tw) continue;
-            mn = min(mn, (int)__ldg(tmin + (size_t)yy * tw + xx));
-            mx = max(mx, (int)__ldg(tmax + (size_t)yy * tw + xx));
+            int v = __ldg(tmm + (size_t)yy * tw + xx);
+            mn = min(mn, v & 255);
+            mx = max(mx, v >> 8);
         }
     }
 }
@@ -71,43 +68,77 @@ __device__ __forceinline__ void dilated_minmax(const uint8_t *tmin, const uint8_
 // list, so that the component / boundary kernels only ever touch the ~1-20 % of the image that has contrast.
 #define CCL_TW 32
 #define CCL_TH 16
-__global__ void k_threshold(const uint8_t *__restrict__ gray, int w, int h, int tw, int th, const uint8_t *__restrict__ tmin,
-                            const uint8_t *__restrict__ tmax, int min_wb_diff, uint8_t *__restrict__ out,
-                            uint8_t *__restrict__ tile_active, int ctw, int cth)
+// Block = 32 x 8 tiles (one warp per tile row).  3x3 dilation of the tile extrema: every lane reduces its own column
+// of three tiles, the horizontal step comes from the neighbouring lanes (the two edge lanes load their outer column).
+__global__ void __launch_bounds__(256) k_threshold(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
+                                                   const uint16_t *__restrict__ tmm, int min_wb_diff, uint8_t *__restrict__ out,
+                                                   uint8_t *__restrict__ tile_active, int ctw, int cth)
 {
-    int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    const int tx = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    const uint16_t *T = tmm + (size_t)f * tw * th;
+    const int lane = threadIdx.x;
+    auto column = [&](int xx, int &cmn, int &cmx) {
+        cmn = 255; cmx = 0;
+        if (xx < 0 || xx >= tw || ty >= th) return;
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+            int yy = ty + dy;
+            if (yy < 0 || yy >= th) continue;
+            int v = __ldg(T + (size_t)yy * tw + xx);
+            cmn = min(cmn, v & 255);
+            cmx = max(cmx, v >> 8);
+        }
+    };
+    int cmn, cmx;
+    column(tx, cmn, cmx);
+    int lmn = __shfl_up_sync(0xffffffffu, cmn, 1), lmx = __shfl_up_sync(0xffffffffu, cmx, 1);
+    int rmn = __shfl_down_sync(0xffffffffu, cmn, 1), rmx = __shfl_down_sync(0xffffffffu, cmx, 1);
+    if (lane == 0) column(tx - 1, lmn, lmx);
+    if (lane == 31) column(tx + 1, rmn, rmx);
     if (tx >= tw || ty >= th) return;
+    const int mn = min(cmn, min(lmn, rmn)), mx = max(cmx, max(lmx, rmx));
     const uint8_t *g = gray + (size_t)f * w * h;
     uint8_t *o = out + (size_t)f * w * h;
-    int mn, mx;
-    dilated_minmax(tmin + (size_t)f * tw * th, tmax + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
     bool low = (mx - mn) < min_wb_diff;
     unsigned thr = mn + (mx - mn) / 2;
-    if (!low) tile_active[((size_t)f * cth + (ty * 4) / CCL_TH) * ctw + (tx * 4) / CCL_TW] = 1;
+    // low-contrast tiles are not written: the ternary image is kept at 127 outside the tiles the previous batch
+    // touched (k_reset_thresh), so 99 % of a sparse frame costs neither a gray read nor a store here
+    if (low) return;
+    tile_active[((size_t)f * cth + (ty * 4) / CCL_TH) * ctw + (tx * 4) / CCL_TW] = 1;
     if ((w & 3) == 0) {
 #pragma unroll
         for (int dy = 0; dy < 4; dy++) {
             size_t p = (size_t)(ty * 4 + dy) * w + tx * 4;
-            uint32_t r = 0x7f7f7f7fu;
-            if (!low) {
-                uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(g + p));
-                r = ((v & 255) > thr ? 0xffu : 0u) | (((v >> 8) & 255) > thr ? 0xff00u : 0u) |
-                    (((v >> 16) & 255) > thr ? 0xff0000u : 0u) | ((v >> 24) > thr ? 0xff000000u : 0u);
-            }
+            uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(g + p));
+            uint32_t r = ((v & 255) > thr ? 0xffu : 0u) | (((v >> 8) & 255) > thr ? 0xff00u : 0u) |
+                         (((v >> 16) & 255) > thr ? 0xff0000u : 0u) | ((v >> 24) > thr ? 0xff000000u : 0u);
             *reinterpret_cast<uint32_t *>(o + p) = r;
         }
     } else {
         for (int dy = 0; dy < 4; dy++)
             for (int dx = 0; dx < 4; dx++) {
                 size_t p = (size_t)(ty * 4 + dy) * w + tx * 4 + dx;
-                o[p] = low ? 127 : (g[p] > thr ? 255 : 0);
+                o[p] = g[p] > thr ? 255 : 0;
             }
+    }
+}
+
+// back to 127 on every CCL tile the previous batch marked active (runs at the start of the next batch)
+__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_reset_thresh(uint8_t *__restrict__ thresh, int w, int h, const uint32_t *__restrict__ list,
+                                                                 const int *__restrict__ n_active, int ctw)
+{
+    const int n = *n_active;
+    for (int it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint32_t e = list[it];
+        const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
+        const int x = txb * CCL_TW + threadIdx.x, y = tyb * CCL_TH + threadIdx.y;
+        if (x < w && y < h) thresh[(size_t)f * w * h + (size_t)y * w + x] = 127;
     }
 }
 
 // right / bottom partial tiles: nearest full tile's dilated threshold, never marked 127
 __global__ void k_threshold_edges(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
-                                  const uint8_t *__restrict__ tmin, const uint8_t *__restrict__ tmax,
+                                  const uint16_t *__restrict__ tmm,
                                   uint8_t *__restrict__ out, uint8_t *__restrict__ tile_active, int ctw, int cth)
 {
     int f = blockIdx.z;
@@ -120,7 +151,7 @@ __global__ void k_threshold_edges(const uint8_t *__restrict__ gray, int w, int h
         if (i < nright * (th * 4)) { y = i / nright; x = tw * 4 + i % nright; }
         else { int j = i - nright * (th * 4); y = th * 4 + j / w; x = j % w; }
         int ty = min(y / 4, th - 1), tx = min(x / 4, tw - 1), mn, mx;
-        dilated_minmax(tmin + (size_t)f * tw * th, tmax + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
+        dilated_minmax(tmm + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
         int thr = mn + (mx - mn) / 2;
         o[(size_t)y * w + x] = g[(size_t)y * w + x] > thr ? 255 : 0;
         tile_active[((size_t)f * cth + y / CCL_TH) * ctw + x / CCL_TW] = 1;
@@ -900,6 +931,8 @@ __global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
 // ---------------------------------------------------------------------------------------------------------
 // host side
 struct DetectExtra {
+    int prev_w = 0, prev_h = 0;      // geometry of the batch whose active tiles are still marked in thresh (0 = none)
+    bool thresh_full = true;         // thresh holds arbitrary data everywhere (first use / after the classic path)
     uint8_t *tile_active;
     uint32_t *tile_list;
     uint32_t *used_slots;
@@ -911,8 +944,7 @@ int apse_detect_alloc(apse_ctx *ctx)
     size_t B = ctx->max_batch, npx = (size_t)ctx->max_w * ctx->max_h;
     size_t ntiles = (size_t)div_up(ctx->max_w, 4) * div_up(ctx->max_h, 4);
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->thresh, B * npx));
-    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmin, B * ntiles));
-    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmax, B * ntiles));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmm, B * ntiles * sizeof(uint16_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->labels, B * npx * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->points, B * APSE_MAX_POINTS * sizeof(uint4)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->hash_keys, B * APSE_HASH_SLOTS * sizeof(unsigned long long)));
@@ -941,7 +973,7 @@ int apse_detect_alloc(apse_ctx *ctx)
 
 void apse_detect_free(apse_ctx *ctx)
 {
-    cudaFree(ctx->thresh); cudaFree(ctx->tmin); cudaFree(ctx->tmax); cudaFree(ctx->labels); cudaFree(ctx->points);
+    cudaFree(ctx->thresh); cudaFree(ctx->tmm); cudaFree(ctx->labels); cudaFree(ctx->points);
     cudaFree(ctx->hash_keys); cudaFree(ctx->hash_count); cudaFree(ctx->hash_offset); cudaFree(ctx->sorted_pts);
     cudaFree(ctx->sort_keys); cudaFree(ctx->lfps); cudaFree(ctx->errs); cudaFree(ctx->clusters); cudaFree(ctx->counters);
     cudaFree(ctx->quads); cudaFree(ctx->quad_order);
@@ -961,6 +993,15 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
     int tw = w / 4, th = h / 4;
+    // ternary image invariant: 127 everywhere except the tiles listed by the previous batch -> reset exactly those
+    if (ex->thresh_full || ex->prev_w != w || ex->prev_h != h) {
+        if (ex->thresh_full || ex->prev_w != 0)
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->thresh, 127, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h, st));
+        ex->thresh_full = false;
+    } else {
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_reset_thresh<<<148 * 4, dim3(CCL_TW, CCL_TH), 0, st>>>(ctx->thresh, w, h, ex->tile_list, ex->work_counter + 1, div_up(w, CCL_TW)));
+    }
+    ex->prev_w = w; ex->prev_h = h;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, 2 * sizeof(int), st));
     const int ctw = div_up(w, CCL_TW), cth = div_up(h, CCL_TH), nct = ctw * cth;
@@ -968,11 +1009,11 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     {
         dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
         if (!have_tile_minmax)
-            KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax));
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, dp.min_white_black_diff, ctx->thresh,
+            KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmm));
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmm, dp.min_white_black_diff, ctx->thresh,
                                                                            ex->tile_active, ctw, cth));
         if (tw * 4 != w || th * 4 != h) {
-            KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmin, ctx->tmax, ctx->thresh,
+            KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmm, ctx->thresh,
                                                                                      ex->tile_active, ctw, cth));
         }
     }
@@ -1005,6 +1046,7 @@ int apse_ccl_binary(apse_ctx *ctx, const uint8_t *bin, int w, int h, int batch, 
 {
     if ((long long)div_up(w, CCL_TW) * div_up(h, CCL_TH) >= (1 << 20)) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
+    ex->thresh_full = true;   // ctx->thresh is the binary image of this path: the APRILTAG invariant (127 background) is gone
     const int ctw = div_up(w, CCL_TW), cth = div_up(h, CCL_TH), nct = ctw * cth;
     int *n_active = ex->work_counter + 1;
     CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, 2 * sizeof(int), st));

@@ -459,3 +459,39 @@ int apse_project_points_multi(apse_ctx *ctx, const double *obj, int n, const int
     KLAUNCH(ctx, KID_PROJECT, (cudaStream_t)stream, k_project_points_multi<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(obj, n, pose_idx, rvecs, tvecs, C, img));
     return APSE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// aruco_detect.py:352-358  LED read-out: sum of the (2 half + 1)^2 gray neighbourhood `gray[y-half:y+half+1,
+// x-half:x+half+1]` of projected points, with the slicing rules of the reference's numpy expression (a negative
+// start wraps around, the stop is clamped: near the top / left edge the slice is empty and the sum is 0, near the
+// bottom / right edge it is truncated).  One warp per point; pts = (frame, x, y) triples.
+__device__ __forceinline__ void np_slice(int start, int stop, int len, int &a, int &b)
+{
+    if (start < 0) { start += len; if (start < 0) start = 0; }
+    if (stop < 0) { stop += len; if (stop < 0) stop = 0; }
+    a = min(start, len); b = min(stop, len);
+}
+
+__global__ void k_patch_sums(const uint8_t *__restrict__ gray, int w, int h, const int32_t *__restrict__ pts, int n, int half,
+                             long long *__restrict__ sums)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int f = pts[3 * i], x = pts[3 * i + 1], y = pts[3 * i + 2];
+    int x0, x1, y0, y1;
+    np_slice(x - half, x + half + 1, w, x0, x1);
+    np_slice(y - half, y + half + 1, h, y0, y1);
+    const int pw = max(x1 - x0, 0), ph = max(y1 - y0, 0);
+    const uint8_t *g = gray + (size_t)f * w * h;
+    long long s = 0;
+    for (int k = lane; k < pw * ph; k += 32) s += g[(size_t)(y0 + k / pw) * w + x0 + k % pw];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) sums[i] = s;
+}
+
+int apse_patch_sums(apse_ctx *ctx, const uint8_t *gray, int w, int h, const int32_t *pts, int n, int half, int64_t *sums, void *stream)
+{
+    if (!ctx || !gray || !pts || !sums || n <= 0 || half < 0 || w <= 0 || h <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "patch_sums: bad argument");
+    KLAUNCH(ctx, KID_PROJECT, (cudaStream_t)stream, k_patch_sums<<<div_up(n * 32, 128), 128, 0, (cudaStream_t)stream>>>(gray, w, h, pts, n, half, (long long *)sums));
+    return APSE_OK;
+}

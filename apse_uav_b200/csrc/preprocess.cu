@@ -387,7 +387,7 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tm
 template <bool WANT_BGR>
 __global__ void __launch_bounds__(P2_THREADS, 2)
 k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
-                 uint8_t *__restrict__ gray, uint8_t *__restrict__ tmin, uint8_t *__restrict__ tmax,
+                 uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm,
                  const float *__restrict__ mapx, const float *__restrict__ mapy, const P2Tables *__restrict__ tables, int w, int h,
                  int batch, int fpb)
 {
@@ -508,7 +508,7 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                 }
             }
         }
-        if (tmin) {
+        if (tmm) {
             // 4x4-tile min / max: this thread holds one column of the tile, 4 lanes hold its columns
             int mn = 255, mx = 0;
             if (valid) {
@@ -519,8 +519,7 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
             mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             if (valid && (lane & 3) == 0) {
                 size_t to = ((size_t)f * (h >> 2) + (y0 >> 2)) * tw4 + (x >> 2);
-                tmin[to] = (uint8_t)mn;
-                tmax[to] = (uint8_t)mx;
+                tmm[to] = (uint16_t)(mn | (mx << 8));
             }
         }
         if (fast) __syncthreads();   // all reads of this frame's buffer done before it is refilled (frame f + 2)
@@ -545,8 +544,8 @@ static PFN_tmapEncodeTiled get_tmap_encoder()
     return fn;
 }
 
-// fused preprocess of a batch; tmin/tmax (nullable) receive the 4x4-tile extrema of gray: [batch][h/4][w/4]
-int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, uint8_t *tmin, uint8_t *tmax, int batch,
+// fused preprocess of a batch; tmm (nullable) receives the 4x4-tile extrema of gray (min | max << 8): [batch][h/4][w/4]
+int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, uint16_t *tmm, int batch,
                        cudaStream_t st)
 {
     int w = ctx->w, h = ctx->h;
@@ -573,12 +572,13 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
         attr_set = true;
     }
     // frames per CTA: the tap set-up (map reads, box reduction, table load) is amortised over up to 20 frames
-    const int nz = div_up(batch, 20), fpb = div_up(batch, nz);
+    static const int fpb_max = getenv("APSE_K1_FPB") ? atoi(getenv("APSE_K1_FPB")) : 20;   // development knob
+    const int nz = div_up(batch, fpb_max), fpb = div_up(batch, nz);
     dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), nz);
     if (bgr_out)
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmin, tmax, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
     else
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmin, tmax, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
     return APSE_OK;
 }
 
@@ -586,7 +586,7 @@ int apse_preprocess(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t
 {
     if (!ctx || !bgr || !gray || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "preprocess: bad argument");
     if (!ctx->has_camera || !ctx->has_lut) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "preprocess: set_camera and set_lut first");
-    int rc = apse_preprocess_ex(ctx, bgr, bgr_out, gray, nullptr, nullptr, batch, (cudaStream_t)stream);
+    int rc = apse_preprocess_ex(ctx, bgr, bgr_out, gray, nullptr, batch, (cudaStream_t)stream);
     return rc < 0 ? rc : APSE_OK;
 }
 

@@ -256,6 +256,29 @@ class Engine:
                                                  out["tvec"].data_ptr(), self._stream()))
         return out
 
+    def preprocess_tiles(self, bgr, gray, stream=None):
+        """first half of process_frames on `stream` (torch stream or None = current): K1t -> gray + tile extrema"""
+        B = bgr.shape[0]
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
+        self._check(self.lib.apse_preprocess_tiles(self.h, bgr.data_ptr(), gray.data_ptr(), B, st))
+
+    def detect_pose_frames(self, gray, out, marker_length, stream=None):
+        """second half of process_frames on `stream`: candidates -> decode -> pose on the gray batch of preprocess_tiles"""
+        torch = self.torch
+        B = gray.shape[0]
+        want_rejected = "rejected" in out
+        d = Detections(out["corners"].shape[1], out["corners"].data_ptr(), out["ids"].data_ptr(), out["n"].data_ptr(),
+                       out["rejected"].data_ptr() if want_rejected else None,
+                       out["n_rejected"].data_ptr() if want_rejected else None, out["status"].data_ptr())
+        ml = None
+        if isinstance(marker_length, torch.Tensor) or np.ndim(marker_length) > 0:
+            ml = torch.as_tensor(marker_length, dtype=torch.float32, device=self.tdev).contiguous()
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
+        self._check(self.lib.apse_detect_pose_frames(self.h, gray.data_ptr(), B, C.byref(d), ml.data_ptr() if ml is not None else None,
+                                                     float(marker_length) if ml is None else 0.0, out["rvec"].data_ptr(),
+                                                     out["tvec"].data_ptr(), st))
+        return out
+
     def debug_apriltag(self, gray, max_quads=512):
         torch = self.torch
         gray = self._u8(gray, "debug_apriltag")
@@ -269,6 +292,20 @@ class Engine:
         nq = min(int(stats[3]), max_quads)
         return dict(thresh=thresh, labels=labels, quads=quads[:nq], points=int(stats[0]), clusters=int(stats[1]),
                     fitted=int(stats[2]), n_quads=int(stats[3]))
+
+    def patch_sums(self, gray, pts, half=2):
+        """Sums of gray[f][y-half:y+half+1, x-half:x+half+1] (numpy slicing rules) for pts = [(f, x, y), ...] -> int64 numpy."""
+        torch = self.torch
+        gray = self._u8(gray, "patch_sums")
+        if gray.dim() == 2:
+            gray = gray[None]
+        _, H, W = gray.shape
+        p = torch.as_tensor(np.asarray(pts, np.int32).reshape(-1, 3), device=self.tdev).contiguous()
+        n = p.shape[0]
+        out = torch.zeros(n, dtype=torch.int64, device=self.tdev)
+        if n:
+            self._check(self.lib.apse_patch_sums(self.h, gray.data_ptr(), W, H, p.data_ptr(), n, int(half), out.data_ptr(), self._stream()))
+        return out.cpu().numpy()
 
     def adaptive_threshold(self, gray, win, c):
         """cv2.adaptiveThreshold(gray, 255, ADAPTIVE_THRESH_MEAN_C, THRESH_BINARY_INV, win, c) on [H,W] or [B,H,W]."""

@@ -14,12 +14,14 @@ from ._lib import ApseError
 
 
 class Pipeline:
-    """`streams` > 1 splits every batch over that many CUDA streams, each with its own context (scratch), so that the
-    latency-bound tail of one sub-batch (cluster scan, quad fit, decode, pose) overlaps the bandwidth/issue-bound
-    preprocess of the next one."""
+    """`streams` > 1 splits every batch into that many sub-batches, each with its own context (scratch), and runs the
+    two halves of the pipeline on different CUDA streams: the fused preprocess kernel (issue / bandwidth bound, fills the
+    whole GPU) of all sub-batches goes to ONE normal-priority stream, the candidate / decode / pose chain (many short,
+    latency-bound kernels) of sub-batch s to high-priority stream s.  The chain of sub-batch k therefore runs under the
+    preprocess of sub-batch k+1 (also across consecutive run_batch calls when `sync=False`)."""
 
     def __init__(self, camera_matrix, dist_coeffs, size, lut, dictionary, params, max_batch=16, device=0,
-                 max_markers=64, marker_length=0.55, streams=1):
+                 max_markers=64, marker_length=0.55, streams=1, ring=4):
         w, h = int(size[0]), int(size[1])
         streams = max(1, min(int(streams), max_batch))
         self.sub_batch = (max_batch + streams - 1) // streams
@@ -34,7 +36,14 @@ class Pipeline:
             self.engines.append(e)
         self.engine = self.engines[0]
         torch = self.engine.torch
-        self.streams = [torch.cuda.Stream(device=self.engine.tdev) for _ in range(streams)] if streams > 1 else []
+        dev = self.engine.tdev
+        self.streams, self.pre_stream, self._gray, self._done = [], None, [], []
+        self._ring, self._ring_size, self._ring_pos = {}, max(2, int(ring)), 0   # result buffers of run_batch(sync=False)
+        if streams > 1:
+            self.pre_stream = torch.cuda.Stream(device=dev, priority=0)
+            self.streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(streams)]
+            self._gray = [torch.empty((self.sub_batch, h, w), dtype=torch.uint8, device=dev) for _ in range(streams)]
+            self._done = [None] * streams          # completion event of the last chain that used engine s
         self.max_batch, self.max_markers, self.marker_length = max_batch, max_markers, float(marker_length)
         self.size = (w, h)
 
@@ -53,34 +62,90 @@ class Pipeline:
         e.process_frames(frames, out, marker_length, gray=gray)   # one library call: K1t -> candidates -> decode -> pose
         return gray
 
-    def run_batch(self, frames, want_gray=False, want_rejected=False, marker_length=None):
-        """frames: [B,H,W,3] uint8 CUDA tensor, B <= max_batch.  Returns dict of device tensors."""
+    def run_batch(self, frames, want_gray=False, want_rejected=False, marker_length=None, serial=False, sync=True,
+                  input_ready=False):
+        """frames: [B,H,W,3] uint8 CUDA tensor, B <= max_batch.  Returns dict of device tensors.
+        serial=True      runs the sub-batches one after the other on the current stream (clean per-kernel timing).
+        sync=False       does not make the current stream wait for the result: call Pipeline.wait(det) (or to_host)
+                         before touching it; lets consecutive batches overlap (multi-stream mode only).  The result
+                         tensors come from a ring of `ring` preallocated sets (no allocation, no fill kernel on the hot
+                         path): a result stays valid until `ring` further run_batch(sync=False) calls.
+        input_ready=True the frames are already complete in device memory (no ordering against the current stream)."""
         e = self.engine
         torch = e.torch
         B = frames.shape[0]
         if B > self.max_batch:
             raise ApseError(-1, f"batch {B} exceeds max_batch {self.max_batch}")
         ml = self.marker_length if marker_length is None else marker_length
-        det = e.alloc_detections(B, self.max_markers, want_rejected, pose=True)
+        overlap = bool(self.streams) and B > 1 and not serial and not sync and not want_gray
+        if overlap:
+            key = (B, bool(want_rejected))
+            if key not in self._ring:
+                self._ring[key] = [e.alloc_detections(B, self.max_markers, want_rejected, pose=True) for _ in range(self._ring_size)]
+                torch.cuda.current_stream(e.tdev).synchronize()
+            det = dict(self._ring[key][self._ring_pos % self._ring_size])
+            self._ring_pos += 1
+        else:
+            det = e.alloc_detections(B, self.max_markers, want_rejected, pose=True)
         if not self.streams or B <= 1:
             gray = self._run_on(e, frames, det, want_gray, ml)
+        elif serial:
+            grays = []
+            for s, eng in enumerate(self.engines):
+                lo, hi = s * self.sub_batch, min(B, (s + 1) * self.sub_batch)
+                if lo >= hi:
+                    break
+                sl = {k: v[lo:hi] for k, v in det.items()}
+                mls = ml[lo:hi] if isinstance(ml, torch.Tensor) else ml
+                grays.append(self._run_on(eng, frames[lo:hi], sl, want_gray, mls))
+            gray = torch.cat(grays, 0) if want_gray else None
         else:
             cur = torch.cuda.current_stream(e.tdev)
-            ready = cur.record_event()
-            grays = []
+            pre = self.pre_stream
+            alloc = None
+            if not overlap:
+                alloc = cur.record_event()          # output tensors are zero-filled on the current stream
+            if not input_ready:
+                pre.wait_event(alloc if alloc is not None else cur.record_event())
+            done, grays = [], []
             for s, (eng, st) in enumerate(zip(self.engines, self.streams)):
                 lo, hi = s * self.sub_batch, min(B, (s + 1) * self.sub_batch)
                 if lo >= hi:
                     break
-                st.wait_event(ready)
-                with torch.cuda.stream(st):
-                    sl = {k: v[lo:hi] for k, v in det.items()}
-                    mls = ml[lo:hi] if isinstance(ml, torch.Tensor) else ml
-                    grays.append(self._run_on(eng, frames[lo:hi], sl, want_gray, mls))
-                cur.wait_stream(st)
+                g = torch.empty((hi - lo,) + frames.shape[1:3], dtype=torch.uint8, device=e.tdev) if want_gray else self._gray[s][:hi - lo]
+                if self._done[s] is not None:
+                    pre.wait_event(self._done[s])   # engine s (scratch, tile extrema, gray buffer) is free again
+                eng.preprocess_tiles(frames[lo:hi], g, stream=pre)
+                ev = pre.record_event()
+                st.wait_event(ev)
+                if alloc is not None:
+                    st.wait_event(alloc)
+                sl = {k: v[lo:hi] for k, v in det.items()}
+                mls = ml[lo:hi] if isinstance(ml, torch.Tensor) else ml
+                with torch.cuda.stream(st):   # (a per-frame marker-length tensor is staged on the chain's stream)
+                    eng.detect_pose_frames(g, sl, mls, stream=st)
+                self._done[s] = st.record_event()
+                done.append(self._done[s])
+                grays.append(g)
             gray = torch.cat(grays, 0) if want_gray else None
+            if overlap:
+                det["_done"] = done
+            else:
+                for ev in done:
+                    cur.wait_event(ev)
         if want_gray:
             det["gray"] = gray
+        return det
+
+    @staticmethod
+    def wait(det):
+        """Make the current stream wait for a result returned by run_batch(sync=False)."""
+        import torch
+        evs = det.pop("_done", None)
+        if evs:
+            cur = torch.cuda.current_stream(det["n"].device)
+            for ev in evs:
+                cur.wait_event(ev)
         return det
 
     def run(self, frames, **kw):
@@ -89,11 +154,52 @@ class Pipeline:
         outs = [self.run_batch(frames[i:i + self.max_batch], **kw) for i in range(0, frames.shape[0], self.max_batch)]
         if len(outs) == 1:
             return outs[0]
+        if "_done" in outs[0]:
+            for o in outs:
+                self.wait(o)
         return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+
+    def run_host_stream(self, host_batches, **kw):
+        """End-to-end path for frames that live in (pinned) host memory: yields one host result dict per batch.
+        Two device staging buffers and a copy stream: the H2D copy of batch k+1 runs while batch k is processed and
+        its detections are read back, so a sequence is bounded by the slower of PCIe and the kernels, not their sum."""
+        torch = self.engine.torch
+        dev = self.engine.tdev
+        main = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            w, h = self.size
+            self._stage = [torch.empty((self.max_batch, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+        cs, stage = self._copy_stream, self._stage
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        it = iter(host_batches)
+        cur = next(it, None)
+        if cur is None:
+            return
+        cs.wait_stream(main)
+        with torch.cuda.stream(cs):
+            stage[0][:len(cur)].copy_(cur, non_blocking=True)
+            ready[0].record(cs)
+        k = 0
+        while cur is not None:
+            nxt = next(it, None)
+            if nxt is not None:
+                if k >= 1:
+                    cs.wait_event(done[(k + 1) % 2])   # the other buffer was the input of batch k-1
+                with torch.cuda.stream(cs):
+                    stage[(k + 1) % 2][:len(nxt)].copy_(nxt, non_blocking=True)
+                    ready[(k + 1) % 2].record(cs)
+            main.wait_event(ready[k % 2])
+            det = self.run_batch(stage[k % 2][:len(cur)], **kw)
+            done[k % 2].record(main)
+            yield self.to_host(det)
+            cur, k = nxt, k + 1
 
     @staticmethod
     def to_host(det):
         """Gather the small per-frame results to the host as numpy arrays (the only D2H traffic of the pipeline)."""
+        Pipeline.wait(det)
         out = {k: v.cpu().numpy() for k, v in det.items() if k != "gray"}
         bad = np.nonzero(out["status"])[0]
         if len(bad):

@@ -87,10 +87,11 @@ def to_pixels(img_pts):
 
 
 class SequencePostPass:
-    def __init__(self, project, start_frame=1, step_frame=1, led_mean=None, leds_threshold=None):
+    def __init__(self, project, start_frame=1, step_frame=1, led_mean=None, leds_threshold=None, led_sums=None):
         """project(obj (n,3), rvec (3,), tvec (3,)) -> (n,2) float64 image points (cv2.projectPoints with K, D).
-        led_mean(x, y) -> mean of the 5x5 gray neighbourhood of the current frame (:356-358), or None to skip LEDs."""
-        self.project, self.led_mean, self.leds_threshold = project, led_mean, leds_threshold
+        led_mean(x, y) -> mean of the 5x5 gray neighbourhood of the current frame (:356-358), or
+        led_sums(xy (8,2) int) -> the 8 neighbourhood SUMS in one call (the GPU read-out); both None skips LEDs."""
+        self.project, self.led_mean, self.leds_threshold, self.led_sums = project, led_mean, leds_threshold, led_sums
         self.start_frame = start_frame
         self.diff_max = 2 / 3 * step_frame * 2           # :524
         self.marker_length = MARKER_LENGTH_ORG           # :521
@@ -110,13 +111,17 @@ class SequencePostPass:
 
     def _leds(self, tvec, rvec, size_corr):
         """:338-373 (read-out only)"""
-        if self.led_mean is None:
+        if self.led_mean is None and self.led_sums is None:
             return self.leds
         px = to_pixels(self.project(LED_AXIS, rvec, tvec / size_corr))
         thr = max(190 + int(tvec[2] / MARKER_DIV), 240) if self.leds_threshold is None else self.leds_threshold
+        if self.led_sums is not None:
+            vals = np.asarray(self.led_sums(px[:8]), np.float64) / 25          # np.sum(np.sum(point)) / 25 (:358)
+        else:
+            vals = [self.led_mean(int(px[j][0]), int(px[j][1])) for j in range(8)]
         leds = 0
         for j in range(8):
-            if self.led_mean(int(px[j][0]), int(px[j][1])) > thr:
+            if vals[j] > thr:
                 leds += 2 ** (7 - j)
         return leds
 

@@ -69,19 +69,25 @@ def exact_pose(records, lengths, pose_fn):
     return out
 
 
-def final_scan(records, project, start_frame=1, led_mean_for_frame=None):
+def final_scan(records, project, start_frame=1, led_mean_for_frame=None, led_sums_for_frame=None):
     pp = SequencePostPass(project, start_frame=start_frame)
     rows = []
     for r in records:
         if led_mean_for_frame is not None:
             pp.led_mean = led_mean_for_frame(r["frame"])
+        if led_sums_for_frame is not None:
+            pp.led_sums = led_sums_for_frame(r["frame"])
         rows.append(pp.step(start_frame + r["frame"], r["ids"] if len(r["ids"]) else None, r["corners"], r["rvec"], r["tvec"]))
     return rows
 
 
-def run_sequence(pipe, frames, rank=0, world=1, group=None, start_frame=1):
+def run_sequence(pipe, frames, rank=0, world=1, group=None, start_frame=1, leds=False):
     """frames: this rank's block of the sequence ([n_local,H,W,3] uint8 CUDA tensor); lo = first global index of the
-    block is derived from shard_bounds over the total length exchanged below.  Returns CSV rows on rank 0."""
+    block is derived from shard_bounds over the total length exchanged below.  Returns CSV rows on rank 0.
+    leds=True (single process): the corrected gray frames stay on the device and the LED strip of the host vehicle
+    (aruco_detect.py:338-373) is read back by the GPU patch-sum kernel in the final scan."""
+    if leds and world > 1:
+        raise ValueError("LED read-out needs the gray frames of every rank on rank 0: run it per rank (world = 1)")
     n_local = int(frames.shape[0])
     if world > 1:
         import torch.distributed as dist
@@ -90,7 +96,9 @@ def run_sequence(pipe, frames, rank=0, world=1, group=None, start_frame=1):
         lo = sum(sizes[:rank])
     else:
         lo = 0
-    host = pipe.to_host(pipe.run(frames)) if n_local else dict(n=np.zeros(0, np.int32))
+    det = pipe.run(frames, want_gray=leds) if n_local else None
+    gray = det.pop("gray") if (leds and det is not None) else None
+    host = pipe.to_host(det) if n_local else dict(n=np.zeros(0, np.int32))
     records = gather_records(pack_results(host, lo) if n_local else [], rank, world, group)
     if rank != 0:
         return None
@@ -103,7 +111,10 @@ def run_sequence(pipe, frames, rank=0, world=1, group=None, start_frame=1):
 
     lengths = scan_marker_lengths(records, project, start_frame)
     records = exact_pose(records, lengths, pose_fn)
-    return final_scan(records, project, start_frame)
+    led_fn = None
+    if gray is not None:
+        led_fn = lambda frame: (lambda xy: e.patch_sums(gray, [(frame, int(x), int(y)) for x, y in xy], half=2))
+    return final_scan(records, project, start_frame, led_sums_for_frame=led_fn)
 
 
 def rows_to_csv(rows):

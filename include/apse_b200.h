@@ -138,6 +138,14 @@ int apse_pose_frames(apse_ctx *ctx, const float *corners, const int32_t *n_marke
 int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, apse_detections *out,
                         const float *marker_len, float marker_len_all, double *rvec, double *tvec, void *stream);
 
+/* The two halves of apse_process_frames as separate calls, so that a caller can put them on different streams
+ * (bandwidth / issue-bound preprocess of batch k+1 on a low-priority stream under the latency-bound candidate /
+ * decode / pose chain of batch k): apse_preprocess_tiles = aruco_detect.py:250-259,592 (+ tile extrema kept in the
+ * context); apse_detect_pose_frames = :267 + :601 on that gray batch (the caller orders the two with an event). */
+int apse_preprocess_tiles(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream);
+int apse_detect_pose_frames(apse_ctx *ctx, const uint8_t *gray, int batch, apse_detections *out, const float *marker_len,
+                            float marker_len_all, double *rvec, double *tvec, void *stream);
+
 /* aruco_detect.py:344,377,424,468  cv2.projectPoints(obj, rvec, tvec, K, D)
  * obj: [n][3] float64, rvec/tvec: [3] float64, img: [n][2] float64 -- all device pointers */
 int apse_project_points(apse_ctx *ctx, const double *obj, int n, const double *rvec, const double *tvec,
@@ -153,6 +161,12 @@ int apse_project_points_multi(apse_ctx *ctx, const double *obj, int n, const int
  * quads [max_quads][8] float32 raw quads (cluster-key order), stats[4] int64 {points, clusters, fitted, quads} */
 int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_t *thresh, uint32_t *labels,
                         float *quads, int max_quads, int64_t *stats_host, void *stream);
+
+/* aruco_detect.py:352-358 (detectAndDrawLEDs): sums of the (2 half + 1)^2 gray neighbourhoods gray[y-half:y+half+1,
+ * x-half:x+half+1] (numpy slicing rules at the image edges) of n points; pts: [n][3] int32 (frame, x, y), sums: [n]
+ * int64 -- device pointers; gray: [frames][h][w] */
+int apse_patch_sums(apse_ctx *ctx, const uint8_t *gray, int w, int h, const int32_t *pts, int n, int half, int64_t *sums,
+                    void *stream);
 
 /* cv2.adaptiveThreshold(gray, 255, ADAPTIVE_THRESH_MEAN_C, THRESH_BINARY_INV, win, c) for a batch [batch][h][w]: the
  * threshold step of the classic candidate path inside aruco.detectMarkers (aruco_detect.py:267 with

@@ -89,10 +89,61 @@ def test_multi_stream_equals_single_stream(pipe, camera, lut, dictionary, ref_pa
     import torch
     import apse_uav_b200 as A
     K, D = camera
-    p3 = A.Pipeline(K, D, (3840, 2160), lut, dictionary, ref_params, max_batch=5, max_markers=256, streams=3)
+    p3 = A.Pipeline(K, D, (3840, 2160), lut, dictionary, ref_params, max_batch=5, max_markers=256, streams=3, ring=6)
     frames = torch.from_numpy(np.stack([frames4k["sparse"], frames4k["dense"], frames4k["sparse"], frames4k["dense"], frames4k["sparse"]])).cuda()
     a = A.Pipeline.to_host(p3.run_batch(frames, want_rejected=True))
     b = A.Pipeline.to_host(pipe.run_batch(frames, want_rejected=True))
     for k in ("n", "ids", "corners", "n_rejected", "rejected", "rvec", "tvec"):
         assert np.array_equal(a[k], b[k]), k
+    # overlapped mode: results are waited for later; consecutive batches share contexts and staging buffers
+    frames2 = torch.roll(frames, shifts=(5, 3), dims=(1, 2))
+    pending = [p3.run_batch(f, want_rejected=True, sync=False, input_ready=True) for f in (frames, frames2, frames, frames2, frames)]
+    outs = [A.Pipeline.to_host(d) for d in pending]
+    b2 = A.Pipeline.to_host(pipe.run_batch(frames2, want_rejected=True))
+    for o, ref in zip(outs, (b, b2, b, b2, b)):
+        for k in ("n", "ids", "corners", "n_rejected", "rejected", "rvec", "tvec"):
+            assert np.array_equal(o[k], ref[k]), k
     p3.close()
+
+
+def test_host_stream_equals_device_batches(pipe, frames4k):
+    """end-to-end host path (double-buffered H2D overlapped with compute) returns what run_batch returns"""
+    import torch
+    f = torch.from_numpy(np.stack([frames4k["sparse"], frames4k["dense"], frames4k["sparse"]]))
+    host = [f[:2].clone().pin_memory(), f[1:].clone().pin_memory(), f[:1].clone().pin_memory()]
+    outs = list(pipe.run_host_stream(host))
+    assert len(outs) == 3
+    for hb, o in zip(host, outs):
+        ref = pipe.to_host(pipe.run_batch(hb.cuda()))
+        for k in ("n", "ids", "corners", "rvec", "tvec"):
+            assert np.array_equal(o[k], ref[k]), k
+
+
+def test_patch_sums_numpy_slicing(pipe):
+    """LED read-out kernel = np.sum(gray[y-2:y+3, x-2:x+3]) including numpy's negative-start / clamped-stop slicing"""
+    import torch
+    rng = np.random.default_rng(9)
+    gray = rng.integers(0, 256, (2, 37, 53), dtype=np.uint8)
+    pts = [(f, x, y) for f in (0, 1) for x in (0, 1, 2, 3, 25, 49, 50, 51, 52, 53, 60) for y in (0, 1, 2, 17, 33, 34, 35, 36, 37, 40)]
+    got = pipe.engine.patch_sums(torch.from_numpy(gray).cuda(), pts, half=2)
+    ref = [int(np.sum(gray[f][y - 2:y + 3, x - 2:x + 3])) for f, x, y in pts]
+    assert got.tolist() == ref
+
+
+def test_sequence_with_leds_matches_reference_script(pipe, dictionary):
+    """frames with a rendered LED strip -> leds_ID column of the reference script's CSV"""
+    import json, os, torch
+    pytest.importorskip("cv2")
+    from conftest import GOLDEN
+    from tools import synth
+    from apse_uav_b200 import shard
+    from apse_uav_b200.postpass import CSV_FIELDS
+    g = json.load(open(os.path.join(GOLDEN, "sequence_4k_leds.json")))
+    ref = np.array([[float(v) for v in line.split(",")] for line in g["csv"][1:]])
+    frames = torch.from_numpy(np.stack(list(synth.make_sequence(dictionary.bytesList, g["base_seed"], g["n_frames"], leds=g["leds"])))).cuda()
+    rows = shard.run_sequence(pipe, frames, leds=True)
+    got = np.array([[float(r[f]) for f in CSV_FIELDS] for r in rows])
+    assert np.array_equal(got[:, [0, 1, 3, 7, 10, 13]], ref[:, [0, 1, 3, 7, 10, 13]])
+    assert got[:, 3].astype(int).tolist() == g["leds"]
+    num = [2, 4, 5, 6, 8, 9, 11, 12, 14, 15]
+    assert np.all(np.abs(got[:, num] - ref[:, num]) <= 1e-4 * np.abs(ref[:, num]) + 0.0101)

@@ -7,8 +7,8 @@ import pytest
 from conftest import GOLDEN, needs_cv2
 
 
-def _golden_rows():
-    g = json.load(open(os.path.join(GOLDEN, "sequence_4k.json")))
+def _golden_rows(name="sequence_4k.json"):
+    g = json.load(open(os.path.join(GOLDEN, name)))
     rows = [[float(v) for v in line.split(",")] for line in g["csv"][1:]]
     return g, np.array(rows)
 
@@ -83,3 +83,33 @@ def test_gating_marks_new_marker_as_false_positive_for_one_frame(oracle, camera)
     c4 = np.stack([sq(1002, 1000), sq(1900, 1100), sq(2201, 900)])          # marker 1 jumped 300 px: gated out
     r4 = pp.step(4, np.array([4, 1, 2]), c4, *pose(c4))
     assert r4["ID_1_detected"] == 0 and r4["ID_2_detected"] == 1 and r4["distance_veh2_aruco"] > 0
+
+
+def test_led_readout_matches_reference_csv(oracle, camera, lut, dictionary, ref_params):
+    """aruco_detect.py:338-373: the LED strip of the host vehicle, read back from the corrected gray frame
+    with the numpy expression of the reference; golden = the reference script's rows for a sequence with rendered LEDs."""
+    pytest.importorskip("cv2")
+    from tools import synth
+    from apse_uav_b200 import shard
+    from apse_uav_b200.postpass import CSV_FIELDS
+    g, ref = _golden_rows("sequence_4k_leds.json")
+    assert sorted(set(ref[:, 3].astype(int))) == [0, 77, 102, 129, 178, 255]      # the patterns that were drawn
+    K, D = camera
+    ox, oy = oracle.init_undistort_map(K, D, 3840, 2160)
+    recs, grays = [], []
+    for k, f in enumerate(synth.make_sequence(dictionary.bytesList, g["base_seed"], g["n_frames"], leds=g["leds"])):
+        _, gray = oracle.preprocess(f, ox, oy, lut)
+        c, ids, _ = oracle.detect_markers_apriltag(gray, dictionary.raw, ref_params)
+        rv, tv = oracle.estimate_pose_single_markers(c, 0.55, K, D)
+        recs.append(dict(frame=k, ids=ids, corners=c, rvec=rv[:, 0], tvec=tv[:, 0]))
+        grays.append(gray)
+    project = lambda obj, r, t: oracle.project_points(obj, r, t, K, D)
+    lengths = shard.scan_marker_lengths(recs, project)
+    recs = shard.exact_pose(recs, lengths, lambda c, ml: tuple(np.concatenate(x) for x in zip(*[
+        (lambda rv, tv: (rv[:, 0], tv[:, 0]))(*oracle.estimate_pose_single_markers(c[i:i + 1], float(ml[i]), K, D)) for i in range(len(c))])))
+    led_mean = lambda frame: (lambda x, y: np.sum(np.sum(grays[frame][y - 2:y + 3, x - 2:x + 3])) / 25)
+    rows = shard.final_scan(recs, project, led_mean_for_frame=led_mean)
+    got = np.array([[float(r[f]) for f in CSV_FIELDS] for r in rows])
+    assert np.array_equal(got[:, [0, 1, 3, 7, 10, 13]], ref[:, [0, 1, 3, 7, 10, 13]])        # incl. leds_ID
+    num = [2, 4, 5, 6, 8, 9, 11, 12, 14, 15]
+    assert np.all(np.abs(got[:, num] - ref[:, num]) <= 1e-4 * np.abs(ref[:, num]) + 0.0101)

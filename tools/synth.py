@@ -80,6 +80,21 @@ def _paste_marker(frame: np.ndarray, tile: np.ndarray, quad: np.ndarray, quiet_f
     frame[y0:y1, x0:x1] = np.clip(np.rint(roi), 0, 255).astype(np.uint8)
 
 
+# LED strip of the host vehicle, metres in the marker frame (x right, y up; aruco_detect.py:340-341), marker side 0.55 m
+LED_AXIS = np.float32([[-0.419, -0.42], [-0.414, -0.305], [-0.409, -0.19], [-0.404, -0.07], [-0.399, 0.065], [-0.393, 0.19],
+                       [-0.388, 0.315], [-0.382, 0.435]])
+
+
+def _draw_leds(frame: np.ndarray, quad: np.ndarray, pattern: int, marker_length: float = 0.55, radius: int = 7) -> None:
+    """Bright disc for every set bit of `pattern` (bit 7 = first LED) at the LED's place in the marker plane."""
+    unit = np.float32([[-0.5, 0.5], [0.5, 0.5], [0.5, -0.5], [-0.5, -0.5]]) * marker_length   # corner order of solvePnP
+    H = cv2.getPerspectiveTransform(unit, quad.astype(np.float32))
+    px = cv2.perspectiveTransform(LED_AXIS.reshape(1, -1, 2), H)[0]
+    for j in range(8):
+        on = (pattern >> (7 - j)) & 1
+        cv2.circle(frame, (int(round(px[j][0])), int(round(px[j][1]))), radius, (255, 255, 255) if on else (25, 25, 25), -1)
+
+
 def _random_quad(rng, cx, cy, side, jitter):
     ang = rng.uniform(0, 2 * np.pi)
     c, s = np.cos(ang), np.sin(ang)
@@ -92,7 +107,7 @@ def _random_quad(rng, cx, cy, side, jitter):
 def make_frame(bytes_list, seed: int, width: int = 3840, height: int = 2160, ids=(1, 2, 3, 4),
                side_range=(50, 90), jitter: float = 0.06, noise_sigma: float = 3.0,
                occlude_frac: float = 0.0, centers=None, angles=None, margin: int = 90,
-               return_truth: bool = False):
+               return_truth: bool = False, leds=None):
     """One synthetic BGR frame (uint8 HxWx3).  `centers` (list of (x,y)) pins marker positions (sequence
     drift); otherwise positions are rejection-sampled without overlap."""
     rng = np.random.default_rng(seed)
@@ -119,6 +134,8 @@ def make_frame(bytes_list, seed: int, width: int = 3840, height: int = 2160, ids
                 rng.uniform(-jitter * side, jitter * side, size=(4, 2)).astype(np.float32)
         tile = render_marker(bytes_list, int(mid))
         _paste_marker(frame, tile, quad, quiet_frac=8.0 / tile.shape[0])
+        if leds is not None and int(mid) == 4:
+            _draw_leds(frame, quad, leds)
         if occlude_frac > 0 and rng.uniform() < occlude_frac:
             ow, oh = rng.uniform(0.15, 0.45, size=2) * side
             ox = cx + rng.uniform(-0.5, 0.5) * side
@@ -141,7 +158,7 @@ def make_dense_frame(bytes_list, seed: int, width: int = 3840, height: int = 216
 
 
 def make_sequence(bytes_list, base_seed: int, n_frames: int, width: int = 3840, height: int = 2160,
-                  noise_sigma: float = 3.0):
+                  noise_sigma: float = 3.0, leds=None):
     """Sparse sequence (ids 1,2,3 = vehicles, 4 = host) with slow drift so that the track gating of
     aruco_detect.py:613 passes.  Frame k uses seed base_seed + k.  Yields frames."""
     rng = np.random.default_rng(base_seed)
@@ -152,4 +169,5 @@ def make_sequence(bytes_list, base_seed: int, n_frames: int, width: int = 3840, 
     for k in range(n_frames):
         centers = start + vel * k
         yield make_frame(bytes_list, base_seed + k, width, height, ids=(1, 2, 3, 4), side_range=(64, 66),
-                         jitter=0.01, noise_sigma=noise_sigma, centers=centers.tolist(), angles=ang.tolist())
+                         jitter=0.01, noise_sigma=noise_sigma, centers=centers.tolist(), angles=ang.tolist(),
+                         leds=None if leds is None else leds[k % len(leds)])
