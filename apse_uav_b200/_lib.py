@@ -82,6 +82,7 @@ SIGNATURES = {
     "apse_kernel_name": [_i],
     "apse_timing_enable": [_vp, _i],
     "apse_timing_collect": [_vp, _dp, C.POINTER(C.c_int64), _i],
+    "apse_timing_trace": [_vp, _dp, _i],
 }
 _RESTYPES = {"apse_destroy": None, "apse_params_default": None, "apse_last_error": C.c_char_p,
              "apse_launch_count": C.c_int64, "apse_kernel_name": C.c_char_p}

@@ -74,6 +74,7 @@ void apse_destroy(apse_ctx *ctx)
     apse_detect_free(ctx);
     apse_decode_free(ctx);
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
+    delete[] ctx->trace;
     cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask);
     delete ctx;
 }
@@ -183,6 +184,9 @@ int apse_set_params(apse_ctx *ctx, const apse_params *p)
 }  // extern "C"
 
 // waits for the recorded events and accumulates their durations per kernel id
+// process-wide time origin of the launch trace (recorded once on the legacy stream)
+static cudaEvent_t g_trace_base = nullptr;
+
 int apse_timing_flush(apse_ctx *ctx)
 {
     for (int i = 0; i < ctx->ev_used; i++) {
@@ -191,9 +195,40 @@ int apse_timing_flush(apse_ctx *ctx)
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_start[i], ctx->ev_stop[i]));
         ctx->kernel_ms[ctx->ev_kid[i]] += ms;
         ctx->kernel_launches[ctx->ev_kid[i]]++;
+        if (ctx->trace && ctx->trace_used < ctx->trace_cap && g_trace_base) {
+            float t0 = 0;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&t0, g_trace_base, ctx->ev_start[i]));
+            double *r = ctx->trace + 3 * (size_t)ctx->trace_used++;
+            r[0] = ctx->ev_kid[i]; r[1] = t0; r[2] = t0 + ms;
+        }
     }
     ctx->ev_used = 0;
     return APSE_OK;
+}
+
+// development aid: keep (kernel id, start ms, end ms) of every timed launch, relative to a process-wide origin, so that
+// the overlap of the streams of several contexts can be drawn as one timeline (tools/timeline.py)
+int apse_timing_trace(apse_ctx *ctx, double *out, int cap_rows)
+{
+    if (!ctx) return APSE_ERR_INVALID_ARG;
+    if (!out) {   // (re)arm with a capacity of cap_rows launches
+        delete[] ctx->trace;
+        ctx->trace = cap_rows > 0 ? new double[3 * (size_t)cap_rows] : nullptr;
+        ctx->trace_cap = cap_rows > 0 ? cap_rows : 0;
+        ctx->trace_used = 0;
+        if (!g_trace_base) {
+            CUDA_TRY(ctx, cudaEventCreate(&g_trace_base));
+            CUDA_TRY(ctx, cudaEventRecord(g_trace_base, 0));
+            CUDA_TRY(ctx, cudaEventSynchronize(g_trace_base));
+        }
+        return APSE_OK;
+    }
+    int rc = apse_timing_flush(ctx);
+    if (rc) return rc;
+    int n = ctx->trace_used < cap_rows ? ctx->trace_used : cap_rows;
+    memcpy(out, ctx->trace, sizeof(double) * 3 * (size_t)n);
+    ctx->trace_used = 0;
+    return n;
 }
 
 int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h)

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <float.h>
+#include <stdlib.h>
 
 #define FQ_THREADS 128
 #define MAXIMA_CAP 16  // aprilTagMaxNmaxima supported up to this value
@@ -68,71 +69,126 @@ __device__ __forceinline__ void dilated_minmax(const uint16_t *tmm, int tw, int 
 // list, so that the component / boundary kernels only ever touch the ~1-20 % of the image that has contrast.
 #define CCL_TW 32
 #define CCL_TH 16
-// Block = 32 x 8 tiles (one warp per tile row).  3x3 dilation of the tile extrema: every lane reduces its own column
-// of three tiles, the horizontal step comes from the neighbouring lanes (the two edge lanes load their outer column).
-__global__ void __launch_bounds__(256) k_threshold(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
-                                                   const uint16_t *__restrict__ tmm, int min_wb_diff, uint8_t *__restrict__ out,
+// Extrema of the 64x32-px blocks (16x8 tiles) from the tile extrema -- only when the fused preprocess kernel, which
+// writes them itself, did not run.  One warp per block, 4 tiles per lane.
+#define BLK_TX 16
+#define BLK_TY 8
+__global__ void __launch_bounds__(128) k_block_minmax(const uint16_t *__restrict__ tmm, int tw, int th, int bw, int bh,
+                                                      uint16_t *__restrict__ bmm)
+{
+    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, f = blockIdx.z;
+    if (wi >= bw * bh) return;
+    const int by = wi / bw, bx = wi - by * bw;
+    const int ty = by * BLK_TY + (lane >> 2), tx0 = bx * BLK_TX + (lane & 3) * 4;
+    int mn = 255, mx = 0;
+    if (ty < th)
+        for (int c = 0; c < 4; c++)
+            if (tx0 + c < tw) { const int e = __ldg(tmm + ((size_t)f * th + ty) * tw + tx0 + c); mn = min(mn, e & 255); mx = max(mx, e >> 8); }
+    mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) bmm[((size_t)f * bh + by) * bw + bx] = (uint16_t)(mn | (mx << 8));
+}
+
+// One warp = one 64x32-px block (16x8 tiles; lane = tile row lane / 4, four consecutive tiles (lane % 4) * 4 ..).  Coarse
+// filter first: every 3x3 tile neighbourhood of the block lies inside the block and its 8 neighbours, so if the gray
+// range over those 9 blocks is below minWhiteBlackDiff no tile of the block can be high-contrast and the warp leaves
+// after 9 two-byte loads -- ~95 % of the blocks of a sparse frame.  Otherwise: 3x3 dilation of the tile extrema in
+// registers, and only the high-contrast tiles touch gray / ternary pixels.
+__global__ void __launch_bounds__(128) k_threshold(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
+                                                   const uint16_t *__restrict__ tmm, const uint16_t *__restrict__ bmm, int bw, int bh,
+                                                   int min_wb_diff, uint8_t *__restrict__ out,
                                                    uint8_t *__restrict__ tile_active, int ctw, int cth)
 {
-    const int tx = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    const uint16_t *T = tmm + (size_t)f * tw * th;
-    const int lane = threadIdx.x;
-    auto column = [&](int xx, int &cmn, int &cmx) {
-        cmn = 255; cmx = 0;
-        if (xx < 0 || xx >= tw || ty >= th) return;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++) {
-            int yy = ty + dy;
-            if (yy < 0 || yy >= th) continue;
-            int v = __ldg(T + (size_t)yy * tw + xx);
-            cmn = min(cmn, v & 255);
-            cmx = max(cmx, v >> 8);
+    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, f = blockIdx.z;
+    if (wi >= bw * bh) return;
+    const int by = wi / bw, bx = wi - by * bw;
+    {
+        int mn = 255, mx = 0;
+        if (lane < 9) {
+            const int yy = by + lane / 3 - 1, xx = bx + lane % 3 - 1;
+            if (yy >= 0 && yy < bh && xx >= 0 && xx < bw) {
+                const int e = __ldg(bmm + ((size_t)f * bh + yy) * bw + xx);
+                mn = e & 255; mx = e >> 8;
+            }
         }
-    };
-    int cmn, cmx;
-    column(tx, cmn, cmx);
-    int lmn = __shfl_up_sync(0xffffffffu, cmn, 1), lmx = __shfl_up_sync(0xffffffffu, cmx, 1);
-    int rmn = __shfl_down_sync(0xffffffffu, cmn, 1), rmx = __shfl_down_sync(0xffffffffu, cmx, 1);
-    if (lane == 0) column(tx - 1, lmn, lmx);
-    if (lane == 31) column(tx + 1, rmn, rmx);
-    if (tx >= tw || ty >= th) return;
-    const int mn = min(cmn, min(lmn, rmn)), mx = max(cmx, max(lmx, rmx));
+        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+        if (mx - mn < min_wb_diff) return;
+    }
+    const int ty = by * BLK_TY + (lane >> 2), tx0 = bx * BLK_TX + (lane & 3) * 4;
+    if (ty >= th || tx0 >= tw) return;
+    const uint16_t *T = tmm + (size_t)f * tw * th;
+    int cmn[6], cmx[6];   // vertical extrema of the tile columns tx0 - 1 .. tx0 + 4
+#pragma unroll
+    for (int c = 0; c < 6; c++) { cmn[c] = 255; cmx[c] = 0; }
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        const int yy = ty + dy;
+        if (yy < 0 || yy >= th) continue;
+        const uint16_t *row = T + (size_t)yy * tw;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const int xx = tx0 + c - 1;
+            if (xx < 0 || xx >= tw) continue;
+            const int e = __ldg(row + xx);
+            cmn[c] = min(cmn[c], e & 255); cmx[c] = max(cmx[c], e >> 8);
+        }
+    }
     const uint8_t *g = gray + (size_t)f * w * h;
     uint8_t *o = out + (size_t)f * w * h;
-    bool low = (mx - mn) < min_wb_diff;
-    unsigned thr = mn + (mx - mn) / 2;
-    // low-contrast tiles are not written: the ternary image is kept at 127 outside the tiles the previous batch
-    // touched (k_reset_thresh), so 99 % of a sparse frame costs neither a gray read nor a store here
-    if (low) return;
-    tile_active[((size_t)f * cth + (ty * 4) / CCL_TH) * ctw + (tx * 4) / CCL_TW] = 1;
-    if ((w & 3) == 0) {
 #pragma unroll
-        for (int dy = 0; dy < 4; dy++) {
-            size_t p = (size_t)(ty * 4 + dy) * w + tx * 4;
-            uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(g + p));
-            uint32_t r = ((v & 255) > thr ? 0xffu : 0u) | (((v >> 8) & 255) > thr ? 0xff00u : 0u) |
-                         (((v >> 16) & 255) > thr ? 0xff0000u : 0u) | ((v >> 24) > thr ? 0xff000000u : 0u);
-            *reinterpret_cast<uint32_t *>(o + p) = r;
-        }
-    } else {
-        for (int dy = 0; dy < 4; dy++)
-            for (int dx = 0; dx < 4; dx++) {
-                size_t p = (size_t)(ty * 4 + dy) * w + tx * 4 + dx;
-                o[p] = g[p] > thr ? 255 : 0;
+    for (int c = 0; c < 4; c++) {
+        const int tx = tx0 + c;
+        if (tx >= tw) break;
+        const int mn = min(cmn[c], min(cmn[c + 1], cmn[c + 2])), mx = max(cmx[c], max(cmx[c + 1], cmx[c + 2]));
+        // low-contrast tiles are not written: the ternary image is kept at 127 outside the tiles the previous batch
+        // touched (k_reset_thresh), so 99 % of a sparse frame costs neither a gray read nor a store here
+        if ((mx - mn) < min_wb_diff) continue;
+        const unsigned thr = mn + (mx - mn) / 2;
+        tile_active[((size_t)f * cth + (ty * 4) / CCL_TH) * ctw + (tx * 4) / CCL_TW] = 1;
+        if ((w & 3) == 0) {
+#pragma unroll
+            for (int dy = 0; dy < 4; dy++) {
+                size_t p = (size_t)(ty * 4 + dy) * w + tx * 4;
+                uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(g + p));
+                uint32_t r = ((v & 255) > thr ? 0xffu : 0u) | (((v >> 8) & 255) > thr ? 0xff00u : 0u) |
+                             (((v >> 16) & 255) > thr ? 0xff0000u : 0u) | ((v >> 24) > thr ? 0xff000000u : 0u);
+                *reinterpret_cast<uint32_t *>(o + p) = r;
             }
+        } else {
+            for (int dy = 0; dy < 4; dy++)
+                for (int dx = 0; dx < 4; dx++) {
+                    size_t p = (size_t)(ty * 4 + dy) * w + tx * 4 + dx;
+                    o[p] = g[p] > thr ? 255 : 0;
+                }
+        }
     }
 }
 
+// The per-tile kernels below run as 128-thread CTAs: lane = tile column, warp wy owns the tile rows wy, wy + 4, wy + 8,
+// wy + 12, i.e. four pixels per thread whose global loads are independent and in flight together (these kernels are
+// latency-bound: a tile is 512 B of ternary image and 2 KB of labels), 16 resident CTAs = 16 tiles in flight per SM.
+#define CCL_THREADS 128
+#define CCL_RPT (CCL_TH / (CCL_THREADS / 32))   // rows per thread = 4
+
 // back to 127 on every CCL tile the previous batch marked active (runs at the start of the next batch)
-__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_reset_thresh(uint8_t *__restrict__ thresh, int w, int h, const uint32_t *__restrict__ list,
-                                                                 const int *__restrict__ n_active, int ctw)
+__global__ void __launch_bounds__(CCL_THREADS) k_reset_thresh(uint8_t *__restrict__ thresh, int w, int h, const uint32_t *__restrict__ list,
+                                                              const int *__restrict__ n_active, int ctw)
 {
     const int n = *n_active;
+    const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
     for (int it = blockIdx.x; it < n; it += gridDim.x) {
         const uint32_t e = list[it];
         const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
-        const int x = txb * CCL_TW + threadIdx.x, y = tyb * CCL_TH + threadIdx.y;
-        if (x < w && y < h) thresh[(size_t)f * w * h + (size_t)y * w + x] = 127;
+        if ((w & 3) == 0) {   // one 32-bit store per thread: thread t covers row t / 8, bytes 4 (t % 8) .. + 3 of the tile
+            const int x = txb * CCL_TW + 4 * (threadIdx.x & 7), y = tyb * CCL_TH + (threadIdx.x >> 3);
+            if (x < w && y < h) *reinterpret_cast<uint32_t *>(thresh + (size_t)f * w * h + (size_t)y * w + x) = 0x7f7f7f7fu;
+            continue;
+        }
+        const int x = txb * CCL_TW + lx;
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int y = tyb * CCL_TH + wy + 4 * r;
+            if (x < w && y < h) thresh[(size_t)f * w * h + (size_t)y * w + x] = 127;
+        }
     }
 }
 
@@ -209,55 +265,75 @@ __device__ __forceinline__ void uf_union_gmem(uint32_t *L, uint32_t a, uint32_t 
     }
 }
 
-// One CTA = one 32x16 tile, one warp per row.  Horizontal runs are labelled with a warp ballot (no atomics); the
+// One CTA = one 32x16 tile per iteration.  Horizontal runs are labelled with a warp ballot (no atomics); the
 // vertical / diagonal joins are union-find merges of run roots, skipping the joins that a left neighbour of the
 // same run already implies, so a solid tile costs ~16 atomics instead of ~1500.
-__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_local(const uint8_t *__restrict__ thresh, int w, int h,
-                                                              uint32_t *__restrict__ labels,
-                                                              const uint32_t *__restrict__ list, const int *__restrict__ n_active,
-                                                              int ctw, int full)
+__global__ void __launch_bounds__(CCL_THREADS) k_ccl_local(const uint8_t *__restrict__ thresh, int w, int h,
+                                                           uint32_t *__restrict__ labels,
+                                                           const uint32_t *__restrict__ list, const int *__restrict__ n_active,
+                                                           int ctw, int full)
 {
     __shared__ int L[CCL_TW * CCL_TH];
     __shared__ uint8_t V[CCL_TH][CCL_TW + 1];
     __shared__ uint32_t JR[CCL_TH];   // bit x of JR[y]: pixel (x,y) is joined with (x+1,y)
-    const int lx = threadIdx.x, ly = threadIdx.y, li = ly * CCL_TW + lx;
+    const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
     const int n = *n_active;
     for (int it = blockIdx.x; it < n; it += gridDim.x) {
         const uint32_t e = list[it];
         const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
-        const int x = txb * CCL_TW + lx, y = tyb * CCL_TH + ly;
+        const int x = txb * CCL_TW + lx;
         const uint8_t *t = thresh + (size_t)f * w * h;
-        const bool in = x < w && y < h;
-        const int v = in ? t[(size_t)y * w + x] : 127;
-        // pixel may initiate joins (full = classic path: every pixel; otherwise the dependency's AprilTag loop ranges)
-        const bool src = v != 127 && (full || (x >= 1 && x <= w - 2 && y <= h - 2));
-        const int vr = __shfl_down_sync(0xffffffffu, v, 1);
-        const bool join_r = src && lx + 1 < CCL_TW && vr == v;
-        const uint32_t jr = __ballot_sync(0xffffffffu, join_r);
-        const uint32_t starts = ~(jr << 1);                                 // bit i: pixel i starts a run
-        const int start = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));
-        V[ly][lx] = (uint8_t)v;
-        L[li] = ly * CCL_TW + start;
-        if (lx == 0) JR[ly] = jr;
+        int v[CCL_RPT];
+        uint32_t jr[CCL_RPT];
+        bool src[CCL_RPT];
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int y = tyb * CCL_TH + wy + 4 * r;
+            v[r] = (x < w && y < h) ? t[(size_t)y * w + x] : 127;
+        }
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int ly = wy + 4 * r, y = tyb * CCL_TH + ly;
+            // pixel may initiate joins (full = classic path: every pixel; otherwise the dependency's AprilTag loop ranges)
+            src[r] = v[r] != 127 && (full || (x >= 1 && x <= w - 2 && y <= h - 2));
+            const int vr = __shfl_down_sync(0xffffffffu, v[r], 1);
+            const bool join_r = src[r] && lx + 1 < CCL_TW && vr == v[r];
+            jr[r] = __ballot_sync(0xffffffffu, join_r);
+            const uint32_t starts = ~(jr[r] << 1);                                 // bit i: pixel i starts a run
+            const int start = 31 - __clz(starts & (0xffffffffu >> (31 - lx)));
+            V[ly][lx] = (uint8_t)v[r];
+            L[ly * CCL_TW + lx] = ly * CCL_TW + start;
+            if (lx == 0) JR[ly] = jr[r];
+        }
         __syncthreads();
-        if (src && ly + 1 < CCL_TH) {
-            const uint32_t jr_b = JR[ly + 1];
-            const bool s_same = V[ly + 1][lx] == v;
-            const bool left_same_run = lx > 0 && ((jr >> (lx - 1)) & 1u);
-            if (s_same) {
-                const bool implied = left_same_run && V[ly + 1][lx - 1] == v && ((jr_b >> (lx - 1)) & 1u);
-                if (!implied) uf_union_smem(L, li, li + CCL_TW);
-            }
-            if (v == 255) {
-                if (lx > 0 && V[ly + 1][lx - 1] == v && !(s_same && ((jr_b >> (lx - 1)) & 1u))) uf_union_smem(L, li, li + CCL_TW - 1);
-                if (lx + 1 < CCL_TW && V[ly + 1][lx + 1] == v && !(s_same && ((jr_b >> lx) & 1u))) uf_union_smem(L, li, li + CCL_TW + 1);
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int ly = wy + 4 * r, li = ly * CCL_TW + lx;
+            if (!__any_sync(0xffffffffu, src[r])) continue;   // rows without foreground cost nothing (warp-uniform)
+            if (src[r] && ly + 1 < CCL_TH) {
+                const uint32_t jr_b = JR[ly + 1];
+                const bool s_same = V[ly + 1][lx] == v[r];
+                const bool left_same_run = lx > 0 && ((jr[r] >> (lx - 1)) & 1u);
+                if (s_same) {
+                    const bool implied = left_same_run && V[ly + 1][lx - 1] == v[r] && ((jr_b >> (lx - 1)) & 1u);
+                    if (!implied) uf_union_smem(L, li, li + CCL_TW);
+                }
+                if (v[r] == 255) {
+                    if (lx > 0 && V[ly + 1][lx - 1] == v[r] && !(s_same && ((jr_b >> (lx - 1)) & 1u))) uf_union_smem(L, li, li + CCL_TW - 1);
+                    if (lx + 1 < CCL_TW && V[ly + 1][lx + 1] == v[r] && !(s_same && ((jr_b >> lx) & 1u))) uf_union_smem(L, li, li + CCL_TW + 1);
+                }
             }
         }
         __syncthreads();
-        if (in && v != 127) {
-            int r = uf_find<int>(L, li);
-            int ry = tyb * CCL_TH + r / CCL_TW, rx = txb * CCL_TW + r % CCL_TW;
-            labels[(size_t)f * w * h + (size_t)y * w + x] = (uint32_t)(ry * w + rx);
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int ly = wy + 4 * r, y = tyb * CCL_TH + ly;
+            if (!__any_sync(0xffffffffu, v[r] != 127)) continue;
+            if (x < w && y < h && v[r] != 127) {
+                int rt = uf_find<int>(L, ly * CCL_TW + lx);
+                int ry = tyb * CCL_TH + rt / CCL_TW, rx = txb * CCL_TW + rt % CCL_TW;
+                labels[(size_t)f * w * h + (size_t)y * w + x] = (uint32_t)(ry * w + rx);
+            }
         }
         __syncthreads();
     }
@@ -300,22 +376,51 @@ __global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, ui
     }
 }
 
-__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_ccl_flatten(const uint8_t *__restrict__ thresh, int w, int h,
-                                                                uint32_t *__restrict__ labels,
-                                                                const uint32_t *__restrict__ list,
-                                                                const int *__restrict__ n_active, int ctw)
+__global__ void __launch_bounds__(CCL_THREADS) k_ccl_flatten(const uint8_t *__restrict__ thresh, int w, int h,
+                                                             uint32_t *__restrict__ labels,
+                                                             const uint32_t *__restrict__ list,
+                                                             const int *__restrict__ n_active, int ctw)
 {
     const int n = *n_active;
+    const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
     for (int it = blockIdx.x; it < n; it += gridDim.x) {
         const uint32_t e = list[it];
         const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
-        const int x = txb * CCL_TW + threadIdx.x, y = tyb * CCL_TH + threadIdx.y;
-        if (x >= w || y >= h) continue;
-        const size_t o = (size_t)f * w * h + (size_t)y * w + x;
-        if (thresh[o] == 127) continue;
+        const int x = txb * CCL_TW + lx;
+        const uint8_t *t = thresh + (size_t)f * w * h;
         uint32_t *L = labels + (size_t)f * w * h;
-        uint32_t r = uf_find<uint32_t>(L, L[(size_t)y * w + x]);
-        L[(size_t)y * w + x] = r;  // racing writers store roots of the same tree; finds stay correct
+        uint32_t o[CCL_RPT], cur[CCL_RPT];
+        bool act[CCL_RPT];
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int y = tyb * CCL_TH + wy + 4 * r;
+            o[r] = (uint32_t)(y * w + x);
+            act[r] = x < w && y < h && t[o[r]] != 127;
+        }
+        if (!__any_sync(0xffffffffu, act[0] | act[1] | act[2] | act[3])) continue;
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) cur[r] = act[r] ? L[o[r]] : 0u;
+        // the four root walks advance together: one independent load per pixel and round
+        bool walk[CCL_RPT];
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) walk[r] = act[r];
+        for (;;) {
+            bool any = false;
+            uint32_t par[CCL_RPT];
+#pragma unroll
+            for (int r = 0; r < CCL_RPT; r++) par[r] = walk[r] ? const_cast<const volatile uint32_t *>(L)[cur[r]] : cur[r];
+#pragma unroll
+            for (int r = 0; r < CCL_RPT; r++) {
+                if (walk[r]) {
+                    if (par[r] == cur[r]) walk[r] = false;
+                    else { cur[r] = par[r]; any = true; }
+                }
+            }
+            if (!any) break;
+        }
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++)
+            if (act[r]) L[o[r]] = cur[r];  // racing writers store roots of the same tree; finds stay correct
     }
 }
 
@@ -328,71 +433,141 @@ __device__ __forceinline__ uint32_t hash64(unsigned long long k)
 }
 #define HASH_EMPTY 0xffffffffffffffffULL
 
-__global__ void __launch_bounds__(CCL_TW *CCL_TH) k_emit_points(const uint8_t *__restrict__ thresh, int w, int h,
-                                                                const uint32_t *__restrict__ labels,
-                                                                const uint32_t *__restrict__ list,
-                                                                const int *__restrict__ n_active, int ctw,
-                                                                unsigned long long *__restrict__ hash_keys,
-                                                                uint32_t *__restrict__ hash_count, uint32_t *__restrict__ used_slots,
-                                                                uint4 *__restrict__ points, int32_t *__restrict__ counters)
+__global__ void __launch_bounds__(CCL_THREADS) k_emit_points(const uint8_t *__restrict__ thresh, int w, int h,
+                                                             const uint32_t *__restrict__ labels,
+                                                             const uint32_t *__restrict__ list,
+                                                             const int *__restrict__ n_active, int ctw,
+                                                             unsigned long long *__restrict__ hash_keys,
+                                                             uint32_t *__restrict__ hash_count, uint32_t *__restrict__ used_slots,
+                                                             uint4 *__restrict__ points, int32_t *__restrict__ counters)
 {
   const int n_act = *n_active;
+  const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
   for (int it = blockIdx.x; it < n_act; it += gridDim.x) {
     const uint32_t e = list[it];
     const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
-    int x = txb * CCL_TW + threadIdx.x, y = tyb * CCL_TH + threadIdx.y;
+    const int x = txb * CCL_TW + lx;
     const uint8_t *t = thresh + (size_t)f * w * h;
     const uint32_t *L = labels + (size_t)f * w * h;
-    bool src = x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2;
-    int v0 = src ? t[(size_t)y * w + x] : 127;
-    src = src && v0 != 127;
-    unsigned long long rep0 = src ? L[(size_t)y * w + x] : 0;
     unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
     uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
     uint4 *pts = points + (size_t)f * APSE_MAX_POINTS;
     int32_t *cnt = counters + f * APSE_COUNTERS;
     const int DX[4] = {1, 0, -1, 1}, DY[4] = {0, 1, 1, 1};
+    // all pixel loads of the thread's four rows first (independent, in flight together): own pixel and the pixel below;
+    // the E / SW / SE neighbours come from the adjacent lanes (the two edge lanes load across the tile border).  Rows
+    // without any black/white crossing -- most rows of a sparse frame -- are skipped warp-uniformly before the label
+    // loads and the hash inserts.
+    bool src[CCL_RPT];
+    int v0[CCL_RPT], v1[CCL_RPT][4];
+    unsigned rows_on = 0;
+    {
+        int vs[CCL_RPT], ve[CCL_RPT], vsw[CCL_RPT], vse[CCL_RPT];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int dx = DX[k], dy = DY[k];
-        int v1 = src ? t[(size_t)(y + dy) * w + x + dx] : 127;
-        bool emit = src && (v0 + v1 == 255);
-        uint32_t slot = 0, rank = 0;
-        if (emit) {
-            unsigned long long rep1 = L[(size_t)(y + dy) * w + x + dx];
-            unsigned long long key = rep0 < rep1 ? (rep1 << 32) + rep0 : (rep0 << 32) + rep1;
-            slot = hash64(key) & (APSE_HASH_SLOTS - 1);
-            int probes = 0;
-            for (;;) {
-                unsigned long long prev = atomicCAS(&hk[slot], HASH_EMPTY, key);
-                if (prev == HASH_EMPTY) {  // this thread created the cluster: list the slot for the scan kernel
-                    used_slots[(size_t)f * APSE_HASH_SLOTS + atomicAdd(&cnt[6], 1)] = slot;
-                    break;
-                }
-                if (prev == key) break;
-                slot = (slot + 1) & (APSE_HASH_SLOTS - 1);
-                if (++probes >= APSE_HASH_SLOTS) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); emit = false; break; }
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int y = tyb * CCL_TH + wy + 4 * r;
+            const bool in = x < w && y < h, inb = x < w && y + 1 < h;
+            v0[r] = in ? t[(size_t)y * w + x] : 127;
+            vs[r] = inb ? t[(size_t)(y + 1) * w + x] : 127;
+            ve[r] = vsw[r] = vse[r] = 127;
+            if (lx == 31 && x + 1 < w) {
+                if (y < h) ve[r] = t[(size_t)y * w + x + 1];
+                if (y + 1 < h) vse[r] = t[(size_t)(y + 1) * w + x + 1];
             }
-            if (emit) rank = atomicAdd(&hc[slot], 1u);
+            if (lx == 0 && x >= 1 && y + 1 < h) vsw[r] = t[(size_t)(y + 1) * w + x - 1];
         }
-        // warp-aggregated append
-        unsigned m = __ballot_sync(0xffffffffu, emit);
-        if (m) {
-            int lane = (threadIdx.y * CCL_TW + threadIdx.x) & 31, leader = __ffs(m) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&cnt[0], __popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (emit) {
-                int idx = base + __popc(m & ((1u << lane) - 1));
-                if (idx < APSE_MAX_POINTS) {
-                    int gx = dx * (v1 - v0), gy = dy * (v1 - v0);
-                    pts[idx] = make_uint4(slot, rank, (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 16),
-                                          ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16));
-                } else {
-                    atomicExch(&cnt[3], APSE_ERR_CAPACITY);
-                }
+#pragma unroll
+        for (int r = 0; r < CCL_RPT; r++) {
+            const int y = tyb * CCL_TH + wy + 4 * r;
+            const int e_ = __shfl_down_sync(0xffffffffu, v0[r], 1), se_ = __shfl_down_sync(0xffffffffu, vs[r], 1);
+            const int sw_ = __shfl_up_sync(0xffffffffu, vs[r], 1);
+            v1[r][0] = lx == 31 ? ve[r] : e_;
+            v1[r][1] = vs[r];
+            v1[r][2] = lx == 0 ? vsw[r] : sw_;
+            v1[r][3] = lx == 31 ? vse[r] : se_;
+            src[r] = x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2 && v0[r] != 127;
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 4; k++) any |= src[r] && (v0[r] + v1[r][k] == 255);
+            if (__any_sync(0xffffffffu, any)) rows_on |= 1u << r;
+        }
+    }
+    if (!rows_on) continue;
+#pragma unroll
+    for (int r = 0; r < CCL_RPT; r++) {
+      // one row of the thread at a time; within it the (up to four) label loads, hash look-ups and rank increments are
+      // issued back to back and consumed afterwards, and the append position costs one atomic per warp and row
+      if (!((rows_on >> r) & 1u)) continue;   // warp-uniform
+      const int y = tyb * CCL_TH + wy + 4 * r;
+      uint32_t rep0, rep1[4];
+      {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool em = src[r] && (v0[r] + v1[r][k] == 255);
+            rep1[k] = em ? L[(size_t)(y + DY[k]) * w + x + DX[k]] : 0u;
+            any |= em;
+        }
+        rep0 = any ? L[(size_t)y * w + x] : 0u;
+      }
+      bool emit[4];
+      uint32_t slot[4], rank[4];
+      unsigned long long key[4], prev[4];
+      int nem = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        emit[k] = src[r] && (v0[r] + v1[r][k] == 255);
+        const unsigned long long a = rep0, b = rep1[k];
+        key[k] = a < b ? (b << 32) + a : (a << 32) + b;
+        slot[k] = hash64(key[k]) & (APSE_HASH_SLOTS - 1);
+        rank[k] = 0; prev[k] = 0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (emit[k]) prev[k] = atomicCAS(&hk[slot[k]], HASH_EMPTY, key[k]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (!emit[k]) continue;
+        int probes = 0;
+        unsigned long long pv = prev[k];
+        for (;;) {
+            if (pv == HASH_EMPTY) {  // this thread created the cluster: list the slot for the scan kernel
+                used_slots[(size_t)f * APSE_HASH_SLOTS + atomicAdd(&cnt[6], 1)] = slot[k];
+                break;
             }
+            if (pv == key[k]) break;
+            slot[k] = (slot[k] + 1) & (APSE_HASH_SLOTS - 1);
+            if (++probes >= APSE_HASH_SLOTS) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); emit[k] = false; break; }
+            pv = atomicCAS(&hk[slot[k]], HASH_EMPTY, key[k]);
         }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (emit[k]) { rank[k] = atomicAdd(&hc[slot[k]], 1u); nem++; }
+      // warp-aggregated append: exclusive prefix of the lanes' point counts
+      int inc = nem;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { int tv = __shfl_up_sync(0xffffffffu, inc, d); if (lx >= d) inc += tv; }
+      const int total = __shfl_sync(0xffffffffu, inc, 31);
+      if (total) {
+        int base = 0;
+        if (lx == 31) base = atomicAdd(&cnt[0], total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int idx = base + inc - nem;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!emit[k]) continue;
+            if (idx < APSE_MAX_POINTS) {
+                const int dx = DX[k], dy = DY[k];
+                int gx = dx * (v1[r][k] - v0[r]), gy = dy * (v1[r][k] - v0[r]);
+                pts[idx] = make_uint4(slot[k], rank[k], (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 16),
+                                      ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16));
+            } else {
+                atomicExch(&cnt[3], APSE_ERR_CAPACITY);
+            }
+            idx++;
+        }
+      }
     }
   }
 }
@@ -729,10 +904,18 @@ __global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
         }
         __syncthreads();
         if (tid < 6) {
-            double acc = lf[tid];
-            for (int i = 1; i < sz; i++) {
-                acc = acc + lf[(size_t)i * 6 + tid];
-                lf[(size_t)i * 6 + tid] = acc;
+            // sequential on purpose (the dependency's summation order); 8 independent loads are in flight per step of
+            // the dependent add chain
+            double acc = 0;
+            for (int base = 0; base < sz; base += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = base + k < sz ? lf[(size_t)(base + k) * 6 + tid] : 0.;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { acc = acc + v[k]; v[k] = acc; }
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (base + k < sz) lf[(size_t)(base + k) * 6 + tid] = v[k];
             }
         }
         __syncthreads();
@@ -779,15 +962,19 @@ __global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
                     if (removed) continue;
                     if (e > best || (e == best && i < bi)) { best = e; bi = i; }
                 }
-                s_best_err[tid] = best;
-                s_best_combo[tid] = (unsigned)bi;
+                for (int d = 16; d > 0; d >>= 1) {   // (largest error, smallest index) over the warp, then over the 4 warps
+                    double ob = __shfl_xor_sync(0xffffffffu, best, d);
+                    int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+                    if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+                }
+                if (lane == 0) { s_best_err[wid] = best; s_best_combo[wid] = (unsigned)bi; }
                 __syncthreads();
                 if (tid == 0) {
                     double b = -HUGE_VAL; int idx = -1;
-                    for (int t = 0; t < FQ_THREADS; t++) {
+                    for (int t = 0; t < FQ_THREADS / 32; t++) {
                         int ti = (int)s_best_combo[t];
                         if (ti < 0) continue;
-                        if (s_best_err[t] > b || (s_best_err[t] == b && ti < idx)) { b = s_best_err[t]; idx = ti; }
+                        if (idx < 0 || s_best_err[t] > b || (s_best_err[t] == b && ti < idx)) { b = s_best_err[t]; idx = ti; }
                     }
                     s_max_idx[r] = idx;
                     s_max_err[r] = b;
@@ -848,14 +1035,18 @@ __global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
                 }
             }
         }
-        s_best_err[tid] = best_err;
-        s_best_combo[tid] = best_combo;
+        for (int d = 16; d > 0; d >>= 1) {   // (smallest error, smallest combination) over the warp, then over the 4 warps
+            double oe = __shfl_xor_sync(0xffffffffu, best_err, d);
+            unsigned oc = __shfl_xor_sync(0xffffffffu, best_combo, d);
+            if (oc != 0xffffffffu && (best_combo == 0xffffffffu || oe < best_err || (oe == best_err && oc < best_combo))) { best_err = oe; best_combo = oc; }
+        }
+        if (lane == 0) { s_best_err[wid] = best_err; s_best_combo[wid] = best_combo; }
         __syncthreads();
         if (tid == 0) {
             double be = HUGE_VAL;
             unsigned bc = 0xffffffffu;
-            for (int t = 0; t < FQ_THREADS; t++)
-                if (s_best_combo[t] != 0xffffffffu && (s_best_err[t] < be || (s_best_err[t] == be && s_best_combo[t] < bc))) {
+            for (int t = 0; t < FQ_THREADS / 32; t++)
+                if (s_best_combo[t] != 0xffffffffu && (bc == 0xffffffffu || s_best_err[t] < be || (s_best_err[t] == be && s_best_combo[t] < bc))) {
                     be = s_best_err[t]; bc = s_best_combo[t];
                 }
             bool ok = bc != 0xffffffffu && (be / sz < (double)A.max_line_fit_mse);
@@ -945,6 +1136,7 @@ int apse_detect_alloc(apse_ctx *ctx)
     size_t ntiles = (size_t)div_up(ctx->max_w, 4) * div_up(ctx->max_h, 4);
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->thresh, B * npx));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmm, B * ntiles * sizeof(uint16_t)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->bmm, B * (size_t)div_up(ctx->max_w, 64) * div_up(ctx->max_h, 32) * sizeof(uint16_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->labels, B * npx * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->points, B * APSE_MAX_POINTS * sizeof(uint4)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->hash_keys, B * APSE_HASH_SLOTS * sizeof(unsigned long long)));
@@ -973,13 +1165,20 @@ int apse_detect_alloc(apse_ctx *ctx)
 
 void apse_detect_free(apse_ctx *ctx)
 {
-    cudaFree(ctx->thresh); cudaFree(ctx->tmm); cudaFree(ctx->labels); cudaFree(ctx->points);
+    cudaFree(ctx->thresh); cudaFree(ctx->tmm); cudaFree(ctx->bmm); cudaFree(ctx->labels); cudaFree(ctx->points);
     cudaFree(ctx->hash_keys); cudaFree(ctx->hash_count); cudaFree(ctx->hash_offset); cudaFree(ctx->sorted_pts);
     cudaFree(ctx->sort_keys); cudaFree(ctx->lfps); cudaFree(ctx->errs); cudaFree(ctx->clusters); cudaFree(ctx->counters);
     cudaFree(ctx->quads); cudaFree(ctx->quad_order);
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
     if (ex) { cudaFree(ex->tile_active); cudaFree(ex->tile_list); cudaFree(ex->used_slots); cudaFree(ex->work_counter); delete ex; }
     ctx->point_rank = nullptr;
+}
+
+// persistent grid of the work-list kernels (development knob APSE_CHAIN_GRID = CTAs per SM, default 4)
+static int chain_grid()
+{
+    static const int g = 148 * (getenv("APSE_CHAIN_GRID") ? atoi(getenv("APSE_CHAIN_GRID")) : 4);
+    return g > 0 ? g : 148;
 }
 
 // runs K2..K5 for `batch` gray frames; leaves quads / counters in the context scratch
@@ -999,7 +1198,7 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->thresh, 127, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h, st));
         ex->thresh_full = false;
     } else {
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_reset_thresh<<<148 * 4, dim3(CCL_TW, CCL_TH), 0, st>>>(ctx->thresh, w, h, ex->tile_list, ex->work_counter + 1, div_up(w, CCL_TW)));
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_reset_thresh<<<chain_grid() * 4, CCL_THREADS, 0, st>>>(ctx->thresh, w, h, ex->tile_list, ex->work_counter + 1, div_up(w, CCL_TW)));
     }
     ex->prev_w = w; ex->prev_h = h;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
@@ -1010,8 +1209,12 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
         if (!have_tile_minmax)
             KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmm));
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmm, dp.min_white_black_diff, ctx->thresh,
-                                                                           ex->tile_active, ctw, cth));
+        const int bw = div_up(w, 64), bh = div_up(h, 32);   // blocks of the fused preprocess kernel (64 x 32 px)
+        dim3 bgrid(div_up(bw * bh * 32, 128), 1, batch);
+        if (!have_tile_minmax)
+            KLAUNCH(ctx, KID_TILE_MINMAX, st, k_block_minmax<<<bgrid, 128, 0, st>>>(ctx->tmm, tw, th, bw, bh, ctx->bmm));
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<bgrid, 128, 0, st>>>(gray, w, h, tw, th, ctx->tmm, ctx->bmm, bw, bh, dp.min_white_black_diff,
+                                                                          ctx->thresh, ex->tile_active, ctw, cth));
         if (tw * 4 != w || th * 4 != h) {
             KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmm, ctx->thresh,
                                                                                      ex->tile_active, ctw, cth));
@@ -1020,10 +1223,10 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     {
         int *n_active = ex->work_counter + 1;
         KLAUNCH(ctx, KID_THRESHOLD, st, k_compact_tiles<<<div_up(batch * nct, 256), 256, 0, st>>>(ex->tile_active, batch * nct, nct, ex->tile_list, n_active));
-        dim3 block(CCL_TW, CCL_TH);
-        const int grid = 148 * 4;   // persistent: 4 CTAs of 512 threads per SM, tiles taken round-robin from the list
+        const int block = CCL_THREADS;
+        const int grid = chain_grid() * 4;   // persistent: 16 CTAs of 128 threads per SM, tiles taken round-robin from the list
         KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
-        KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<148 * 4, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
+        KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid() * 2, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
         KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
         KLAUNCH(ctx, KID_EMIT, st, k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, ctx->hash_keys,
                                                                           ctx->hash_count, ex->used_slots, ctx->points, ctx->counters));
@@ -1036,7 +1239,7 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     A.sort_keys = ctx->sort_keys; A.lfps = ctx->lfps; A.errs = ctx->errs; A.counters = ctx->counters; A.quads = ctx->quads;
     A.quad_order = ctx->quad_order; A.work_counter = ex->work_counter; A.max_nmaxima = dp.max_nmaxima;
     A.critical_rad = dp.critical_rad; A.max_line_fit_mse = dp.max_line_fit_mse; A.max_dot = dp.max_dot;
-    KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<148 * 4, FQ_THREADS, 0, st>>>(A));
+    KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<chain_grid(), FQ_THREADS, 0, st>>>(A));
     return APSE_OK;
 }
 
@@ -1052,10 +1255,10 @@ int apse_ccl_binary(apse_ctx *ctx, const uint8_t *bin, int w, int h, int batch, 
     CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, 2 * sizeof(int), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ex->tile_active, 1, (size_t)batch * nct, st));   // no low-contrast class: all tiles
     KLAUNCH(ctx, KID_THRESHOLD, st, k_compact_tiles<<<div_up(batch * nct, 256), 256, 0, st>>>(ex->tile_active, batch * nct, nct, ex->tile_list, n_active));
-    dim3 block(CCL_TW, CCL_TH);
-    const int grid = 148 * 4;
+    const int block = CCL_THREADS;
+    const int grid = chain_grid() * 4;
     KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
-    KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<148 * 4, 256, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
+    KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid() * 2, 256, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
     KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw));
     return APSE_OK;
 }

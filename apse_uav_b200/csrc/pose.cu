@@ -352,6 +352,309 @@ __device__ void solve_pnp_planar(const double *obj, const double *img, const Cam
     for (int a = 0; a < 3; a++) { rvec[a] = param[a]; tvec[a] = param[3 + a]; }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Four lanes per marker (lane j of a group owns corner j).  The single-thread solver above keeps its arrays in local
+// memory and is one long dependent FP64 chain (~0.4 ms per launch whatever the marker count); here the projection with
+// its Jacobian rows, the residuals and the partial normal equations are computed per corner in registers, the 27
+// normal-equation sums are combined with two butterfly shuffles (every lane of the group ends up with bit-identical
+// values, so the group's control flow never diverges), and the 6x6 Cholesky solve is unrolled in registers.
+__device__ __forceinline__ double gsum4(unsigned gmask, double v)
+{
+    v += __shfl_xor_sync(gmask, v, 1);
+    v += __shfl_xor_sync(gmask, v, 2);
+    return v;
+}
+
+// one object point: image point and (optionally) its 2x3 derivative blocks w.r.t. rvec (through dRdr) and tvec
+template <bool JAC>
+__device__ __forceinline__ void project_one(double X, double Y, double Z, const double *R, const double *dRdr, const double *tvec,
+                                            const CamModel &C, double &u, double &v, double *dr, double *dt)
+{
+    const double *k = C.k;
+    double x = R[0] * X + R[1] * Y + R[2] * Z + tvec[0];
+    double y = R[3] * X + R[4] * Y + R[5] * Z + tvec[1];
+    double z = R[6] * X + R[7] * Y + R[8] * Z + tvec[2];
+    z = z ? 1. / z : 1;
+    x *= z; y *= z;
+    double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+    double cdist = 1 + k[0] * r2 + k[1] * r4 + k[4] * r6;
+    double icdist2 = 1. / (1 + k[5] * r2 + k[6] * r4 + k[7] * r6);
+    double xd = x * cdist * icdist2 + k[2] * a1 + k[3] * a2 + k[8] * r2 + k[9] * r4;
+    double yd = y * cdist * icdist2 + k[2] * a3 + k[3] * a1 + k[10] * r2 + k[11] * r4;
+    u = xd * C.fx + C.cx;
+    v = yd * C.fy + C.cy;
+    if (JAC) {
+        const double dxdt[3] = {z, 0, -x * z}, dydt[3] = {0, z, -y * z};
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double dr2dt = 2 * x * dxdt[j] + 2 * y * dydt[j];
+            double dcdist_dt = k[0] * dr2dt + 2 * k[1] * r2 * dr2dt + 3 * k[4] * r4 * dr2dt;
+            double dicdist2_dt = -icdist2 * icdist2 * (k[5] * dr2dt + 2 * k[6] * r2 * dr2dt + 3 * k[7] * r4 * dr2dt);
+            double da1dt = 2 * (x * dydt[j] + y * dxdt[j]);
+            double dmxdt = dxdt[j] * cdist * icdist2 + x * dcdist_dt * icdist2 + x * cdist * dicdist2_dt + k[2] * da1dt +
+                           k[3] * (dr2dt + 4 * x * dxdt[j]) + k[8] * dr2dt + 2 * r2 * k[9] * dr2dt;
+            double dmydt = dydt[j] * cdist * icdist2 + y * dcdist_dt * icdist2 + y * cdist * dicdist2_dt +
+                           k[2] * (dr2dt + 4 * y * dydt[j]) + k[3] * da1dt + k[10] * dr2dt + 2 * r2 * k[11] * dr2dt;
+            dt[j] = C.fx * dmxdt;
+            dt[3 + j] = C.fy * dmydt;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            double dx0 = X * dRdr[j * 9 + 0] + Y * dRdr[j * 9 + 1] + Z * dRdr[j * 9 + 2];
+            double dy0 = X * dRdr[j * 9 + 3] + Y * dRdr[j * 9 + 4] + Z * dRdr[j * 9 + 5];
+            double dz0 = X * dRdr[j * 9 + 6] + Y * dRdr[j * 9 + 7] + Z * dRdr[j * 9 + 8];
+            double dxdr = z * (dx0 - x * dz0), dydr = z * (dy0 - y * dz0);
+            double dr2dr = 2 * x * dxdr + 2 * y * dydr;
+            double dcdist_dr = (k[0] + 2 * k[1] * r2 + 3 * k[4] * r4) * dr2dr;
+            double dicdist2_dr = -icdist2 * icdist2 * (k[5] + 2 * k[6] * r2 + 3 * k[7] * r4) * dr2dr;
+            double da1dr = 2 * (x * dydr + y * dxdr);
+            double dmxdr = dxdr * cdist * icdist2 + x * dcdist_dr * icdist2 + x * cdist * dicdist2_dr + k[2] * da1dr +
+                           k[3] * (dr2dr + 4 * x * dxdr) + (k[8] + 2 * r2 * k[9]) * dr2dr;
+            double dmydr = dydr * cdist * icdist2 + y * dcdist_dr * icdist2 + y * cdist * dicdist2_dr +
+                           k[2] * (dr2dr + 4 * y * dydr) + k[3] * da1dr + (k[10] + 2 * r2 * k[11]) * dr2dr;
+            dr[j] = C.fx * dmxdr;
+            dr[3 + j] = C.fy * dmydr;
+        }
+    }
+}
+
+// rodrigues_vec2mat with every loop unrolled (registers only)
+template <bool JAC>
+__device__ __forceinline__ void rodrigues_reg(const double *r_in, double *R, double *J)
+{
+    double rx = r_in[0], ry = r_in[1], rz = r_in[2];
+    double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    if (theta < DBL_EPSILON) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = (i == 0 || i == 4 || i == 8) ? 1. : 0.;
+        if (JAC) {
+#pragma unroll
+            for (int i = 0; i < 27; i++) J[i] = (i == 5 || i == 15 || i == 19) ? -1. : (i == 7 || i == 11 || i == 21) ? 1. : 0.;
+        }
+        return;
+    }
+    double c = cos(theta), s = sin(theta), c1 = 1. - c, itheta = 1. / theta;
+    rx *= itheta; ry *= itheta; rz *= itheta;
+    const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+    const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = c * I[k] + c1 * rrt[k] + s * r_x[k];
+    if (JAC) {
+        const double drrt[27] = {rx + rx, ry, rz, ry, 0, 0, rz, 0, 0, 0, rx, 0, rx, ry + ry, rz, 0, rz, 0,
+                                 0, 0, rx, 0, 0, ry, rx, ry, rz + rz};
+        const double d_r_x[27] = {0, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 1, 0, 0, 0, -1, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0, 0};
+        const double rv[3] = {rx, ry, rz};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double ri = rv[i];
+            double a0 = -s * ri, a1 = (s - 2 * c1 * itheta) * ri, a2 = c1 * itheta;
+            double a3 = (c - s * itheta) * ri, a4 = s * itheta;
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                J[i * 9 + k] = a0 * I[k] + a1 * rrt[k] + a2 * drrt[i * 9 + k] + a3 * r_x[k] + a4 * d_r_x[i * 9 + k];
+        }
+    }
+}
+
+// Cholesky solve of the damped 6x6 normal matrix held as its lower triangle in registers; false = not positive
+// definite (the caller falls back to the eigen-decomposition of sym_solve6)
+__device__ __forceinline__ bool chol_solve6_reg(const double *Al /* 21: row-major lower triangle */, const double *b, double *x)
+{
+#define AL(i, j) Al[(i) * ((i) + 1) / 2 + (j)]
+#define LL(i, j) Lm[(i) * ((i) + 1) / 2 + (j)]
+    // one reciprocal square root per column instead of a square root and up to six divisions: the solve is the
+    // longest dependent chain of an LM iteration
+    double Lm[21], inv[6], tr = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) tr += AL(i, i);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double d = AL(j, j);
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= LL(j, k) * LL(j, k);
+        if (!(d > tr * 1e-13)) ok = false;
+        const double rs = rsqrt(d);
+        inv[j] = rs;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double s = AL(i, j);
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= LL(i, k) * LL(j, k);
+            LL(i, j) = s * rs;
+        }
+    }
+    if (!ok) return false;
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= LL(i, k) * y[k];
+        y[i] = s * inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) s -= LL(k, i) * x[k];
+        x[i] = s * inv[i];
+    }
+    return true;
+#undef AL
+#undef LL
+}
+
+// damping factors 10^k, k = -16 .. 16 (the dependency evaluates exp(k ln 10); the difference is a few ulp of lambda)
+__constant__ double c_pow10[33] = {1e-16, 1e-15, 1e-14, 1e-13, 1e-12, 1e-11, 1e-10, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1e0,
+                                   1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16};
+
+__device__ __noinline__ void sym_solve6_fallback(const double *Al, const double *b, double *x)
+{
+    double A[36];
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j <= i; j++) A[i * 6 + j] = A[j * 6 + i] = Al[i * (i + 1) / 2 + j];
+    sym_solve6(A, b, x);
+}
+
+// planar-homography initial pose from the 4 normalised points (all lanes of a group compute it redundantly)
+__device__ __noinline__ void pnp_init_planar(const double *obj_xy /* 8 */, const double *mn /* 8 */, double *param)
+{
+    double A[64], b[8];
+    for (int i = 0; i < 64; i++) A[i] = 0;
+    for (int i = 0; i < 4; i++) {
+        double X = obj_xy[2 * i], Y = obj_xy[2 * i + 1], x = mn[2 * i], y = mn[2 * i + 1];
+        double *r0 = A + i * 8, *r1 = A + (i + 4) * 8;
+        r0[0] = X; r0[1] = Y; r0[2] = 1; r0[6] = -x * X; r0[7] = -x * Y; b[i] = x;
+        r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -y * X; r1[7] = -y * Y; b[i + 4] = y;
+    }
+    for (int a = 0; a < 6; a++) param[a] = 0;
+    if (lu_solve8(A, b)) {
+        const double H[9] = {b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.};
+        double h1n = sqrt(H[0] * H[0] + H[3] * H[3] + H[6] * H[6]);
+        double h2n = sqrt(H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
+        double s1 = 1. / fmax(h1n, DBL_EPSILON), s2 = 1. / fmax(h2n, DBL_EPSILON), st = 2. / fmax(h1n + h2n, DBL_EPSILON);
+        double h1[3] = {H[0] * s1, H[3] * s1, H[6] * s1}, h2[3] = {H[1] * s2, H[4] * s2, H[7] * s2};
+        double h3[3] = {h1[1] * h2[2] - h1[2] * h2[1], h1[2] * h2[0] - h1[0] * h2[2], h1[0] * h2[1] - h1[1] * h2[0]};
+        double R0[9] = {h1[0], h2[0], h3[0], h1[1], h2[1], h3[1], h1[2], h2[2], h3[2]};
+        double r[3], R[9];
+        rodrigues_mat2vec(R0, r);
+        rodrigues_vec2mat(r, R, nullptr);
+        rodrigues_mat2vec(R, r);
+        param[0] = r[0]; param[1] = r[1]; param[2] = r[2];
+        param[3] = H[2] * st; param[4] = H[5] * st; param[5] = H[8] * st;
+    }
+}
+
+// all 4 lanes of the group call this together; j = lane's corner, (u, v) its image point, h = half marker length
+__device__ void solve_pnp_planar_g4(unsigned gmask, int gbase, int j, double h, double u, double v, const CamModel &C,
+                                    double *rvec_out, double *tvec_out)
+{
+    const double *k = C.k;
+    const double X = (j == 0 || j == 3) ? -h : h, Y = (j < 2) ? h : -h;
+    double mx, my;
+    {   // undistortPoints, exactly 5 iterations, own corner
+        const double ifx = 1. / C.fx, ify = 1. / C.fy;
+        double x = (u - C.cx) * ifx, y = (v - C.cy) * ify, x0 = x, y0 = y;
+        for (int it = 0; it < 5; it++) {
+            double r2 = x * x + y * y;
+            double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+            if (icdist < 0) { x = (u - C.cx) * ifx; y = (v - C.cy) * ify; break; }
+            double dX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+            double dY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+            x = (x0 - dX) * icdist;
+            y = (y0 - dY) * icdist;
+        }
+        mx = x; my = y;
+    }
+    double param[6];
+    {
+        double oxy[8], mn[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            oxy[2 * q] = (q == 0 || q == 3) ? -h : h; oxy[2 * q + 1] = (q < 2) ? h : -h;
+            mn[2 * q] = __shfl_sync(gmask, mx, gbase + q); mn[2 * q + 1] = __shfl_sync(gmask, my, gbase + q);
+        }
+        pnp_init_planar(oxy, mn, param);
+    }
+    double prev[6], JtJ[21], JtErr[6], R[9], dRdr[27];
+    double prevErrNorm = DBL_MAX, errNorm = 0;
+    int lambdaLg10 = -3, iters = 0;
+    for (;;) {
+        double pu, pv, dr[6], dt[6];
+        rodrigues_reg<true>(param, R, dRdr);
+        project_one<true>(X, Y, 0., R, dRdr, param + 3, C, pu, pv, dr, dt);
+        const double e0 = pu - u, e1 = pv - v;
+        double j0[6] = {dr[0], dr[1], dr[2], dt[0], dt[1], dt[2]}, j1[6] = {dr[3], dr[4], dr[5], dt[3], dt[4], dt[5]};
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+#pragma unroll
+            for (int b = 0; b <= a; b++) JtJ[a * (a + 1) / 2 + b] = gsum4(gmask, j0[a] * j0[b] + j1[a] * j1[b]);
+            JtErr[a] = gsum4(gmask, j0[a] * e0 + j1[a] * e1);
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) prev[a] = param[a];
+        if (iters == 0) prevErrNorm = sqrt(gsum4(gmask, e0 * e0 + e1 * e1));
+        for (;;) {
+            double A[21], d[6], lambda = c_pow10[min(max(lambdaLg10, -16), 16) + 16];
+#pragma unroll
+            for (int i = 0; i < 21; i++) A[i] = JtJ[i];
+#pragma unroll
+            for (int a = 0; a < 6; a++) A[a * (a + 1) / 2 + a] *= 1. + lambda;
+            if (!chol_solve6_reg(A, JtErr, d)) sym_solve6_fallback(A, JtErr, d);
+#pragma unroll
+            for (int a = 0; a < 6; a++) param[a] = prev[a] - d[a];
+            rodrigues_reg<false>(param, R, nullptr);
+            project_one<false>(X, Y, 0., R, nullptr, param + 3, C, pu, pv, nullptr, nullptr);
+            const double f0 = pu - u, f1 = pv - v;
+            errNorm = sqrt(gsum4(gmask, f0 * f0 + f1 * f1));
+            if (errNorm > prevErrNorm && ++lambdaLg10 <= 16) continue;
+            break;
+        }
+        lambdaLg10 = max(lambdaLg10 - 1, -16);
+        double nd = 0, np = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) { double dd = param[a] - prev[a]; nd += dd * dd; np += prev[a] * prev[a]; }
+        if (++iters >= 20 || sqrt(nd) / sqrt(np) < FLT_EPSILON) break;
+        prevErrNorm = errNorm;
+    }
+    if (j == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { rvec_out[a] = param[a]; tvec_out[a] = param[3 + a]; }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pose4(const float *__restrict__ corners, int n, const float *__restrict__ marker_len,
+                                               float marker_len_all, CamModel C, double *__restrict__ rvec, double *__restrict__ tvec)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t >> 2, j = t & 3, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const float L = marker_len ? marker_len[i] : marker_len_all;
+    const float hh = L / 2.f;  // legacy API: float marker length, float32 object points
+    const unsigned gmask = 0xfu << (lane & ~3);
+    solve_pnp_planar_g4(gmask, lane & ~3, j, (double)hh, (double)corners[8 * (size_t)i + 2 * j], (double)corners[8 * (size_t)i + 2 * j + 1], C,
+                        rvec + 3 * (size_t)i, tvec + 3 * (size_t)i);
+}
+
+__global__ void __launch_bounds__(128) k_pose_frames4(const float *__restrict__ corners, const int32_t *__restrict__ n_markers, int batch,
+                                                      int max_markers, const float *__restrict__ marker_len, float marker_len_all, CamModel C,
+                                                      double *__restrict__ rvec, double *__restrict__ tvec)
+{
+    // work item = marker slot (f, m), compacted over the frames' marker counts would need a scan; slots beyond
+    // n_markers[f] exit at once (4 lanes of a slot together)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, i = t >> 2, j = t & 3, lane = threadIdx.x & 31;
+    if (i >= batch * max_markers) return;
+    const int f = i / max_markers, m = i - f * max_markers;
+    if (m >= n_markers[f]) return;
+    const float L = marker_len ? marker_len[f] : marker_len_all;
+    const float hh = L / 2.f;
+    const unsigned gmask = 0xfu << (lane & ~3);
+    solve_pnp_planar_g4(gmask, lane & ~3, j, (double)hh, (double)corners[8 * (size_t)i + 2 * j], (double)corners[8 * (size_t)i + 2 * j + 1], C,
+                        rvec + 3 * (size_t)i, tvec + 3 * (size_t)i);
+}
+
 __global__ void k_pose(const float *__restrict__ corners, int n, const float *__restrict__ marker_len, float marker_len_all,
                        CamModel C, double *__restrict__ rvec, double *__restrict__ tvec)
 {
@@ -420,7 +723,7 @@ int apse_pose(apse_ctx *ctx, const float *corners, int n, const float *marker_le
     CamModel C;
     int rc = make_cam(ctx, K, D, &C);
     if (rc) return rc;
-    KLAUNCH(ctx, KID_POSE, (cudaStream_t)stream, k_pose<<<div_up(n, 64), 64, 0, (cudaStream_t)stream>>>(corners, n, marker_len, marker_len_all, C, rvec, tvec));
+    KLAUNCH(ctx, KID_POSE, (cudaStream_t)stream, k_pose4<<<div_up(4 * n, 128), 128, 0, (cudaStream_t)stream>>>(corners, n, marker_len, marker_len_all, C, rvec, tvec));
     return APSE_OK;
 }
 
@@ -444,7 +747,7 @@ int apse_pose_frames(apse_ctx *ctx, const float *corners, const int32_t *n_marke
     CamModel C;
     int rc = make_cam(ctx, K, D, &C);
     if (rc) return rc;
-    KLAUNCH(ctx, KID_POSE, (cudaStream_t)stream, k_pose_frames<<<div_up(batch * max_markers, 64), 64, 0, (cudaStream_t)stream>>>(corners, n_markers, batch, max_markers, marker_len,
+    KLAUNCH(ctx, KID_POSE, (cudaStream_t)stream, k_pose_frames4<<<div_up(4 * batch * max_markers, 128), 128, 0, (cudaStream_t)stream>>>(corners, n_markers, batch, max_markers, marker_len,
                                                                                marker_len_all, C, rvec, tvec));
     return APSE_OK;
 }

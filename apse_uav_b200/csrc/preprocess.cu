@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 #define P2_RAW_STRIDE (P2_RAW_BYTES + 128)    // two staging buffers (double-buffered over frames), 128 B slack each
 #define P2_OFF_TABLES (2 * P2_RAW_STRIDE)
 #define P2_OFF_MISC (P2_OFF_TABLES + (int)sizeof(P2Tables))
-#define P2_SMEM_BYTES (P2_OFF_MISC + 32)
+#define P2_SMEM_BYTES (P2_OFF_MISC + 48)
 #define XZ_MAGIC 551553470                    // ceil(108 * 2^32 / 841)
 
 static void build_p2_tables_host(P2Tables &P, const LabTables &T)
@@ -354,9 +354,9 @@ __device__ __forceinline__ int chain_px(const P2Tables *T, int c0, int c1, int c
     int r0 = (12615 * X - 6296 * y - 2223 * Z + 8192) >> 14;
     int r1 = (-3773 * X + 7684 * y + 185 * Z + 8192) >> 14;
     int r2 = (217 * X - 836 * y + 4715 * Z + 8192) >> 14;
-    o0 = T->invgamma[min(max(r0, 0), 4095)];
-    o1 = T->invgamma[min(max(r1, 0), 4095)];
-    o2 = T->invgamma[min(max(r2, 0), 4095)];
+    o0 = T->invgamma[__vimin_s32_relu(r0, 4095)];   // clamp to [0, 4095] in one instruction
+    o1 = T->invgamma[__vimin_s32_relu(r1, 4095)];
+    o2 = T->invgamma[__vimin_s32_relu(r2, 4095)];
     return gray_px(o0, o1, o2);
 }
 
@@ -384,17 +384,49 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tm
         : "memory");
 }
 
+// one thread, one frame: the four pixels of the thread's column sampled from staging buffer `boff` and pushed through the
+// colour chain
 template <bool WANT_BGR>
-__global__ void __launch_bounds__(P2_THREADS, 2)
+__device__ __forceinline__ void k1t_pixels(const P2Tables *T, const uint32_t (&addr)[P2_NPX], const uint32_t (&shf)[P2_NPX],
+                                           const uint32_t (&wA)[P2_NPX], const uint32_t (&wB)[P2_NPX], uint32_t boff,
+                                           int (&g)[P2_NPX], int (&o0)[P2_NPX], int (&o1)[P2_NPX], int (&o2)[P2_NPX])
+{
+#pragma unroll
+    for (int k = 0; k < P2_NPX; k++) {
+        const uint32_t a = addr[k] + boff;
+        uint32_t r00, r01, r02, r10, r11, r12;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r00) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r01) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r02) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(r10) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1+260];" : "=r"(r11) : "r"(a));
+        asm volatile("ld.shared.u32 %0, [%1+264];" : "=r"(r12) : "r"(a));
+        // bytes b .. b+5 of each row: (c0 c1 c2 of tap ix, c0 c1 c2 of tap ix+1)
+        const uint32_t X0 = __funnelshift_r(r00, r01, shf[k]), X1 = __funnelshift_r(r01, r02, shf[k]);
+        const uint32_t Y0 = __funnelshift_r(r10, r11, shf[k]), Y1 = __funnelshift_r(r11, r12, shf[k]);
+        const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);   // (c0, c0', c1, c1')
+        const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);   // (c2, c2', ..)
+        int c0 = (int)(__dp2a_lo(wA[k], T0, __dp2a_lo(wB[k], T1, 512u)) >> 10);
+        int c1 = (int)(__dp2a_hi(wA[k], T0, __dp2a_hi(wB[k], T1, 512u)) >> 10);
+        int c2 = (int)(__dp2a_lo(wA[k], U0, __dp2a_lo(wB[k], U1, 512u)) >> 10);
+        g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
+    }
+}
+
+// WC: compile-time frame width (0 = run-time): row offsets of the stores become immediates for the 3840-px footage
+template <bool WANT_BGR, int NREG, int WC>
+__global__ void __maxnreg__(NREG)
 k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
-                 uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm,
-                 const float *__restrict__ mapx, const float *__restrict__ mapy, const P2Tables *__restrict__ tables, int w, int h,
+                 uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm, uint16_t *__restrict__ bmm,
+                 const float *__restrict__ mapx, const float *__restrict__ mapy, const P2Tables *__restrict__ tables, int w_rt, int h,
                  int batch, int fpb)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     P2Tables *T = reinterpret_cast<P2Tables *>(smem + P2_OFF_TABLES);
     unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);   // two barriers
     int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 16);   // xmin, xmax, ymin, ymax
+    int *blk = reinterpret_cast<int *>(smem + P2_OFF_MISC + 32);   // block extrema of gray, double-buffered: {min, max} x 2
+    const int w = WC ? WC : w_rt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mbar0 = smem_u32(mbar_p), raw0 = smem_u32(smem);
 
@@ -408,6 +440,7 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         box[0] = INT32_MAX; box[1] = INT32_MIN; box[2] = INT32_MAX; box[3] = INT32_MIN;
+        blk[0] = 255; blk[1] = 0; blk[2] = 255; blk[3] = 0;
     }
     __syncthreads();
 
@@ -454,75 +487,98 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     const int f0 = blockIdx.z * fpb, f1 = min(batch, f0 + fpb);
     const int tw4 = w >> 2;
     const int c0x = (bx0 * 3) >> 2;
-    if (fast && tid == 0) tma_load_box(raw0, &tmap, c0x, by0, f0, mbar0);
+    // output cursors of this thread, advanced by one frame per iteration
+    uint8_t *gp = gray + (size_t)f0 * frame_px + (size_t)(valid ? y0 : 0) * w + (valid ? x : 0);
+    uint8_t *cp = WANT_BGR ? bgr_out + ((size_t)f0 * frame_px + (size_t)(valid ? y0 : 0) * w + (valid ? x : 0)) * 3 : nullptr;
+    const size_t tile_stride = (size_t)(h >> 2) * tw4;
+    uint16_t *tp = tmm ? tmm + (size_t)f0 * tile_stride + (size_t)((valid ? y0 : 0) >> 2) * tw4 + ((valid ? x : 0) >> 2) : nullptr;
+    const bool tile_writer = valid && (lane & 3) == 0;
+    const size_t blk_stride = (size_t)gridDim.x * gridDim.y;
+    uint16_t *bp = bmm ? bmm + (size_t)f0 * blk_stride + (size_t)blockIdx.y * gridDim.x + blockIdx.x : nullptr;
 
-    for (int f = f0; f < f1; f++) {
-        int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
-        if (fast) {
-            const int cur = (f - f0) & 1;
-            // the other buffer was last read in the previous iteration (all threads passed its closing barrier)
-            if (tid == 0 && f + 1 < f1) tma_load_box(raw0 + (cur ^ 1) * P2_RAW_STRIDE, &tmap, c0x, by0, f + 1, mbar0 + (cur ^ 1) * 8);
-            mbar_wait(mbar0 + cur * 8, ((f - f0) >> 1) & 1);
-            if (valid) {
-                const uint32_t boff = cur * P2_RAW_STRIDE;
-#pragma unroll
-                for (int k = 0; k < P2_NPX; k++) {
-                    const uint32_t a = addr[k] + boff;
-                    uint32_t r00, r01, r02, r10, r11, r12;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r00) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r01) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r02) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(r10) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+260];" : "=r"(r11) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+264];" : "=r"(r12) : "r"(a));
-                    // bytes b .. b+5 of each row: (c0 c1 c2 of tap ix, c0 c1 c2 of tap ix+1)
-                    const uint32_t X0 = __funnelshift_r(r00, r01, shf[k]), X1 = __funnelshift_r(r01, r02, shf[k]);
-                    const uint32_t Y0 = __funnelshift_r(r10, r11, shf[k]), Y1 = __funnelshift_r(r11, r12, shf[k]);
-                    const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);   // (c0, c0', c1, c1')
-                    const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);   // (c2, c2', ..)
-                    int c0 = (int)(__dp2a_lo(wA[k], T0, __dp2a_lo(wB[k], T1, 512u)) >> 10);
-                    int c1 = (int)(__dp2a_hi(wA[k], T0, __dp2a_hi(wB[k], T1, 512u)) >> 10);
-                    int c2 = (int)(__dp2a_lo(wA[k], U0, __dp2a_lo(wB[k], U1, 512u)) >> 10);
-                    g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
-                }
-            }
-        } else if (valid) {
-            // direct-gather path (source box larger than the staging buffer)
-            const uint8_t *src = bgr + (size_t)f * frame_px * 3;
-#pragma unroll
-            for (int k = 0; k < P2_NPX; k++) {
-                size_t o = (size_t)(y0 + k) * w + x;
-                Taps t = make_taps(__ldg(mapx + o), __ldg(mapy + o), w, h, 3);
-                int c0 = sample(src, t, w * 3, 3, 0), c1 = sample(src, t, w * 3, 3, 1), c2 = sample(src, t, w * 3, 3, 2);
-                g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
-            }
-        }
+    // stores of one frame + the 4x4-tile extrema (this thread holds one column of a tile, 4 lanes hold its columns) + the
+    // extrema of the whole 64x32 block (coarse filter of the threshold stage), then advance the cursors
+    auto finish = [&](const int (&g)[P2_NPX], const int (&o0)[P2_NPX], const int (&o1)[P2_NPX], const int (&o2)[P2_NPX], int par) {
         if (valid) {
-            size_t o = (size_t)f * frame_px + (size_t)y0 * w + x;
 #pragma unroll
             for (int k = 0; k < P2_NPX; k++) {
-                gray[o + (size_t)k * w] = (uint8_t)g[k];
+                gp[(size_t)k * w] = (uint8_t)g[k];
                 if (WANT_BGR) {
-                    uint8_t *d = bgr_out + (o + (size_t)k * w) * 3;
+                    uint8_t *d = cp + (size_t)k * w * 3;
                     d[0] = (uint8_t)o0[k]; d[1] = (uint8_t)o1[k]; d[2] = (uint8_t)o2[k];
                 }
             }
         }
         if (tmm) {
-            // 4x4-tile min / max: this thread holds one column of the tile, 4 lanes hold its columns
             int mn = 255, mx = 0;
             if (valid) {
                 mn = min(min(g[0], g[1]), min(g[2], g[3]));
                 mx = max(max(g[0], g[1]), max(g[2], g[3]));
             }
+            if (bmm) {
+                const int wmn = __reduce_min_sync(0xffffffffu, mn), wmx = __reduce_max_sync(0xffffffffu, mx);
+                if (lane == 0) { atomicMin(&blk[2 * par], wmn); atomicMax(&blk[2 * par + 1], wmx); }
+            }
             mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            if (valid && (lane & 3) == 0) {
-                size_t to = ((size_t)f * (h >> 2) + (y0 >> 2)) * tw4 + (x >> 2);
-                tmm[to] = (uint16_t)(mn | (mx << 8));
+            if (tile_writer) *tp = (uint16_t)(mn | (mx << 8));
+            tp += tile_stride;
+        }
+        gp += frame_px;
+        if (WANT_BGR) cp += frame_px * 3;
+    };
+    // after the frame's closing barrier: thread 0 publishes the block extrema and re-arms the slot (used again in two frames)
+    auto publish = [&](int par) {
+        if (bmm && tid == 0) {
+            *bp = (uint16_t)(blk[2 * par] | (blk[2 * par + 1] << 8));
+            blk[2 * par] = 255; blk[2 * par + 1] = 0;
+        }
+        if (bmm) bp += blk_stride;
+    };
+
+    if (fast) {
+        if (tid == 0) tma_load_box(raw0, &tmap, c0x, by0, f0, mbar0);
+        // two frames per trip: staging buffer, barrier and extrema slot of a frame are compile-time constants
+        for (int f = f0; f < f1; f += 2) {
+            const uint32_t ph = (uint32_t)((f - f0) >> 1) & 1u;
+            {
+                if (warp == 0) { if (lane == 0 && f + 1 < f1) tma_load_box(raw0 + P2_RAW_STRIDE, &tmap, c0x, by0, f + 1, mbar0 + 8); }
+                mbar_wait(mbar0, ph);
+                int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
+                if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, 0u, g, o0, o1, o2);
+                finish(g, o0, o1, o2, 0);
+                __syncthreads();   // all reads of this frame's buffer done before it is refilled (frame f + 2)
+                publish(0);
+            }
+            if (f + 1 < f1) {
+                if (warp == 0) { if (lane == 0 && f + 2 < f1) tma_load_box(raw0, &tmap, c0x, by0, f + 2, mbar0); }
+                mbar_wait(mbar0 + 8, ph);
+                int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
+                if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, (uint32_t)P2_RAW_STRIDE, g, o0, o1, o2);
+                finish(g, o0, o1, o2, 1);
+                __syncthreads();
+                publish(1);
             }
         }
-        if (fast) __syncthreads();   // all reads of this frame's buffer done before it is refilled (frame f + 2)
+    } else {
+        // direct-gather path (source box larger than the staging buffer: folded corners of the rational model)
+        for (int f = f0; f < f1; f++) {
+            int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
+            if (valid) {
+                const uint8_t *src = bgr + (size_t)f * frame_px * 3;
+#pragma unroll
+                for (int k = 0; k < P2_NPX; k++) {
+                    size_t o = (size_t)(y0 + k) * w + x;
+                    Taps t = make_taps(__ldg(mapx + o), __ldg(mapy + o), w, h, 3);
+                    int c0 = sample(src, t, w * 3, 3, 0), c1 = sample(src, t, w * 3, 3, 1), c2 = sample(src, t, w * 3, 3, 2);
+                    g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
+                }
+            }
+            const int par = (f - f0) & 1;
+            finish(g, o0, o1, o2, par);
+            if (bmm) __syncthreads();
+            publish(par);
+        }
     }
 }
 
@@ -567,18 +623,24 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     if (r != CUDA_SUCCESS) CTX_FAIL(ctx, APSE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<true, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         attr_set = true;
     }
     // frames per CTA: the tap set-up (map reads, box reduction, table load) is amortised over up to 20 frames
     static const int fpb_max = getenv("APSE_K1_FPB") ? atoi(getenv("APSE_K1_FPB")) : 20;   // development knob
     const int nz = div_up(batch, fpb_max), fpb = div_up(batch, nz);
     dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), nz);
+    uint16_t *bmm = tmm ? ctx->bmm : nullptr;   // block extrema accompany the tile extrema (threshold stage)
+#define K1T_ARGS tmap, bgr, bgr_out, gray, tmm, bmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb
     if (bgr_out)
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true, 64, 0><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+    else if (w == 3840)
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 64, 3840><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(tmap, bgr, bgr_out, gray, tmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 64, 0><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+#undef K1T_ARGS
     return APSE_OK;
 }
 

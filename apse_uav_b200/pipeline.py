@@ -7,6 +7,8 @@ aruco_detect.py:598-782 runs afterwards on the host over the small per-frame res
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .engine import Engine
@@ -40,8 +42,11 @@ class Pipeline:
         self.streams, self.pre_stream, self._gray, self._done = [], None, [], []
         self._ring, self._ring_size, self._ring_pos = {}, max(2, int(ring)), 0   # result buffers of run_batch(sync=False)
         if streams > 1:
-            self.pre_stream = torch.cuda.Stream(device=dev, priority=0)
-            self.streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(streams)]
+            # development knobs: stream priorities of the two halves (default: chain above preprocess)
+            pre_prio = int(os.environ.get("APSE_PRE_PRIO", "0"))
+            chain_prio = int(os.environ.get("APSE_CHAIN_PRIO", "-1"))
+            self.pre_stream = torch.cuda.Stream(device=dev, priority=pre_prio)
+            self.streams = [torch.cuda.Stream(device=dev, priority=chain_prio) for _ in range(streams)]
             self._gray = [torch.empty((self.sub_batch, h, w), dtype=torch.uint8, device=dev) for _ in range(streams)]
             self._done = [None] * streams          # completion event of the last chain that used engine s
         self.max_batch, self.max_markers, self.marker_length = max_batch, max_markers, float(marker_length)

@@ -188,6 +188,9 @@ int apse_kernel_count(void);
 const char *apse_kernel_name(int kid);
 int apse_timing_enable(apse_ctx *ctx, int on);
 int apse_timing_collect(apse_ctx *ctx, double *ms_host, int64_t *launches_host, int reset);
+/* Development aid.  out == NULL: arm a trace of up to cap_rows launches.  Otherwise copy the rows {kernel id, start ms,
+ * end ms} (relative to a process-wide origin) of the launches timed since, return their number and clear the trace. */
+int apse_timing_trace(apse_ctx *ctx, double *out, int cap_rows);
 
 #ifdef __cplusplus
 }
