@@ -92,7 +92,6 @@ struct apse_ctx {
     // APRILTAG scratch (sized for max_batch frames of max_w x max_h)
     uint8_t *thresh = nullptr;
     uint16_t *tmm = nullptr;          // 4x4-tile extrema of gray, min | max << 8, [batch][h/4][w/4]
-    uint16_t *bmm = nullptr;          // extrema of the 64x32-px blocks (16x8 tiles), [batch][ceil(h/32)][ceil(w/64)]: coarse filter of k_threshold
     uint32_t *labels = nullptr;
     uint4 *points = nullptr;          // {key_lo, key_hi, xy, slot|g}
     uint32_t *point_rank = nullptr;

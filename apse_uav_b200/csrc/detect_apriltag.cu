@@ -69,133 +69,139 @@ __device__ __forceinline__ void dilated_minmax(const uint16_t *tmm, int tw, int 
 // list, so that the component / boundary kernels only ever touch the ~1-20 % of the image that has contrast.
 #define CCL_TW 32
 #define CCL_TH 16
-// Extrema of the 64x32-px blocks (16x8 tiles) from the tile extrema -- only when the fused preprocess kernel, which
-// writes them itself, did not run.  One warp per block, 4 tiles per lane.
-#define BLK_TX 16
-#define BLK_TY 8
-__global__ void __launch_bounds__(128) k_block_minmax(const uint16_t *__restrict__ tmm, int tw, int th, int bw, int bh,
-                                                      uint16_t *__restrict__ bmm)
-{
-    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, f = blockIdx.z;
-    if (wi >= bw * bh) return;
-    const int by = wi / bw, bx = wi - by * bw;
-    const int ty = by * BLK_TY + (lane >> 2), tx0 = bx * BLK_TX + (lane & 3) * 4;
-    int mn = 255, mx = 0;
-    if (ty < th)
-        for (int c = 0; c < 4; c++)
-            if (tx0 + c < tw) { const int e = __ldg(tmm + ((size_t)f * th + ty) * tw + tx0 + c); mn = min(mn, e & 255); mx = max(mx, e >> 8); }
-    mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
-    if (lane == 0) bmm[((size_t)f * bh + by) * bw + bx] = (uint16_t)(mn | (mx << 8));
-}
+// ---- active-tile list ("A-list") -------------------------------------------------------------------------------
+// Everything after the threshold decision works on the 4x4 tiles that are not low-contrast (1 % of a sparse frame,
+// ~16 % of a dense one): k_threshold_scan appends them to a list, and the pixel work of the threshold itself, the reset
+// of the ternary image before the next batch and the search for black/white crossings run over that list with full
+// warps instead of over whole 32x16 CCL tiles in which four pixels out of five are background.
+// Entry: tx | ty << 13 | frame << 26 (frames per launch <= 64, tile coordinates < 8192); alist_thr[i] = threshold.
+#define ATILE(f, tx, ty) ((uint32_t)(tx) | ((uint32_t)(ty) << 13) | ((uint32_t)(f) << 26))
+#define ATILE_TX(e) ((int)((e) & 0x1fffu))
+#define ATILE_TY(e) ((int)(((e) >> 13) & 0x1fffu))
+#define ATILE_F(e) ((int)((e) >> 26))
 
-// One warp = one 64x32-px block (16x8 tiles; lane = tile row lane / 4, four consecutive tiles (lane % 4) * 4 ..).  Coarse
-// filter first: every 3x3 tile neighbourhood of the block lies inside the block and its 8 neighbours, so if the gray
-// range over those 9 blocks is below minWhiteBlackDiff no tile of the block can be high-contrast and the warp leaves
-// after 9 two-byte loads -- ~95 % of the blocks of a sparse frame.  Otherwise: 3x3 dilation of the tile extrema in
-// registers, and only the high-contrast tiles touch gray / ternary pixels.
-__global__ void __launch_bounds__(128) k_threshold(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
-                                                   const uint16_t *__restrict__ tmm, const uint16_t *__restrict__ bmm, int bw, int bh,
-                                                   int min_wb_diff, uint8_t *__restrict__ out,
-                                                   uint8_t *__restrict__ tile_active, int ctw, int cth)
+// One thread = 8 consecutive tiles of a tile row (one 128-bit load of the extrema per tile row when the row stride
+// allows it) plus the two outer columns: 3x3 dilation of the tile extrema in registers; high-contrast tiles are
+// appended to the A-list (one atomic per warp) and flag their CCL tile.  No pixel is touched here.
+#define THR_TPT 8
+__global__ void __launch_bounds__(128) k_threshold_scan(int w, int h, int tw, int th, const uint16_t *__restrict__ tmm, int min_wb_diff,
+                                                        uint32_t *__restrict__ alist, uint8_t *__restrict__ alist_thr,
+                                                        int *__restrict__ acount, int acap,
+                                                        uint8_t *__restrict__ tile_active, int ctw, int cth)
 {
-    const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, f = blockIdx.z;
-    if (wi >= bw * bh) return;
-    const int by = wi / bw, bx = wi - by * bw;
-    {
-        int mn = 255, mx = 0;
-        if (lane < 9) {
-            const int yy = by + lane / 3 - 1, xx = bx + lane % 3 - 1;
-            if (yy >= 0 && yy < bh && xx >= 0 && xx < bw) {
-                const int e = __ldg(bmm + ((size_t)f * bh + yy) * bw + xx);
-                mn = e & 255; mx = e >> 8;
-            }
-        }
-        mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
-        if (mx - mn < min_wb_diff) return;
-    }
-    const int ty = by * BLK_TY + (lane >> 2), tx0 = bx * BLK_TX + (lane & 3) * 4;
-    if (ty >= th || tx0 >= tw) return;
-    const uint16_t *T = tmm + (size_t)f * tw * th;
-    int cmn[6], cmx[6];   // vertical extrema of the tile columns tx0 - 1 .. tx0 + 4
+    const int groups = (tw + THR_TPT - 1) / THR_TPT;
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y, f = blockIdx.z, lane = threadIdx.x & 31;
+    const int tx0 = gi * THR_TPT;
+    int cmn[THR_TPT + 2], cmx[THR_TPT + 2];   // vertical extrema of columns tx0 - 1 .. tx0 + 8
 #pragma unroll
-    for (int c = 0; c < 6; c++) { cmn[c] = 255; cmx[c] = 0; }
+    for (int c = 0; c < THR_TPT + 2; c++) { cmn[c] = 255; cmx[c] = 0; }
+    if (gi < groups) {
+        const uint16_t *T = tmm + (size_t)f * tw * th;
+        const bool vec = (tw % THR_TPT) == 0;     // rows are 16-byte aligned and every group is complete
 #pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-        const int yy = ty + dy;
-        if (yy < 0 || yy >= th) continue;
-        const uint16_t *row = T + (size_t)yy * tw;
+        for (int dy = -1; dy <= 1; dy++) {
+            const int yy = ty + dy;
+            if (yy < 0 || yy >= th) continue;
+            const uint16_t *row = T + (size_t)yy * tw;
+            uint32_t wv[4];
+            if (vec) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row + tx0));
+                wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+            } else {
 #pragma unroll
-        for (int c = 0; c < 6; c++) {
-            const int xx = tx0 + c - 1;
-            if (xx < 0 || xx >= tw) continue;
-            const int e = __ldg(row + xx);
-            cmn[c] = min(cmn[c], e & 255); cmx[c] = max(cmx[c], e >> 8);
-        }
-    }
-    const uint8_t *g = gray + (size_t)f * w * h;
-    uint8_t *o = out + (size_t)f * w * h;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const int tx = tx0 + c;
-        if (tx >= tw) break;
-        const int mn = min(cmn[c], min(cmn[c + 1], cmn[c + 2])), mx = max(cmx[c], max(cmx[c + 1], cmx[c + 2]));
-        // low-contrast tiles are not written: the ternary image is kept at 127 outside the tiles the previous batch
-        // touched (k_reset_thresh), so 99 % of a sparse frame costs neither a gray read nor a store here
-        if ((mx - mn) < min_wb_diff) continue;
-        const unsigned thr = mn + (mx - mn) / 2;
-        tile_active[((size_t)f * cth + (ty * 4) / CCL_TH) * ctw + (tx * 4) / CCL_TW] = 1;
-        if ((w & 3) == 0) {
-#pragma unroll
-            for (int dy = 0; dy < 4; dy++) {
-                size_t p = (size_t)(ty * 4 + dy) * w + tx * 4;
-                uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(g + p));
-                uint32_t r = ((v & 255) > thr ? 0xffu : 0u) | (((v >> 8) & 255) > thr ? 0xff00u : 0u) |
-                             (((v >> 16) & 255) > thr ? 0xff0000u : 0u) | ((v >> 24) > thr ? 0xff000000u : 0u);
-                *reinterpret_cast<uint32_t *>(o + p) = r;
-            }
-        } else {
-            for (int dy = 0; dy < 4; dy++)
-                for (int dx = 0; dx < 4; dx++) {
-                    size_t p = (size_t)(ty * 4 + dy) * w + tx * 4 + dx;
-                    o[p] = g[p] > thr ? 255 : 0;
+                for (int c = 0; c < 4; c++) {
+                    const int xa = tx0 + 2 * c, xb = xa + 1;
+                    const uint32_t a = xa < tw ? __ldg(row + xa) : 0x00ffu, b = xb < tw ? __ldg(row + xb) : 0x00ffu;
+                    wv[c] = a | (b << 16);
                 }
+            }
+#pragma unroll
+            for (int c = 0; c < THR_TPT; c++) {
+                const uint32_t e = (wv[c >> 1] >> ((c & 1) * 16)) & 0xffffu;
+                cmn[c + 1] = min(cmn[c + 1], (int)(e & 255u)); cmx[c + 1] = max(cmx[c + 1], (int)(e >> 8));
+            }
+            if (tx0 > 0) { const int e = __ldg(row + tx0 - 1); cmn[0] = min(cmn[0], e & 255); cmx[0] = max(cmx[0], e >> 8); }
+            if (tx0 + THR_TPT < tw) { const int e = __ldg(row + tx0 + THR_TPT); cmn[THR_TPT + 1] = min(cmn[THR_TPT + 1], e & 255); cmx[THR_TPT + 1] = max(cmx[THR_TPT + 1], e >> 8); }
+        }
+    }
+    unsigned on = 0;       // bit c: tile tx0 + c is high-contrast
+    uint32_t thr8[2] = {0, 0};
+#pragma unroll
+    for (int c = 0; c < THR_TPT; c++) {
+        const int mn = min(cmn[c], min(cmn[c + 1], cmn[c + 2])), mx = max(cmx[c], max(cmx[c + 1], cmx[c + 2]));
+        if (gi < groups && tx0 + c < tw && (mx - mn) >= min_wb_diff) {
+            on |= 1u << c;
+            thr8[c >> 2] |= (uint32_t)(mn + (mx - mn) / 2) << ((c & 3) * 8);
+        }
+    }
+    if (!__any_sync(0xffffffffu, on != 0)) return;
+    const int cnt = __popc(on);
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    int base = 0;
+    if (lane == 31) base = atomicAdd(acount, inc);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+#pragma unroll
+    for (int c = 0; c < THR_TPT; c++) {
+        if (!((on >> c) & 1u)) continue;
+        const int tx = tx0 + c;
+        if (base < acap) { alist[base] = ATILE(f, tx, ty); alist_thr[base] = (uint8_t)(thr8[c >> 2] >> ((c & 3) * 8)); }
+        base++;
+        tile_active[((size_t)f * cth + (ty * 4) / CCL_TH) * ctw + (tx * 4) / CCL_TW] = 1;
+    }
+}
+
+// ternary pixels of the listed tiles: one thread per tile row (a 32-bit word of gray in, a word of {0, 255} out)
+__global__ void __launch_bounds__(256) k_threshold_apply(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
+                                                         const uint32_t *__restrict__ alist, const uint8_t *__restrict__ alist_thr,
+                                                         const int *__restrict__ acount, int acap, uint8_t *__restrict__ out)
+{
+    const int n = min(*acount, acap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n; i += gridDim.x * blockDim.x) {
+        const uint32_t e = alist[i >> 2];
+        const int tx = ATILE_TX(e), ty = ATILE_TY(e), f = ATILE_F(e), dy = i & 3;
+        if (tx >= tw || ty >= th) continue;   // partial edge tiles are written by k_threshold_edges
+        const unsigned thr = alist_thr[i >> 2];
+        const size_t p = (size_t)f * w * h + (size_t)(ty * 4 + dy) * w + tx * 4;
+        if ((w & 3) == 0) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(gray + p));
+            const uint32_t r = ((v & 255) > thr ? 0xffu : 0u) | (((v >> 8) & 255) > thr ? 0xff00u : 0u) |
+                               (((v >> 16) & 255) > thr ? 0xff0000u : 0u) | ((v >> 24) > thr ? 0xff000000u : 0u);
+            *reinterpret_cast<uint32_t *>(out + p) = r;
+        } else {
+            for (int dx = 0; dx < 4; dx++) out[p + dx] = gray[p + dx] > thr ? 255 : 0;
         }
     }
 }
 
-// The per-tile kernels below run as 128-thread CTAs: lane = tile column, warp wy owns the tile rows wy, wy + 4, wy + 8,
+// back to 127 on every tile of the previous batch's A-list (runs at the start of the next batch)
+__global__ void __launch_bounds__(256) k_reset_thresh(uint8_t *__restrict__ thresh, int w, int h, const uint32_t *__restrict__ alist,
+                                                      const int *__restrict__ acount, int acap)
+{
+    const int n = min(*acount, acap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n; i += gridDim.x * blockDim.x) {
+        const uint32_t e = alist[i >> 2];
+        const int x = ATILE_TX(e) * 4, y = ATILE_TY(e) * 4 + (i & 3), f = ATILE_F(e);
+        if (y >= h) continue;
+        uint8_t *p = thresh + (size_t)f * w * h + (size_t)y * w + x;
+        if ((w & 3) == 0) *reinterpret_cast<uint32_t *>(p) = 0x7f7f7f7fu;
+        else for (int dx = 0; dx < 4 && x + dx < w; dx++) p[dx] = 127;
+    }
+}
+
+// The per-tile CCL kernels below run as 128-thread CTAs: lane = tile column, warp wy owns the tile rows wy, wy + 4, wy + 8,
 // wy + 12, i.e. four pixels per thread whose global loads are independent and in flight together (these kernels are
 // latency-bound: a tile is 512 B of ternary image and 2 KB of labels), 16 resident CTAs = 16 tiles in flight per SM.
 #define CCL_THREADS 128
 #define CCL_RPT (CCL_TH / (CCL_THREADS / 32))   // rows per thread = 4
 
-// back to 127 on every CCL tile the previous batch marked active (runs at the start of the next batch)
-__global__ void __launch_bounds__(CCL_THREADS) k_reset_thresh(uint8_t *__restrict__ thresh, int w, int h, const uint32_t *__restrict__ list,
-                                                              const int *__restrict__ n_active, int ctw)
-{
-    const int n = *n_active;
-    const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
-    for (int it = blockIdx.x; it < n; it += gridDim.x) {
-        const uint32_t e = list[it];
-        const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
-        if ((w & 3) == 0) {   // one 32-bit store per thread: thread t covers row t / 8, bytes 4 (t % 8) .. + 3 of the tile
-            const int x = txb * CCL_TW + 4 * (threadIdx.x & 7), y = tyb * CCL_TH + (threadIdx.x >> 3);
-            if (x < w && y < h) *reinterpret_cast<uint32_t *>(thresh + (size_t)f * w * h + (size_t)y * w + x) = 0x7f7f7f7fu;
-            continue;
-        }
-        const int x = txb * CCL_TW + lx;
-#pragma unroll
-        for (int r = 0; r < CCL_RPT; r++) {
-            const int y = tyb * CCL_TH + wy + 4 * r;
-            if (x < w && y < h) thresh[(size_t)f * w * h + (size_t)y * w + x] = 127;
-        }
-    }
-}
-
-// right / bottom partial tiles: nearest full tile's dilated threshold, never marked 127
+// right / bottom partial tiles: nearest full tile's dilated threshold, never marked 127; every partial tile goes to
+// the A-list (coordinates tx == tw or ty == th; the list consumers clip to the image)
 __global__ void k_threshold_edges(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
                                   const uint16_t *__restrict__ tmm,
-                                  uint8_t *__restrict__ out, uint8_t *__restrict__ tile_active, int ctw, int cth)
+                                  uint8_t *__restrict__ out, uint8_t *__restrict__ tile_active, int ctw, int cth,
+                                  uint32_t *__restrict__ alist, uint8_t *__restrict__ alist_thr, int *__restrict__ acount, int acap)
 {
     int f = blockIdx.z;
     int nright = w - tw * 4, nbottom = h - th * 4;
@@ -211,6 +217,10 @@ __global__ void k_threshold_edges(const uint8_t *__restrict__ gray, int w, int h
         int thr = mn + (mx - mn) / 2;
         o[(size_t)y * w + x] = g[(size_t)y * w + x] > thr ? 255 : 0;
         tile_active[((size_t)f * cth + y / CCL_TH) * ctw + x / CCL_TW] = 1;
+        if ((x & 3) == 0 && (y & 3) == 0) {   // first pixel of a partial tile
+            int k = atomicAdd(acount, 1);
+            if (k < acap) { alist[k] = ATILE(f, x / 4, y / 4); alist_thr[k] = (uint8_t)thr; }
+        }
     }
 }
 
@@ -433,143 +443,88 @@ __device__ __forceinline__ uint32_t hash64(unsigned long long k)
 }
 #define HASH_EMPTY 0xffffffffffffffffULL
 
-__global__ void __launch_bounds__(CCL_THREADS) k_emit_points(const uint8_t *__restrict__ thresh, int w, int h,
-                                                             const uint32_t *__restrict__ labels,
-                                                             const uint32_t *__restrict__ list,
-                                                             const int *__restrict__ n_active, int ctw,
-                                                             unsigned long long *__restrict__ hash_keys,
-                                                             uint32_t *__restrict__ hash_count, uint32_t *__restrict__ used_slots,
-                                                             uint4 *__restrict__ points, int32_t *__restrict__ counters)
+// Phase 1: one thread per pixel of an A-list tile (16 lanes per tile) looks at the E, S, SW, SE neighbours (tiles that
+// are not listed hold 127) and appends one record per black/white crossing to the frame's point array:
+// {x | y << 16, k | (v0 == 255) << 8, -, -}.  One atomic per tile with crossings.
+__global__ void __launch_bounds__(256) k_emit_scan(const uint8_t *__restrict__ thresh, int w, int h, const uint32_t *__restrict__ alist,
+                                                   const int *__restrict__ acount, int acap, uint4 *__restrict__ points,
+                                                   int32_t *__restrict__ counters)
 {
-  const int n_act = *n_active;
-  const int lx = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  for (int it = blockIdx.x; it < n_act; it += gridDim.x) {
-    const uint32_t e = list[it];
-    const int f = e >> 20, tile = e & 0xfffff, tyb = tile / ctw, txb = tile - tyb * ctw;
-    const int x = txb * CCL_TW + lx;
-    const uint8_t *t = thresh + (size_t)f * w * h;
-    const uint32_t *L = labels + (size_t)f * w * h;
-    unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
-    uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
-    uint4 *pts = points + (size_t)f * APSE_MAX_POINTS;
-    int32_t *cnt = counters + f * APSE_COUNTERS;
+    const int n = min(*acount, acap);
+    const int lane = threadIdx.x & 31, sub = lane & 15;
+    // uniform trip count per warp: both half-warps stay together for the shuffles
+    for (int it = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; it - (lane >> 4) < n; it += (gridDim.x * blockDim.x) >> 4) {
+        const bool live = it < n;
+        const uint32_t e = live ? alist[it] : 0u;
+        const int f = ATILE_F(e), x = ATILE_TX(e) * 4 + (sub & 3), y = ATILE_TY(e) * 4 + (sub >> 2);
+        const uint8_t *t = thresh + (size_t)f * w * h;
+        const bool src = live && x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2;
+        const int v0 = src ? t[(size_t)y * w + x] : 127;
+        unsigned mask = 0;
+        if (src && v0 != 127) {
+            const int want = 255 - v0;
+            const uint8_t *r1 = t + (size_t)(y + 1) * w + x;
+            mask = (t[(size_t)y * w + x + 1] == want ? 1u : 0u) | (r1[0] == want ? 2u : 0u) | (r1[-1] == want ? 4u : 0u) | (r1[1] == want ? 8u : 0u);
+        }
+        const int cnt = __popc(mask);
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) { int tv = __shfl_up_sync(0xffffffffu, inc, d, 16); if (sub >= d) inc += tv; }
+        const int total = __shfl_sync(0xffffffffu, inc, 15, 16);
+        int pos = 0;
+        if (sub == 15 && total) pos = atomicAdd(&counters[f * APSE_COUNTERS], total);
+        pos = __shfl_sync(0xffffffffu, pos, 15, 16) + inc - cnt;
+        uint4 *pts = points + (size_t)f * APSE_MAX_POINTS;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!((mask >> k) & 1u)) continue;
+            if (pos < APSE_MAX_POINTS) pts[pos] = make_uint4((uint32_t)x | ((uint32_t)y << 16), (uint32_t)k | (v0 == 255 ? 256u : 0u), 0u, 0u);
+            else atomicExch(&counters[f * APSE_COUNTERS + 3], APSE_ERR_CAPACITY);
+            pos++;
+        }
+    }
+}
+
+// Phase 2: one thread per record: component pair -> cluster hash slot and rank, record rewritten in place as
+// {slot, rank, 2x + dx | (2y + dy) << 16, gx | gy << 16}.  Every lane has a point.
+__global__ void __launch_bounds__(256) k_emit_insert(int w, int h, const uint32_t *__restrict__ labels,
+                                                     unsigned long long *__restrict__ hash_keys, uint32_t *__restrict__ hash_count,
+                                                     uint32_t *__restrict__ used_slots, uint4 *__restrict__ points,
+                                                     int32_t *__restrict__ counters, int batch)
+{
     const int DX[4] = {1, 0, -1, 1}, DY[4] = {0, 1, 1, 1};
-    // all pixel loads of the thread's four rows first (independent, in flight together): own pixel and the pixel below;
-    // the E / SW / SE neighbours come from the adjacent lanes (the two edge lanes load across the tile border).  Rows
-    // without any black/white crossing -- most rows of a sparse frame -- are skipped warp-uniformly before the label
-    // loads and the hash inserts.
-    bool src[CCL_RPT];
-    int v0[CCL_RPT], v1[CCL_RPT][4];
-    unsigned rows_on = 0;
-    {
-        int vs[CCL_RPT], ve[CCL_RPT], vsw[CCL_RPT], vse[CCL_RPT];
-#pragma unroll
-        for (int r = 0; r < CCL_RPT; r++) {
-            const int y = tyb * CCL_TH + wy + 4 * r;
-            const bool in = x < w && y < h, inb = x < w && y + 1 < h;
-            v0[r] = in ? t[(size_t)y * w + x] : 127;
-            vs[r] = inb ? t[(size_t)(y + 1) * w + x] : 127;
-            ve[r] = vsw[r] = vse[r] = 127;
-            if (lx == 31 && x + 1 < w) {
-                if (y < h) ve[r] = t[(size_t)y * w + x + 1];
-                if (y + 1 < h) vse[r] = t[(size_t)(y + 1) * w + x + 1];
+    for (int f = blockIdx.y; f < batch; f += gridDim.y) {
+        int32_t *cnt = counters + f * APSE_COUNTERS;
+        const int n = min(cnt[0], APSE_MAX_POINTS);
+        const uint32_t *L = labels + (size_t)f * w * h;
+        unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
+        uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
+        uint4 *pts = points + (size_t)f * APSE_MAX_POINTS;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const uint4 rec = pts[i];
+            const int x = rec.x & 0xffff, y = rec.x >> 16, k = rec.y & 3, v0 = (rec.y & 256u) ? 255 : 0, v1 = 255 - v0;
+            const int dx = DX[k], dy = DY[k];
+            const unsigned long long a = L[(size_t)y * w + x], b = L[(size_t)(y + dy) * w + x + dx];
+            const unsigned long long key = a < b ? (b << 32) + a : (a << 32) + b;
+            uint32_t slot = hash64(key) & (APSE_HASH_SLOTS - 1);
+            bool ok = true;
+            int probes = 0;
+            for (;;) {
+                unsigned long long prev = atomicCAS(&hk[slot], HASH_EMPTY, key);
+                if (prev == HASH_EMPTY) {  // this thread created the cluster: list the slot for the scan kernel
+                    used_slots[(size_t)f * APSE_HASH_SLOTS + atomicAdd(&cnt[6], 1)] = slot;
+                    break;
+                }
+                if (prev == key) break;
+                slot = (slot + 1) & (APSE_HASH_SLOTS - 1);
+                if (++probes >= APSE_HASH_SLOTS) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); ok = false; break; }
             }
-            if (lx == 0 && x >= 1 && y + 1 < h) vsw[r] = t[(size_t)(y + 1) * w + x - 1];
-        }
-#pragma unroll
-        for (int r = 0; r < CCL_RPT; r++) {
-            const int y = tyb * CCL_TH + wy + 4 * r;
-            const int e_ = __shfl_down_sync(0xffffffffu, v0[r], 1), se_ = __shfl_down_sync(0xffffffffu, vs[r], 1);
-            const int sw_ = __shfl_up_sync(0xffffffffu, vs[r], 1);
-            v1[r][0] = lx == 31 ? ve[r] : e_;
-            v1[r][1] = vs[r];
-            v1[r][2] = lx == 0 ? vsw[r] : sw_;
-            v1[r][3] = lx == 31 ? vse[r] : se_;
-            src[r] = x >= 1 && x <= w - 2 && y >= 1 && y <= h - 2 && v0[r] != 127;
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < 4; k++) any |= src[r] && (v0[r] + v1[r][k] == 255);
-            if (__any_sync(0xffffffffu, any)) rows_on |= 1u << r;
+            if (!ok) { pts[i] = make_uint4(0xffffffffu, 0u, 0u, 0u); continue; }
+            const uint32_t rank = atomicAdd(&hc[slot], 1u);
+            const int gx = dx * (v1 - v0), gy = dy * (v1 - v0);
+            pts[i] = make_uint4(slot, rank, (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 16), ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16));
         }
     }
-    if (!rows_on) continue;
-#pragma unroll
-    for (int r = 0; r < CCL_RPT; r++) {
-      // one row of the thread at a time; within it the (up to four) label loads, hash look-ups and rank increments are
-      // issued back to back and consumed afterwards, and the append position costs one atomic per warp and row
-      if (!((rows_on >> r) & 1u)) continue;   // warp-uniform
-      const int y = tyb * CCL_TH + wy + 4 * r;
-      uint32_t rep0, rep1[4];
-      {
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const bool em = src[r] && (v0[r] + v1[r][k] == 255);
-            rep1[k] = em ? L[(size_t)(y + DY[k]) * w + x + DX[k]] : 0u;
-            any |= em;
-        }
-        rep0 = any ? L[(size_t)y * w + x] : 0u;
-      }
-      bool emit[4];
-      uint32_t slot[4], rank[4];
-      unsigned long long key[4], prev[4];
-      int nem = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        emit[k] = src[r] && (v0[r] + v1[r][k] == 255);
-        const unsigned long long a = rep0, b = rep1[k];
-        key[k] = a < b ? (b << 32) + a : (a << 32) + b;
-        slot[k] = hash64(key[k]) & (APSE_HASH_SLOTS - 1);
-        rank[k] = 0; prev[k] = 0;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (emit[k]) prev[k] = atomicCAS(&hk[slot[k]], HASH_EMPTY, key[k]);
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (!emit[k]) continue;
-        int probes = 0;
-        unsigned long long pv = prev[k];
-        for (;;) {
-            if (pv == HASH_EMPTY) {  // this thread created the cluster: list the slot for the scan kernel
-                used_slots[(size_t)f * APSE_HASH_SLOTS + atomicAdd(&cnt[6], 1)] = slot[k];
-                break;
-            }
-            if (pv == key[k]) break;
-            slot[k] = (slot[k] + 1) & (APSE_HASH_SLOTS - 1);
-            if (++probes >= APSE_HASH_SLOTS) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); emit[k] = false; break; }
-            pv = atomicCAS(&hk[slot[k]], HASH_EMPTY, key[k]);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (emit[k]) { rank[k] = atomicAdd(&hc[slot[k]], 1u); nem++; }
-      // warp-aggregated append: exclusive prefix of the lanes' point counts
-      int inc = nem;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { int tv = __shfl_up_sync(0xffffffffu, inc, d); if (lx >= d) inc += tv; }
-      const int total = __shfl_sync(0xffffffffu, inc, 31);
-      if (total) {
-        int base = 0;
-        if (lx == 31) base = atomicAdd(&cnt[0], total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int idx = base + inc - nem;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (!emit[k]) continue;
-            if (idx < APSE_MAX_POINTS) {
-                const int dx = DX[k], dy = DY[k];
-                int gx = dx * (v1[r][k] - v0[r]), gy = dy * (v1[r][k] - v0[r]);
-                pts[idx] = make_uint4(slot[k], rank[k], (uint32_t)(2 * x + dx) | ((uint32_t)(2 * y + dy) << 16),
-                                      ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16));
-            } else {
-                atomicExch(&cnt[3], APSE_ERR_CAPACITY);
-            }
-            idx++;
-        }
-      }
-    }
-  }
 }
 
 // one block per frame: size filter + exclusive scan of the kept clusters' counts over the list of used hash slots;
@@ -636,6 +591,7 @@ __global__ void k_scatter_points(const uint4 *__restrict__ points, const uint32_
         uint2 *sp = sorted_pts + (size_t)f * APSE_MAX_POINTS;
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             uint4 p = pts[i];
+            if (p.x == 0xffffffffu) continue;   // hash table full (status already set)
             uint32_t off = ho[p.x];
             if (off != 0xffffffffu) sp[off + p.y] = make_uint2(p.z, p.w);
         }
@@ -1127,7 +1083,11 @@ struct DetectExtra {
     uint8_t *tile_active;
     uint32_t *tile_list;
     uint32_t *used_slots;
-    int *work_counter;   // [0] quad-fit work counter, [1] number of active tiles
+    int *work_counter;   // [0] quad-fit work counter, [1] number of active CCL tiles, [2], [3] entries of the two A-lists
+    // A-list of high-contrast 4x4 tiles, double-buffered: the list of batch k drives the reset at the start of batch k + 1
+    uint32_t *alist[2] = {nullptr, nullptr};
+    uint8_t *alist_thr[2] = {nullptr, nullptr};
+    int acap = 0, acur = 0;
 };
 
 int apse_detect_alloc(apse_ctx *ctx)
@@ -1136,7 +1096,6 @@ int apse_detect_alloc(apse_ctx *ctx)
     size_t ntiles = (size_t)div_up(ctx->max_w, 4) * div_up(ctx->max_h, 4);
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->thresh, B * npx));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmm, B * ntiles * sizeof(uint16_t)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->bmm, B * (size_t)div_up(ctx->max_w, 64) * div_up(ctx->max_h, 32) * sizeof(uint16_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->labels, B * npx * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->points, B * APSE_MAX_POINTS * sizeof(uint4)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->hash_keys, B * APSE_HASH_SLOTS * sizeof(unsigned long long)));
@@ -1154,7 +1113,13 @@ int apse_detect_alloc(apse_ctx *ctx)
     size_t nct = (size_t)div_up(ctx->max_w, CCL_TW) * div_up(ctx->max_h, CCL_TH);
     CUDA_TRY(ctx, cudaMalloc((void **)&ex->tile_active, B * nct));
     CUDA_TRY(ctx, cudaMalloc((void **)&ex->tile_list, B * nct * sizeof(uint32_t)));
-    CUDA_TRY(ctx, cudaMalloc((void **)&ex->work_counter, 2 * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc((void **)&ex->work_counter, 4 * sizeof(int)));
+    CUDA_TRY(ctx, cudaMemset(ex->work_counter, 0, 4 * sizeof(int)));
+    ex->acap = (int)(B * ntiles + B * (size_t)(div_up(ctx->max_w, 4) + div_up(ctx->max_h, 4) + 1));   // + partial edge tiles
+    for (int k = 0; k < 2; k++) {
+        CUDA_TRY(ctx, cudaMalloc((void **)&ex->alist[k], (size_t)ex->acap * sizeof(uint32_t)));
+        CUDA_TRY(ctx, cudaMalloc((void **)&ex->alist_thr[k], (size_t)ex->acap));
+    }
     CUDA_TRY(ctx, cudaMalloc((void **)&ex->used_slots, B * APSE_HASH_SLOTS * sizeof(uint32_t)));
     // the hash tables are cleared once; k_cluster_scan resets exactly the slots a batch used
     CUDA_TRY(ctx, cudaMemset(ctx->hash_keys, 0xff, B * APSE_HASH_SLOTS * sizeof(unsigned long long)));
@@ -1165,12 +1130,16 @@ int apse_detect_alloc(apse_ctx *ctx)
 
 void apse_detect_free(apse_ctx *ctx)
 {
-    cudaFree(ctx->thresh); cudaFree(ctx->tmm); cudaFree(ctx->bmm); cudaFree(ctx->labels); cudaFree(ctx->points);
+    cudaFree(ctx->thresh); cudaFree(ctx->tmm); cudaFree(ctx->labels); cudaFree(ctx->points);
     cudaFree(ctx->hash_keys); cudaFree(ctx->hash_count); cudaFree(ctx->hash_offset); cudaFree(ctx->sorted_pts);
     cudaFree(ctx->sort_keys); cudaFree(ctx->lfps); cudaFree(ctx->errs); cudaFree(ctx->clusters); cudaFree(ctx->counters);
     cudaFree(ctx->quads); cudaFree(ctx->quad_order);
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
-    if (ex) { cudaFree(ex->tile_active); cudaFree(ex->tile_list); cudaFree(ex->used_slots); cudaFree(ex->work_counter); delete ex; }
+    if (ex) {
+        cudaFree(ex->tile_active); cudaFree(ex->tile_list); cudaFree(ex->used_slots); cudaFree(ex->work_counter);
+        for (int k = 0; k < 2; k++) { cudaFree(ex->alist[k]); cudaFree(ex->alist_thr[k]); }
+        delete ex;
+    }
     ctx->point_rank = nullptr;
 }
 
@@ -1192,33 +1161,37 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: unsupported image size");
     DetectExtra *ex = reinterpret_cast<DetectExtra *>(ctx->point_rank);
     int tw = w / 4, th = h / 4;
-    // ternary image invariant: 127 everywhere except the tiles listed by the previous batch -> reset exactly those
+    // ternary image invariant: 127 everywhere except the tiles of the previous batch's A-list -> reset exactly those
+    const int prev = ex->acur, cur = prev ^ 1;
+    ex->acur = cur;
     if (ex->thresh_full || ex->prev_w != w || ex->prev_h != h) {
         if (ex->thresh_full || ex->prev_w != 0)
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->thresh, 127, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h, st));
         ex->thresh_full = false;
     } else {
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_reset_thresh<<<chain_grid() * 4, CCL_THREADS, 0, st>>>(ctx->thresh, w, h, ex->tile_list, ex->work_counter + 1, div_up(w, CCL_TW)));
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_reset_thresh<<<chain_grid(), 256, 0, st>>>(ctx->thresh, w, h, ex->alist[prev], ex->work_counter + 2 + prev, ex->acap));
     }
     ex->prev_w = w; ex->prev_h = h;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
     CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter, 0, 2 * sizeof(int), st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ex->work_counter + 2 + cur, 0, sizeof(int), st));
     const int ctw = div_up(w, CCL_TW), cth = div_up(h, CCL_TH), nct = ctw * cth;
     CUDA_TRY(ctx, cudaMemsetAsync(ex->tile_active, 0, (size_t)batch * nct, st));
+    int *acount = ex->work_counter + 2 + cur;
     {
         dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
         if (!have_tile_minmax)
             KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmm));
-        const int bw = div_up(w, 64), bh = div_up(h, 32);   // blocks of the fused preprocess kernel (64 x 32 px)
-        dim3 bgrid(div_up(bw * bh * 32, 128), 1, batch);
-        if (!have_tile_minmax)
-            KLAUNCH(ctx, KID_TILE_MINMAX, st, k_block_minmax<<<bgrid, 128, 0, st>>>(ctx->tmm, tw, th, bw, bh, ctx->bmm));
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold<<<bgrid, 128, 0, st>>>(gray, w, h, tw, th, ctx->tmm, ctx->bmm, bw, bh, dp.min_white_black_diff,
-                                                                          ctx->thresh, ex->tile_active, ctw, cth));
+        dim3 tgrid(div_up(div_up(tw, THR_TPT), 128), th, batch);
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_scan<<<tgrid, 128, 0, st>>>(w, h, tw, th, ctx->tmm, dp.min_white_black_diff, ex->alist[cur],
+                                                                               ex->alist_thr[cur], acount, ex->acap, ex->tile_active, ctw, cth));
         if (tw * 4 != w || th * 4 != h) {
             KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmm, ctx->thresh,
-                                                                                     ex->tile_active, ctw, cth));
+                                                                                     ex->tile_active, ctw, cth, ex->alist[cur], ex->alist_thr[cur],
+                                                                                     acount, ex->acap));
         }
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_apply<<<chain_grid(), 256, 0, st>>>(gray, w, h, tw, th, ex->alist[cur], ex->alist_thr[cur], acount,
+                                                                                      ex->acap, ctx->thresh));
     }
     {
         int *n_active = ex->work_counter + 1;
@@ -1228,8 +1201,9 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
         KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid() * 2, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
         KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
-        KLAUNCH(ctx, KID_EMIT, st, k_emit_points<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, ctx->hash_keys,
-                                                                          ctx->hash_count, ex->used_slots, ctx->points, ctx->counters));
+        KLAUNCH(ctx, KID_EMIT, st, k_emit_scan<<<chain_grid(), 256, 0, st>>>(ctx->thresh, w, h, ex->alist[cur], acount, ex->acap, ctx->points, ctx->counters));
+        KLAUNCH(ctx, KID_EMIT, st, k_emit_insert<<<dim3(148, min(batch, 8)), 256, 0, st>>>(w, h, ctx->labels, ctx->hash_keys, ctx->hash_count, ex->used_slots,
+                                                                                         ctx->points, ctx->counters, batch));
     }
     KLAUNCH(ctx, KID_CLUSTER_SCAN, st, k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ex->used_slots, ctx->clusters, ctx->counters,
                                            dp.min_cluster_pixels, dp.max_cluster_points));

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 #define P2_RAW_STRIDE (P2_RAW_BYTES + 128)    // two staging buffers (double-buffered over frames), 128 B slack each
 #define P2_OFF_TABLES (2 * P2_RAW_STRIDE)
 #define P2_OFF_MISC (P2_OFF_TABLES + (int)sizeof(P2Tables))
-#define P2_SMEM_BYTES (P2_OFF_MISC + 48)
+#define P2_SMEM_BYTES (P2_OFF_MISC + 32)
 #define XZ_MAGIC 551553470                    // ceil(108 * 2^32 / 841)
 
 static void build_p2_tables_host(P2Tables &P, const LabTables &T)
@@ -417,7 +417,7 @@ __device__ __forceinline__ void k1t_pixels(const P2Tables *T, const uint32_t (&a
 template <bool WANT_BGR, int NREG, int WC>
 __global__ void __maxnreg__(NREG)
 k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
-                 uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm, uint16_t *__restrict__ bmm,
+                 uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm,
                  const float *__restrict__ mapx, const float *__restrict__ mapy, const P2Tables *__restrict__ tables, int w_rt, int h,
                  int batch, int fpb)
 {
@@ -425,7 +425,6 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     P2Tables *T = reinterpret_cast<P2Tables *>(smem + P2_OFF_TABLES);
     unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);   // two barriers
     int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 16);   // xmin, xmax, ymin, ymax
-    int *blk = reinterpret_cast<int *>(smem + P2_OFF_MISC + 32);   // block extrema of gray, double-buffered: {min, max} x 2
     const int w = WC ? WC : w_rt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mbar0 = smem_u32(mbar_p), raw0 = smem_u32(smem);
@@ -440,7 +439,6 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8));
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         box[0] = INT32_MAX; box[1] = INT32_MIN; box[2] = INT32_MAX; box[3] = INT32_MIN;
-        blk[0] = 255; blk[1] = 0; blk[2] = 255; blk[3] = 0;
     }
     __syncthreads();
 
@@ -493,12 +491,10 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     const size_t tile_stride = (size_t)(h >> 2) * tw4;
     uint16_t *tp = tmm ? tmm + (size_t)f0 * tile_stride + (size_t)((valid ? y0 : 0) >> 2) * tw4 + ((valid ? x : 0) >> 2) : nullptr;
     const bool tile_writer = valid && (lane & 3) == 0;
-    const size_t blk_stride = (size_t)gridDim.x * gridDim.y;
-    uint16_t *bp = bmm ? bmm + (size_t)f0 * blk_stride + (size_t)blockIdx.y * gridDim.x + blockIdx.x : nullptr;
 
-    // stores of one frame + the 4x4-tile extrema (this thread holds one column of a tile, 4 lanes hold its columns) + the
-    // extrema of the whole 64x32 block (coarse filter of the threshold stage), then advance the cursors
-    auto finish = [&](const int (&g)[P2_NPX], const int (&o0)[P2_NPX], const int (&o1)[P2_NPX], const int (&o2)[P2_NPX], int par) {
+    // stores of one frame + the 4x4-tile extrema (this thread holds one column of a tile, 4 lanes hold its columns),
+    // then advance the cursors
+    auto finish = [&](const int (&g)[P2_NPX], const int (&o0)[P2_NPX], const int (&o1)[P2_NPX], const int (&o2)[P2_NPX]) {
         if (valid) {
 #pragma unroll
             for (int k = 0; k < P2_NPX; k++) {
@@ -515,10 +511,6 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                 mn = min(min(g[0], g[1]), min(g[2], g[3]));
                 mx = max(max(g[0], g[1]), max(g[2], g[3]));
             }
-            if (bmm) {
-                const int wmn = __reduce_min_sync(0xffffffffu, mn), wmx = __reduce_max_sync(0xffffffffu, mx);
-                if (lane == 0) { atomicMin(&blk[2 * par], wmn); atomicMax(&blk[2 * par + 1], wmx); }
-            }
             mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             if (tile_writer) *tp = (uint16_t)(mn | (mx << 8));
@@ -527,15 +519,6 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         gp += frame_px;
         if (WANT_BGR) cp += frame_px * 3;
     };
-    // after the frame's closing barrier: thread 0 publishes the block extrema and re-arms the slot (used again in two frames)
-    auto publish = [&](int par) {
-        if (bmm && tid == 0) {
-            *bp = (uint16_t)(blk[2 * par] | (blk[2 * par + 1] << 8));
-            blk[2 * par] = 255; blk[2 * par + 1] = 0;
-        }
-        if (bmm) bp += blk_stride;
-    };
-
     if (fast) {
         if (tid == 0) tma_load_box(raw0, &tmap, c0x, by0, f0, mbar0);
         // two frames per trip: staging buffer, barrier and extrema slot of a frame are compile-time constants
@@ -546,18 +529,16 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                 mbar_wait(mbar0, ph);
                 int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
                 if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, 0u, g, o0, o1, o2);
-                finish(g, o0, o1, o2, 0);
+                finish(g, o0, o1, o2);
                 __syncthreads();   // all reads of this frame's buffer done before it is refilled (frame f + 2)
-                publish(0);
             }
             if (f + 1 < f1) {
                 if (warp == 0) { if (lane == 0 && f + 2 < f1) tma_load_box(raw0, &tmap, c0x, by0, f + 2, mbar0); }
                 mbar_wait(mbar0 + 8, ph);
                 int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
                 if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, (uint32_t)P2_RAW_STRIDE, g, o0, o1, o2);
-                finish(g, o0, o1, o2, 1);
+                finish(g, o0, o1, o2);
                 __syncthreads();
-                publish(1);
             }
         }
     } else {
@@ -574,10 +555,7 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                     g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
                 }
             }
-            const int par = (f - f0) & 1;
-            finish(g, o0, o1, o2, par);
-            if (bmm) __syncthreads();
-            publish(par);
+            finish(g, o0, o1, o2);
         }
     }
 }
@@ -632,8 +610,7 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     static const int fpb_max = getenv("APSE_K1_FPB") ? atoi(getenv("APSE_K1_FPB")) : 20;   // development knob
     const int nz = div_up(batch, fpb_max), fpb = div_up(batch, nz);
     dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), nz);
-    uint16_t *bmm = tmm ? ctx->bmm : nullptr;   // block extrema accompany the tile extrema (threshold stage)
-#define K1T_ARGS tmap, bgr, bgr_out, gray, tmm, bmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb
+#define K1T_ARGS tmap, bgr, bgr_out, gray, tmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb
     if (bgr_out)
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true, 64, 0><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840)
