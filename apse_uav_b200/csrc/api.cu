@@ -370,7 +370,7 @@ int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_
     cudaStream_t st = (cudaStream_t)stream;
     DeviceParams dp;
     apse_fill_device_params(ctx, &dp, w, h);
-    int rc = apse_apriltag_quads(ctx, gray, w, h, 1, dp, st);
+    int rc = apse_apriltag_quads(ctx, gray, w, h, 1, dp, st, false, true);
     if (rc) return rc;
     size_t npx = (size_t)w * h;
     if (thresh) CUDA_TRY(ctx, cudaMemcpyAsync(thresh, ctx->thresh, npx, cudaMemcpyDeviceToDevice, st));

@@ -165,7 +165,8 @@ int apse_decode_alloc(apse_ctx *ctx);
 void apse_decode_free(apse_ctx *ctx);
 int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h);
 int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
-                        cudaStream_t st, bool have_tile_minmax = false);   // true: ctx->tmm already holds this batch's tile extrema
+                        cudaStream_t st, bool have_tile_minmax = false,    // true: ctx->tmm already holds this batch's tile extrema
+                        bool flat_labels = false);                         // true: ctx->labels fully flattened (debug entry point)
 int apse_decode_big_scratch(apse_ctx *ctx);
 int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out, cudaStream_t st);
 int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, cudaStream_t st);

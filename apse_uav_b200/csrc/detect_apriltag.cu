@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(256) k_emit_scan(const uint8_t *__restrict__ t
 
 // Phase 2: one thread per record: component pair -> cluster hash slot and rank, record rewritten in place as
 // {slot, rank, 2x + dx | (2y + dy) << 16, gx | gy << 16}.  Every lane has a point.
-__global__ void __launch_bounds__(256) k_emit_insert(int w, int h, const uint32_t *__restrict__ labels,
+__global__ void __launch_bounds__(256) k_emit_insert(int w, int h, uint32_t *__restrict__ labels,
                                                      unsigned long long *__restrict__ hash_keys, uint32_t *__restrict__ hash_count,
                                                      uint32_t *__restrict__ used_slots, uint4 *__restrict__ points,
                                                      int32_t *__restrict__ counters, int batch)
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256) k_emit_insert(int w, int h, const uint32_
     for (int f = blockIdx.y; f < batch; f += gridDim.y) {
         int32_t *cnt = counters + f * APSE_COUNTERS;
         const int n = min(cnt[0], APSE_MAX_POINTS);
-        const uint32_t *L = labels + (size_t)f * w * h;
+        uint32_t *L = labels + (size_t)f * w * h;
         unsigned long long *hk = hash_keys + (size_t)f * APSE_HASH_SLOTS;
         uint32_t *hc = hash_count + (size_t)f * APSE_HASH_SLOTS;
         uint4 *pts = points + (size_t)f * APSE_MAX_POINTS;
@@ -504,7 +504,13 @@ __global__ void __launch_bounds__(256) k_emit_insert(int w, int h, const uint32_
             const uint4 rec = pts[i];
             const int x = rec.x & 0xffff, y = rec.x >> 16, k = rec.y & 3, v0 = (rec.y & 256u) ? 255 : 0, v1 = 255 - v0;
             const int dx = DX[k], dy = DY[k];
-            const unsigned long long a = L[(size_t)y * w + x], b = L[(size_t)(y + dy) * w + x + dx];
+            // component ids: root walks from the two pixels (pixel -> tile-local root -> roots merged across tiles), with the
+            // root written back to the pixel; only crossing pixels ever pay for this, there is no flatten pass over all pixels
+            const uint32_t pa = (uint32_t)(y * w + x), pb = (uint32_t)((y + dy) * w + x + dx);
+            const uint32_t ra = uf_find<uint32_t>(L, pa), rb = uf_find<uint32_t>(L, pb);
+            if (L[pa] != ra) L[pa] = ra;
+            if (L[pb] != rb) L[pb] = rb;
+            const unsigned long long a = ra, b = rb;
             const unsigned long long key = a < b ? (b << 32) + a : (a << 32) + b;
             uint32_t slot = hash64(key) & (APSE_HASH_SLOTS - 1);
             bool ok = true;
@@ -1143,16 +1149,16 @@ void apse_detect_free(apse_ctx *ctx)
     ctx->point_rank = nullptr;
 }
 
-// persistent grid of the work-list kernels (development knob APSE_CHAIN_GRID = CTAs per SM, default 4)
+// persistent grid of the work-list kernels (development knob APSE_CHAIN_GRID = CTAs per SM, default 2)
 static int chain_grid()
 {
-    static const int g = 148 * (getenv("APSE_CHAIN_GRID") ? atoi(getenv("APSE_CHAIN_GRID")) : 4);
+    static const int g = 148 * (getenv("APSE_CHAIN_GRID") ? atoi(getenv("APSE_CHAIN_GRID")) : 2);
     return g > 0 ? g : 148;
 }
 
 // runs K2..K5 for `batch` gray frames; leaves quads / counters in the context scratch
 int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp, cudaStream_t st,
-                        bool have_tile_minmax)
+                        bool have_tile_minmax, bool flat_labels)
 {
     if (w > ctx->max_w || h > ctx->max_h || batch > ctx->max_batch || batch > 64)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: frame %dx%d x%d exceeds the context capacity %dx%d x%d (64 max)", w, h,
@@ -1200,7 +1206,8 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         const int grid = chain_grid() * 4;   // persistent: 16 CTAs of 128 threads per SM, tiles taken round-robin from the list
         KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
         KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid() * 2, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
-        KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
+        if (flat_labels)   // every pixel labelled with its component root: only the debug entry point wants that
+            KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
         KLAUNCH(ctx, KID_EMIT, st, k_emit_scan<<<chain_grid(), 256, 0, st>>>(ctx->thresh, w, h, ex->alist[cur], acount, ex->acap, ctx->points, ctx->counters));
         KLAUNCH(ctx, KID_EMIT, st, k_emit_insert<<<dim3(148, min(batch, 8)), 256, 0, st>>>(w, h, ctx->labels, ctx->hash_keys, ctx->hash_count, ex->used_slots,
                                                                                          ctx->points, ctx->counters, batch));
