@@ -23,12 +23,10 @@ struct LabTables {  // integer sRGB<->Lab tables; ly/lf already 
     uint8_t invgamma[4096];
 };
 
-struct P2Tables {   // composed tables of the TMA-staged preprocess kernel (preprocess.cu, K1t)
+struct P2Tables {   // tables of the TMA-staged preprocess kernel (preprocess.cu, K1t), 8.8 KB of shared memory
     uint16_t gamma[256];     // 8-bit sRGB -> linear * 2040
-    int16_t at[1008];        // (500 (fX - fY) + c) >> 15, offset 372 -> X-axis shift of Lab2RGB (clip to 8 bit folded in)
-    int16_t bt[408];         // (200 (fY - fZ) + c) >> 15, offset 72  -> Z-axis shift
     uint16_t cb[2048];       // cube-root table on the 0..2040 index range
-    uint2 yt[2048];          // idxY -> {cbrt | y << 16, f}: L, the gamma LUT on L and LabToYF composed
+    uint32_t yf[256];        // L -> y | f << 16: the gamma LUT on L and LabToYF composed
     uint8_t invgamma[4096];
 };
 

@@ -294,25 +294,8 @@ static void build_p2_tables_host(P2Tables &P, const LabTables &T)
     memcpy(P.gamma, T.gamma, sizeof P.gamma);
     memcpy(P.invgamma, T.invgamma, sizeof P.invgamma);
     memset(P.cb, 0, sizeof P.cb);
-    memset(P.yt, 0, sizeof P.yt);
-    for (int i = 0; i <= 2040; i++) {
-        int fY = T.cbrt[i];
-        int L = (296 * fY - 1336934 + 16384) >> 15;
-        L = L < 0 ? 0 : L > 255 ? 255 : L;
-        P.cb[i] = (uint16_t)fY;
-        P.yt[i].x = (uint32_t)fY | ((uint32_t)T.ly[L] << 16);
-        P.yt[i].y = T.lf[L];
-    }
-    for (int i = 0; i < 1008; i++) {
-        int a = i - 372;
-        a = a < 0 ? 0 : a > 255 ? 255 : a;
-        P.at[i] = (int16_t)(((5 * a * 53687 + 128) >> 13) - 4194);
-    }
-    for (int i = 0; i < 408; i++) {
-        int b = i - 72;
-        b = b < 0 ? 0 : b > 255 ? 255 : b;
-        P.bt[i] = (int16_t)(((b * 41943 + 16) >> 9) - 10485 + 1);
-    }
+    for (int i = 0; i <= 2040; i++) P.cb[i] = T.cbrt[i];
+    for (int L = 0; L < 256; L++) P.yf[L] = (uint32_t)T.ly[L] | ((uint32_t)T.lf[L] << 16);   // ly / lf: gamma LUT on L composed in
 }
 
 int apse_upload_p2_tables(apse_ctx *ctx, const uint8_t *lut, P2Tables **dev, cudaStream_t st)
@@ -338,19 +321,25 @@ __device__ __forceinline__ int xz_px(int v)
     return v <= 3390 ? lo : hi;
 }
 
-// colour chain of one pixel on the composed tables: (c0,c1,c2) -> corrected (o0,o1,o2) and gray
+// colour chain of one pixel on the composed tables: (c0,c1,c2) -> corrected (o0,o1,o2) and gray.
+// Shared-memory wavefronts are what the kernel runs out of first (84 % of the pipe), so the chain spends a few integer
+// instructions where that saves look-ups with scattered indices: L comes from fY arithmetically and indexes a 256-entry
+// {y, f} table (narrow index spread, ~1 wavefront) instead of an 8-byte entry per idxY (5.5 wavefronts), and the two
+// chroma shifts are computed (clamp + multiply + shift) instead of being read from tables.
 __device__ __forceinline__ int chain_px(const P2Tables *T, int c0, int c1, int c2, int &o0, int &o1, int &o2)
 {
     int R = T->gamma[c0], G = T->gamma[c1], B = T->gamma[c2];
     int iX = (R * 1777 + G * 1541 + B * 778 + 2048) >> 12;
     int iY = (R * 871 + G * 2929 + B * 296 + 2048) >> 12;
     int iZ = (R * 73 + G * 448 + B * 3575 + 2048) >> 12;
-    uint2 yv = T->yt[iY];
-    int fX = T->cb[iX], fZ = T->cb[iZ];
-    int fY = yv.x & 0xffff, y = yv.x >> 16, f = (int)yv.y;
-    int ia = (500 * (fX - fY) + 128 * 32768 + 16384) >> 15;
-    int ib = (200 * (fY - fZ) + 128 * 32768 + 16384) >> 15;
-    int X = xz_px(f + T->at[ia + 372]), Z = xz_px(f - T->bt[ib + 72]);
+    int fX = T->cb[iX], fY = T->cb[iY], fZ = T->cb[iZ];
+    const int L = __vimin_s32_relu((296 * fY - 1336934 + 16384) >> 15, 255);
+    const uint32_t yf = T->yf[L];
+    const int y = (int)(yf & 0xffffu), f = (int)(yf >> 16);
+    const int a = __vimin_s32_relu((500 * (fX - fY) + 128 * 32768 + 16384) >> 15, 255);
+    const int b = __vimin_s32_relu((200 * (fY - fZ) + 128 * 32768 + 16384) >> 15, 255);
+    const int adiv = ((a * (5 * 53687) + 128) >> 13) - 4194, bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
+    int X = xz_px(f + adiv), Z = xz_px(f - bdiv);
     int r0 = (12615 * X - 6296 * y - 2223 * Z + 8192) >> 14;
     int r1 = (-3773 * X + 7684 * y + 185 * Z + 8192) >> 14;
     int r2 = (217 * X - 836 * y + 4715 * Z + 8192) >> 14;
