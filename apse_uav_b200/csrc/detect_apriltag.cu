@@ -92,49 +92,86 @@ __global__ void __launch_bounds__(128) k_threshold_scan(int w, int h, int tw, in
     const int groups = (tw + THR_TPT - 1) / THR_TPT;
     const int gi = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y, f = blockIdx.z, lane = threadIdx.x & 31;
     const int tx0 = gi * THR_TPT;
-    int cmn[THR_TPT + 2], cmx[THR_TPT + 2];   // vertical extrema of columns tx0 - 1 .. tx0 + 8
-#pragma unroll
-    for (int c = 0; c < THR_TPT + 2; c++) { cmn[c] = 255; cmx[c] = 0; }
-    if (gi < groups) {
-        const uint16_t *T = tmm + (size_t)f * tw * th;
-        const bool vec = (tw % THR_TPT) == 0;     // rows are 16-byte aligned and every group is complete
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++) {
-            const int yy = ty + dy;
-            if (yy < 0 || yy >= th) continue;
-            const uint16_t *row = T + (size_t)yy * tw;
-            uint32_t wv[4];
-            if (vec) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row + tx0));
-                wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
-            } else {
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const int xa = tx0 + 2 * c, xb = xa + 1;
-                    const uint32_t a = xa < tw ? __ldg(row + xa) : 0x00ffu, b = xb < tw ? __ldg(row + xb) : 0x00ffu;
-                    wv[c] = a | (b << 16);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < THR_TPT; c++) {
-                const uint32_t e = (wv[c >> 1] >> ((c & 1) * 16)) & 0xffffu;
-                cmn[c + 1] = min(cmn[c + 1], (int)(e & 255u)); cmx[c + 1] = max(cmx[c + 1], (int)(e >> 8));
-            }
-            if (tx0 > 0) { const int e = __ldg(row + tx0 - 1); cmn[0] = min(cmn[0], e & 255); cmx[0] = max(cmx[0], e >> 8); }
-            if (tx0 + THR_TPT < tw) { const int e = __ldg(row + tx0 + THR_TPT); cmn[THR_TPT + 1] = min(cmn[THR_TPT + 1], e & 255); cmx[THR_TPT + 1] = max(cmx[THR_TPT + 1], e >> 8); }
-        }
-    }
+    const uint16_t *T = tmm + (size_t)f * tw * th;
     unsigned on = 0;       // bit c: tile tx0 + c is high-contrast
     uint32_t thr8[2] = {0, 0};
+    if ((tw % THR_TPT) == 0) {
+        // rows are 16-byte aligned and every group is complete: two tiles per register, 16-bit SIMD min / max
+        // (VIMNMX3.U16x2).  hmn[j] / hmx[j] = dilated extrema of tiles tx0 + 2j (low half) and tx0 + 2j + 1 (high half).
+        uint32_t hmn[4], hmx[4];
+        if (gi < groups) {
+            uint32_t mn[3][5], mx[3][5];   // [row][pair 0..3, 4 = {left column, right column}]
 #pragma unroll
-    for (int c = 0; c < THR_TPT; c++) {
-        const int mn = min(cmn[c], min(cmn[c + 1], cmn[c + 2])), mx = max(cmx[c], max(cmx[c + 1], cmx[c + 2]));
-        if (gi < groups && tx0 + c < tw && (mx - mn) >= min_wb_diff) {
-            on |= 1u << c;
-            thr8[c >> 2] |= (uint32_t)(mn + (mx - mn) / 2) << ((c & 3) * 8);
+            for (int r = 0; r < 3; r++) {
+                const int yy = ty + r - 1;
+                uint32_t wv[5] = {0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu};   // (min 255, max 0)
+                if (yy >= 0 && yy < th) {
+                    const uint16_t *row = T + (size_t)yy * tw;
+                    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row + tx0));
+                    wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+                    const uint32_t l = tx0 > 0 ? __ldg(row + tx0 - 1) : 0x00ffu, rr = tx0 + THR_TPT < tw ? __ldg(row + tx0 + THR_TPT) : 0x00ffu;
+                    wv[4] = l | (rr << 16);
+                }
+#pragma unroll
+                for (int c = 0; c < 5; c++) { mn[r][c] = wv[c] & 0x00ff00ffu; mx[r][c] = __byte_perm(wv[c], 0u, 0x4341); }
+            }
+            uint32_t vmn[5], vmx[5];
+#pragma unroll
+            for (int c = 0; c < 5; c++) { vmn[c] = __vimin3_u16x2(mn[0][c], mn[1][c], mn[2][c]); vmx[c] = __vimax3_u16x2(mx[0][c], mx[1][c], mx[2][c]); }
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t ln = c == 0 ? __byte_perm(vmn[4], vmn[0], 0x5410) : __byte_perm(vmn[c - 1], vmn[c], 0x5432);
+                const uint32_t rn = c == 3 ? __byte_perm(vmn[3], vmn[4], 0x7632) : __byte_perm(vmn[c], vmn[c + 1], 0x5432);
+                const uint32_t lx_ = c == 0 ? __byte_perm(vmx[4], vmx[0], 0x5410) : __byte_perm(vmx[c - 1], vmx[c], 0x5432);
+                const uint32_t rx = c == 3 ? __byte_perm(vmx[3], vmx[4], 0x7632) : __byte_perm(vmx[c], vmx[c + 1], 0x5432);
+                hmn[c] = __vimin3_u16x2(ln, vmn[c], rn);
+                hmx[c] = __vimax3_u16x2(lx_, vmx[c], rx);
+            }
+            // range >= diff  <=>  bit 15 of (range + 0x8000 - diff) per 16-bit lane (range <= 255, no carry between lanes)
+            const int d = min(max(min_wb_diff, 0), 0x7fff);
+            const uint32_t kk = (uint32_t)(0x8000 - d) * 0x00010001u;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t t = (hmx[c] - hmn[c]) + kk;
+                on |= ((t >> 15) & 1u) << (2 * c) | (t >> 31) << (2 * c + 1);
+            }
         }
+        if (!__any_sync(0xffffffffu, on != 0)) return;
+#pragma unroll
+        for (int c = 0; c < THR_TPT; c++) {
+            if (!((on >> c) & 1u)) continue;
+            const uint32_t a = (hmn[c >> 1] >> ((c & 1) * 16)) & 0xffffu, b = (hmx[c >> 1] >> ((c & 1) * 16)) & 0xffffu;
+            thr8[c >> 2] |= (a + (b - a) / 2) << ((c & 3) * 8);
+        }
+    } else {
+        int cmn[THR_TPT + 2], cmx[THR_TPT + 2];   // vertical extrema of columns tx0 - 1 .. tx0 + 8
+#pragma unroll
+        for (int c = 0; c < THR_TPT + 2; c++) { cmn[c] = 255; cmx[c] = 0; }
+        if (gi < groups) {
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++) {
+                const int yy = ty + dy;
+                if (yy < 0 || yy >= th) continue;
+                const uint16_t *row = T + (size_t)yy * tw;
+#pragma unroll
+                for (int c = 0; c < THR_TPT + 2; c++) {
+                    const int xx = tx0 + c - 1;
+                    if (xx < 0 || xx >= tw) continue;
+                    const int e = __ldg(row + xx);
+                    cmn[c] = min(cmn[c], e & 255); cmx[c] = max(cmx[c], e >> 8);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < THR_TPT; c++) {
+            const int mn = min(cmn[c], min(cmn[c + 1], cmn[c + 2])), mx = max(cmx[c], max(cmx[c + 1], cmx[c + 2]));
+            if (gi < groups && tx0 + c < tw && (mx - mn) >= min_wb_diff) {
+                on |= 1u << c;
+                thr8[c >> 2] |= (uint32_t)(mn + (mx - mn) / 2) << ((c & 3) * 8);
+            }
+        }
+        if (!__any_sync(0xffffffffu, on != 0)) return;
     }
-    if (!__any_sync(0xffffffffu, on != 0)) return;
     const int cnt = __popc(on);
     int inc = cnt;
 #pragma unroll

@@ -1,5 +1,5 @@
-// pose.cu -- batched per-marker pose and point projection (FP64, one thread per marker / point):
-//   k_pose            aruco_detect.py:601  aruco.estimatePoseSingleMarkers = solvePnP(ITERATIVE) per marker
+// pose.cu -- batched per-marker pose (FP64, four lanes per marker) and point projection (one thread per point):
+//   k_pose4 / k_pose_frames4   aruco_detect.py:601  aruco.estimatePoseSingleMarkers = solvePnP(ITERATIVE) per marker
 //   k_project_points  aruco_detect.py:344,377,424,468  cv2.projectPoints with the 14-coefficient model
 // Recipe of the dependency: 5 fixed-point undistortion iterations -> planar homography
 // initialisation -> Levenberg-Marquardt (lambda = 10^k, diag*(1+lambda), <= 20 accepted iterations,
@@ -256,104 +256,9 @@ __device__ void sym_solve6(const double *Ain, const double *b, double *x)
     }
 }
 
-__device__ double norm_n(const double *a, int n)
-{
-    double s = 0;
-    for (int i = 0; i < n; i++) s += a[i] * a[i];
-    return sqrt(s);
-}
-
-__device__ void solve_pnp_planar(const double *obj, const double *img, const CamModel &C, double *rvec, double *tvec)
-{
-    const int n = 4;
-    const double *k = C.k;
-    double mn[8];
-    const double ifx = 1. / C.fx, ify = 1. / C.fy;
-    for (int i = 0; i < n; i++) {  // undistortPoints, exactly 5 iterations
-        double u = img[2 * i], v = img[2 * i + 1];
-        double x = (u - C.cx) * ifx, y = (v - C.cy) * ify, x0 = x, y0 = y;
-        for (int j = 0; j < 5; j++) {
-            double r2 = x * x + y * y;
-            double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
-            if (icdist < 0) { x = (u - C.cx) * ifx; y = (v - C.cy) * ify; break; }
-            double dX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
-            double dY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
-            x = (x0 - dX) * icdist;
-            y = (y0 - dY) * icdist;
-        }
-        mn[2 * i] = x; mn[2 * i + 1] = y;
-    }
-    double param[6] = {0, 0, 0, 0, 0, 0};
-    {
-        double A[64], b[8];
-        for (int i = 0; i < 64; i++) A[i] = 0;
-        for (int i = 0; i < 4; i++) {
-            double X = obj[3 * i], Y = obj[3 * i + 1], x = mn[2 * i], y = mn[2 * i + 1];
-            double *r0 = A + i * 8, *r1 = A + (i + 4) * 8;
-            r0[0] = X; r0[1] = Y; r0[2] = 1; r0[6] = -x * X; r0[7] = -x * Y; b[i] = x;
-            r1[3] = X; r1[4] = Y; r1[5] = 1; r1[6] = -y * X; r1[7] = -y * Y; b[i + 4] = y;
-        }
-        if (lu_solve8(A, b)) {
-            const double H[9] = {b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], 1.};
-            double h1n = sqrt(H[0] * H[0] + H[3] * H[3] + H[6] * H[6]);
-            double h2n = sqrt(H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
-            double s1 = 1. / fmax(h1n, DBL_EPSILON), s2 = 1. / fmax(h2n, DBL_EPSILON), st = 2. / fmax(h1n + h2n, DBL_EPSILON);
-            double h1[3] = {H[0] * s1, H[3] * s1, H[6] * s1}, h2[3] = {H[1] * s2, H[4] * s2, H[7] * s2};
-            double h3[3] = {h1[1] * h2[2] - h1[2] * h2[1], h1[2] * h2[0] - h1[0] * h2[2], h1[0] * h2[1] - h1[1] * h2[0]};
-            double R0[9] = {h1[0], h2[0], h3[0], h1[1], h2[1], h3[1], h1[2], h2[2], h3[2]};
-            double r[3], R[9];
-            rodrigues_mat2vec(R0, r);
-            rodrigues_vec2mat(r, R, nullptr);
-            rodrigues_mat2vec(R, r);
-            param[0] = r[0]; param[1] = r[1]; param[2] = r[2];
-            param[3] = H[2] * st; param[4] = H[5] * st; param[5] = H[8] * st;
-        }
-    }
-    double prev[6], J[48], err[8], JtJ[36], JtErr[6], proj[8], dpdr[24], dpdt[24];
-    double prevErrNorm = DBL_MAX, errNorm = 0;
-    int lambdaLg10 = -3, iters = 0;
-    const double LOG10 = log(10.);
-    for (;;) {
-        project_points(obj, n, param, param + 3, C, proj, dpdr, dpdt);
-        for (int i = 0; i < 2 * n; i++) {
-            err[i] = proj[i] - img[i];
-            for (int j = 0; j < 3; j++) { J[i * 6 + j] = dpdr[i * 3 + j]; J[i * 6 + 3 + j] = dpdt[i * 3 + j]; }
-        }
-        for (int a = 0; a < 6; a++) {
-            for (int b = 0; b < 6; b++) {
-                double s = 0;
-                for (int i = 0; i < 2 * n; i++) s += J[i * 6 + a] * J[i * 6 + b];
-                JtJ[a * 6 + b] = s;
-            }
-            double s = 0;
-            for (int i = 0; i < 2 * n; i++) s += J[i * 6 + a] * err[i];
-            JtErr[a] = s;
-        }
-        for (int a = 0; a < 6; a++) prev[a] = param[a];
-        if (iters == 0) prevErrNorm = norm_n(err, 2 * n);
-        for (;;) {
-            double A[36], d[6], lambda = exp(lambdaLg10 * LOG10);
-            for (int i = 0; i < 36; i++) A[i] = JtJ[i];
-            for (int a = 0; a < 6; a++) A[a * 6 + a] *= 1. + lambda;
-            sym_solve6(A, JtErr, d);
-            for (int a = 0; a < 6; a++) param[a] = prev[a] - d[a];
-            project_points(obj, n, param, param + 3, C, proj, nullptr, nullptr);
-            for (int i = 0; i < 2 * n; i++) err[i] = proj[i] - img[i];
-            errNorm = norm_n(err, 2 * n);
-            if (errNorm > prevErrNorm && ++lambdaLg10 <= 16) continue;
-            break;
-        }
-        lambdaLg10 = max(lambdaLg10 - 1, -16);
-        double dd[6];
-        for (int a = 0; a < 6; a++) dd[a] = param[a] - prev[a];
-        if (++iters >= 20 || norm_n(dd, 6) / norm_n(prev, 6) < FLT_EPSILON) break;
-        prevErrNorm = errNorm;
-    }
-    for (int a = 0; a < 3; a++) { rvec[a] = param[a]; tvec[a] = param[3 + a]; }
-}
 
 // ---------------------------------------------------------------------------------------------------------
-// Four lanes per marker (lane j of a group owns corner j).  The single-thread solver above keeps its arrays in local
+// Four lanes per marker (lane j of a group owns corner j).  A thread-per-marker solver keeps its arrays in local
 // memory and is one long dependent FP64 chain (~0.4 ms per launch whatever the marker count); here the projection with
 // its Jacobian rows, the residuals and the partial normal equations are computed per corner in registers, the 27
 // normal-equation sums are combined with two butterfly shuffles (every lane of the group ends up with bit-identical
@@ -655,20 +560,6 @@ __global__ void __launch_bounds__(128) k_pose_frames4(const float *__restrict__ 
                         rvec + 3 * (size_t)i, tvec + 3 * (size_t)i);
 }
 
-__global__ void k_pose(const float *__restrict__ corners, int n, const float *__restrict__ marker_len, float marker_len_all,
-                       CamModel C, double *__restrict__ rvec, double *__restrict__ tvec)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float L = marker_len ? marker_len[i] : marker_len_all;
-    float hh = L / 2.f;  // legacy API: float marker length, float32 object points
-    double h = hh;
-    const double obj[12] = {-h, h, 0, h, h, 0, h, -h, 0, -h, -h, 0};
-    double img[8];
-    for (int j = 0; j < 8; j++) img[j] = corners[8 * (size_t)i + j];
-    solve_pnp_planar(obj, img, C, rvec + 3 * (size_t)i, tvec + 3 * (size_t)i);
-}
-
 __global__ void k_project_points(const double *__restrict__ obj, int n, const double *__restrict__ rvec,
                                  const double *__restrict__ tvec, CamModel C, double *__restrict__ img)
 {
@@ -676,23 +567,6 @@ __global__ void k_project_points(const double *__restrict__ obj, int n, const do
     if (i >= n) return;
     double r[3] = {rvec[0], rvec[1], rvec[2]}, t[3] = {tvec[0], tvec[1], tvec[2]};
     project_points(obj + 3 * (size_t)i, 1, r, t, C, img + 2 * (size_t)i, nullptr, nullptr);
-}
-
-__global__ void k_pose_frames(const float *__restrict__ corners, const int32_t *__restrict__ n_markers, int batch,
-                              int max_markers, const float *__restrict__ marker_len, float marker_len_all, CamModel C,
-                              double *__restrict__ rvec, double *__restrict__ tvec)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= batch * max_markers) return;
-    int f = i / max_markers, m = i - f * max_markers;
-    if (m >= n_markers[f]) return;
-    float L = marker_len ? marker_len[f] : marker_len_all;
-    float hh = L / 2.f;
-    double h = hh;
-    const double obj[12] = {-h, h, 0, h, h, 0, h, -h, 0, -h, -h, 0};
-    double img[8];
-    for (int j = 0; j < 8; j++) img[j] = corners[8 * (size_t)i + j];
-    solve_pnp_planar(obj, img, C, rvec + 3 * (size_t)i, tvec + 3 * (size_t)i);
 }
 
 __global__ void k_project_points_multi(const double *__restrict__ obj, int n, const int32_t *__restrict__ pose_idx,
