@@ -588,16 +588,16 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)bgr, dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) CTX_FAIL(ctx, APSE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    // registers per thread (development knob APSE_K1_NREG): 64 = two 512-thread CTAs fill the register file; 56 / 48 leave
-    // 7 K / 16 K registers per SM for co-resident CTAs of the candidate / decode / pose chain running on other streams
-    // (48: +4 % frames/s on the 3-stream pipeline, no spills)
-    static const int nreg = getenv("APSE_K1_NREG") ? atoi(getenv("APSE_K1_NREG")) : 48;
+    // registers per thread (development knob APSE_K1_NREG): 64 = two 512-thread CTAs fill the register file and every CTA of
+    // the candidate / decode / pose chain on the other streams displaces one of them; 48 leaves 16 K registers per SM for
+    // co-resident chain CTAs (+4 % frames/s); 40 (no spills) makes room for a third preprocess CTA per SM (+2 % more)
+    static const int nreg = getenv("APSE_K1_NREG") ? atoi(getenv("APSE_K1_NREG")) : 40;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<true, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 56, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 40, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 48, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         attr_set = true;
     }
@@ -608,8 +608,8 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
 #define K1T_ARGS tmap, bgr, bgr_out, gray, tmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb
     if (bgr_out)
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true, 64, 0><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
-    else if (w == 3840 && nreg == 56)
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 56, 3840><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+    else if (w == 3840 && nreg == 40)
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 40, 3840><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840 && nreg == 48)
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 3840><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840)
