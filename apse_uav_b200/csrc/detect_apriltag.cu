@@ -341,6 +341,12 @@ __global__ void __launch_bounds__(CCL_THREADS) k_ccl_local(const uint8_t *__rest
 #pragma unroll
         for (int r = 0; r < CCL_RPT; r++) {
             const int ly = wy + 4 * r, y = tyb * CCL_TH + ly;
+            if (!__any_sync(0xffffffffu, v[r] != 127)) {   // background row: only what the rows above / below read of it
+                V[ly][lx] = 127;
+                if (lx == 0) JR[ly] = 0;
+                src[r] = false; jr[r] = 0;
+                continue;
+            }
             // pixel may initiate joins (full = classic path: every pixel; otherwise the dependency's AprilTag loop ranges)
             src[r] = v[r] != 127 && (full || (x >= 1 && x <= w - 2 && y <= h - 2));
             const int vr = __shfl_down_sync(0xffffffffu, v[r], 1);

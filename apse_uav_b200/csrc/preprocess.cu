@@ -500,9 +500,11 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                 mn = min(min(g[0], g[1]), min(g[2], g[3]));
                 mx = max(max(g[0], g[1]), max(g[2], g[3]));
             }
-            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 1)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            if (tile_writer) *tp = (uint16_t)(mn | (mx << 8));
+            // min and (255 - max) side by side in one register: one shuffle + one VIMNMX.U16x2 per butterfly step
+            uint32_t pk = (uint32_t)mn | ((uint32_t)(255 - mx) << 16);
+            pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 1));
+            pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 2));
+            if (tile_writer) *tp = (uint16_t)((pk & 0xffu) | ((255u - (pk >> 16)) << 8));
             tp += tile_stride;
         }
         gp += frame_px;
