@@ -45,7 +45,12 @@ class Pipeline:
             # development knobs: stream priorities of the two halves (default: chain above preprocess)
             pre_prio = int(os.environ.get("APSE_PRE_PRIO", "0"))
             chain_prio = int(os.environ.get("APSE_CHAIN_PRIO", "-1"))
-            self.pre_stream = torch.cuda.Stream(device=dev, priority=pre_prio)
+            # consecutive preprocess launches are independent (different frames, different contexts): alternating between
+            # two streams lets the next launch fill the SMs while the last wave of the previous one drains
+            n_pre = max(1, int(os.environ.get("APSE_PRE_STREAMS", "2")))
+            self.pre_streams = [torch.cuda.Stream(device=dev, priority=pre_prio) for _ in range(n_pre)]
+            self.pre_stream = self.pre_streams[0]
+            self._pre_pos = 0
             self.streams = [torch.cuda.Stream(device=dev, priority=chain_prio) for _ in range(streams)]
             self._gray = [torch.empty((self.sub_batch, h, w), dtype=torch.uint8, device=dev) for _ in range(streams)]
             self._done = [None] * streams          # completion event of the last chain that used engine s
@@ -106,17 +111,21 @@ class Pipeline:
             gray = torch.cat(grays, 0) if want_gray else None
         else:
             cur = torch.cuda.current_stream(e.tdev)
-            pre = self.pre_stream
             alloc = None
             if not overlap:
                 alloc = cur.record_event()          # output tensors are zero-filled on the current stream
+            ready = None
             if not input_ready:
-                pre.wait_event(alloc if alloc is not None else cur.record_event())
+                ready = alloc if alloc is not None else cur.record_event()
             done, grays = [], []
             for s, (eng, st) in enumerate(zip(self.engines, self.streams)):
                 lo, hi = s * self.sub_batch, min(B, (s + 1) * self.sub_batch)
                 if lo >= hi:
                     break
+                pre = self.pre_streams[self._pre_pos % len(self.pre_streams)]
+                self._pre_pos += 1
+                if ready is not None:
+                    pre.wait_event(ready)
                 g = torch.empty((hi - lo,) + frames.shape[1:3], dtype=torch.uint8, device=e.tdev) if want_gray else self._gray[s][:hi - lo]
                 if self._done[s] is not None:
                     pre.wait_event(self._done[s])   # engine s (scratch, tile extrema, gray buffer) is free again
