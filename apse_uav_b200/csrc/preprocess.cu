@@ -276,11 +276,15 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 // The kernel also emits the 4x4-tile min / max of gray that the APRILTAG threshold needs (a6.A1), so the
 // candidate stage does not have to re-read gray for it.
 #define P2_TW 64
+#ifndef P2_TH
 #define P2_TH 32
 #define P2_THREADS 512
+#endif
 #define P2_NPX 4
 #define P2_BOX_WORDS 64                       // 256 B = 85 px + 1 B per box row
+#ifndef P2_BOX_H
 #define P2_BOX_H 40
+#endif
 #define P2_BOX_PX 85
 #define P2_RAW_BYTES (P2_BOX_WORDS * 4 * P2_BOX_H)
 #define P2_RAW_STRIDE (P2_RAW_BYTES + 128)    // two staging buffers (double-buffered over frames), 128 B slack each
