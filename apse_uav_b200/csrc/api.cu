@@ -315,10 +315,14 @@ int apse_preprocess_tiles(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int 
     if (!ctx || !bgr || !gray || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "preprocess_tiles: bad argument");
     if (!ctx->has_camera || !ctx->has_lut) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "preprocess_tiles: set_camera and set_lut first");
     if (batch > ctx->max_batch) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "preprocess_tiles: batch %d exceeds the context capacity %d", batch, ctx->max_batch);
-    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm, batch, (cudaStream_t)stream);
+    // two tile-extrema buffers: the preprocess of the next sub-batch may run while the chain of the previous one (which
+    // reads its own buffer) is still in flight; the caller alternates the gray buffers accordingly (Pipeline)
+    const int slot = ctx->tiles_slot;
+    ctx->tiles_slot ^= 1;
+    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm_buf[slot], batch, (cudaStream_t)stream);
     if (rc < 0) return rc;
-    ctx->tiles_gray = rc == APSE_OK ? gray : nullptr;   // the extrema in ctx->tmm belong to exactly this gray batch
-    ctx->tiles_batch = batch;
+    ctx->tiles_gray[slot] = rc == APSE_OK ? gray : nullptr;   // the extrema in tmm_buf[slot] belong to exactly this gray batch
+    ctx->tiles_batch[slot] = batch;
     return APSE_OK;
 }
 
@@ -327,8 +331,13 @@ int apse_detect_pose_frames(apse_ctx *ctx, const uint8_t *gray, int batch, apse_
 {
     if (!ctx || !gray || !out || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect_pose_frames: bad argument");
     if (!ctx->has_camera || !ctx->has_dict) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "detect_pose_frames: set_camera and set_dictionary first");
-    const bool have_minmax = ctx->tiles_gray == gray && ctx->tiles_batch == batch;
-    ctx->tiles_gray = nullptr;                            // consumed: a later call on other data recomputes the extrema
+    bool have_minmax = false;
+    for (int slot = 0; slot < 2 && !have_minmax; slot++)
+        if (ctx->tiles_gray[slot] == gray && ctx->tiles_batch[slot] == batch) {
+            have_minmax = true;
+            ctx->tmm = ctx->tmm_buf[slot];
+            ctx->tiles_gray[slot] = nullptr;              // consumed: a later call on other data recomputes the extrema
+        }
     int rc = apse_detect_impl(ctx, gray, ctx->w, ctx->h, batch, out, (cudaStream_t)stream, have_minmax);
     if (rc) return rc;
     if (rvec && tvec)

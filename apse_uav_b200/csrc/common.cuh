@@ -89,7 +89,8 @@ struct apse_ctx {
     apse_params params;
     // APRILTAG scratch (sized for max_batch frames of max_w x max_h)
     uint8_t *thresh = nullptr;
-    uint16_t *tmm = nullptr;          // 4x4-tile extrema of gray, min | max << 8, [batch][h/4][w/4]
+    uint16_t *tmm = nullptr;          // 4x4-tile extrema of gray, min | max << 8, [batch][h/4][w/4] (= one of tmm_buf)
+    uint16_t *tmm_buf[2] = {nullptr, nullptr};   // apse_preprocess_tiles alternates between them
     uint32_t *labels = nullptr;
     uint4 *points = nullptr;          // {key_lo, key_hi, xy, slot|g}
     uint32_t *point_rank = nullptr;
@@ -105,8 +106,8 @@ struct apse_ctx {
     uint32_t *quad_order = nullptr;   // cluster index of each quad (for deterministic ordering)
     // decode scratch
     void *decode_scratch = nullptr;
-    const uint8_t *tiles_gray = nullptr;   // gray batch whose tile extrema are in tmm (apse_preprocess_tiles -> apse_detect_pose_frames)
-    int tiles_batch = 0;
+    const uint8_t *tiles_gray[2] = {nullptr, nullptr};   // gray batch whose tile extrema are in tmm_buf[i] (apse_preprocess_tiles -> apse_detect_pose_frames)
+    int tiles_batch[2] = {0, 0}, tiles_slot = 0;
     uint8_t *nbr_mask = nullptr;      // [max_batch][h][w] 8-neighbour foreground masks of the classic path (first use)
     uint8_t *gray_scratch = nullptr;  // [max_batch][h][w], allocated on first use by apse_process_frames(gray = NULL)
 };

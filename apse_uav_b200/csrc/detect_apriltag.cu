@@ -1144,7 +1144,8 @@ int apse_detect_alloc(apse_ctx *ctx)
     size_t B = ctx->max_batch, npx = (size_t)ctx->max_w * ctx->max_h;
     size_t ntiles = (size_t)div_up(ctx->max_w, 4) * div_up(ctx->max_h, 4);
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->thresh, B * npx));
-    CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmm, B * ntiles * sizeof(uint16_t)));
+    for (int k = 0; k < 2; k++) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tmm_buf[k], B * ntiles * sizeof(uint16_t)));
+    ctx->tmm = ctx->tmm_buf[0];
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->labels, B * npx * sizeof(uint32_t)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->points, B * APSE_MAX_POINTS * sizeof(uint4)));
     CUDA_TRY(ctx, cudaMalloc((void **)&ctx->hash_keys, B * APSE_HASH_SLOTS * sizeof(unsigned long long)));
@@ -1179,7 +1180,7 @@ int apse_detect_alloc(apse_ctx *ctx)
 
 void apse_detect_free(apse_ctx *ctx)
 {
-    cudaFree(ctx->thresh); cudaFree(ctx->tmm); cudaFree(ctx->labels); cudaFree(ctx->points);
+    cudaFree(ctx->thresh); cudaFree(ctx->tmm_buf[0]); cudaFree(ctx->tmm_buf[1]); cudaFree(ctx->labels); cudaFree(ctx->points);
     cudaFree(ctx->hash_keys); cudaFree(ctx->hash_count); cudaFree(ctx->hash_offset); cudaFree(ctx->sorted_pts);
     cudaFree(ctx->sort_keys); cudaFree(ctx->lfps); cudaFree(ctx->errs); cudaFree(ctx->clusters); cudaFree(ctx->counters);
     cudaFree(ctx->quads); cudaFree(ctx->quad_order);

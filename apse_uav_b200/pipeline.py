@@ -52,8 +52,12 @@ class Pipeline:
             self.pre_stream = self.pre_streams[0]
             self._pre_pos = 0
             self.streams = [torch.cuda.Stream(device=dev, priority=chain_prio) for _ in range(streams)]
-            self._gray = [torch.empty((self.sub_batch, h, w), dtype=torch.uint8, device=dev) for _ in range(streams)]
-            self._done = [None] * streams          # completion event of the last chain that used engine s
+            # two gray buffers per engine (the library keeps two tile-extrema buffers to match): the preprocess of the next
+            # use of engine s may run while the chain of the previous use still reads its gray / extrema; chains of one
+            # engine are ordered by their stream, and a buffer is rewritten only after the chain two uses back has finished
+            self._gray = [[torch.empty((self.sub_batch, h, w), dtype=torch.uint8, device=dev) for _ in range(2)] for _ in range(streams)]
+            self._done = [[None, None] for _ in range(streams)]   # completion event of the chain that last used (engine s, buffer p)
+            self._use = [0] * streams
         self.max_batch, self.max_markers, self.marker_length = max_batch, max_markers, float(marker_length)
         self.size = (w, h)
 
@@ -126,9 +130,11 @@ class Pipeline:
                 self._pre_pos += 1
                 if ready is not None:
                     pre.wait_event(ready)
-                g = torch.empty((hi - lo,) + frames.shape[1:3], dtype=torch.uint8, device=e.tdev) if want_gray else self._gray[s][:hi - lo]
-                if self._done[s] is not None:
-                    pre.wait_event(self._done[s])   # engine s (scratch, tile extrema, gray buffer) is free again
+                par = self._use[s] & 1
+                self._use[s] += 1
+                g = torch.empty((hi - lo,) + frames.shape[1:3], dtype=torch.uint8, device=e.tdev) if want_gray else self._gray[s][par][:hi - lo]
+                if self._done[s][par] is not None:
+                    pre.wait_event(self._done[s][par])   # this gray / extrema buffer pair of engine s is free again
                 eng.preprocess_tiles(frames[lo:hi], g, stream=pre)
                 ev = pre.record_event()
                 st.wait_event(ev)
@@ -138,8 +144,8 @@ class Pipeline:
                 mls = ml[lo:hi] if isinstance(ml, torch.Tensor) else ml
                 with torch.cuda.stream(st):   # (a per-frame marker-length tensor is staged on the chain's stream)
                     eng.detect_pose_frames(g, sl, mls, stream=st)
-                self._done[s] = st.record_event()
-                done.append(self._done[s])
+                self._done[s][par] = st.record_event()
+                done.append(self._done[s][par])
                 grays.append(g)
             gray = torch.cat(grays, 0) if want_gray else None
             if overlap:
