@@ -263,9 +263,9 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 // ---------------------------------------------------------------------------------------------------------
 // K1t: TMA-staged fused preprocess (the hot-path variant; k_preprocess_fused above stays as the generic path).
 //
-// One CTA (512 threads) owns a 64x32 output tile and walks `fpb` frames of the batch.  The bilinear taps of the
+// One CTA (384 threads) owns a 64x24 output tile and walks `fpb` frames of the batch.  The bilinear taps of the
 // tile (smem offset + two packed Q10 weight pairs per pixel) are computed once from the undistort map and stay in
-// registers.  Per frame the bounding box of the tile's source pixels (<= 74 x 40 px for this camera; the map is
+// registers.  Per frame the bounding box of the tile's source pixels (<= 74 x 32 px for this camera; the map is
 // smooth) is fetched by ONE bulk tensor copy (TMA, 3-D map over [batch][h][w*3/4] u32 words, out-of-image words
 // zero-filled = BORDER_CONSTANT 0) into one of two staging buffers and sampled in place: three aligned 32-bit LDS per
 // tap row, a funnel shift to the tap's byte offset, PRMT, and IDP.2A (16-bit weight x 8-bit pixel dot products).
@@ -277,13 +277,13 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 // candidate stage does not have to re-read gray for it.
 #define P2_TW 64
 #ifndef P2_TH
-#define P2_TH 32
-#define P2_THREADS 512
+#define P2_TH 24                              // 2160 = 90 x 24: no partial block row at 4K
+#define P2_THREADS 384                        // 12 warps; 3 CTAs per SM at 48 registers
 #endif
 #define P2_NPX 4
 #define P2_BOX_WORDS 64                       // 256 B = 85 px + 1 B per box row
 #ifndef P2_BOX_H
-#define P2_BOX_H 40
+#define P2_BOX_H 32
 #endif
 #define P2_BOX_PX 85
 #define P2_RAW_BYTES (P2_BOX_WORDS * 4 * P2_BOX_H)
@@ -594,10 +594,10 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)bgr, dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) CTX_FAIL(ctx, APSE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    // registers per thread (development knob APSE_K1_NREG): 64 = two 512-thread CTAs fill the register file and every CTA of
-    // the candidate / decode / pose chain on the other streams displaces one of them; 48 leaves 16 K registers per SM for
-    // co-resident chain CTAs (+4 % frames/s); 40 (no spills) makes room for a third preprocess CTA per SM (+2 % more)
-    static const int nreg = getenv("APSE_K1_NREG") ? atoi(getenv("APSE_K1_NREG")) : 40;
+    // registers per thread (development knob APSE_K1_NREG): at 64 the resident preprocess CTAs fill the register file and
+    // every CTA of the candidate / decode / pose chain on the other streams displaces one of them; 48 (no spills, 9 % fewer
+    // instructions than the 40-register build) = three 384-thread CTAs per SM with 10 K registers left for chain CTAs
+    static const int nreg = getenv("APSE_K1_NREG") ? atoi(getenv("APSE_K1_NREG")) : 48;
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
