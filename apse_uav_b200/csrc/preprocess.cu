@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 #define P2_RAW_STRIDE (P2_RAW_BYTES + 128)    // two staging buffers (double-buffered over frames), 128 B slack each
 #define P2_OFF_TABLES (2 * P2_RAW_STRIDE)
 #define P2_OFF_MISC (P2_OFF_TABLES + (int)sizeof(P2Tables))
-#define P2_SMEM_BYTES (P2_OFF_MISC + 32)
+#define P2_SMEM_BYTES (P2_OFF_MISC + 48)
+#define P2_CTA_THREADS (P2_THREADS + 32)       // 12 consumer warps + 1 TMA producer warp
 #define XZ_MAGIC 551553470                    // ceil(108 * 2^32 / 841)
 
 static void build_p2_tables_host(P2Tables &P, const LabTables &T)
@@ -407,7 +408,7 @@ __device__ __forceinline__ void k1t_pixels(const P2Tables *T, const uint32_t (&a
 }
 
 // WC: compile-time frame width (0 = run-time): row offsets of the stores become immediates for the 3840-px footage
-template <bool WANT_BGR, int NREG, int WC>
+template <bool WANT_BGR, int NREG, int WC, bool FULL = false>   // FULL: every thread of every CTA has pixels (w % 64 == 0, h % 24 == 0)
 __global__ void __maxnreg__(NREG)
 k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
                  uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm,
@@ -416,8 +417,8 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
 {
     extern __shared__ __align__(128) uint8_t smem[];
     P2Tables *T = reinterpret_cast<P2Tables *>(smem + P2_OFF_TABLES);
-    unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);   // two barriers
-    int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 16);   // xmin, xmax, ymin, ymax
+    unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);   // full[2], empty[2]
+    int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 32);   // xmin, xmax, ymin, ymax
     const int w = WC ? WC : w_rt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mbar0 = smem_u32(mbar_p), raw0 = smem_u32(smem);
@@ -425,11 +426,13 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     {   // tables -> shared memory
         const uint4 *src = reinterpret_cast<const uint4 *>(tables);
         uint4 *dst = reinterpret_cast<uint4 *>(T);
-        for (int i = tid; i < (int)(sizeof(P2Tables) / 16); i += P2_THREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < (int)(sizeof(P2Tables) / 16); i += P2_CTA_THREADS) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0));          // full[0]: the producer's expect_tx arrival
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8));      // full[1]
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar0 + 16), "r"(P2_THREADS / 32));   // empty[0]: one arrival per consumer warp
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar0 + 24), "r"(P2_THREADS / 32));   // empty[1]
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         box[0] = INT32_MAX; box[1] = INT32_MIN; box[2] = INT32_MAX; box[3] = INT32_MIN;
     }
@@ -438,7 +441,8 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     // ---- taps of this thread's 4 pixels: column x, rows y0..y0+3
     const int x = blockIdx.x * P2_TW + (warp & 1) * 32 + lane;
     const int y0 = blockIdx.y * P2_TH + (warp >> 1) * 4;
-    const bool valid = x < w && y0 < h;           // h % 4 == 0: a 4-row group is inside or outside as a whole
+    const bool producer = warp == P2_THREADS / 32;   // 13th warp: issues the bulk tensor copies, owns no pixels
+    const bool valid = !producer && (FULL || (x < w && y0 < h));   // h % 4 == 0: a 4-row group is inside or outside as a whole
     int ixs[P2_NPX], iys[P2_NPX];
     uint32_t wA[P2_NPX], wB[P2_NPX];
     int xmin = INT32_MAX, xmax = INT32_MIN, ymin = INT32_MAX, ymax = INT32_MIN;
@@ -515,28 +519,42 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         if (WANT_BGR) cp += frame_px * 3;
     };
     if (fast) {
-        if (tid == 0) tma_load_box(raw0, &tmap, c0x, by0, f0, mbar0);
-        // two frames per trip: staging buffer, barrier and extrema slot of a frame are compile-time constants
-        for (int f = f0; f < f1; f += 2) {
-            const uint32_t ph = (uint32_t)((f - f0) >> 1) & 1u;
+        // Producer / consumer over two staging buffers with full / empty mbarriers; no CTA-wide barrier in the frame loop, so
+        // the consumer warps drift apart and hide each other's shared-memory latency.
+        //   producer (one lane): wait until the 12 consumer warps have released buffer b, arm full[b], issue the copy of frame i
+        //   consumer warp:       wait full[b], sample + colour chain + stores, release buffer b (one arrival per warp)
+        const int nf = f1 - f0;
+        if (producer) {
+            if (lane == 0) {
+                for (int i = 0; i < nf; i++) {
+                    const int b = i & 1;
+                    if (i >= 2) mbar_wait(mbar0 + 16 + b * 8, (uint32_t)((i >> 1) - 1) & 1u);
+                    tma_load_box(raw0 + b * P2_RAW_STRIDE, &tmap, c0x, by0, f0 + i, mbar0 + b * 8);
+                }
+            }
+            return;
+        }
+        // two frames per trip: staging buffer and barriers of a frame are compile-time constants
+        for (int i = 0; i < nf; i += 2) {
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
             {
-                if (warp == 0) { if (lane == 0 && f + 1 < f1) tma_load_box(raw0 + P2_RAW_STRIDE, &tmap, c0x, by0, f + 1, mbar0 + 8); }
                 mbar_wait(mbar0, ph);
                 int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
                 if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, 0u, g, o0, o1, o2);
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar0 + 16) : "memory");
                 finish(g, o0, o1, o2);
-                __syncthreads();   // all reads of this frame's buffer done before it is refilled (frame f + 2)
             }
-            if (f + 1 < f1) {
-                if (warp == 0) { if (lane == 0 && f + 2 < f1) tma_load_box(raw0, &tmap, c0x, by0, f + 2, mbar0); }
+            if (i + 1 < nf) {
                 mbar_wait(mbar0 + 8, ph);
                 int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
                 if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, (uint32_t)P2_RAW_STRIDE, g, o0, o1, o2);
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar0 + 24) : "memory");
                 finish(g, o0, o1, o2);
-                __syncthreads();
             }
         }
-    } else {
+    } else if (!producer) {
         // direct-gather path (source box larger than the staging buffer: folded corners of the rational model)
         for (int f = f0; f < f1; f++) {
             int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
@@ -605,6 +623,7 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<true, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 40, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 48, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 48, 3840, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         attr_set = true;
     }
     // frames per CTA: the tap set-up (map reads, box reduction, table load) is amortised over up to 20 frames
@@ -613,15 +632,17 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), nz);
 #define K1T_ARGS tmap, bgr, bgr_out, gray, tmm, ctx->mapx, ctx->mapy, ctx->tables2, w, h, batch, fpb
     if (bgr_out)
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true, 64, 0><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true, 64, 0><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840 && nreg == 40)
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 40, 3840><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 40, 3840><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+    else if (w == 3840 && nreg == 48 && h % P2_TH == 0 && !getenv("APSE_K1_NOFULL"))
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 3840, true><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840 && nreg == 48)
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 3840><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 3840><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840)
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 64, 3840><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 64, 3840><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else
-        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 64, 0><<<grid, P2_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 64, 0><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
 #undef K1T_ARGS
     return APSE_OK;
 }
