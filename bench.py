@@ -366,8 +366,8 @@ def run_ours(args, rank, world, local_rank):
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "traffic_source": traffic_src,
                          "bound_note": "HBM is the roofline SURVEY.md 8(d) prescribes; the kernel itself is bound by SM issue (86 %), "
-                                       "the shared-memory wavefront pipe (80 %) and the ALU pipe (74 %) -- "
-                                       "profiles/r01d_k_preprocess_tma_ncu_full.csv -- not by DRAM (12.5 %)",
+                                       "the shared-memory wavefront pipe (82 %) and the ALU pipe (76 %) -- "
+                                       "profiles/r01e_k_preprocess_tma_ncu_full.csv -- not by DRAM (13 %)",
                          "share_of_kernel_time": kms / ksum if ksum else None,
                          "algorithmic_bytes_per_launch": alg, "launches": kcount, "avg_ms": kms / max(kcount, 1)},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(ktimes.items(), key=lambda kv: -kv[1][0])},
