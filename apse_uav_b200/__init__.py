@@ -92,12 +92,12 @@ def LUT(src, lut, dst=None):
 
 
 def undistort(src, cameraMatrix, distCoeffs, dst=None, newCameraMatrix=None):
-    """remap through the float32 undistort maps (what aruco_detect.py:252,568 does; cv2.undistort itself rounds
-    the FP64 coordinate directly and differs in ~0.4 % of the pixels)."""
+    """cv2.undistort (dcnn/scripts/tests/visualize_uav.py:62): bit-exact with the dependency, which rounds the FP64 source
+    coordinate to the Q5 grid directly -- NOT the same pixels as initUndistortRectifyMap(CV_32FC1) + remap
+    (aruco_detect.py:568,252), which go through float32 maps; both variants are provided."""
     h, w = src.shape[:2]
     e = default_engine(w, h)
-    mx, my = e.init_undistort_map(cameraMatrix, distCoeffs, w, h)
-    return _out(e.remap(src, mx, my), src)
+    return _out(e.undistort(src, cameraMatrix, distCoeffs, newCameraMatrix), src)
 
 
 def projectPoints(objectPoints, rvec, tvec, cameraMatrix, distCoeffs, imagePoints=None, jacobian=None, aspectRatio=0):

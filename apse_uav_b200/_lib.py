@@ -60,6 +60,7 @@ SIGNATURES = {
     "apse_set_params": [_vp, C.POINTER(Params)],
     "apse_init_undistort_map": [_vp, _dp, _dp, _i, _i, _vp, _vp, _vp],
     "apse_remap": [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
+    "apse_undistort": [_vp, _vp, _i, _i, _i, _dp, _dp, _dp, _vp, _vp],
     "apse_cvt_rgb2lab": [_vp, _vp, _i64, _vp, _vp],
     "apse_cvt_lab2rgb": [_vp, _vp, _i64, _vp, _vp],
     "apse_cvt_bgr2gray": [_vp, _vp, _i64, _vp, _vp],

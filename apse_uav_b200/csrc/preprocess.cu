@@ -679,6 +679,65 @@ int apse_remap(apse_ctx *ctx, const uint8_t *src, int sw, int sh, int cn, const 
     return APSE_OK;
 }
 
+// cv2.undistort (SURVEY.md row a2 note, dcnn/scripts/tests/visualize_uav.py:62): the dependency builds CV_16SC2 maps, i.e. the
+// FP64 source coordinate is scaled by 32 and rounded to the Q5 grid directly (no float32 map in between), then the same
+// Q15 bilinear remap with BORDER_CONSTANT 0.  Map and sample in one pass; A = new camera matrix (fx', fy', cx', cy').
+__global__ void k_undistort(const uint8_t *__restrict__ src, int w, int h, int cn, double fx, double fy, double u0, double v0,
+                            double afx, double afy, double au0, double av0, double k1, double k2, double p1, double p2, double k3,
+                            double k4, double k5, double k6, double s1, double s2, double s3, double s4, uint8_t *__restrict__ dst)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= w || i >= h) return;
+    double ir0 = 1.0 / afx, ir2 = -au0 / afx, ir4 = 1.0 / afy, ir5 = -av0 / afy;
+    double x = __dadd_rn(__dmul_rn(j, ir0), ir2), y = __dadd_rn(__dmul_rn(i, ir4), ir5);
+    double x2 = __dmul_rn(x, x), y2 = __dmul_rn(y, y);
+    double r2 = __dadd_rn(x2, y2), _2xy = __dmul_rn(__dmul_rn(2, x), y);
+    double num = __dadd_rn(1, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2));
+    double den = __dadd_rn(1, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k6, r2), k5), r2), k4), r2));
+    double kr = __ddiv_rn(num, den);
+    double xd = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, kr), __dmul_rn(p1, _2xy)),
+                                              __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(2, x2)))),
+                                    __dmul_rn(s1, r2)),
+                          __dmul_rn(__dmul_rn(s2, r2), r2));
+    double yd = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(y, kr), __dmul_rn(p1, __dadd_rn(r2, __dmul_rn(2, y2)))),
+                                              __dmul_rn(p2, _2xy)),
+                                    __dmul_rn(s3, r2)),
+                          __dmul_rn(__dmul_rn(s4, r2), r2));
+    double u = __dadd_rn(__dmul_rn(fx, xd), u0), v = __dadd_rn(__dmul_rn(fy, yd), v0);
+    int sx = __double2int_rn(__dmul_rn(u, 32.0)), sy = __double2int_rn(__dmul_rn(v, 32.0));   // saturating, round-half-even
+    int ix = sx >> 5, iy = sy >> 5, fxq = sx & 31, fyq = sy & 31;
+    Taps t;
+    t.w00 = min(32767, (32 - fyq) * (32 - fxq) * 32);
+    t.w01 = (32 - fyq) * fxq * 32;
+    t.w10 = fyq * (32 - fxq) * 32;
+    t.w11 = fyq * fxq * 32;
+    // far-away coordinates (saturated) have no tap inside; the 64-bit offset below is never dereferenced then
+    bool x0 = ix >= 0 && ix < w, x1 = ix + 1 >= 0 && ix + 1 < w && ix < w;
+    bool y0 = iy >= 0 && iy < h, y1 = iy + 1 >= 0 && iy + 1 < h && iy < h;
+    t.mask = (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 2u : 0u) | (x0 && y1 ? 4u : 0u) | (x1 && y1 ? 8u : 0u);
+    if (t.mask == 0) {
+        for (int c = 0; c < cn; c++) dst[((size_t)i * w + j) * cn + c] = 0;
+        return;
+    }
+    t.off00 = (iy * w + ix) * cn;
+    for (int c = 0; c < cn; c++) dst[((size_t)i * w + j) * cn + c] = (uint8_t)sample(src, t, w * cn, cn, c);
+}
+
+int apse_undistort(apse_ctx *ctx, const uint8_t *src, int w, int h, int cn, const double K[9], const double D[14], const double newK[9],
+                   uint8_t *dst, void *stream)
+{
+    if (!ctx || !src || !dst || !K || !D || w <= 0 || h <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "undistort: bad argument");
+    if (cn != 1 && cn != 3) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "undistort: only 1- or 3-channel 8-bit images");
+    if ((int64_t)w * h * cn >= (1ll << 31)) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "undistort: image too large");
+    if (D[12] != 0 || D[13] != 0) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "tilted sensor model (tauX/tauY) is not supported");
+    const double *A = newK ? newK : K;
+    dim3 grid(div_up(w, 256), h);
+    KLAUNCH(ctx, KID_REMAP, (cudaStream_t)stream, k_undistort<<<grid, 256, 0, (cudaStream_t)stream>>>(src, w, h, cn, K[0], K[4], K[2], K[5], A[0], A[4], A[2], A[5],
+                                                                                            D[0], D[1], D[2], D[3], D[4], D[5], D[6], D[7], D[8], D[9],
+                                                                                            D[10], D[11], dst));
+    return APSE_OK;
+}
+
 __global__ void __launch_bounds__(256) k_rgb2lab(const uint8_t *__restrict__ src, int64_t npx, uint8_t *__restrict__ dst,
                                                  const LabTables *__restrict__ tables)
 {

@@ -140,6 +140,19 @@ class Engine:
                                         mapy.data_ptr(), dw, dh, dst.data_ptr(), self._stream()))
         return dst
 
+    def undistort(self, src, K, D, newK=None):
+        """cv2.undistort(src, K, D, None, newK): FP64 coordinates rounded to Q5 directly, bilinear, BORDER_CONSTANT 0"""
+        torch = self.torch
+        src = self._u8(src, "undistort")
+        cn = 1 if src.dim() == 2 else src.shape[2]
+        h, w = src.shape[:2]
+        dst = torch.empty_like(src)
+        _, kp = _lib.darr(K)
+        _, dp = _lib.darr(_lib.dist14(D))
+        na, npp = _lib.darr(newK) if newK is not None else (None, None)
+        self._check(self.lib.apse_undistort(self.h, src.data_ptr(), w, h, cn, kp, dp, npp, dst.data_ptr(), self._stream()))
+        return dst
+
     def cvt(self, src, kind):
         torch = self.torch
         src = self._u8(src, "cvtColor")

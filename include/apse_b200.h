@@ -101,6 +101,12 @@ int apse_init_undistort_map(apse_ctx *ctx, const double K_host[9], const double 
 /* aruco_detect.py:252  cv2.remap(src, mapx, mapy, INTER_LINEAR), BORDER_CONSTANT 0; cn = 1 or 3 */
 int apse_remap(apse_ctx *ctx, const uint8_t *src, int sw, int sh, int cn, const float *mapx, const float *mapy,
                int dw, int dh, uint8_t *dst, void *stream);
+
+/* cv2.undistort(src, K, D, None, newK) (dcnn/scripts/tests/visualize_uav.py:62): FP64 source coordinate rounded to the Q5
+ * grid directly (the dependency's CV_16SC2 maps) + the bilinear remap of apse_remap; newK == NULL means K.  Differs from
+ * initUndistortRectifyMap(CV_32FC1) + remap (aruco_detect.py:568,252) in ~0.1 % of the pixels, exactly as in the dependency. */
+int apse_undistort(apse_ctx *ctx, const uint8_t *src, int w, int h, int channels, const double K[9], const double D[14],
+                   const double newK[9], uint8_t *dst, void *stream);
 /* aruco_detect.py:255  cv2.cvtColor(.., COLOR_RGB2LAB) on 8-bit 3-channel pixels */
 int apse_cvt_rgb2lab(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream);
 /* aruco_detect.py:257  cv2.cvtColor(.., COLOR_LAB2RGB) */

@@ -61,6 +61,20 @@ def remap(src, mapx, mapy):
     return dst
 
 
+def undistort(src, K, D, newK=None):
+    """cv2.undistort(src, K, D, None, newK) for 8-bit 1- or 3-channel images (FP64 coordinate rounded to Q5 directly)"""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape[:2]
+    cn = 1 if src.ndim == 2 else src.shape[2]
+    dst = np.empty_like(src)
+    Kc = np.ascontiguousarray(K, np.float64).ravel()
+    Dc = _k14(D)
+    Nc = np.ascontiguousarray(newK, np.float64).ravel() if newK is not None else None
+    dp = lambda a: _p(a, C.c_double)
+    lib().orc_undistort(u8p(src), w, h, cn, dp(Kc), dp(Dc), dp(Nc) if Nc is not None else None, u8p(dst))
+    return dst
+
+
 def rgb2lab(src):
     src = np.ascontiguousarray(src)
     dst = np.empty_like(src)

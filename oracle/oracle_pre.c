@@ -222,3 +222,44 @@ void orc_set_cbrt_entry(int i, int v)
     if (!g_lab_ready) build_lab_tables();
     t_cbrt[i] = (uint16_t)v;
 }
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* cv2.undistort(src, K, D[, newK]) (dcnn/scripts/tests/visualize_uav.py:62): the dependency builds
+ * CV_16SC2 maps, i.e. the FP64 source coordinate is scaled by 32 and rounded directly (no float32 map in between),
+ * then the same Q5 / Q15 bilinear remap with BORDER_CONSTANT 0 */
+void orc_undistort(const uint8_t *src, int w, int h, int cn, const double *K, const double *D, const double *newK, uint8_t *dst)
+{
+    if (!g_wtab_ready) build_wtab();
+    const double *A = newK ? newK : K;
+    double fx = K[0], fy = K[4], u0 = K[2], v0 = K[5];
+    double k1 = D[0], k2 = D[1], p1 = D[2], p2 = D[3], k3 = D[4], k4 = D[5], k5 = D[6], k6 = D[7];
+    double s1 = D[8], s2 = D[9], s3 = D[10], s4 = D[11];
+    double ir0 = 1.0 / A[0], ir2 = -A[2] / A[0], ir4 = 1.0 / A[4], ir5 = -A[5] / A[4];
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++) {
+            double x = j * ir0 + ir2, y = i * ir4 + ir5;
+            double x2 = x * x, y2 = y * y;
+            double r2 = x2 + y2, _2xy = 2 * x * y;
+            double kr = (1 + ((k3 * r2 + k2) * r2 + k1) * r2) / (1 + ((k6 * r2 + k5) * r2 + k4) * r2);
+            double xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2) + s1 * r2 + s2 * r2 * r2;
+            double yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy + s3 * r2 + s4 * r2 * r2;
+            double u = fx * xd + u0, v = fy * yd + v0;
+            long sx = lrint(u * 32.0), sy = lrint(v * 32.0);
+            if (sx < -2147483647L) sx = -2147483647L;
+            if (sx > 2147483647L) sx = 2147483647L;
+            if (sy < -2147483647L) sy = -2147483647L;
+            if (sy > 2147483647L) sy = 2147483647L;
+            int ix = (int)(sx >> 5), iy = (int)(sy >> 5);
+            const int16_t *wt = g_wtab[(sy & 31) * 32 + (sx & 31)];
+            size_t o = (size_t)i * w + j;
+            for (int c = 0; c < cn; c++) {
+                int acc = 0;
+                for (int k = 0; k < 4; k++) {
+                    int xx = ix + (k & 1), yy = iy + (k >> 1);
+                    int p = (xx >= 0 && xx < w && yy >= 0 && yy < h) ? src[((size_t)yy * w + xx) * cn + c] : 0;
+                    acc += wt[k] * p;
+                }
+                dst[o * cn + c] = (uint8_t)((acc + 16384) >> 15);
+            }
+        }
+}

@@ -108,3 +108,22 @@ def test_dropin_functions_match_reference_call_sequence(camera, lut, frames4k, o
         cv2.cvtColor(f, 40)  # BGR2HSV is not on the hot path
     with pytest.raises(cv2.error):
         cv2.remap(frame, mapx, mapy, cv2.INTER_NEAREST)
+
+
+def test_undistort_dropin_bit_exact(oracle, camera, frames4k):
+    """cv2.undistort drop-in (apse_undistort): FP64 coordinate -> Q5, bit-exact with the oracle (pinned against cv2.undistort
+    on the CPU) and with cv2 itself when importable; 3-channel 4K, 1-channel with a new camera matrix, ragged size."""
+    import apse_uav_b200 as A
+    K, D = camera
+    frame = frames4k["sparse"]
+    out = A.undistort(frame, K, D)
+    assert isinstance(out, np.ndarray) and np.array_equal(out, oracle.undistort(frame, K, D))
+    Ks = K.copy(); Ks[:2] *= 0.25
+    newK = Ks.copy(); newK[0, 0] *= 0.9; newK[1, 1] *= 0.95; newK[0, 2] += 7.3
+    rng = np.random.default_rng(4)
+    g = rng.integers(0, 256, (541, 963), dtype=np.uint8)
+    assert np.array_equal(A.undistort(g, Ks, D, None, newK), oracle.undistort(g, Ks, D, newK))
+    if has_cv2():
+        import cv2
+        assert np.array_equal(out, cv2.undistort(frame, K, D))
+        assert np.array_equal(A.undistort(g, Ks, D[:5]), cv2.undistort(g, Ks, D[:5]))

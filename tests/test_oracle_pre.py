@@ -55,3 +55,21 @@ def test_preprocess_vs_golden(oracle, name):
     assert zlib.crc32(out.tobytes()) == int(g["corrected_crc"])
     assert zlib.crc32(gray.tobytes()) == int(g["gray_crc"])
     assert np.array_equal(gray[::37], g["gray_rows"])
+
+
+@needs_cv2
+def test_undistort_equals_cv2_undistort(oracle, camera):
+    """cv2.undistort rounds the FP64 source coordinate to the Q5 grid directly (CV_16SC2 maps): not the float32-map remap"""
+    import cv2
+    K, D = camera
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (2160, 3840, 3), dtype=np.uint8)
+    ref = cv2.undistort(img, K, D)
+    assert np.array_equal(oracle.undistort(img, K, D), ref)
+    mx, my = oracle.init_undistort_map(K, D, 3840, 2160)
+    assert 0 < (oracle.remap(img, mx, my) != ref).sum() < 0.01 * ref.size     # the two variants really differ
+    Ks = K.copy(); Ks[:2] *= 0.25
+    newK = Ks.copy(); newK[0, 0] *= 0.9; newK[1, 1] *= 0.95; newK[0, 2] += 7.3
+    g = rng.integers(0, 256, (540, 960), dtype=np.uint8)
+    assert np.array_equal(oracle.undistort(g, Ks, D, newK), cv2.undistort(g, Ks, D, None, newK))
+    assert np.array_equal(oracle.undistort(g, Ks, D[:5]), cv2.undistort(g, Ks, D[:5]))
