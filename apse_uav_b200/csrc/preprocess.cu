@@ -616,6 +616,7 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     // every CTA of the candidate / decode / pose chain on the other streams displaces one of them; 48 (no spills, 9 % fewer
     // instructions than the 40-register build) = three 384-thread CTAs per SM with 10 K registers left for chain CTAs
     static const int nreg = getenv("APSE_K1_NREG") ? atoi(getenv("APSE_K1_NREG")) : 48;
+    static const bool no_full = getenv("APSE_K1_NOFULL") != nullptr;   // development switch: no all-valid specialisation
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
@@ -635,7 +636,7 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<true, 64, 0><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840 && nreg == 40)
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 40, 3840><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
-    else if (w == 3840 && nreg == 48 && h % P2_TH == 0 && !getenv("APSE_K1_NOFULL"))
+    else if (w == 3840 && nreg == 48 && h % P2_TH == 0 && !no_full)
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 3840, true><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
     else if (w == 3840 && nreg == 48)
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 3840><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
