@@ -908,7 +908,9 @@ __device__ void bitonic_sort_u64(unsigned long long *keys, int npow2)
         }
 }
 
-__global__ void __launch_bounds__(FQ_THREADS) k_fit_quads(FitArgs A)
+// 40 registers (a few hundred bytes of spills in this latency-bound kernel): a CTA then needs 5 K registers and fits beside the
+// three resident preprocess CTAs of an SM instead of displacing one of them for the ~0.3 ms it lives
+__global__ void __maxnreg__(40) k_fit_quads(FitArgs A)
 {
     __shared__ unsigned long long s_keys[APSE_SORT_SMEM];
     __shared__ int s_prefix[65];       // cluster count prefix over frames (batch <= 64 per launch)
