@@ -43,6 +43,20 @@ class Detections(C.Structure):
                 ("rejected", C.c_void_p), ("n_rejected", C.c_void_p), ("status", C.c_void_p)]
 
 
+class SeqConfig(C.Structure):
+    """apse_seq_config: constants of the reference's frame loop (aruco_detect.py:13-18,36,519-524)."""
+    _fields_ = [("start_frame", C.c_int), ("step_frame", C.c_int), ("marker_length_org", C.c_double), ("marker_div", C.c_double),
+                ("div", C.c_double), ("width", C.c_int), ("height", C.c_int), ("leds_threshold", C.c_int), ("leds", C.c_int)]
+
+
+# numpy views of the sequence post-pass structs (apse_seq_job / apse_seq_job_result / apse_seq_row)
+SEQ_JOB_DTYPE = [("frame", "<i4"), ("kind", "<i4"), ("rvec", "<f8", 3), ("tvec", "<f8", 3), ("dim", "<f8", 4), ("src", "<f4", 2),
+                 ("tgt", "<f4", 2), ("scale", "<f8"), ("led_threshold", "<i4"), ("pad_", "<i4")]
+SEQ_RESULT_DTYPE = [("dist_aruco", "<f8"), ("dist_bbox", "<f8"), ("leds", "<i4"), ("valid", "<i4")]
+SEQ_ROW_DTYPE = [("frame_id", "<i4"), ("detected", "<i4", 4), ("host_fields", "<i4"), ("leds", "<i4"), ("job_led", "<i4"),
+                 ("job_dist", "<i4", 3), ("pad_", "<i4"), ("marker_length", "<f8"), ("altitude", "<f8"), ("fov_width", "<f8"),
+                 ("fov_height", "<f8"), ("dist_aruco", "<f8", 3), ("dist_bbox", "<f8", 3)]
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
@@ -78,6 +92,11 @@ SIGNATURES = {
     "apse_patch_sums": [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp],
     "apse_adaptive_threshold": [_vp, _vp, _i, _i, _i, _i, C.c_double, _vp, _vp],
     "apse_debug_classic": [_vp, _vp, _i, _i, _vp, _vp, _i, C.POINTER(C.c_int64), _vp],
+    "apse_seq_config_default": [C.POINTER(SeqConfig)],
+    "apse_sequence_scan": [C.POINTER(SeqConfig), _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(C.c_int)],
+    "apse_sequence_jobs": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _dp, _dp, _vp, _vp],
+    "apse_sequence_finish": [_i, _vp, _vp, _i],
+    "apse_sequence_csv": [_vp, _i, _i, _vp, _i64],
     "apse_launch_count": [_vp],
     "apse_kernel_count": [],
     "apse_kernel_name": [_i],
@@ -85,7 +104,7 @@ SIGNATURES = {
     "apse_timing_collect": [_vp, _dp, C.POINTER(C.c_int64), _i],
     "apse_timing_trace": [_vp, _dp, _i],
 }
-_RESTYPES = {"apse_destroy": None, "apse_params_default": None, "apse_last_error": C.c_char_p,
+_RESTYPES = {"apse_destroy": None, "apse_params_default": None, "apse_seq_config_default": None, "apse_sequence_csv": C.c_int64, "apse_last_error": C.c_char_p,
              "apse_launch_count": C.c_int64, "apse_kernel_name": C.c_char_p}
 
 _lib = None

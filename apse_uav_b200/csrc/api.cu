@@ -50,10 +50,16 @@ int apse_create(apse_ctx **out, int device, int max_w, int max_h, int max_batch)
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return APSE_ERR_CUDA;
+    int caller_dev = -1;
+    cudaGetDevice(&caller_dev);
     if (cudaSetDevice(device) != cudaSuccess) return APSE_ERR_CUDA;
+    // the caller's current device is restored on every exit path: a context never changes the thread's device for good,
+    // and every launch checks that the thread is on the context's device (KLAUNCH)
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{caller_dev};
     apse_ctx *ctx = new (std::nothrow) apse_ctx();
     if (!ctx) return APSE_ERR_CUDA;
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->max_batch = max_batch;
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->sm_count <= 0) ctx->sm_count = 148;
     apse_params_default(&ctx->params);
     int rc = apse_detect_alloc(ctx);
     if (rc == APSE_OK) rc = apse_decode_alloc(ctx);
@@ -70,12 +76,15 @@ int apse_create(apse_ctx **out, int device, int max_w, int max_h, int max_batch)
 void apse_destroy(apse_ctx *ctx)
 {
     if (!ctx) return;
+    int caller_dev = -1;
+    cudaGetDevice(&caller_dev);
     cudaSetDevice(ctx->device);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{caller_dev};
     apse_detect_free(ctx);
     apse_decode_free(ctx);
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
     delete[] ctx->trace;
-    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask);
+    cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask); cudaFree(ctx->seq_jobs); cudaFree(ctx->seq_results);
     delete ctx;
 }
 
@@ -87,7 +96,7 @@ static const char *KERNEL_NAMES[KID_COUNT] = {
     "k_build_undistort_map", "k_preprocess_fused", "k_remap", "k_cvt", "k_lut", "k_tile_minmax", "k_threshold",
     "k_ccl_local", "k_ccl_merge", "k_ccl_flatten", "k_emit_points", "k_cluster_scan", "k_scatter_points", "k_fit_quads",
     "k_decode", "k_pose", "k_project_points", "k_classic", "k_adaptive_threshold", "k_border_jobs", "k_trace_borders",
-    "k_approx_quads", "k_corner_subpix", "k_decode_bits"};
+    "k_approx_quads", "k_corner_subpix", "k_decode_bits", "k_sequence_jobs"};
 
 int apse_kernel_count(void) { return KID_COUNT; }
 const char *apse_kernel_name(int kid) { return kid >= 0 && kid < KID_COUNT ? KERNEL_NAMES[kid] : ""; }
@@ -121,6 +130,7 @@ int apse_set_camera(apse_ctx *ctx, const double K[9], const double D[14], int w,
     }
     int rc = apse_init_undistort_map(ctx, K, D, w, h, ctx->mapx, ctx->mapy, stream);
     if (rc) return rc;
+    ctx->tiles_gray[0] = ctx->tiles_gray[1] = nullptr;   // cached tile extrema (apse_preprocess_tiles) never survive another entry point
     memcpy(ctx->K, K, sizeof ctx->K);
     memcpy(ctx->D, D, sizeof ctx->D);
     ctx->w = w; ctx->h = h;
@@ -132,6 +142,7 @@ int apse_set_lut(apse_ctx *ctx, const uint8_t lut[256], void *stream)
 {
     if (!ctx || !lut) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_lut: bad argument");
     memcpy(ctx->lut, lut, 256);
+    ctx->tiles_gray[0] = ctx->tiles_gray[1] = nullptr;   // cached tile extrema (apse_preprocess_tiles) never survive another entry point
     int rc = apse_upload_tables(ctx, lut, &ctx->tables, (cudaStream_t)stream);
     if (rc) return rc;
     rc = apse_upload_p2_tables(ctx, lut, &ctx->tables2, (cudaStream_t)stream);
@@ -176,6 +187,7 @@ int apse_set_params(apse_ctx *ctx, const apse_params *p)
     if (p->cornerRefinementMethod == 2) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: CORNER_REFINE_CONTOUR is not supported");
     if (p->aprilTagMaxNmaxima < 4 || p->aprilTagMaxNmaxima > 16)
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagMaxNmaxima must be in [4,16]");
+    ctx->tiles_gray[0] = ctx->tiles_gray[1] = nullptr;   // cached tile extrema (apse_preprocess_tiles) never survive another entry point
     ctx->params = *p;
     ctx->has_params = true;
     return APSE_OK;
@@ -283,6 +295,7 @@ int apse_detect(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, aps
 {
     if (!ctx || !gray || !out || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: bad argument");
     if (!ctx->has_dict) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "detect: set_dictionary first");
+    ctx->tiles_gray[0] = ctx->tiles_gray[1] = nullptr;   // cached tile extrema (apse_preprocess_tiles) never survive another entry point
     return apse_detect_impl(ctx, gray, w, h, batch, out, (cudaStream_t)stream, false);
 }
 
@@ -293,6 +306,7 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
     if (!ctx->has_camera || !ctx->has_lut || !ctx->has_dict)
         CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "process_frames: set_camera, set_lut and set_dictionary first");
     if (batch > ctx->max_batch) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "process_frames: batch %d exceeds the context capacity %d", batch, ctx->max_batch);
+    ctx->tiles_gray[0] = ctx->tiles_gray[1] = nullptr;   // cached tile extrema (apse_preprocess_tiles) never survive another entry point
     cudaStream_t st = (cudaStream_t)stream;
     const int w = ctx->w, h = ctx->h;
     if (!gray) {

@@ -571,8 +571,8 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
         if (rc) return rc;
         KLAUNCH(ctx, KID_BORDER_JOBS, st, k_mark_outside<<<div_up(2 * (w + h) * batch, 256), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, batch));
         // per window: reset the job / border / point counters, keep quads and status
-        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_border_jobs<<<dim3(148 * 2, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, ctx->nbr_mask));
-        KLAUNCH(ctx, KID_TRACE, st, k_trace_borders<<<dim3(148, batch), 128, 0, st>>>(ctx->nbr_mask, w, h, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, min_px,
+        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_border_jobs<<<dim3(ctx->sm_count * 2, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, ctx->nbr_mask));
+        KLAUNCH(ctx, KID_TRACE, st, k_trace_borders<<<dim3(ctx->sm_count, batch), 128, 0, st>>>(ctx->nbr_mask, w, h, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, min_px,
                                                                                 max_px, reinterpret_cast<uint32_t *>(ctx->sorted_pts), pts_cap,
                                                                                 reinterpret_cast<ContourDesc *>(ctx->clusters), desc_cap, batch));
         ClassicArgs A;
@@ -581,7 +581,7 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
         A.counters = ctx->counters; A.quads = ctx->quads; A.quad_keys = ctx->sort_keys; A.quad_cap = APSE_MAX_QUADS;
         A.w = w; A.h = h; A.window_index = s;
         A.accuracy_rate = p.polygonalApproxAccuracyRate; A.min_corner_rate = p.minCornerDistanceRate;
-        KLAUNCH(ctx, KID_APPROX, st, k_approx_quads<<<dim3(148, batch), AQ_WARPS * 32, 0, st>>>(A));
+        KLAUNCH(ctx, KID_APPROX, st, k_approx_quads<<<dim3(ctx->sm_count, batch), AQ_WARPS * 32, 0, st>>>(A));
         // counters [0] (jobs), [1] (borders), [5] (points) restart for the next window
         CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters, APSE_COUNTERS * sizeof(int32_t), 0, 2 * sizeof(int32_t), batch, st));
         CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters + 5, APSE_COUNTERS * sizeof(int32_t), 0, sizeof(int32_t), batch, st));

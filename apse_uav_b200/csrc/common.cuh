@@ -52,12 +52,13 @@ struct DeviceParams {  // what the detection kernels need of apse_params (+ deri
 enum KernelId {
     KID_BUILD_MAP = 0, KID_PREPROCESS, KID_REMAP, KID_CVT, KID_LUT, KID_TILE_MINMAX, KID_THRESHOLD, KID_CCL_LOCAL,
     KID_CCL_MERGE, KID_CCL_FLATTEN, KID_EMIT, KID_CLUSTER_SCAN, KID_SCATTER, KID_FIT_QUADS, KID_DECODE, KID_POSE,
-    KID_PROJECT, KID_CLASSIC, KID_ADAPTIVE, KID_BORDER_JOBS, KID_TRACE, KID_APPROX, KID_SUBPIX, KID_DECODE_BITS, KID_COUNT
+    KID_PROJECT, KID_CLASSIC, KID_ADAPTIVE, KID_BORDER_JOBS, KID_TRACE, KID_APPROX, KID_SUBPIX, KID_DECODE_BITS, KID_SEQ_JOBS, KID_COUNT
 };
 #define APSE_EVENT_POOL 2048
 
 struct apse_ctx {
     int device = 0, max_w = 0, max_h = 0, max_batch = 0;
+    int sm_count = 148;               // queried at apse_create; persistent grids are sized in multiples of it
     std::string err;
     int64_t launches = 0;
     // optional per-kernel CUDA-event timing (bench.py roofline): event pairs recorded around each launch
@@ -110,6 +111,9 @@ struct apse_ctx {
     int tiles_batch[2] = {0, 0}, tiles_slot = 0;
     uint8_t *nbr_mask = nullptr;      // [max_batch][h][w] 8-neighbour foreground masks of the classic path (first use)
     uint8_t *gray_scratch = nullptr;  // [max_batch][h][w], allocated on first use by apse_process_frames(gray = NULL)
+    void *seq_jobs = nullptr, *seq_results = nullptr;   // device staging of apse_sequence_jobs (grown on demand)
+    int seq_cap = 0;
+    bool k1_attr_set = false;         // dynamic shared-memory attribute of the K1t instantiations set on this context's device
 };
 
 #define APSE_COUNTERS 8
@@ -135,7 +139,9 @@ int apse_timing_flush(apse_ctx *ctx);
 // enabled -- brackets it with CUDA events on the launching stream.
 #define KLAUNCH(ctx, kid, st, ...)                                                          \
     do {                                                                                    \
-        int _slot = -1;                                                                     \
+        int _slot = -1, _dev = -1;                                                          \
+        if (cudaGetDevice(&_dev) == cudaSuccess && _dev != (ctx)->device)                   \
+            CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "the calling thread's current CUDA device is %d but this context lives on device %d", _dev, (ctx)->device); \
         if ((ctx)->timing) {                                                                \
             if ((ctx)->ev_used == APSE_EVENT_POOL) { int _r = apse_timing_flush(ctx); if (_r) return _r; } \
             _slot = (ctx)->ev_used++;                                                       \

@@ -1314,10 +1314,10 @@ void apse_detect_free(apse_ctx *ctx)
 }
 
 // persistent grid of the work-list kernels (development knob APSE_CHAIN_GRID = CTAs per SM, default 2)
-static int chain_grid()
+static int chain_grid(const apse_ctx *ctx)
 {
-    static const int g = 148 * (getenv("APSE_CHAIN_GRID") ? atoi(getenv("APSE_CHAIN_GRID")) : 2);
-    return g > 0 ? g : 148;
+    static const int per_sm = getenv("APSE_CHAIN_GRID") ? atoi(getenv("APSE_CHAIN_GRID")) : 2;
+    return ctx->sm_count * (per_sm > 0 ? per_sm : 1);
 }
 
 // runs K2..K5 for `batch` gray frames; leaves quads / counters in the context scratch
@@ -1339,7 +1339,7 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
             CUDA_TRY(ctx, cudaMemsetAsync(ctx->thresh, 127, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h, st));
         ex->thresh_full = false;
     } else {
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_reset_thresh<<<chain_grid(), 256, 0, st>>>(ctx->thresh, w, h, ex->alist[prev], ex->work_counter + 2 + prev, ex->acap));
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_reset_thresh<<<chain_grid(ctx), 256, 0, st>>>(ctx->thresh, w, h, ex->alist[prev], ex->work_counter + 2 + prev, ex->acap));
     }
     ex->prev_w = w; ex->prev_h = h;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
@@ -1360,7 +1360,7 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
                                                                                      ex->tile_active, ctw, cth, ex->alist[cur], ex->alist_thr[cur],
                                                                                      acount, ex->acap));
         }
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_apply<<<chain_grid(), 256, 0, st>>>(gray, w, h, tw, th, ex->alist[cur], ex->alist_thr[cur], acount,
+        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_apply<<<chain_grid(ctx), 256, 0, st>>>(gray, w, h, tw, th, ex->alist[cur], ex->alist_thr[cur], acount,
                                                                                       ex->acap, ctx->thresh));
     }
     {
@@ -1374,29 +1374,30 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
             int *n_active = ex->work_counter + 1;
             KLAUNCH(ctx, KID_THRESHOLD, st, k_compact_tiles<<<div_up(batch * nct, 256), 256, 0, st>>>(ex->tile_active, batch * nct, nct, ex->tile_list, n_active));
             const int block = CCL_THREADS;
-            const int grid = chain_grid() * 4;   // persistent: 16 CTAs of 128 threads per SM, tiles taken round-robin from the list
+            const int grid = chain_grid(ctx) * 4;   // persistent: 16 CTAs of 128 threads per SM, tiles taken round-robin from the list
             KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
-            KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid() * 2, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
+            KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid(ctx) * 2, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw, 0));
             if (flat_labels)
                 KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->tile_list, n_active, ctw));
         } else {
-            KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_atile_local<<<chain_grid(), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->alist[cur], acount, ex->acap));
-            static const int mg = 148 * (getenv("APSE_MERGE_GRID") ? atoi(getenv("APSE_MERGE_GRID")) : 16);   // latency-bound root walks: many tiles in flight
+            KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_atile_local<<<chain_grid(ctx), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->alist[cur], acount, ex->acap));
+            static const int mg_per_sm = getenv("APSE_MERGE_GRID") ? atoi(getenv("APSE_MERGE_GRID")) : 16;
+            const int mg = ctx->sm_count * mg_per_sm;   // latency-bound root walks: many tiles in flight
             KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_atile_merge<<<mg, 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, ex->alist[cur], acount, ex->acap));
         }
-        KLAUNCH(ctx, KID_EMIT, st, k_emit_scan<<<chain_grid(), 256, 0, st>>>(ctx->thresh, w, h, ex->alist[cur], acount, ex->acap, ctx->points, ctx->counters));
-        KLAUNCH(ctx, KID_EMIT, st, k_emit_insert<<<dim3(148, min(batch, 8)), 256, 0, st>>>(w, h, ctx->labels, ctx->hash_keys, ctx->hash_count, ex->used_slots,
+        KLAUNCH(ctx, KID_EMIT, st, k_emit_scan<<<chain_grid(ctx), 256, 0, st>>>(ctx->thresh, w, h, ex->alist[cur], acount, ex->acap, ctx->points, ctx->counters));
+        KLAUNCH(ctx, KID_EMIT, st, k_emit_insert<<<dim3(ctx->sm_count, min(batch, 8)), 256, 0, st>>>(w, h, ctx->labels, ctx->hash_keys, ctx->hash_count, ex->used_slots,
                                                                                          ctx->points, ctx->counters, batch));
     }
     KLAUNCH(ctx, KID_CLUSTER_SCAN, st, k_cluster_scan<<<batch, 1024, 0, st>>>(ctx->hash_keys, ctx->hash_count, ctx->hash_offset, ex->used_slots, ctx->clusters, ctx->counters,
                                            dp.min_cluster_pixels, dp.max_cluster_points));
-    KLAUNCH(ctx, KID_SCATTER, st, k_scatter_points<<<dim3(148, min(batch, 8)), 256, 0, st>>>(ctx->points, ctx->hash_offset, ctx->counters, ctx->sorted_pts, batch));
+    KLAUNCH(ctx, KID_SCATTER, st, k_scatter_points<<<dim3(ctx->sm_count, min(batch, 8)), 256, 0, st>>>(ctx->points, ctx->hash_offset, ctx->counters, ctx->sorted_pts, batch));
     FitArgs A;
     A.gray = gray; A.w = w; A.h = h; A.batch = batch; A.clusters = ctx->clusters; A.sorted_pts = ctx->sorted_pts;
     A.sort_keys = ctx->sort_keys; A.lfps = ctx->lfps; A.errs = ctx->errs; A.counters = ctx->counters; A.quads = ctx->quads;
     A.quad_order = ctx->quad_order; A.work_counter = ex->work_counter; A.max_nmaxima = dp.max_nmaxima;
     A.critical_rad = dp.critical_rad; A.max_line_fit_mse = dp.max_line_fit_mse; A.max_dot = dp.max_dot;
-    KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<chain_grid(), FQ_THREADS, 0, st>>>(A));
+    KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<chain_grid(ctx), FQ_THREADS, 0, st>>>(A));
     return APSE_OK;
 }
 
@@ -1413,9 +1414,9 @@ int apse_ccl_binary(apse_ctx *ctx, const uint8_t *bin, int w, int h, int batch, 
     CUDA_TRY(ctx, cudaMemsetAsync(ex->tile_active, 1, (size_t)batch * nct, st));   // no low-contrast class: all tiles
     KLAUNCH(ctx, KID_THRESHOLD, st, k_compact_tiles<<<div_up(batch * nct, 256), 256, 0, st>>>(ex->tile_active, batch * nct, nct, ex->tile_list, n_active));
     const int block = CCL_THREADS;
-    const int grid = chain_grid() * 4;
+    const int grid = chain_grid(ctx) * 4;
     KLAUNCH(ctx, KID_CCL_LOCAL, st, k_ccl_local<<<grid, block, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
-    KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid() * 2, 256, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
+    KLAUNCH(ctx, KID_CCL_MERGE, st, k_ccl_merge<<<chain_grid(ctx) * 2, 256, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw, 1));
     KLAUNCH(ctx, KID_CCL_FLATTEN, st, k_ccl_flatten<<<grid, block, 0, st>>>(bin, w, h, ctx->labels, ex->tile_list, n_active, ctw));
     return APSE_OK;
 }

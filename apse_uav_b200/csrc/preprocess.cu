@@ -598,34 +598,37 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     int w = ctx->w, h = ctx->h;
     PFN_tmapEncodeTiled enc = get_tmap_encoder();
     static const bool force_generic = getenv("APSE_K1_GENERIC") != nullptr;   // development switch: generic kernel only
-    bool tma_ok = !force_generic && enc && (w % 4) == 0 && (h % 4) == 0 && w >= P2_TW && h >= P2_TH && ((uintptr_t)bgr % 16) == 0 && ctx->tables2;
+    bool tma_ok = !force_generic && enc && (w % 4) == 0 && (h % 4) == 0 && ((w * 3) % 16) == 0 && w >= P2_TW && h >= P2_TH && ((uintptr_t)bgr % 16) == 0 && ctx->tables2;
+    CUtensorMap tmap;
+    if (tma_ok) {
+        // every global stride must be a multiple of 16 bytes (checked above); an encoder that still refuses the frame geometry
+        // sends the batch to the generic kernel instead of failing the call
+        cuuint64_t dims[3] = {(cuuint64_t)(w * 3 / 4), (cuuint64_t)h, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * 3 * h};
+        cuuint32_t boxd[3] = {P2_BOX_WORDS, P2_BOX_H, 1}, estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)bgr, dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) tma_ok = false;
+    }
     if (!tma_ok) {
         int fpb = batch >= 8 ? 8 : batch;
         dim3 grid(div_up(w, 32 * K1_PX), div_up(h, 8), div_up(batch, fpb));
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_fused<<<grid, 256, 0, st>>>(bgr, bgr_out, gray, ctx->mapx, ctx->mapy, ctx->tables, w, h, batch, fpb));
         return 1;   // tile extrema not produced
     }
-    CUtensorMap tmap;
-    cuuint64_t dims[3] = {(cuuint64_t)(w * 3 / 4), (cuuint64_t)h, (cuuint64_t)batch};
-    cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * 3 * h};
-    cuuint32_t boxd[3] = {P2_BOX_WORDS, P2_BOX_H, 1}, estr[3] = {1, 1, 1};
-    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)bgr, dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) CTX_FAIL(ctx, APSE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     // registers per thread (development knob APSE_K1_NREG): at 64 the resident preprocess CTAs fill the register file and
     // every CTA of the candidate / decode / pose chain on the other streams displaces one of them; 48 (no spills, 9 % fewer
     // instructions than the 40-register build) = three 384-thread CTAs per SM with 10 K registers left for chain CTAs
     static const int nreg = getenv("APSE_K1_NREG") ? atoi(getenv("APSE_K1_NREG")) : 48;
     static const bool no_full = getenv("APSE_K1_NOFULL") != nullptr;   // development switch: no all-valid specialisation
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->k1_attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<true, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 40, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 48, 3840>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 48, 3840, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
-        attr_set = true;
+        ctx->k1_attr_set = true;
     }
     // frames per CTA: the tap set-up (map reads, box reduction, table load) is amortised over up to 20 frames
     static const int fpb_max = getenv("APSE_K1_FPB") ? atoi(getenv("APSE_K1_FPB")) : 20;   // development knob
@@ -785,24 +788,24 @@ __global__ void k_lut(const uint8_t *__restrict__ src, int64_t n, int sstride, c
         dst[i * dstride] = L[src[i * sstride]];
 }
 
-static int grid_for(int64_t n) { return (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16); }
+static int grid_for(const apse_ctx *ctx, int64_t n) { const int64_t cap = (int64_t)ctx->sm_count * 16; return (int)((n + 255) / 256 < cap ? (n + 255) / 256 : cap); }
 
 int apse_cvt_rgb2lab(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream)
 {
     if (!ctx || !src || !dst || npx <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "cvt_rgb2lab: bad argument");
-    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_rgb2lab<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id));
+    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_rgb2lab<<<grid_for(ctx, npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id));
     return APSE_OK;
 }
 int apse_cvt_lab2rgb(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream)
 {
     if (!ctx || !src || !dst || npx <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "cvt_lab2rgb: bad argument");
-    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_lab2rgb<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id));
+    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_lab2rgb<<<grid_for(ctx, npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst, ctx->tables_id));
     return APSE_OK;
 }
 int apse_cvt_bgr2gray(apse_ctx *ctx, const uint8_t *src, int64_t npx, uint8_t *dst, void *stream)
 {
     if (!ctx || !src || !dst || npx <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "cvt_bgr2gray: bad argument");
-    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_bgr2gray<<<grid_for(npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst));
+    KLAUNCH(ctx, KID_CVT, (cudaStream_t)stream, k_bgr2gray<<<grid_for(ctx, npx), 256, 0, (cudaStream_t)stream>>>(src, npx, dst));
     return APSE_OK;
 }
 int apse_lut(apse_ctx *ctx, const uint8_t *src, int64_t n, int src_stride, const uint8_t *lut_dev, uint8_t *dst,
@@ -810,6 +813,6 @@ int apse_lut(apse_ctx *ctx, const uint8_t *src, int64_t n, int src_stride, const
 {
     if (!ctx || !src || !dst || !lut_dev || n <= 0 || src_stride <= 0 || dst_stride <= 0)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "lut: bad argument");
-    KLAUNCH(ctx, KID_LUT, (cudaStream_t)stream, k_lut<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(src, n, src_stride, lut_dev, dst, dst_stride));
+    KLAUNCH(ctx, KID_LUT, (cudaStream_t)stream, k_lut<<<grid_for(ctx, n), 256, 0, (cudaStream_t)stream>>>(src, n, src_stride, lut_dev, dst, dst_stride));
     return APSE_OK;
 }

@@ -69,30 +69,41 @@ class Pipeline:
         for e in self.engines:
             e.close()
 
-    def _run_on(self, e, frames, out, want_gray, marker_length):
-        gray = None
-        if want_gray:
+    def _run_on(self, e, frames, out, want_gray, marker_length, gray_out=None):
+        gray = gray_out
+        if want_gray and gray is None:
             gray = e.torch.empty(frames.shape[:3], dtype=e.torch.uint8, device=e.tdev)
         e.process_frames(frames, out, marker_length, gray=gray)   # one library call: K1t -> candidates -> decode -> pose
         return gray
 
     def run_batch(self, frames, want_gray=False, want_rejected=False, marker_length=None, serial=False, sync=True,
-                  input_ready=False):
+                  input_ready=False, gray_out=None, out=None):
         """frames: [B,H,W,3] uint8 CUDA tensor, B <= max_batch.  Returns dict of device tensors.
         serial=True      runs the sub-batches one after the other on the current stream (clean per-kernel timing).
         sync=False       does not make the current stream wait for the result: call Pipeline.wait(det) (or to_host)
                          before touching it; lets consecutive batches overlap (multi-stream mode only).  The result
                          tensors come from a ring of `ring` preallocated sets (no allocation, no fill kernel on the hot
                          path): a result stays valid until `ring` further run_batch(sync=False) calls.
-        input_ready=True the frames are already complete in device memory (no ordering against the current stream)."""
+        input_ready=True the frames are already complete in device memory (no ordering against the current stream).
+        gray_out         [B,H,W] uint8 CUDA tensor (e.g. a slice of a sequence-long buffer): the corrected gray frames are
+                         written there instead of the pipeline's scratch (LED read-out, aruco_detect.py:338-373, needs them
+                         after the poses are known); nothing is allocated, so batches still overlap with sync=False.
+        out              dict of result tensors to write into (slices of a sequence-long set from alloc_detections(pose=True))
+                         instead of the ring / a fresh allocation."""
         e = self.engine
         torch = e.torch
         B = frames.shape[0]
         if B > self.max_batch:
             raise ApseError(-1, f"batch {B} exceeds max_batch {self.max_batch}")
         ml = self.marker_length if marker_length is None else marker_length
+        if gray_out is not None:
+            if tuple(gray_out.shape) != tuple(frames.shape[:3]) or gray_out.dtype != torch.uint8 or not gray_out.is_contiguous():
+                raise ApseError(-1, "gray_out must be a contiguous uint8 tensor of shape [B,H,W]")
+            want_gray = False
         overlap = bool(self.streams) and B > 1 and not serial and not sync and not want_gray
-        if overlap:
+        if out is not None:
+            det = dict(out)
+        elif overlap:
             key = (B, bool(want_rejected))
             if key not in self._ring:
                 self._ring[key] = [e.alloc_detections(B, self.max_markers, want_rejected, pose=True) for _ in range(self._ring_size)]
@@ -102,7 +113,7 @@ class Pipeline:
         else:
             det = e.alloc_detections(B, self.max_markers, want_rejected, pose=True)
         if not self.streams or B <= 1:
-            gray = self._run_on(e, frames, det, want_gray, ml)
+            gray = self._run_on(e, frames, det, want_gray, ml, gray_out)
         elif serial:
             grays = []
             for s, eng in enumerate(self.engines):
@@ -111,12 +122,12 @@ class Pipeline:
                     break
                 sl = {k: v[lo:hi] for k, v in det.items()}
                 mls = ml[lo:hi] if isinstance(ml, torch.Tensor) else ml
-                grays.append(self._run_on(eng, frames[lo:hi], sl, want_gray, mls))
+                grays.append(self._run_on(eng, frames[lo:hi], sl, want_gray, mls, None if gray_out is None else gray_out[lo:hi]))
             gray = torch.cat(grays, 0) if want_gray else None
         else:
             cur = torch.cuda.current_stream(e.tdev)
             alloc = None
-            if not overlap:
+            if not overlap and out is None:
                 alloc = cur.record_event()          # output tensors are zero-filled on the current stream
             ready = None
             if not input_ready:
@@ -132,7 +143,12 @@ class Pipeline:
                     pre.wait_event(ready)
                 par = self._use[s] & 1
                 self._use[s] += 1
-                g = torch.empty((hi - lo,) + frames.shape[1:3], dtype=torch.uint8, device=e.tdev) if want_gray else self._gray[s][par][:hi - lo]
+                if gray_out is not None:
+                    g = gray_out[lo:hi]
+                elif want_gray:
+                    g = torch.empty((hi - lo,) + frames.shape[1:3], dtype=torch.uint8, device=e.tdev)
+                else:
+                    g = self._gray[s][par][:hi - lo]
                 if self._done[s][par] is not None:
                     pre.wait_event(self._done[s][par])   # this gray / extrema buffer pair of engine s is free again
                 eng.preprocess_tiles(frames[lo:hi], g, stream=pre)
@@ -147,12 +163,14 @@ class Pipeline:
                 self._done[s][par] = st.record_event()
                 done.append(self._done[s][par])
                 grays.append(g)
-            gray = torch.cat(grays, 0) if want_gray else None
             if overlap:
                 det["_done"] = done
             else:
                 for ev in done:
                     cur.wait_event(ev)
+            # (after the waits: the gray sub-batches are written on the preprocess streams, which the current stream has only
+            # now been ordered behind through the chains' completion events)
+            gray = torch.cat(grays, 0) if want_gray else None
         if want_gray:
             det["gray"] = gray
         return det
@@ -166,6 +184,29 @@ class Pipeline:
             cur = torch.cuda.current_stream(det["n"].device)
             for ev in evs:
                 cur.wait_event(ev)
+        return det
+
+    def run_sequence(self, frames, gray_out=None, want_rejected=False, marker_length=None):
+        """A whole HBM-resident sequence [n,H,W,3] through the pipeline, batch after batch without host synchronisation
+        (the chain of batch k runs under the preprocess of batch k+1); results of all n frames in one set of device tensors.
+        gray_out: [n,H,W] uint8 CUDA tensor that receives the corrected gray frames (LED read-out), or None."""
+        e = self.engine
+        torch = e.torch
+        n = int(frames.shape[0])
+        det = e.alloc_detections(n, self.max_markers, want_rejected, pose=True)
+        cur = torch.cuda.current_stream(e.tdev)
+        filled = cur.record_event()   # the fills of alloc_detections run on the current stream; the chains write on their own
+        for st in self.streams:
+            st.wait_event(filled)
+        pending = []
+        for lo in range(0, n, self.max_batch):
+            hi = min(n, lo + self.max_batch)
+            sl = {k: v[lo:hi] for k, v in det.items()}
+            r = self.run_batch(frames[lo:hi], want_rejected=want_rejected, marker_length=marker_length, sync=False, input_ready=False,
+                               gray_out=None if gray_out is None else gray_out[lo:hi], out=sl)
+            pending.extend(r.get("_done", ()))
+        for ev in pending:
+            cur.wait_event(ev)
         return det
 
     def run(self, frames, **kw):

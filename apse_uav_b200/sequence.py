@@ -1,0 +1,147 @@
+"""Native sequence post-pass: aruco_detect.py:598-782 (marker gating, marker-length recurrence, LED read-out, vehicle
+distances) and the CSV rows of :146-185 for a whole sequence, on top of the apse_sequence_* entry points of
+libapse_b200.so (csrc/sequence.cu).
+
+The frame loop of the reference is sequential only through a handful of scalars (markerLength, previous marker centres,
+detected flags); everything heavy in it -- the cv2.projectPoints calls for the LED strip and the vehicle outlines -- feeds
+outputs only.  So the post-pass is: a native O(markers) scan on the host (microseconds per thousand frames), ONE batched
+second pose launch with the exact per-frame marker lengths, the scan again, ONE launch for all projection jobs, rows.
+postpass.py holds the same logic as readable per-frame Python (the mirror of the reference's text); the parity tests check
+the two against each other and against the reference script's own CSV.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ApseError, SeqConfig, SEQ_JOB_DTYPE, SEQ_RESULT_DTYPE, SEQ_ROW_DTYPE
+
+
+def seq_config(start_frame=1, step_frame=1, leds=False, leds_threshold=None, width=3840, height=2160) -> SeqConfig:
+    c = SeqConfig()
+    _lib.load().apse_seq_config_default(C.byref(c))
+    c.start_frame, c.step_frame, c.width, c.height = int(start_frame), int(step_frame), int(width), int(height)
+    c.leds = 1 if leds else 0
+    c.leds_threshold = -1 if leds_threshold is None else int(leds_threshold)
+    return c
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def scan(cfg: SeqConfig, n, ids, corners, rvec, tvec, rescale_tvec=False, want_rows=True):
+    """apse_sequence_scan on host arrays n [F], ids [F,M], corners [F,M,4,2], rvec / tvec [F,M,3].
+    Returns (lengths [F] float64, rows | None, jobs | None)."""
+    lib = _lib.load()
+    n = np.ascontiguousarray(n, np.int32)
+    F = int(n.shape[0])
+    ids = np.ascontiguousarray(ids, np.int32).reshape(F, -1)
+    M = int(ids.shape[1]) if F else 1
+    corners = np.ascontiguousarray(corners, np.float32).reshape(F, M, 4, 2)
+    rvec = np.ascontiguousarray(rvec, np.float64).reshape(F, M, 3)
+    tvec = np.ascontiguousarray(tvec, np.float64).reshape(F, M, 3)
+    lengths = np.empty(F, np.float64)
+    rows = jobs = None
+    nj = C.c_int(0)
+    if want_rows:
+        rows = np.zeros(F, SEQ_ROW_DTYPE)
+        cap = 4 * F + 64
+        while True:
+            jobs = np.zeros(cap, SEQ_JOB_DTYPE)
+            rc = lib.apse_sequence_scan(C.byref(cfg), F, M, _ptr(n), _ptr(ids), _ptr(corners), _ptr(rvec), _ptr(tvec),
+                                        1 if rescale_tvec else 0, _ptr(lengths), _ptr(rows), _ptr(jobs), cap, C.byref(nj))
+            if rc != -4:   # APSE_ERR_CAPACITY: duplicated marker ids, retry with a larger job list
+                break
+            cap *= 4
+        jobs = jobs[:nj.value]
+    else:
+        rc = lib.apse_sequence_scan(C.byref(cfg), F, M, _ptr(n), _ptr(ids), _ptr(corners), _ptr(rvec), _ptr(tvec),
+                                    1 if rescale_tvec else 0, _ptr(lengths), None, None, 0, None)
+    if rc != 0:
+        raise ApseError(rc, "apse_sequence_scan failed")
+    return lengths, rows, jobs
+
+
+def run_jobs(engine, jobs, gray=None, frame0=0, results=None):
+    """apse_sequence_jobs: all deferred projections of a sequence in one launch.  gray: [n,H,W] uint8 CUDA tensor holding the
+    corrected gray frames frame0 .. frame0+n-1 (LED jobs of other frames keep valid = 0), or None."""
+    lib = _lib.load()
+    if results is None:
+        results = np.zeros(len(jobs), SEQ_RESULT_DTYPE)
+    if len(jobs) == 0:
+        return results
+    jobs = np.ascontiguousarray(jobs)
+    (_, kp), (_, dp) = _lib.darr(engine.K), _lib.darr(engine.D)
+    w, h = engine.size
+    gptr, ng = (gray.data_ptr(), int(gray.shape[0])) if gray is not None else (None, 0)
+    rc = lib.apse_sequence_jobs(engine.h, _ptr(jobs), len(jobs), gptr, int(frame0), ng, w, h, kp, dp, _ptr(results), engine._stream())
+    if rc != 0:
+        raise ApseError(rc, lib.apse_last_error(engine.h).decode())
+    return results
+
+
+def finish(rows, results):
+    rc = _lib.load().apse_sequence_finish(len(rows), _ptr(rows), _ptr(results) if len(results) else None, len(results))
+    if rc != 0:
+        raise ApseError(rc, "apse_sequence_finish failed")
+    return rows
+
+
+def rows_to_csv(rows, header=True) -> str:
+    """The text aruco_detect.py:131-139,146-185 writes for these rows."""
+    rows = np.ascontiguousarray(rows)
+    cap = 512 * (len(rows) + 2)
+    buf = C.create_string_buffer(cap)
+    nb = _lib.load().apse_sequence_csv(_ptr(rows), len(rows), 1 if header else 0, buf, cap)
+    if nb < 0:
+        raise ApseError(int(nb), "apse_sequence_csv failed")
+    return buf.raw[:nb].decode()
+
+
+def rows_to_dicts(rows):
+    """Rows in the shape postpass.SequencePostPass.step returns (for comparisons in the tests)."""
+    out = []
+    for r in rows:
+        d = {"frame_ID": int(r["frame_id"]), "ID_4_detected": int(r["detected"][3])}
+        if r["host_fields"]:
+            d.update(markerLength=float(r["marker_length"]), leds_ID=int(r["leds"]), UAV_altitude=float(r["altitude"]),
+                     fov_width=float(r["fov_width"]), fov_height=float(r["fov_height"]))
+        else:
+            d.update(markerLength=0, leds_ID=0, UAV_altitude=0, fov_width=0, fov_height=0)
+        for v in (1, 2, 3):
+            if r["detected"][v - 1]:
+                d[f"ID_{v}_detected"] = 1
+                d[f"distance_veh{v}_aruco"] = float(r["dist_aruco"][v - 1])
+                d[f"distance_veh{v}_aruco_bbox"] = float(r["dist_bbox"][v - 1])
+            else:
+                d[f"ID_{v}_detected"] = d[f"distance_veh{v}_aruco"] = d[f"distance_veh{v}_aruco_bbox"] = 0
+        out.append(d)
+    return out
+
+
+def postpass_device(engine, det, start_frame=1, leds=False, leds_threshold=None, gray=None, frame0=0, exchange=None):
+    """Post-pass of one sequence whose per-frame results `det` (dict of CUDA tensors n [F], ids [F,M], corners [F,M,4,2],
+    rvec / tvec [F,M,3], poses computed with the nominal marker length) are on this rank's device.  Returns the rows.
+    exchange(jobs, results) (frame-sharded runs): lets the other ranks fill the LED jobs of the frames they own."""
+    torch = engine.torch
+    F = int(det["n"].shape[0])
+    w, h = engine.size
+    cfg = seq_config(start_frame, 1, leds, leds_threshold, w, h)
+    n = det["n"].cpu().numpy()
+    ids = det["ids"].cpu().numpy()
+    corners = det["corners"].cpu().numpy()
+    rvec = det["rvec"].cpu().numpy()
+    tvec = det["tvec"].cpu().numpy()
+    # pass 1: marker length of every frame from the nominal-length poses (tvec is linear in the marker length)
+    lengths, _, _ = scan(cfg, n, ids, corners, rvec, tvec, rescale_tvec=True, want_rows=False)
+    # pass 2: exact poses with those lengths, one launch for the sequence (aruco_detect.py:601 with that frame's markerLength)
+    ml = torch.from_numpy(lengths.astype(np.float32)).to(engine.tdev)
+    rv2, tv2 = engine.pose_frames(det["corners"], det["n"], ml)
+    lengths2, rows, jobs = scan(cfg, n, ids, corners, rv2.cpu().numpy(), tv2.cpu().numpy(), rescale_tvec=False, want_rows=True)
+    results = run_jobs(engine, jobs, gray=gray if leds else None, frame0=frame0)
+    if exchange is not None:
+        results = exchange(jobs, results)
+    return finish(rows, results)

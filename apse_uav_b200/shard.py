@@ -3,10 +3,13 @@ path) and the two-pass handling of the only cross-frame co
 recurrence of aruco_detect.py:306-308,601,623,641.
 
 Pass 1 (parallel, per rank): preprocess + detect + pose with the nominal marker length on the rank's block of frames.
-Gather  (off the hot path): the per-frame results (a few KB per frame) go to rank 0 (gather_object).
-Scan    (rank 0, sequential): the post-pass over frames in order with tvec scaled by L_k / L_nominal (tvec is
-        linear in the marker length), which yields the marker length L_k each frame's pose must use.
-Pass 2 (rank 0, one batched launch): exact pose of every frame with its L_k, then the final sequential scan.
+Gather  (after the hot path): the per-frame results (~5 KB per frame) go to rank 0 as tensors (dist.gather).
+Scan    (rank 0, sequential, native: sequence.py / csrc/sequence.cu): the marker logic over frames in order with tvec scaled
+        by L_k / L_nominal (tvec is linear in the marker length), which yields the marker length L_k each frame's pose must use.
+Pass 2 (rank 0, one batched launch): exact pose of every frame with its L_k, the final scan, one launch for all
+        projection jobs (vehicle outlines, LED strip), CSV rows.
+The *_python functions below are the per-frame Python mirror of the same flow (postpass.SequencePostPass); the tests check the
+native path against them.
 """
 from __future__ import annotations
 
@@ -81,27 +84,167 @@ def final_scan(records, project, start_frame=1, led_mean_for_frame=None, led_sum
     return rows
 
 
-def run_sequence(pipe, frames, rank=0, world=1, group=None, start_frame=1, leds=False):
-    """frames: this rank's block of the sequence ([n_local,H,W,3] uint8 CUDA tensor); lo = first global index of the
-    block is derived from shard_bounds over the total length exchanged below.  Returns CSV rows on rank 0.
-    leds=True (single process): the corrected gray frames stay on the device and the LED strip of the host vehicle
-    (aruco_detect.py:338-373) is read back by the GPU patch-sum kernel in the final scan."""
-    if leds and world > 1:
-        raise ValueError("LED read-out needs the gray frames of every rank on rank 0: run it per rank (world = 1)")
-    n_local = int(frames.shape[0])
-    if world > 1:
-        import torch.distributed as dist
-        sizes = [None] * world
-        dist.all_gather_object(sizes, n_local, group=group)
-        lo = sum(sizes[:rank])
-    else:
-        lo = 0
-    det = pipe.run(frames, want_gray=leds) if n_local else None
-    gray = det.pop("gray") if (leds and det is not None) else None
-    host = pipe.to_host(det) if n_local else dict(n=np.zeros(0, np.int32))
-    records = gather_records(pack_results(host, lo) if n_local else [], rank, world, group)
-    if rank != 0:
+def gather_detections(det, n_local, rank=0, world=1, group=None):
+    """Per-frame results of every rank's block on rank 0, in frame order, as one dict of tensors (device tensors over
+    NCCL, CPU tensors over gloo).  This is the only data-path exchange of a frame-sharded run: ~5 KB per frame."""
+    keys = ("n", "ids", "corners", "rvec", "tvec", "status")
+    if world == 1:
+        return {k: det[k] for k in keys}, [n_local]
+    import torch
+    import torch.distributed as dist
+    sizes = [None] * world
+    dist.all_gather_object(sizes, int(n_local), group=group)
+    cap = max(max(sizes), 1)
+    out = {}
+    for k in keys:
+        t = det[k]
+        pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:n_local] = t[:n_local]
+        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, parts, dst=0, group=group)
+        if rank == 0:
+            out[k] = torch.cat([p_[:sz] for p_, sz in zip(parts, sizes)], 0)
+    return (out if rank == 0 else None), sizes
+
+
+def _exchange_led_jobs(engine, gray, frame0, rank, world, group):
+    """LED read-out of a frame-sharded run (aruco_detect.py:338-373 needs the gray pixels of the frame, which live on the
+    rank that processed it): rank 0 broadcasts the job list, every rank evaluates the LED jobs of its own frames, rank 0
+    collects the results.  A few hundred KB per sequence, after the hot path."""
+    import torch
+    import torch.distributed as dist
+    from . import sequence
+    from ._lib import SEQ_JOB_DTYPE, SEQ_RESULT_DTYPE
+    dev = engine.tdev
+
+    def exchange(jobs, results):
+        cnt = torch.tensor([len(jobs) if rank == 0 else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(cnt, 0, group=group)
+        nj = int(cnt.item())
+        if nj == 0:
+            return results
+        buf = torch.empty(nj * np.dtype(SEQ_JOB_DTYPE).itemsize, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.from_numpy(np.ascontiguousarray(jobs).view(np.uint8).reshape(-1)))
+        dist.broadcast(buf, 0, group=group)
+        if rank != 0:
+            jobs_l = buf.cpu().numpy().view(SEQ_JOB_DTYPE)
+            led = jobs_l["kind"] == 0
+            res_l = np.zeros(nj, SEQ_RESULT_DTYPE)
+            if led.any():
+                res_l[led] = sequence.run_jobs(engine, jobs_l[led], gray=gray, frame0=frame0)
+        else:
+            res_l = results
+        rt = torch.from_numpy(np.ascontiguousarray(res_l).view(np.uint8).reshape(-1).copy()).to(dev)
+        parts = [torch.empty_like(rt) for _ in range(world)] if rank == 0 else None
+        dist.gather(rt, parts, dst=0, group=group)
+        if rank == 0:
+            merged = results.copy()
+            for p_ in parts[1:]:
+                r = p_.cpu().numpy().view(SEQ_RESULT_DTYPE)
+                take = (r["valid"] == 1) & (merged["valid"] == 0)
+                merged[take] = r[take]
+            return merged
         return None
+    return exchange
+
+
+def run_sequence(pipe, frames, rank=0, world=1, group=None, start_frame=1, leds=False, leds_threshold=None, as_rows=False):
+    """aruco_detect.py:571-810 for a frame-sharded sequence.  frames: this rank's contiguous block ([n_local,H,W,3] uint8 CUDA
+    tensor); the blocks of ranks 0..world-1 concatenate to the sequence.  Returns on rank 0 the list of CSV row dicts
+    (as_rows=True: the native row array, for sequence.rows_to_csv) and None elsewhere.
+    Pipeline of one run: batched GPU pipeline per rank (nominal marker length) -> gather of the per-frame results on rank 0
+    -> native post-pass (sequence.postpass_device: scan, one exact-pose launch, scan, one projection-job launch).
+    leds=True: the corrected gray frames stay on the device of the rank that produced them and the LED strip of the host
+    vehicle (:338-373) is read there."""
+    e = pipe.engine
+    torch = e.torch
+    n_local = int(frames.shape[0])
+    w, h = pipe.size
+    gray = torch.empty((n_local, h, w), dtype=torch.uint8, device=e.tdev) if leds and n_local else None
+    if n_local:
+        det = pipe.run_sequence(frames, gray_out=gray)
+    else:
+        det = e.alloc_detections(0, pipe.max_markers, False, pose=True)
+    return _finish_sequence(pipe, det, gray, n_local, rank, world, group, start_frame, leds, leds_threshold, as_rows)
+
+
+def run_sequence_host(pipe, host_batches, n_local, rank=0, world=1, group=None, start_frame=1, leds=False, leds_threshold=None,
+                      as_rows=False):
+    """run_sequence for frames that live in (pinned) HOST memory: host_batches yields this rank's block as uint8 tensors
+    [b,H,W,3] with b <= pipe.max_batch, n_local frames in total.  Two device staging buffers and a copy stream: the H2D copy
+    of batch k+1 runs under the kernels of batch k; everything after the pipeline is the same as run_sequence."""
+    e = pipe.engine
+    torch = e.torch
+    dev = e.tdev
+    w, h = pipe.size
+    gray = torch.empty((n_local, h, w), dtype=torch.uint8, device=dev) if leds and n_local else None
+    det = e.alloc_detections(n_local, pipe.max_markers, False, pose=True)
+    main = torch.cuda.current_stream(dev)
+    if not hasattr(pipe, "_copy_stream"):
+        pipe._copy_stream = torch.cuda.Stream(device=dev)
+        pipe._stage = [torch.empty((pipe.max_batch, h, w, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    cs, stage = pipe._copy_stream, pipe._stage
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [None, None]                      # completion events of the batch that last read staging buffer i
+    filled = main.record_event()
+    for st in pipe.streams:
+        st.wait_event(filled)
+    cs.wait_event(filled)
+    pending, lo = [], 0
+    for k, hb in enumerate(host_batches):
+        b = int(hb.shape[0])
+        buf = k % 2
+        for ev in free[buf] or ():
+            cs.wait_event(ev)
+        with torch.cuda.stream(cs):
+            stage[buf][:b].copy_(hb, non_blocking=True)
+            ready[buf].record(cs)
+        main.wait_event(ready[buf])
+        sl = {key: v[lo:lo + b] for key, v in det.items()}
+        r = pipe.run_batch(stage[buf][:b], sync=False, input_ready=False, gray_out=None if gray is None else gray[lo:lo + b], out=sl)
+        done = list(r.get("_done", ()))
+        if not done:
+            done = [main.record_event()]
+        free[buf] = done
+        pending.extend(done)
+        lo += b
+    if lo != n_local:
+        raise ValueError(f"host_batches held {lo} frames, expected {n_local}")
+    for ev in pending:
+        main.wait_event(ev)
+    return _finish_sequence(pipe, det, gray, n_local, rank, world, group, start_frame, leds, leds_threshold, as_rows)
+
+
+def _finish_sequence(pipe, det, gray, n_local, rank, world, group, start_frame, leds, leds_threshold, as_rows):
+    from . import sequence
+    e = pipe.engine
+    torch = e.torch
+    all_det, sizes = gather_detections(det, n_local, rank, world, group)
+    frame0 = sum(sizes[:rank])
+    exchange = _exchange_led_jobs(e, gray, frame0, rank, world, group) if (leds and world > 1) else None
+    if rank != 0:
+        if exchange is not None:
+            exchange(None, None)
+        return None
+    bad = torch.nonzero(all_det["status"]).flatten()
+    if bad.numel():
+        from ._lib import ApseError
+        raise ApseError(int(all_det["status"][bad[0]]), f"work-buffer capacity exceeded in frames {bad.tolist()[:8]}")
+    rows = sequence.postpass_device(e, all_det, start_frame=start_frame, leds=leds, leds_threshold=leds_threshold, gray=gray,
+                                    frame0=0, exchange=exchange)
+    return rows if as_rows else sequence.rows_to_dicts(rows)
+
+
+def run_sequence_python(pipe, frames, start_frame=1, leds=False):
+    """Single-process run with the per-frame Python mirror of the reference's loop (postpass.SequencePostPass) instead of the
+    native post-pass: every cv2.projectPoints of the reference becomes one kernel launch.  Kept for the parity tests (the
+    native rows must equal these) -- orders of magnitude slower per frame than run_sequence."""
+    n_local = int(frames.shape[0])
+    det = pipe.run(frames, want_gray=leds)
+    gray = det.pop("gray") if leds else None
+    host = pipe.to_host(det)
+    records = gather_records(pack_results(host, 0))
     e = pipe.engine
     project = lambda obj, rvec, tvec: e.project_points(obj, rvec, tvec).cpu().numpy()
 

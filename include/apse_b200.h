@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define APSE_ABI_VERSION 1
+#define APSE_ABI_VERSION 2
 
 typedef enum {
     APSE_OK = 0,
@@ -184,6 +184,67 @@ int apse_adaptive_threshold(apse_ctx *ctx, const uint8_t *gray, int w, int h, in
  * order [max_quads] = rank of each quad in the dependency's candidate order; stats[0] = number of quads */
 int apse_debug_classic(apse_ctx *ctx, const uint8_t *gray, int w, int h, float *quads, uint32_t *order, int max_quads,
                        int64_t *stats_host, void *stream);
+
+/* ---- sequence post-pass (aruco_detect.py:598-782, CSV row :146-185) --------------------------------------------
+ * The marker logic of the reference's frame loop over the per-frame results of apse_process_frames, for a whole
+ * sequence at once.  Only the O(markers) state machine is sequential (apse_sequence_scan, host); every
+ * cv2.projectPoints call of the loop (:344 LED strip, :468 vehicle outline) feeds outputs only and is deferred as a
+ * job, evaluated for all frames in one launch (apse_sequence_jobs, device).  All arrays of the three host functions
+ * are HOST pointers. */
+typedef struct apse_seq_config {
+    int start_frame, step_frame;                   /* aruco_detect.py:13,18; DIFF_MAX = 2/3 * step_frame * 2 (:524) */
+    double marker_length_org, marker_div, div;     /* :520-523 */
+    int width, height;                             /* :519 (field-of-view columns of the CSV) */
+    int leds_threshold;                            /* LEDs_threshold (:36); < 0 = the default rule max(190 + int(tvec_z / marker_div), 240) */
+    int leds;                                      /* 1 = emit LED read-out jobs (needs the corrected gray frames on the device) */
+} apse_seq_config;
+
+typedef struct apse_seq_job {                      /* one deferred projection job */
+    int32_t frame;                                 /* index of the frame in the sequence */
+    int32_t kind;                                  /* 0 = LED strip of the host vehicle (:338-373); 1..3 = distance host -> vehicle `kind` (:729-780) */
+    double rvec[3], tvec[3];                       /* pose of the marker, tvec already divided by size_corr */
+    double dim[4];                                 /* kind >= 1: scaled vehicle outline back, front, left, right (:406-420) */
+    float src[2], tgt[2];                          /* kind >= 1: host-marker centre, vehicle-marker centre (:271-274) */
+    double scale;                                  /* kind >= 1: markerLength / ((msp4 + msp_v) / 2)  (:489-490) */
+    int32_t led_threshold, pad_;
+} apse_seq_job;
+
+typedef struct apse_seq_job_result {
+    double dist_aruco, dist_bbox;                  /* kind >= 1, metres, unrounded */
+    int32_t leds;                                  /* kind 0: the 8-bit LED code */
+    int32_t valid;                                 /* 1 once a device has filled this result */
+} apse_seq_job_result;
+
+typedef struct apse_seq_row {                      /* one CSV row (:146-185); float fields carry Python's round() */
+    int32_t frame_id;
+    int32_t detected[4];                           /* detected_ID[0..3] = vehicles 1, 2, 3, host */
+    int32_t host_fields;                           /* 1: markerLength .. fov_height are written as floats, 0: the reference writes integer zeros */
+    int32_t leds;
+    int32_t job_led, job_dist[3];                  /* jobs whose results this frame takes (-1: value stays stale) */
+    int32_t pad_;
+    double marker_length, altitude, fov_width, fov_height;
+    double dist_aruco[3], dist_bbox[3];
+} apse_seq_row;
+
+void apse_seq_config_default(apse_seq_config *c);
+/* Sequential scan over n_frames frames: n_markers [F], ids [F][M] int32, corners [F][M][4][2] float32, rvec / tvec [F][M][3]
+ * float64 (the layout apse_process_frames writes).  lengths (nullable) [F] receives the marker length the pose of each frame
+ * must be computed with (:601 uses the global markerLength left by the previous frames).  rescale_tvec = 1: the poses were
+ * computed with marker_length_org and tvec is scaled by markerLength / marker_length_org on the fly (first pass, only
+ * `lengths` is meaningful).  rows / jobs / n_jobs nullable together (first pass).  Returns APSE_ERR_CAPACITY if job_cap is
+ * too small (4 jobs per frame always suffice when marker ids are unique). */
+int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers, const int32_t *n_markers, const int32_t *ids,
+                       const float *corners, const double *rvec, const double *tvec, int rescale_tvec, double *lengths,
+                       apse_seq_row *rows, apse_seq_job *jobs, int job_cap, int *n_jobs);
+/* Evaluates the jobs on the device (one warp per job) and copies the results back; synchronous on `stream`.
+ * gray (DEVICE, nullable): corrected gray frames [n_gray_frames][h][w] of the sequence frames frame0 .. frame0 + n_gray_frames - 1;
+ * LED jobs of other frames are left with valid = 0 (frame-sharded runs: every rank fills the LED jobs of its own frames). */
+int apse_sequence_jobs(apse_ctx *ctx, const apse_seq_job *jobs_host, int n_jobs, const uint8_t *gray, int frame0, int n_gray_frames,
+                       int w, int h, const double K_host[9], const double D_host[14], apse_seq_job_result *results_host, void *stream);
+/* Job results -> rows: values the reference leaves stale between frames stay stale; rounding of :146-185 */
+int apse_sequence_finish(int n_frames, apse_seq_row *rows, const apse_seq_job_result *results, int n_jobs);
+/* The CSV text of :131-139,146-185 (Python's str() of ints and floats); returns the number of bytes written or a negative status */
+int64_t apse_sequence_csv(const apse_seq_row *rows, int n_frames, int with_header, char *buf, int64_t cap);
 
 /* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
 int64_t apse_launch_count(apse_ctx *ctx);

@@ -93,3 +93,33 @@ def cv2_params(p):
     for k, v in vars(p).items():
         setattr(q, k, v)
     return q
+
+
+# ---- CSV rows of aruco_detect.py:146-185: comparison with the reference script's own output -----------------------------
+CSV_EXACT_COLS = [0, 1, 3, 7, 10, 13]                       # frame id, detection flags, leds_ID: integers, must be equal
+# one unit in the last place the reference prints (round(.., 5 / 2 / 3)) on top of north_star's 1e-4 relative bar
+CSV_QUANTUM = {2: 1e-5, 4: 1e-2, 5: 1e-2, 6: 1e-2, 8: 1e-3, 9: 1e-3, 11: 1e-3, 12: 1e-3, 14: 1e-3, 15: 1e-3}
+
+
+def golden_csv(name):
+    g = json.load(open(os.path.join(GOLDEN, name)))
+    return g, np.array([[float(v) for v in line.split(",")] for line in g["csv"][1:]])
+
+
+def golden_events(g):
+    ev = g.get("events")
+    if not ev:
+        return None
+    return {int(k): {"hide": v["hide"], "jump": {int(i): tuple(x) for i, x in v["jump"].items()}} for k, v in ev.items()}
+
+
+def assert_csv_rows_match(rows, ref):
+    """rows: list of row dicts (postpass.CSV_FIELDS) or an (n,16) array; ref: the reference script's rows as floats."""
+    from apse_uav_b200.postpass import CSV_FIELDS
+    got = rows if isinstance(rows, np.ndarray) else np.array([[float(r[f]) for f in CSV_FIELDS] for r in rows])
+    assert got.shape == ref.shape
+    assert np.array_equal(got[:, CSV_EXACT_COLS], ref[:, CSV_EXACT_COLS]), "frame ids / detection flags / leds_ID differ"
+    for col, q in CSV_QUANTUM.items():
+        err = np.abs(got[:, col] - ref[:, col])
+        tol = 1e-4 * np.abs(ref[:, col]) + q * 1.0001
+        assert np.all(err <= tol), (col, int(np.argmax(err - tol)), got[:, col][np.argmax(err - tol)], ref[:, col][np.argmax(err - tol)])

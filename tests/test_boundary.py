@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/apse_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(syms), set(_lib.SIGNATURES) ^ set(syms)
-    assert _lib.load().apse_abi_version() == 1
+    assert _lib.load().apse_abi_version() == 2
 
 
 def test_params_struct_matches_c_defaults():

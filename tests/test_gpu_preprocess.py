@@ -127,3 +127,53 @@ def test_undistort_dropin_bit_exact(oracle, camera, frames4k):
         import cv2
         assert np.array_equal(out, cv2.undistort(frame, K, D))
         assert np.array_equal(A.undistort(g, Ks, D[:5]), cv2.undistort(g, Ks, D[:5]))
+
+
+def test_fused_kernel_all_colours(oracle, lut):
+    """The colour chain INSIDE the TMA-staged fused kernel (its own composed tables and arithmetic, not the stand-alone
+    cvtColor kernels) on every 8-bit colour: identity camera (fx = fy = 1, cx = cy = 0, no distortion -> the undistort map is
+    the identity and the bilinear remap copies the pixel), three 3840x2160 frames hold all 2^24 colours.  Both output variants
+    (gray only = the hot path with the compile-time width, gray + corrected BGR) against the oracle chain."""
+    import torch
+    from apse_uav_b200.engine import Engine
+    W, H = 3840, 2160
+    c = np.arange(3 * W * H, dtype=np.uint32) & 0xFFFFFF
+    cols = np.stack([(c >> 16) & 255, (c >> 8) & 255, c & 255], -1).astype(np.uint8).reshape(3, H, W, 3)
+    assert len(np.unique(c)) == 1 << 24
+    e = Engine(0, W, H, 3)
+    e.set_camera(np.eye(3), np.zeros(14), W, H)
+    e.set_lut(lut)
+    t = torch.from_numpy(cols).cuda()
+    out, gray = e.preprocess(t, want_bgr=True)
+    _, gray_only = e.preprocess(t)
+    flat = cols.reshape(-1, W, 3)
+    lab = oracle.rgb2lab(flat)
+    lab[..., 0] = lut[lab[..., 0]]
+    ref = oracle.lab2rgb(lab)
+    assert np.array_equal(out.cpu().numpy().reshape(ref.shape), ref)
+    ref_gray = oracle.bgr2gray(ref)
+    assert np.array_equal(gray.cpu().numpy().reshape(ref_gray.shape), ref_gray)
+    assert np.array_equal(gray_only.cpu().numpy().reshape(ref_gray.shape), ref_gray)
+    e.close()
+
+
+@pytest.mark.parametrize("size", [(1080, 720), (1000, 564), (644, 360)])
+def test_fused_preprocess_widths_without_tma(oracle, camera, lut, size):
+    """Frame widths whose row pitch (3 w bytes) is not a multiple of 16 cannot be described by a TMA tensor map: the
+    batch takes the generic fused kernel instead of failing, with the same bit-exact result."""
+    import torch
+    from apse_uav_b200.engine import Engine
+    K, D = camera
+    w, h = size
+    Ks = K.copy(); Ks[:2] *= w / 3840.0
+    rng = np.random.default_rng(w)
+    frames = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    e = Engine(0, w, h, 2)
+    e.set_camera(Ks, D, w, h)
+    e.set_lut(lut)
+    out, gray = e.preprocess(torch.from_numpy(frames).cuda(), want_bgr=True)
+    ox, oy = oracle.init_undistort_map(Ks, D, w, h)
+    for i in range(2):
+        rb, rg = oracle.preprocess(frames[i], ox, oy, lut)
+        assert np.array_equal(out[i].cpu().numpy(), rb) and np.array_equal(gray[i].cpu().numpy(), rg)
+    e.close()

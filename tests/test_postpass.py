@@ -50,14 +50,10 @@ def test_two_pass_sequence_matches_reference_csv(sequence_records, oracle, camer
                                 (lambda rv, tv: (rv[:, 0], tv[:, 0]))(*oracle.estimate_pose_single_markers(c[i:i + 1], float(ml[i]), K, D))
                                 for i in range(len(c))])))
     rows = shard.final_scan(recs, project)
-    from apse_uav_b200.postpass import CSV_FIELDS, csv_line
-    got = np.array([[float(r[f]) for f in CSV_FIELDS] for r in rows])
-    assert got.shape == ref.shape
-    assert np.array_equal(got[:, [0, 1, 3, 7, 10, 13]], ref[:, [0, 1, 3, 7, 10, 13]])        # frame ids, detection flags, leds
-    num = [2, 4, 5, 6, 8, 9, 11, 12, 14, 15]
-    # values are rounded to 2-5 decimals in the CSV: allow one unit in the last printed place on top of 1e-4 relative
-    assert np.all(np.abs(got[:, num] - ref[:, num]) <= 1e-4 * np.abs(ref[:, num]) + 0.0101)
-    assert np.abs(got[:, 2] - ref[:, 2]).max() <= 1.01e-5                                        # markerLength (5 decimals)
+    from apse_uav_b200.postpass import csv_line
+    from conftest import assert_csv_rows_match
+    # values are rounded to 2-5 decimals in the CSV: one unit in the last printed place of each column on top of 1e-4 relative
+    assert_csv_rows_match(rows, ref)
     assert len(csv_line(rows[0]).split(",")) == 16
 
 
@@ -109,7 +105,46 @@ def test_led_readout_matches_reference_csv(oracle, camera, lut, dictionary, ref_
         (lambda rv, tv: (rv[:, 0], tv[:, 0]))(*oracle.estimate_pose_single_markers(c[i:i + 1], float(ml[i]), K, D)) for i in range(len(c))])))
     led_mean = lambda frame: (lambda x, y: np.sum(np.sum(grays[frame][y - 2:y + 3, x - 2:x + 3])) / 25)
     rows = shard.final_scan(recs, project, led_mean_for_frame=led_mean)
-    got = np.array([[float(r[f]) for f in CSV_FIELDS] for r in rows])
-    assert np.array_equal(got[:, [0, 1, 3, 7, 10, 13]], ref[:, [0, 1, 3, 7, 10, 13]])        # incl. leds_ID
-    num = [2, 4, 5, 6, 8, 9, 11, 12, 14, 15]
-    assert np.all(np.abs(got[:, num] - ref[:, num]) <= 1e-4 * np.abs(ref[:, num]) + 0.0101)
+    from conftest import assert_csv_rows_match
+    assert_csv_rows_match(rows, ref)                                                             # incl. leds_ID
+
+
+def test_events_sequence_matches_reference_csv(oracle, camera, lut, dictionary, ref_params):
+    """64 frames in which a vehicle vanishes and returns, a vehicle and the host jump further than DIFF_MAX, the host
+    vanishes (altitude fallback, aruco_detect.py:639-642) and one frame has no marker at all (:599): the gating / relabel
+    branches (:613,637,669) and every stale value of the CSV, through BOTH host implementations of the loop -- the Python
+    mirror (postpass.py) and the native scan (csrc/sequence.cu) -- against the reference script's own rows."""
+    pytest.importorskip("cv2")
+    from tools import synth
+    from apse_uav_b200 import shard, sequence
+    from conftest import assert_csv_rows_match, golden_csv, golden_events
+    from test_sequence_native import eval_jobs_numpy
+    g, ref = golden_csv("sequence_4k_events.json")
+    flags = ref[:, [7, 10, 13, 1]]
+    assert (flags == 0).any() and (ref[40] == [41] + [0] * 15).all()
+    K, D = camera
+    ox, oy = oracle.init_undistort_map(K, D, 3840, 2160)
+    recs, grays = [], []
+    for k, f in enumerate(synth.make_sequence(dictionary.bytesList, g["base_seed"], g["n_frames"], leds=g["leds"], events=golden_events(g))):
+        _, gray = oracle.preprocess(f, ox, oy, lut)
+        c, ids, _ = oracle.detect_markers_apriltag(gray, dictionary.raw, ref_params)
+        rv, tv = oracle.estimate_pose_single_markers(c, 0.55, K, D) if len(ids) else (np.zeros((0, 1, 3)), np.zeros((0, 1, 3)))
+        recs.append(dict(frame=k, ids=ids, corners=c, rvec=rv[:, 0], tvec=tv[:, 0]))
+        grays.append(gray)
+    project = lambda obj, r, t: oracle.project_points(obj, r, t, K, D)
+    pose_each = lambda c, ml: tuple(np.concatenate(x) for x in zip(*[
+        (lambda rv, tv: (rv[:, 0], tv[:, 0]))(*oracle.estimate_pose_single_markers(c[i:i + 1], float(ml[i]), K, D)) for i in range(len(c))]))
+    lengths = shard.scan_marker_lengths(recs, project)
+    recs2 = shard.exact_pose(recs, lengths, pose_each)
+    led_mean = lambda frame: (lambda x, y: np.sum(np.sum(grays[frame][y - 2:y + 3, x - 2:x + 3])) / 25)
+    rows = shard.final_scan(recs2, project, led_mean_for_frame=led_mean)
+    assert_csv_rows_match(rows, ref)
+    # the native scan on the same records: identical rows
+    F, M = len(recs), 8
+    n = np.array([len(r["ids"]) for r in recs2], np.int32)
+    ids = np.full((F, M), -1, np.int32); corners = np.zeros((F, M, 4, 2), np.float32); rvec = np.zeros((F, M, 3)); tvec = np.zeros((F, M, 3))
+    for k, r in enumerate(recs2):
+        ids[k, :n[k]], corners[k, :n[k]], rvec[k, :n[k]], tvec[k, :n[k]] = r["ids"], r["corners"].reshape(-1, 4, 2), r["rvec"], r["tvec"]
+    _, nrows, jobs = sequence.scan(sequence.seq_config(leds=True), n, ids, corners, rvec, tvec)
+    res = eval_jobs_numpy(jobs, project, lambda k, x, y: led_mean(k)(x, y))
+    assert sequence.rows_to_dicts(sequence.finish(nrows, res)) == rows

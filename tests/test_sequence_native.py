@@ -1,0 +1,131 @@
+"""CPU: the native sequence post-pass (csrc/sequence.cu: apse_sequence_scan / _finish / _csv, host code) against the
+per-frame Python mirror of aruco_detect.py:598-782 (apse_uav_b200/postpass.py) on fabricated detection records with
+drop-outs, jumps beyond DIFF_MAX, re-appearances, duplicated and foreign ids.  The device half (apse_sequence_jobs) is
+replaced here by a numpy evaluation of the same jobs through the oracle's projectPoints; tests/test_gpu_pipeline.py runs the
+real kernel."""
+import numpy as np
+import pytest
+
+from apse_uav_b200 import postpass, sequence, shard
+from apse_uav_b200._lib import SEQ_RESULT_DTYPE
+
+
+def fabricate(oracle, K, D, F=160, M=8, seed=0):
+    """Detection records of a synthetic flight: ids 1-4 drift, vanish, jump and come back; id 7 and a duplicate appear."""
+    rng = np.random.default_rng(seed)
+    pos = {4: np.array([1000., 1000.]), 1: np.array([1700., 1150.]), 2: np.array([2300., 800.]), 3: np.array([2600., 1500.])}
+    vel = {i: rng.normal(0, 1.2, 2) for i in pos}
+    sq = lambda c, s, a: (np.array([[-s, -s], [s, -s], [s, s], [-s, s]]) @ np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]).T + c)
+    n = np.zeros(F, np.int32)
+    ids = np.full((F, M), -1, np.int32)
+    corners = np.zeros((F, M, 4, 2), np.float32)
+    for k in range(F):
+        present = []
+        for i in (4, 1, 2, 3):
+            pos[i] = pos[i] + vel[i] + rng.normal(0, 0.2, 2)
+            if rng.random() < 0.03:
+                pos[i] = pos[i] + rng.normal(0, 150, 2)            # a jump far beyond DIFF_MAX
+            gone = rng.random() < (0.10 if i != 4 else 0.06)
+            if not gone:
+                present.append(i)
+        order = list(rng.permutation(present))
+        if rng.random() < 0.08:
+            order.append(7)                                          # foreign id
+        if rng.random() < 0.04 and present:
+            order.append(present[0])                                 # the same id twice in one frame
+        for j, i in enumerate(order[:M]):
+            c = pos[i] if i in pos else np.array([500., 1800.])
+            if j >= len(present) and i in pos:
+                c = c + np.array([300., -200.])
+            corners[k, j] = sq(c, 30 + (i % 3) + rng.normal(0, 0.3), rng.uniform(-0.5, 0.5)).astype(np.float32)
+            ids[k, j] = i
+        n[k] = min(len(order), M)
+    rvec = np.zeros((F, M, 3))
+    tvec = np.zeros((F, M, 3))
+    for k in range(F):
+        if n[k]:
+            rv, tv = oracle.estimate_pose_single_markers(corners[k, :n[k]], 0.55, K, D)
+            rvec[k, :n[k]], tvec[k, :n[k]] = rv[:, 0], tv[:, 0]
+    return n, ids, corners, rvec, tvec
+
+
+def eval_jobs_numpy(jobs, project, gray_mean=None):
+    """apse_sequence_jobs restated with numpy (projection through `project`)."""
+    res = np.zeros(len(jobs), SEQ_RESULT_DTYPE)
+    for i, J in enumerate(jobs):
+        if J["kind"] == 0:
+            px = postpass.to_pixels(project(postpass.LED_AXIS, J["rvec"], J["tvec"]))
+            leds = 0
+            for j in range(8):
+                if gray_mean(int(J["frame"]), int(px[j][0]), int(px[j][1])) > J["led_threshold"]:
+                    leds += 2 ** (7 - j)
+            res[i]["leds"] = leds
+        else:
+            px = postpass.to_pixels(project(postpass.bbox_points(J["dim"]), J["rvec"], J["tvec"]))
+            d = np.sqrt((np.float64(J["src"][0]) - px[:, 0]) ** 2 + (np.float64(J["src"][1]) - px[:, 1]) ** 2)
+            t = int(np.argmin(d))
+            a = np.sqrt((J["src"][0] - J["tgt"][0]) * (J["src"][0] - J["tgt"][0]) + (J["src"][1] - J["tgt"][1]) * (J["src"][1] - J["tgt"][1]))
+            b = np.sqrt((J["src"][0] - px[t][0]) * (J["src"][0] - px[t][0]) + (J["src"][1] - px[t][1]) * (J["src"][1] - px[t][1]))
+            res[i]["dist_aruco"], res[i]["dist_bbox"] = float(a * J["scale"]), float(b * J["scale"])
+        res[i]["valid"] = 1
+    return res
+
+
+def python_rows(n, ids, corners, rvec, tvec, project, led_mean=None):
+    pp = postpass.SequencePostPass(project, start_frame=1)
+    rows, lengths = [], []
+    for k in range(len(n)):
+        lengths.append(pp.marker_length)
+        if led_mean is not None:
+            pp.led_mean = lambda x, y, k=k: led_mean(k, x, y)
+        m = int(n[k])
+        rows.append(pp.step(1 + k, ids[k, :m] if m else None, corners[k, :m], rvec[k, :m], tvec[k, :m]))
+    return rows, lengths
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_native_scan_equals_python_mirror(oracle, camera, seed):
+    K, D = camera
+    n, ids, corners, rvec, tvec = fabricate(oracle, K, D, seed=seed)
+    project = lambda obj, r, t: oracle.project_points(obj, r, t, K, D)
+    # deterministic stand-in for the gray frames of the LED read-out
+    led_mean = lambda k, x, y: float((k * 37 + x * 11 + y * 7) % 256)
+    want, want_len = python_rows(n, ids, corners, rvec, tvec, project, led_mean)
+    cfg = sequence.seq_config(start_frame=1, leds=True)
+    lengths, rows, jobs = sequence.scan(cfg, n, ids, corners, rvec, tvec)
+    assert np.array_equal(lengths, np.array(want_len)), "marker length recurrence differs"
+    res = eval_jobs_numpy(jobs, project, led_mean)
+    rows = sequence.finish(rows, res)
+    got = sequence.rows_to_dicts(rows)
+    assert got == want
+    # the branches the golden sequences never reach (aruco_detect.py:613,637,669): gated-out markers and re-appearances
+    det = np.array([[r[f"ID_{v}_detected"] for v in (1, 2, 3)] + [r["ID_4_detected"]] for r in want])
+    assert (det == 0).any() and (det[1:] != det[:-1]).any()
+    # CSV text: Python's str() of every field
+    assert sequence.rows_to_csv(rows) == shard.rows_to_csv(want)
+
+
+def test_native_first_pass_lengths_equal_python(oracle, camera):
+    K, D = camera
+    n, ids, corners, rvec, tvec = fabricate(oracle, K, D, F=60, seed=5)
+    project = lambda obj, r, t: oracle.project_points(obj, r, t, K, D)
+    recs = [dict(frame=k, ids=ids[k, :n[k]], corners=corners[k, :n[k]], rvec=rvec[k, :n[k]], tvec=tvec[k, :n[k]]) for k in range(len(n))]
+    want = shard.scan_marker_lengths(recs, project)
+    lengths, _, _ = sequence.scan(sequence.seq_config(), n, ids, corners, rvec, tvec, rescale_tvec=True, want_rows=False)
+    assert np.array_equal(lengths, np.array(want))
+
+
+def test_csv_float_formatting_matches_python_str():
+    rows = np.zeros(6, sequence.SEQ_ROW_DTYPE)
+    vals = [0.53467, 26.74, 100.0, 1e-05, 123456.789, 0.001]
+    for i, v in enumerate(vals):
+        rows[i]["frame_id"] = i + 1
+        rows[i]["detected"] = [1, 0, 1, 1]
+        rows[i]["host_fields"] = 1
+        rows[i]["marker_length"], rows[i]["altitude"], rows[i]["fov_width"], rows[i]["fov_height"] = v, -v, v * 3, 0.0
+        rows[i]["dist_aruco"] = [v, 0, 2 * v]
+        rows[i]["dist_bbox"] = [0.0, 0, 7.0]
+    text = sequence.rows_to_csv(rows, header=False).splitlines()
+    for i, v in enumerate(vals):
+        want = ",".join(str(x) for x in [i + 1, 1, v, 0, -v, v * 3, 0.0, 1, v, 0.0, 0, 0, 0, 1, 2 * v, 7.0])
+        assert text[i] == want

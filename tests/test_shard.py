@@ -65,3 +65,53 @@ def test_world2_gloo_matches_single_process(tmp_path, oracle, camera):
     lengths, rows = pickle.load(open(str(data) + ".out", "rb"))
     assert lengths == ref_lengths and rows == ref_rows
     assert rows[4]["ID_1_detected"] == 0 and rows[5]["ID_1_detected"] == 1
+
+
+WORKER_NATIVE = r'''
+import os, pickle, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch
+import torch.distributed as dist
+from apse_uav_b200 import shard, sequence
+from oracle import oracle as O
+from test_sequence_native import eval_jobs_numpy
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[3], rank=rank, world_size=world)
+arrs, K, D = pickle.load(open(sys.argv[2], "rb"))
+F = len(arrs["n"])
+lo, hi = shard.shard_bounds(F, world)[rank]
+det = {k: torch.from_numpy(v[lo:hi].copy()) for k, v in arrs.items()}
+det["status"] = torch.zeros(hi - lo, dtype=torch.int32)
+allv, sizes = shard.gather_detections(det, hi - lo, rank, world)
+if rank == 0:
+    assert sizes == [b - a for a, b in shard.shard_bounds(F, world)]
+    h = {k: v.numpy() for k, v in allv.items()}
+    project = lambda obj, r, t: O.project_points(obj, r, t, K, D)
+    lengths, rows, jobs = sequence.scan(sequence.seq_config(), h["n"], h["ids"], h["corners"], h["rvec"], h["tvec"])
+    rows = sequence.finish(rows, eval_jobs_numpy(jobs, project))
+    pickle.dump((lengths, sequence.rows_to_dicts(rows)), open(sys.argv[2] + ".out", "wb"))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_world3_gloo_tensor_gather_and_native_scan(tmp_path, oracle, camera):
+    """the N > 1 host path as shard.run_sequence runs it: unequal blocks, results gathered as padded tensors (dist.gather),
+    native scan on rank 0 == the same scan on the unsharded arrays"""
+    from apse_uav_b200 import sequence
+    from test_sequence_native import fabricate, eval_jobs_numpy
+    K, D = camera
+    n, ids, corners, rvec, tvec = fabricate(oracle, K, D, F=50, seed=11)
+    project = lambda obj, r, t: oracle.project_points(obj, r, t, K, D)
+    ref_len, rows, jobs = sequence.scan(sequence.seq_config(), n, ids, corners, rvec, tvec)
+    ref_rows = sequence.rows_to_dicts(sequence.finish(rows, eval_jobs_numpy(jobs, project)))
+    data = tmp_path / "arrs.pkl"
+    pickle.dump((dict(n=n, ids=ids, corners=corners, rvec=rvec, tvec=tvec), K, D), open(data, "wb"))
+    script = tmp_path / "worker_native.py"
+    script.write_text(WORKER_NATIVE)
+    port = str(29900 + os.getpid() % 90)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(data), port],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="3")) for r in range(3)]
+    assert all(p.wait(timeout=300) == 0 for p in procs)
+    lengths, got = pickle.load(open(str(data) + ".out", "rb"))
+    assert np.array_equal(lengths, ref_len) and got == ref_rows

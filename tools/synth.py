@@ -158,16 +158,25 @@ def make_dense_frame(bytes_list, seed: int, width: int = 3840, height: int = 216
 
 
 def make_sequence(bytes_list, base_seed: int, n_frames: int, width: int = 3840, height: int = 2160,
-                  noise_sigma: float = 3.0, leds=None):
+                  noise_sigma: float = 3.0, leds=None, events=None):
     """Sparse sequence (ids 1,2,3 = vehicles, 4 = host) with slow drift so that the track gating of
-    aruco_detect.py:613 passes.  Frame k uses seed base_seed + k.  Yields frames."""
+    aruco_detect.py:613 passes.  Frame k uses seed base_seed + k.  Yields frames.
+    events (optional): {frame index: {"hide": [ids not drawn in that frame], "jump": {id: (dx, dy)}}} -- a jump is a
+    persistent teleport from that frame on (further than DIFF_MAX of aruco_detect.py:524), a hidden marker simply is not
+    rendered; together they drive the gating / relabel branches of aruco_detect.py:613,637,669."""
     rng = np.random.default_rng(base_seed)
     start = np.array([[0.30, 0.35], [0.55, 0.30], [0.70, 0.60], [0.45, 0.65]]) * [width, height]
     start += rng.uniform(-0.04, 0.04, size=start.shape) * [width, height]
     vel = rng.uniform(-1.5, 1.5, size=start.shape)  # px / frame
     ang = rng.uniform(0, 2 * np.pi, size=4)
+    all_ids = (1, 2, 3, 4)
+    offset = np.zeros_like(start)
     for k in range(n_frames):
-        centers = start + vel * k
-        yield make_frame(bytes_list, base_seed + k, width, height, ids=(1, 2, 3, 4), side_range=(64, 66),
-                         jitter=0.01, noise_sigma=noise_sigma, centers=centers.tolist(), angles=ang.tolist(),
-                         leds=None if leds is None else leds[k % len(leds)])
+        ev = (events or {}).get(k, {})
+        for mid, (dx, dy) in ev.get("jump", {}).items():
+            offset[all_ids.index(int(mid))] += (dx, dy)
+        centers = start + vel * k + offset
+        keep = [i for i, mid in enumerate(all_ids) if mid not in ev.get("hide", ())]
+        yield make_frame(bytes_list, base_seed + k, width, height, ids=tuple(all_ids[i] for i in keep), side_range=(64, 66),
+                         jitter=0.01, noise_sigma=noise_sigma, centers=[centers[i].tolist() for i in keep],
+                         angles=[float(ang[i]) for i in keep], leds=None if leds is None else leds[k % len(leds)])
