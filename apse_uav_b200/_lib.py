@@ -93,6 +93,7 @@ SIGNATURES = {
     "apse_adaptive_threshold": [_vp, _vp, _i, _i, _i, _i, C.c_double, _vp, _vp],
     "apse_debug_classic": [_vp, _vp, _i, _i, _vp, _vp, _i, C.POINTER(C.c_int64), _vp],
     "apse_seq_config_default": [C.POINTER(SeqConfig)],
+    "apse_py_round": [C.c_double, _i],
     "apse_sequence_scan": [C.POINTER(SeqConfig), _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(C.c_int)],
     "apse_sequence_jobs": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _dp, _dp, _vp, _vp],
     "apse_sequence_finish": [_i, _vp, _vp, _i],
@@ -104,7 +105,7 @@ SIGNATURES = {
     "apse_timing_collect": [_vp, _dp, C.POINTER(C.c_int64), _i],
     "apse_timing_trace": [_vp, _dp, _i],
 }
-_RESTYPES = {"apse_destroy": None, "apse_params_default": None, "apse_seq_config_default": None, "apse_sequence_csv": C.c_int64, "apse_last_error": C.c_char_p,
+_RESTYPES = {"apse_destroy": None, "apse_params_default": None, "apse_seq_config_default": None, "apse_py_round": C.c_double, "apse_sequence_csv": C.c_int64, "apse_last_error": C.c_char_p,
              "apse_launch_count": C.c_int64, "apse_kernel_name": C.c_char_p}
 
 _lib = None

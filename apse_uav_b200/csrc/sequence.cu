@@ -27,13 +27,40 @@ static const double VEH_DIM[5][4] = {{0, 0, 0, 0},
 __constant__ float c_led_axis[8][3] = {{-0.419f, -0.42f, 0}, {-0.414f, -0.305f, 0}, {-0.409f, -0.19f, 0}, {-0.404f, -0.07f, 0},
                                        {-0.399f, 0.065f, 0}, {-0.393f, 0.19f, 0},  {-0.388f, 0.315f, 0}, {-0.382f, 0.435f, 0}};
 
-// Python's round(x, nd) on a float: the decimal string of x correctly rounded to nd places, converted back
-static double py_round(double x, int nd)
+// Python's round(x, nd) on a float: the exact binary value of x rounded half-to-even to nd decimals (what _Py_dg_dtoa mode 3
+// yields), converted back to the nearest double.  For the magnitudes of this path (|x| * 10^nd < 2^53, nd <= 5) that is exact
+// 128-bit integer arithmetic: x = m * 2^e, q = round_half_even(m * 10^nd * 2^e), result = q / 10^nd (one IEEE division of two
+// exactly representable integers = the correctly rounded value of the decimal string).  Anything else takes the string path.
+static double py_round_slow(double x, int nd)
 {
-    if (!isfinite(x)) return x;
     char buf[400];
     snprintf(buf, sizeof buf, "%.*f", nd, x);
     return strtod(buf, nullptr);
+}
+
+static double py_round(double x, int nd)
+{
+    if (!isfinite(x) || x == 0) return x;
+    static const double P10[6] = {1, 10, 100, 1000, 10000, 100000};
+    const double a = fabs(x);
+    if (nd < 0 || nd > 5 || a * P10[nd] >= 4.0e15 || a < 1e-300) return py_round_slow(x, nd);
+    int e;
+    const double fr = frexp(a, &e);                                   // a = fr * 2^e, fr in [0.5, 1)
+    const unsigned long long m = (unsigned long long)ldexp(fr, 53);   // 53-bit integer mantissa, a = m * 2^(e - 53)
+    const int sh = 53 - e;                                            // a * 10^nd = (m * 10^nd) / 2^sh
+    const unsigned __int128 prod = (unsigned __int128)m * (unsigned long long)P10[nd];
+    unsigned long long q;
+    if (sh <= 0) {
+        q = (unsigned long long)(prod << (-sh));
+    } else if (sh >= 127) {
+        q = 0;
+    } else {
+        const unsigned __int128 one = (unsigned __int128)1 << sh, rem = prod & (one - 1), half = one >> 1;
+        q = (unsigned long long)(prod >> sh);
+        if (rem > half || (rem == half && (q & 1))) q++;
+    }
+    const double r = (double)q / P10[nd];
+    return x < 0 ? -r : r;
 }
 
 struct SeqState {   // module globals of the reference that survive from frame to frame
@@ -67,6 +94,8 @@ static double yaw_zxy_deg(const double r[3])
 }
 
 extern "C" {
+
+double apse_py_round(double x, int ndigits) { return py_round(x, ndigits); }
 
 void apse_seq_config_default(apse_seq_config *c)
 {
@@ -179,7 +208,7 @@ int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers
                             nj++;
                         }
                         S.prev_xy[vid][0] = cx; S.prev_xy[vid][1] = cy;
-                        {   // drawBoundingBox (:406-420), the dimension scaling only
+                        if (jobs) {   // drawBoundingBox (:406-420), the dimension scaling only (feeds the distance jobs)
                             double ah = atan(tv[0] / tv[2]), av = atan(tv[1] / tv[2]);
                             const double yaw = py_round(yaw_zxy_deg(frv + 3 * i), 2);
                             if (!(yaw < 0)) { ah = -ah; av = -av; }

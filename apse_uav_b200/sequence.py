@@ -122,25 +122,58 @@ def rows_to_dicts(rows):
     return out
 
 
+def _host_copy(engine, tensors):
+    """One D2H transfer of several small device tensors: packed into one byte buffer on the device, copied into a cached
+    pinned buffer, returned as numpy views (valid until the next call on this engine)."""
+    torch = engine.torch
+    flat = [t.contiguous().view(torch.uint8).reshape(-1) for t in tensors]
+    sizes = [int(f.numel()) for f in flat]
+    offs = np.concatenate([[0], np.cumsum([(s + 15) // 16 * 16 for s in sizes])]).astype(np.int64)
+    total = int(offs[-1])
+    pin = getattr(engine, "_seq_pin", None)
+    if pin is None or pin.numel() < total:
+        pin = engine._seq_pin = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
+    dev = torch.empty(max(total, 1), dtype=torch.uint8, device=engine.tdev)
+    for f, o, s in zip(flat, offs, sizes):
+        dev[int(o):int(o) + s] = f
+    pin[:total].copy_(dev[:total], non_blocking=True)
+    torch.cuda.current_stream(engine.tdev).synchronize()
+    host = pin.numpy()
+    return [host[int(o):int(o) + s].view(_NP[t.dtype]).reshape(tuple(t.shape)) for t, o, s in zip(tensors, offs, sizes)]
+
+
+_NP = {}
+
+
+def _np_types(torch):
+    if not _NP:
+        _NP.update({torch.int32: np.int32, torch.float32: np.float32, torch.float64: np.float64, torch.uint8: np.uint8})
+
+
 def postpass_device(engine, det, start_frame=1, leds=False, leds_threshold=None, gray=None, frame0=0, exchange=None):
     """Post-pass of one sequence whose per-frame results `det` (dict of CUDA tensors n [F], ids [F,M], corners [F,M,4,2],
     rvec / tvec [F,M,3], poses computed with the nominal marker length) are on this rank's device.  Returns the rows.
+    Only the first max(n) marker slots of every frame travel to the host (one packed pinned transfer per direction).
     exchange(jobs, results) (frame-sharded runs): lets the other ranks fill the LED jobs of the frames they own."""
     torch = engine.torch
+    _np_types(torch)
     F = int(det["n"].shape[0])
     w, h = engine.size
     cfg = seq_config(start_frame, 1, leds, leds_threshold, w, h)
-    n = det["n"].cpu().numpy()
-    ids = det["ids"].cpu().numpy()
-    corners = det["corners"].cpu().numpy()
-    rvec = det["rvec"].cpu().numpy()
-    tvec = det["tvec"].cpu().numpy()
+    if F == 0:
+        return np.zeros(0, SEQ_ROW_DTYPE)
+    M = int(det["ids"].shape[1])
+    m = max(1, min(M, int(det["n"].max().item())))           # marker slots in use (one 4-byte read-back)
+    n, ids, corners, rvec, tvec = _host_copy(engine, [det["n"], det["ids"][:, :m], det["corners"][:, :m], det["rvec"][:, :m], det["tvec"][:, :m]])
     # pass 1: marker length of every frame from the nominal-length poses (tvec is linear in the marker length)
     lengths, _, _ = scan(cfg, n, ids, corners, rvec, tvec, rescale_tvec=True, want_rows=False)
     # pass 2: exact poses with those lengths, one launch for the sequence (aruco_detect.py:601 with that frame's markerLength)
     ml = torch.from_numpy(lengths.astype(np.float32)).to(engine.tdev)
-    rv2, tv2 = engine.pose_frames(det["corners"], det["n"], ml)
-    lengths2, rows, jobs = scan(cfg, n, ids, corners, rv2.cpu().numpy(), tv2.cpu().numpy(), rescale_tvec=False, want_rows=True)
+    corners_d = det["corners"][:, :m].contiguous() if m < M else det["corners"]
+    rv2, tv2 = engine.pose_frames(corners_d, det["n"], ml)
+    n, ids, corners = n.copy(), ids.copy(), corners.copy()   # the pinned buffer is reused by the next transfer
+    rv2h, tv2h = _host_copy(engine, [rv2, tv2])
+    lengths2, rows, jobs = scan(cfg, n, ids, corners, rv2h, tv2h, rescale_tvec=False, want_rows=True)
     results = run_jobs(engine, jobs, gray=gray if leds else None, frame0=frame0)
     if exchange is not None:
         results = exchange(jobs, results)

@@ -227,6 +227,8 @@ typedef struct apse_seq_row {                      /* one CSV row (:146-185); fl
 } apse_seq_row;
 
 void apse_seq_config_default(apse_seq_config *c);
+/* Python's round(x, ndigits) on a float, as the CSV columns of :146-185 need it (exact half-to-even on the binary value) */
+double apse_py_round(double x, int ndigits);
 /* Sequential scan over n_frames frames: n_markers [F], ids [F][M] int32, corners [F][M][4][2] float32, rvec / tvec [F][M][3]
  * float64 (the layout apse_process_frames writes).  lengths (nullable) [F] receives the marker length the pose of each frame
  * must be computed with (:601 uses the global markerLength left by the previous frames).  rescale_tvec = 1: the poses were

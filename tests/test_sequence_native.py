@@ -129,3 +129,19 @@ def test_csv_float_formatting_matches_python_str():
     for i, v in enumerate(vals):
         want = ",".join(str(x) for x in [i + 1, 1, v, 0, -v, v * 3, 0.0, 1, v, 0.0, 0, 0, 0, 1, 2 * v, 7.0])
         assert text[i] == want
+
+
+def test_py_round_equals_python_round():
+    """The CSV columns of aruco_detect.py:146-185 are Python round(float, n): the native 128-bit integer path equals the
+    interpreter on random values, exact decimal ties in binary (k / 2^j) and values one ulp either side of a tie."""
+    from apse_uav_b200 import _lib
+    f = _lib.load().apse_py_round
+    rng = np.random.default_rng(3)
+    vals = list(rng.uniform(-4000, 4000, 40000)) + list(rng.uniform(-2, 2, 20000)) + list(rng.normal(0, 1e-3, 5000))
+    vals += [k / 8 for k in range(-400, 400)] + [k / 16 + 0.03125 for k in range(-200, 200)] + [k / 64 for k in range(-999, 999)]
+    vals += [0.5, 1.5, 2.5, 0.125, 0.375, 2.675, 1.005, 1e-9, -1e-9, 123456.789, 0.0005, 0.00049999999999999, 1e15, 3.9e15, 1e300]
+    ties = [k / 1000 + 0.0005 for k in range(0, 3000, 7)]
+    vals += ties + [float(np.nextafter(v, np.inf)) for v in ties] + [float(np.nextafter(v, -np.inf)) for v in ties]
+    for nd in (0, 2, 3, 5):
+        for v in vals:
+            assert f(float(v), nd) == round(float(v), nd), (v, nd)
