@@ -85,6 +85,7 @@ SIGNATURES = {
     "apse_pose_frames": [_vp, _vp, _vp, _i, _i, _vp, _f, _dp, _dp, _vp, _vp, _vp],
     "apse_process_frames": [_vp, _vp, _vp, _i, C.POINTER(Detections), _vp, _f, _vp, _vp, _vp],
     "apse_preprocess_tiles": [_vp, _vp, _vp, _i, _vp],
+    "apse_preprocess_tiles_sparse": [_vp, _vp, _vp, _i, _vp],
     "apse_detect_pose_frames": [_vp, _vp, _i, C.POINTER(Detections), _vp, _f, _vp, _vp, _vp],
     "apse_project_points": [_vp, _vp, _i, _vp, _vp, _dp, _dp, _vp, _vp],
     "apse_project_points_multi": [_vp, _vp, _i, _vp, _vp, _vp, _dp, _dp, _vp, _vp],
@@ -98,6 +99,7 @@ SIGNATURES = {
     "apse_sequence_jobs": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _dp, _dp, _vp, _vp],
     "apse_sequence_finish": [_i, _vp, _vp, _i],
     "apse_sequence_csv": [_vp, _i, _i, _vp, _i64],
+    "apse_debug_sparse": [_vp, _vp, _vp, _i, C.POINTER(C.c_int), _vp],
     "apse_launch_count": [_vp],
     "apse_kernel_count": [],
     "apse_kernel_name": [_i],

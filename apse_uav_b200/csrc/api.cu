@@ -82,6 +82,7 @@ void apse_destroy(apse_ctx *ctx)
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{caller_dev};
     apse_detect_free(ctx);
     apse_decode_free(ctx);
+    apse_sparse_free(ctx);
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
     delete[] ctx->trace;
     cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask); cudaFree(ctx->seq_jobs); cudaFree(ctx->seq_results);
@@ -96,7 +97,7 @@ static const char *KERNEL_NAMES[KID_COUNT] = {
     "k_build_undistort_map", "k_preprocess_fused", "k_remap", "k_cvt", "k_lut", "k_tile_minmax", "k_threshold",
     "k_ccl_local", "k_ccl_merge", "k_ccl_flatten", "k_emit_points", "k_cluster_scan", "k_scatter_points", "k_fit_quads",
     "k_decode", "k_pose", "k_project_points", "k_classic", "k_adaptive_threshold", "k_border_jobs", "k_trace_borders",
-    "k_approx_quads", "k_corner_subpix", "k_decode_bits", "k_sequence_jobs"};
+    "k_approx_quads", "k_corner_subpix", "k_decode_bits", "k_sequence_jobs", "k_sparse_flags", "k_sparse_exact"};
 
 int apse_kernel_count(void) { return KID_COUNT; }
 const char *apse_kernel_name(int kid) { return kid >= 0 && kid < KID_COUNT ? KERNEL_NAMES[kid] : ""; }
@@ -146,6 +147,7 @@ int apse_set_lut(apse_ctx *ctx, const uint8_t lut[256], void *stream)
     int rc = apse_upload_tables(ctx, lut, &ctx->tables, (cudaStream_t)stream);
     if (rc) return rc;
     rc = apse_upload_p2_tables(ctx, lut, &ctx->tables2, (cudaStream_t)stream);
+    if (!rc) rc = apse_build_bound_table(ctx, (cudaStream_t)stream);   // sparse evaluation: gray bounds per colour cell, from the chain itself
     if (rc) return rc;
     ctx->has_lut = true;
     return APSE_OK;
@@ -268,6 +270,13 @@ int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h)
     return APSE_OK;
 }
 
+// development switch: APSE_DENSE=1 turns the sparse evaluation off everywhere (A/B runs of the two preprocess paths)
+static bool sparse_enabled()
+{
+    static const bool off = getenv("APSE_DENSE") != nullptr && getenv("APSE_DENSE")[0] == '1';
+    return !off;
+}
+
 // candidates (APRILTAG quad detector or the classic threshold / contour path) -> grouping + decoding -> SUBPIX
 static int apse_detect_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, cudaStream_t st,
                             bool have_tile_minmax)
@@ -309,22 +318,35 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
     ctx->tiles_gray[0] = ctx->tiles_gray[1] = nullptr;   // cached tile extrema (apse_preprocess_tiles) never survive another entry point
     cudaStream_t st = (cudaStream_t)stream;
     const int w = ctx->w, h = ctx->h;
+    const bool want_sparse = gray == nullptr;
     if (!gray) {
         if (!ctx->gray_scratch) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->gray_scratch, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h));
         gray = ctx->gray_scratch;
     }
-    // K1 writes the 4x4-tile extrema of gray straight into the candidate stage's tile arrays
-    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm, batch, st);
+    // K1 writes the 4x4-tile extrema of gray straight into the candidate stage's tile arrays.  A caller that does not ask for
+    // the gray frames gets the sparse evaluation (identical detections; gray is computed only where the detector reads it).
+    int rc = 1;
+    const bool sparse = want_sparse && sparse_enabled() && ctx->params.cornerRefinementMethod == 3;
+    if (sparse) {
+        rc = apse_preprocess_sparse(ctx, bgr, gray, ctx->tmm, 0, batch, ctx->params.aprilTagMinWhiteBlackDiff, st);
+        if (rc < 0) return rc;
+        if (rc == APSE_OK) {
+            ctx->sparse_active = true;
+            ctx->sparse_src = SparseSrc{bgr, ctx->mapx, ctx->mapy, ctx->tables2, ctx->eflag[0], w / 4, h / 4};
+        }
+    }
+    if (rc == 1) rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm, batch, st);
     if (rc < 0) return rc;
     const bool have_minmax = rc == APSE_OK;
     rc = apse_detect_impl(ctx, gray, w, h, batch, out, st, have_minmax);
+    ctx->sparse_active = false;
     if (rc) return rc;
     if (rvec && tvec)
         rc = apse_pose_frames(ctx, out->corners, out->n_markers, batch, out->max_markers, marker_len, marker_len_all, ctx->K, ctx->D, rvec, tvec, stream);
     return rc;
 }
 
-int apse_preprocess_tiles(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream)
+static int preprocess_tiles_impl(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream, bool want_sparse)
 {
     if (!ctx || !bgr || !gray || batch <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "preprocess_tiles: bad argument");
     if (!ctx->has_camera || !ctx->has_lut) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "preprocess_tiles: set_camera and set_lut first");
@@ -333,11 +355,29 @@ int apse_preprocess_tiles(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int 
     // reads its own buffer) is still in flight; the caller alternates the gray buffers accordingly (Pipeline)
     const int slot = ctx->tiles_slot;
     ctx->tiles_slot ^= 1;
-    int rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm_buf[slot], batch, (cudaStream_t)stream);
+    int rc = 1;
+    ctx->tiles_sparse[slot] = false;
+    for (int k = 0; k < 2; k++) if (ctx->sparse_gray[k] == gray) ctx->sparse_gray[k] = nullptr;   // the buffer is rewritten now
+    if (want_sparse && sparse_enabled() && ctx->params.cornerRefinementMethod == 3) {
+        rc = apse_preprocess_sparse(ctx, bgr, gray, ctx->tmm_buf[slot], slot, batch, ctx->params.aprilTagMinWhiteBlackDiff, (cudaStream_t)stream);
+        if (rc < 0) return rc;
+        if (rc == APSE_OK) { ctx->tiles_sparse[slot] = true; ctx->tiles_bgr[slot] = bgr; ctx->sparse_gray[slot] = gray; }
+    }
+    if (rc == 1) rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm_buf[slot], batch, (cudaStream_t)stream);
     if (rc < 0) return rc;
     ctx->tiles_gray[slot] = rc == APSE_OK ? gray : nullptr;   // the extrema in tmm_buf[slot] belong to exactly this gray batch
     ctx->tiles_batch[slot] = batch;
     return APSE_OK;
+}
+
+int apse_preprocess_tiles(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream)
+{
+    return preprocess_tiles_impl(ctx, bgr, gray, batch, stream, false);
+}
+
+int apse_preprocess_tiles_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream)
+{
+    return preprocess_tiles_impl(ctx, bgr, gray, batch, stream, true);
 }
 
 int apse_detect_pose_frames(apse_ctx *ctx, const uint8_t *gray, int batch, apse_detections *out, const float *marker_len,
@@ -351,8 +391,20 @@ int apse_detect_pose_frames(apse_ctx *ctx, const uint8_t *gray, int batch, apse_
             have_minmax = true;
             ctx->tmm = ctx->tmm_buf[slot];
             ctx->tiles_gray[slot] = nullptr;              // consumed: a later call on other data recomputes the extrema
+            if (ctx->tiles_sparse[slot]) {
+                ctx->sparse_active = true;
+                ctx->sparse_src = SparseSrc{ctx->tiles_bgr[slot], ctx->mapx, ctx->mapy, ctx->tables2, ctx->eflag[slot], ctx->w / 4, ctx->h / 4};
+                ctx->tiles_sparse[slot] = false;
+                ctx->sparse_gray[slot] = nullptr;
+            }
         }
+    // a gray batch of the sparse evaluation is only complete together with its tile flags: without them (another entry point
+    // came in between) the detector would read pixels that were never computed
+    if (!have_minmax && (ctx->sparse_gray[0] == gray || ctx->sparse_gray[1] == gray))
+        CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect_pose_frames: this gray batch comes from apse_preprocess_tiles_sparse and its tile flags are gone "
+                                            "(another call on the context came in between); preprocess it again");
     int rc = apse_detect_impl(ctx, gray, ctx->w, ctx->h, batch, out, (cudaStream_t)stream, have_minmax);
+    ctx->sparse_active = false;
     if (rc) return rc;
     if (rvec && tvec)
         rc = apse_pose_frames(ctx, out->corners, out->n_markers, batch, out->max_markers, marker_len, marker_len_all, ctx->K, ctx->D, rvec, tvec, stream);
@@ -383,6 +435,25 @@ int apse_debug_classic(apse_ctx *ctx, const uint8_t *gray, int w, int h, float *
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
     }
     if (stats_host) { stats_host[0] = cnt[2]; stats_host[1] = 0; stats_host[2] = 0; stats_host[3] = 0; }
+    return APSE_OK;
+}
+
+int apse_debug_sparse(apse_ctx *ctx, uint16_t *bound_table_host, uint8_t *eflag_dev, int batch, int *n_exact_host, void *stream)
+{
+    if (!ctx) return APSE_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bound_table_host) {
+        if (!ctx->btable) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "debug_sparse: set_lut first");
+        CUDA_TRY(ctx, cudaMemcpyAsync(bound_table_host, ctx->btable, 16 * 32 * 32 * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    const int slot = ctx->tiles_slot ^ 1;   // the slot the last apse_preprocess_tiles[_sparse] call used
+    if (eflag_dev || n_exact_host) {
+        if (!ctx->eflag[slot]) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "debug_sparse: no sparse batch was preprocessed on this context");
+        if (eflag_dev) CUDA_TRY(ctx, cudaMemcpyAsync(eflag_dev, ctx->eflag[slot], (size_t)batch * (ctx->w / 4) * (ctx->h / 4), cudaMemcpyDeviceToDevice, st));
+        if (n_exact_host) CUDA_TRY(ctx, cudaMemcpyAsync(n_exact_host, ctx->ecount[slot], sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    }
     return APSE_OK;
 }
 

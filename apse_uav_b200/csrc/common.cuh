@@ -30,6 +30,20 @@ struct P2Tables {   // tables of the TMA-staged preprocess kernel (preprocess.cu
     uint8_t invgamma[4096];
 };
 
+// tile list entry: tx | ty << 13 | frame << 26 (frames per launch <= 64, tile coordinates < 8192)
+#define ATILE(f, tx, ty) ((uint32_t)(tx) | ((uint32_t)(ty) << 13) | ((uint32_t)(f) << 26))
+#define ATILE_TX(e) ((int)((e) & 0x1fffu))
+#define ATILE_TY(e) ((int)(((e) >> 13) & 0x1fffu))
+#define ATILE_F(e) ((int)((e) >> 26))
+
+struct SparseSrc {   // sparse evaluation (preprocess.cu): what a consumer needs to compute the gray of a pixel on demand
+    const uint8_t *bgr;       // [batch][h][w][3] source frames of the batch
+    const float *mapx, *mapy;
+    const P2Tables *tables;   // device (global memory) copy of the colour tables
+    const uint8_t *eflag;     // [batch][h/4][w/4]: non-zero = the gray buffer holds the exact values of this tile
+    int tw, th;
+};
+
 struct ClusterDesc {
     uint32_t offset;  // into the frame's sorted point array
     uint32_t count;
@@ -52,7 +66,8 @@ struct DeviceParams {  // what the detection kernels need of apse_params (+ deri
 enum KernelId {
     KID_BUILD_MAP = 0, KID_PREPROCESS, KID_REMAP, KID_CVT, KID_LUT, KID_TILE_MINMAX, KID_THRESHOLD, KID_CCL_LOCAL,
     KID_CCL_MERGE, KID_CCL_FLATTEN, KID_EMIT, KID_CLUSTER_SCAN, KID_SCATTER, KID_FIT_QUADS, KID_DECODE, KID_POSE,
-    KID_PROJECT, KID_CLASSIC, KID_ADAPTIVE, KID_BORDER_JOBS, KID_TRACE, KID_APPROX, KID_SUBPIX, KID_DECODE_BITS, KID_SEQ_JOBS, KID_COUNT
+    KID_PROJECT, KID_CLASSIC, KID_ADAPTIVE, KID_BORDER_JOBS, KID_TRACE, KID_APPROX, KID_SUBPIX, KID_DECODE_BITS, KID_SEQ_JOBS,
+    KID_SPARSE_FLAGS, KID_SPARSE_EXACT, KID_COUNT
 };
 #define APSE_EVENT_POOL 2048
 
@@ -113,6 +128,17 @@ struct apse_ctx {
     uint8_t *gray_scratch = nullptr;  // [max_batch][h][w], allocated on first use by apse_process_frames(gray = NULL)
     void *seq_jobs = nullptr, *seq_results = nullptr;   // device staging of apse_sequence_jobs (grown on demand)
     int seq_cap = 0;
+    // sparse evaluation (apse_preprocess_tiles_sparse / apse_process_frames without a gray output), one set per tiles slot
+    uint16_t *btable = nullptr;       // [SB_ENTRIES] bound table: min | (255 - max) << 8 of gray over the colours of a cell
+    uint16_t *tbounds[2] = {nullptr, nullptr};   // [max_batch][h/4][w/4] per-tile bounds of gray (lo | hi << 8)
+    uint8_t *eflag[2] = {nullptr, nullptr};      // [max_batch][h/4][w/4] 1 = tile evaluated exactly
+    uint32_t *elist[2] = {nullptr, nullptr};     // tiles to evaluate exactly (ATILE entries), capacity = every tile of the batch
+    int *ecount[2] = {nullptr, nullptr};
+    const uint8_t *tiles_bgr[2] = {nullptr, nullptr};   // source frames of the batch in slot i (sparse batches only)
+    bool tiles_sparse[2] = {false, false};
+    const uint8_t *sparse_gray[2] = {nullptr, nullptr};   // gray buffer a sparse batch was written into (partial: only valid with its slot)
+    bool sparse_active = false;       // the detect call in flight reads gray through sparse_src
+    SparseSrc sparse_src;
     bool k1_attr_set = false;         // dynamic shared-memory attribute of the K1t instantiations set on this context's device
 };
 
@@ -164,6 +190,12 @@ static __host__ __device__ inline int div_up(int a, int b) { return (a + b - 1) 
 // internal entry points implemented per translation unit
 int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint8_t *gray, uint16_t *tmm, int batch,
                        cudaStream_t st);   // returns 1 when the tile extrema were not produced (generic path)
+// sparse evaluation: bounds pass + flags + exact chain on the flagged tiles; fills tmm and ctx->eflag[slot].  Returns 1 when the
+// frame geometry has no TMA path (the caller falls back to the dense kernel)
+int apse_preprocess_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, uint16_t *tmm, int slot, int batch, int min_wb_diff,
+                           cudaStream_t st);
+int apse_build_bound_table(apse_ctx *ctx, cudaStream_t st);
+void apse_sparse_free(apse_ctx *ctx);
 int apse_detect_alloc(apse_ctx *ctx);
 void apse_detect_free(apse_ctx *ctx);
 int apse_decode_alloc(apse_ctx *ctx);

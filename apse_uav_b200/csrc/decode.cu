@@ -8,6 +8,7 @@
 //   * nesting hierarchy + depth-ordered acceptance, corner rotation, output
 // Compiled with -fmad=false (homography / Otsu arithmetic follows the dependency's evaluation order).
 #include "common.cuh"
+#include "chain.cuh"
 #include <math.h>
 #include <float.h>
 
@@ -171,7 +172,11 @@ __device__ void inverse_homography(const float *src, int S, double *Mi)
 }
 
 // one warp: _identifyOneCandidate.  Returns (valid, id, rot) on every lane.
+// SPARSE: the gray buffer holds exact values only on the tiles flagged in S.eflag; every other sample is computed on demand
+// from the source frame (same remap + colour chain as the preprocess kernels, bit-identical by construction)
+template <bool SPARSE>
 __device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, const float *corners, const DeviceParams &P,
+                                 const SparseSrc &SS, int frame,
                                  const uint8_t *__restrict__ dict, uint8_t *img, int *hist, uint8_t *bits, bool &valid,
                                  int &id, int &rot)
 {
@@ -194,7 +199,13 @@ __device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, c
         fX = fmin(fmax(fX, (double)INT32_MIN), (double)INT32_MAX);
         fY = fmin(fmax(fY, (double)INT32_MIN), (double)INT32_MAX);
         long long X = __double2ll_rn(fX), Y = __double2ll_rn(fY);
-        int v = (X >= 0 && X < w && Y >= 0 && Y < h) ? im[(size_t)Y * w + X] : 0;
+        int v = 0;
+        if (X >= 0 && X < w && Y >= 0 && Y < h) {
+            if (!SPARSE || SS.eflag[((size_t)frame * SS.th + ((int)Y >> 2)) * SS.tw + ((int)X >> 2)])
+                v = im[(size_t)Y * w + X];
+            else
+                v = exact_gray_px(SS.bgr + (size_t)frame * w * h * 3, SS.mapx, SS.mapy, SS.tables, w, h, (int)X, (int)Y);
+        }
         img[p] = (uint8_t)v;
         atomicAdd(&hist[v], 1);
         if (x >= c0 && x < c1 && y >= c0 && y < c1) { s1 += v; s2 += v * v; }
@@ -276,9 +287,10 @@ __device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, c
 
 // _identifyOneCandidate for every raw quad of the batch: warp per candidate, grid = (candidate groups, frames).
 // Results (valid | rot << 1 | id << 8) are indexed like the raw quads; k_decode picks them up after its sort.
+template <bool SPARSE>
 __global__ void __launch_bounds__(DEC_THREADS) k_decode_bits(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
                                                              const int32_t *__restrict__ counters, DeviceParams P,
-                                                             const uint8_t *__restrict__ dict, int32_t *__restrict__ dec_raw)
+                                                             const uint8_t *__restrict__ dict, int32_t *__restrict__ dec_raw, SparseSrc S)
 {
     __shared__ uint8_t s_img[DEC_WARPS][DEC_MAX_S * DEC_MAX_S];
     __shared__ int s_hist[DEC_WARPS][256];
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode_bits(const uint8_t *__re
     const uint8_t *im = gray + (size_t)f * w * h;
     for (int i = blockIdx.x * DEC_WARPS + wid; i < nq; i += gridDim.x * DEC_WARPS) {
         bool v; int id, rot;
-        decode_candidate(im, w, h, quads + ((size_t)f * APSE_MAX_QUADS + i) * 8, P, dict, s_img[wid], s_hist[wid], s_bits[wid], v, id, rot);
+        decode_candidate<SPARSE>(im, w, h, quads + ((size_t)f * APSE_MAX_QUADS + i) * 8, P, S, f, dict, s_img[wid], s_hist[wid], s_bits[wid], v, id, rot);
         if (lane == 0) dec_raw[(size_t)f * APSE_MAX_QUADS + i] = (v ? 1 : 0) | (rot << 1) | (id << 8);
         __syncwarp();
     }
@@ -596,7 +608,10 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
     // hierarchy scratch of the quad fit is free at this point: [batch][APSE_MAX_QUADS] decode results
     int32_t *dec_raw = reinterpret_cast<int32_t *>(ctx->errs);
     const int cand_blocks = ctx->params.cornerRefinementMethod == 3 ? 4 : 32;   // classic path: hundreds of candidates per frame
-    KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<<<dim3(cand_blocks, batch), DEC_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw));
+    if (ctx->sparse_active)
+        KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<true><<<dim3(cand_blocks, batch), DEC_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, ctx->sparse_src));
+    else
+        KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<false><<<dim3(cand_blocks, batch), DEC_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, SparseSrc{}));
     KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem) + decode_arrays_bytes(DEC_SMEMC), st>>>(
                 gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, dec_raw, skip,
                 (unsigned char *)ctx->decode_scratch, decode_arrays_bytes(DEC_MAXC), *out));

@@ -75,10 +75,7 @@ __device__ __forceinline__ void dilated_minmax(const uint16_t *tmm, int tw, int 
 // of the ternary image before the next batch and the search for black/white crossings run over that list with full
 // warps instead of over whole 32x16 CCL tiles in which four pixels out of five are background.
 // Entry: tx | ty << 13 | frame << 26 (frames per launch <= 64, tile coordinates < 8192); alist_thr[i] = threshold.
-#define ATILE(f, tx, ty) ((uint32_t)(tx) | ((uint32_t)(ty) << 13) | ((uint32_t)(f) << 26))
-#define ATILE_TX(e) ((int)((e) & 0x1fffu))
-#define ATILE_TY(e) ((int)(((e) >> 13) & 0x1fffu))
-#define ATILE_F(e) ((int)((e) >> 26))
+// (ATILE / ATILE_TX / ATILE_TY / ATILE_F: common.cuh)
 
 // One thread = 8 consecutive tiles of a tile row (one 128-bit load of the extrema per tile row when the row stride
 // allows it) plus the two outer columns: 3x3 dilation of the tile extrema in registers; high-contrast tiles are
@@ -127,12 +124,14 @@ __global__ void __launch_bounds__(128) k_threshold_scan(int w, int h, int tw, in
                 hmn[c] = __vimin3_u16x2(ln, vmn[c], rn);
                 hmx[c] = __vimax3_u16x2(lx_, vmx[c], rx);
             }
-            // range >= diff  <=>  bit 15 of (range + 0x8000 - diff) per 16-bit lane (range <= 255, no carry between lanes)
-            const int d = min(max(min_wb_diff, 0), 0x7fff);
-            const uint32_t kk = (uint32_t)(0x8000 - d) * 0x00010001u;
+            // range >= diff  <=>  bit 15 of (0x8000 + range - diff) per 16-bit lane.  The range is in [-255, 255]: neighbourhoods
+            // made of neutral tiles only (min 255, max 0 -- the sparse evaluation writes them for tiles that cannot be
+            // high-contrast) have max < min, so bit 15 is set BEFORE the subtraction and no lane ever borrows from its neighbour
+            const int d = min(max(min_wb_diff, 0), 256);
+            const uint32_t kk = (uint32_t)d * 0x00010001u;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const uint32_t t = (hmx[c] - hmn[c]) + kk;
+                const uint32_t t = ((hmx[c] | 0x80008000u) - hmn[c]) - kk;
                 on |= ((t >> 15) & 1u) << (2 * c) | (t >> 31) << (2 * c + 1);
             }
         }

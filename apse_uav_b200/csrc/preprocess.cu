@@ -5,6 +5,7 @@
 // Integer pipeline, bit-exact with the dependency's 8-bit paths.  HBM-bound by design:
 // one pass over the BGR frame (24.9 MB read) producing gray (8.3 MB) and optionally the corrected BGR frame.
 #include "common.cuh"
+#include "chain.cuh"
 #include <cuda.h>
 #include <math.h>
 #include <string.h>
@@ -115,11 +116,6 @@ __device__ __forceinline__ void lab2rgb_px(const SmemTables *T, int L, int a, in
     o2 = T->invgamma[min(max(r2, 0), 4095)];
 }
 
-__device__ __forceinline__ int gray_px(int c0, int c1, int c2) { return (c0 * 3735 + c1 * 19235 + c2 * 9798 + 16384) >> 15; }
-
-// Q5 fixed-point source coordinate of the dependency's remap: rint(map * 32) evaluated in float32
-__device__ __forceinline__ int q5(float m) { return __float2int_rn(__fmul_rn(m, 32.f)); }
-
 // ---------------------------------------------------------------------------------------------------------
 // K0: undistort map (FP64 per pixel, init only)
 __global__ void k_build_undistort_map(int w, int h, double fx, double fy, double u0, double v0, double k1, double k2,
@@ -159,45 +155,6 @@ int apse_init_undistort_map(apse_ctx *ctx, const double K[9], const double D[14]
                                                                     D[4], D[5], D[6], D[7], D[8], D[9], D[10], D[11],
                                                                     mapx, mapy));
     return APSE_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// bilinear tap set of one output pixel
-struct Taps {
-    int off00;      // byte offset of tap (ix,iy) channel 0 in the source frame
-    int w00, w01, w10, w11;
-    unsigned mask;  // bit k set = tap k inside the image (k = 0:(ix,iy) 1:(ix+1,iy) 2:(ix,iy+1) 3:(ix+1,iy+1))
-};
-
-__device__ __forceinline__ Taps make_taps(float mx, float my, int sw, int sh, int cn)
-{
-    Taps t;
-    int sx = q5(mx), sy = q5(my);
-    int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
-    t.w00 = min(32767, (32 - fy) * (32 - fx) * 32);
-    t.w01 = (32 - fy) * fx * 32;
-    t.w10 = fy * (32 - fx) * 32;
-    t.w11 = fy * fx * 32;
-    bool x0 = ix >= 0 && ix < sw, x1 = ix + 1 >= 0 && ix + 1 < sw;
-    bool y0 = iy >= 0 && iy < sh, y1 = iy + 1 >= 0 && iy + 1 < sh;
-    t.mask = (x0 && y0 ? 1u : 0u) | (x1 && y0 ? 2u : 0u) | (x0 && y1 ? 4u : 0u) | (x1 && y1 ? 8u : 0u);
-    t.off00 = (iy * sw + ix) * cn;
-    return t;
-}
-
-__device__ __forceinline__ int sample(const uint8_t *__restrict__ src, const Taps &t, int rowbytes, int cn, int c)
-{
-    const uint8_t *p = src + t.off00 + c;
-    int acc = 16384;
-    if (t.mask == 15u) {
-        acc += t.w00 * __ldg(p) + t.w01 * __ldg(p + cn) + t.w10 * __ldg(p + rowbytes) + t.w11 * __ldg(p + rowbytes + cn);
-    } else {
-        if (t.mask & 1u) acc += t.w00 * __ldg(p);
-        if (t.mask & 2u) acc += t.w01 * __ldg(p + cn);
-        if (t.mask & 4u) acc += t.w10 * __ldg(p + rowbytes);
-        if (t.mask & 8u) acc += t.w11 * __ldg(p + rowbytes + cn);
-    }
-    return acc >> 15;
 }
 
 // K1: fused preprocess.  Block = 256 threads = 8 rows x 32 lanes, each lane 4 consecutive pixels (128 x 8 tile).
@@ -287,12 +244,20 @@ __global__ void __launch_bounds__(256, 4) k_preprocess_fused(const uint8_t *__re
 #endif
 #define P2_BOX_PX 85
 #define P2_RAW_BYTES (P2_BOX_WORDS * 4 * P2_BOX_H)
-#define P2_RAW_STRIDE (P2_RAW_BYTES + 128)    // two staging buffers (double-buffered over frames), 128 B slack each
-#define P2_OFF_TABLES (2 * P2_RAW_STRIDE)
-#define P2_OFF_MISC (P2_OFF_TABLES + (int)sizeof(P2Tables))
-#define P2_SMEM_BYTES (P2_OFF_MISC + 48)
+#define P2_RAW_STRIDE (P2_RAW_BYTES + 128)    // staging buffers (a ring over frames), 128 B slack each
+// ring depth: the full colour chain (MODE 0) spends ~2 us per frame and CTA, which covers the latency of one bulk copy; the
+// bounds pass (MODE 1) is 3.4 x shorter per frame and needs more copies in flight
+#define P2_STAGES(MODE) ((MODE) ? 4 : 2)
+#define P2_OFF_TABLES_N(NS) ((NS) * P2_RAW_STRIDE)
+// MODE 0: colour tables (P2Tables), gray + exact tile extrema out.  MODE 1 (sparse evaluation, see "sparse evaluation" below):
+// the 16 KB gray-bound table, only per-tile BOUNDS of gray out.
+#define SB_ENTRIES (16 * 32 * 32)             // cells of the bound table: (c0 >> 4, c1 >> 3, c2 >> 3), 32 KB
+#define P2_TABLE_BYTES(MODE) ((MODE) ? SB_ENTRIES * 2 : (int)sizeof(P2Tables))
+#define P2_OFF_MISC_N(MODE, NS) (P2_OFF_TABLES_N(NS) + P2_TABLE_BYTES(MODE))
+#define P2_SMEM_BYTES_N(MODE, NS) (P2_OFF_MISC_N(MODE, NS) + 16 * (NS) + 16)   // full[NS], empty[NS] mbarriers, source box
+#define P2_SMEM_BYTES_M(MODE) P2_SMEM_BYTES_N(MODE, P2_STAGES(MODE))
+#define P2_SMEM_BYTES P2_SMEM_BYTES_M(0)
 #define P2_CTA_THREADS (P2_THREADS + 32)       // 12 consumer warps + 1 TMA producer warp
-#define XZ_MAGIC 551553470                    // ceil(108 * 2^32 / 841)
 
 static void build_p2_tables_host(P2Tables &P, const LabTables &T)
 {
@@ -316,42 +281,6 @@ int apse_upload_p2_tables(apse_ctx *ctx, const uint8_t *lut, P2Tables **dev, cud
     delete P;
     CUDA_TRY(ctx, e);
     return APSE_OK;
-}
-
-__device__ __forceinline__ int xz_px(int v)
-{
-    // v <= 3390: trunc(v*108/841) - 290 (signed high product + 1 for negative v); else floor(floor(v^2/2^14) v / 2^14)
-    int lo = __mulhi(v, XZ_MAGIC) + (int)((unsigned)v >> 31) - 290;
-    int hi = (((v * v) >> 14) * v) >> 14;
-    return v <= 3390 ? lo : hi;
-}
-
-// colour chain of one pixel on the composed tables: (c0,c1,c2) -> corrected (o0,o1,o2) and gray.
-// Shared-memory wavefronts are what the kernel runs out of first (84 % of the pipe), so the chain spends a few integer
-// instructions where that saves look-ups with scattered indices: L comes from fY arithmetically and indexes a 256-entry
-// {y, f} table (narrow index spread, ~1 wavefront) instead of an 8-byte entry per idxY (5.5 wavefronts), and the two
-// chroma shifts are computed (clamp + multiply + shift) instead of being read from tables.
-__device__ __forceinline__ int chain_px(const P2Tables *T, int c0, int c1, int c2, int &o0, int &o1, int &o2)
-{
-    int R = T->gamma[c0], G = T->gamma[c1], B = T->gamma[c2];
-    int iX = (R * 1777 + G * 1541 + B * 778 + 2048) >> 12;
-    int iY = (R * 871 + G * 2929 + B * 296 + 2048) >> 12;
-    int iZ = (R * 73 + G * 448 + B * 3575 + 2048) >> 12;
-    int fX = T->cb[iX], fY = T->cb[iY], fZ = T->cb[iZ];
-    const int L = __vimin_s32_relu((296 * fY - 1336934 + 16384) >> 15, 255);
-    const uint32_t yf = T->yf[L];
-    const int y = (int)(yf & 0xffffu), f = (int)(yf >> 16);
-    const int a = __vimin_s32_relu((500 * (fX - fY) + 128 * 32768 + 16384) >> 15, 255);
-    const int b = __vimin_s32_relu((200 * (fY - fZ) + 128 * 32768 + 16384) >> 15, 255);
-    const int adiv = ((a * (5 * 53687) + 128) >> 13) - 4194, bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
-    int X = xz_px(f + adiv), Z = xz_px(f - bdiv);
-    int r0 = (12615 * X - 6296 * y - 2223 * Z + 8192) >> 14;
-    int r1 = (-3773 * X + 7684 * y + 185 * Z + 8192) >> 14;
-    int r2 = (217 * X - 836 * y + 4715 * Z + 8192) >> 14;
-    o0 = T->invgamma[__vimin_s32_relu(r0, 4095)];   // clamp to [0, 4095] in one instruction
-    o1 = T->invgamma[__vimin_s32_relu(r1, 4095)];
-    o2 = T->invgamma[__vimin_s32_relu(r2, 4095)];
-    return gray_px(o0, o1, o2);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -378,6 +307,26 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tm
         : "memory");
 }
 
+// bilinear sample of pixel k of this thread from staging buffer `boff`: the three channel sums, Q10 (value = sum >> 10)
+__device__ __forceinline__ void k1t_sample(uint32_t a, uint32_t shf, uint32_t wA, uint32_t wB, uint32_t &d0, uint32_t &d1, uint32_t &d2)
+{
+    uint32_t r00, r01, r02, r10, r11, r12;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r00) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r01) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r02) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(r10) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+260];" : "=r"(r11) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+264];" : "=r"(r12) : "r"(a));
+    // bytes b .. b+5 of each row: (c0 c1 c2 of tap ix, c0 c1 c2 of tap ix+1)
+    const uint32_t X0 = __funnelshift_r(r00, r01, shf), X1 = __funnelshift_r(r01, r02, shf);
+    const uint32_t Y0 = __funnelshift_r(r10, r11, shf), Y1 = __funnelshift_r(r11, r12, shf);
+    const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);   // (c0, c0', c1, c1')
+    const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);   // (c2, c2', ..)
+    d0 = __dp2a_lo(wA, T0, __dp2a_lo(wB, T1, 512u));
+    d1 = __dp2a_hi(wA, T0, __dp2a_hi(wB, T1, 512u));
+    d2 = __dp2a_lo(wA, U0, __dp2a_lo(wB, U1, 512u));
+}
+
 // one thread, one frame: the four pixels of the thread's column sampled from staging buffer `boff` and pushed through the
 // colour chain
 template <bool WANT_BGR>
@@ -387,52 +336,63 @@ __device__ __forceinline__ void k1t_pixels(const P2Tables *T, const uint32_t (&a
 {
 #pragma unroll
     for (int k = 0; k < P2_NPX; k++) {
-        const uint32_t a = addr[k] + boff;
-        uint32_t r00, r01, r02, r10, r11, r12;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r00) : "r"(a));
-        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r01) : "r"(a));
-        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r02) : "r"(a));
-        asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(r10) : "r"(a));
-        asm volatile("ld.shared.u32 %0, [%1+260];" : "=r"(r11) : "r"(a));
-        asm volatile("ld.shared.u32 %0, [%1+264];" : "=r"(r12) : "r"(a));
-        // bytes b .. b+5 of each row: (c0 c1 c2 of tap ix, c0 c1 c2 of tap ix+1)
-        const uint32_t X0 = __funnelshift_r(r00, r01, shf[k]), X1 = __funnelshift_r(r01, r02, shf[k]);
-        const uint32_t Y0 = __funnelshift_r(r10, r11, shf[k]), Y1 = __funnelshift_r(r11, r12, shf[k]);
-        const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);   // (c0, c0', c1, c1')
-        const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);   // (c2, c2', ..)
-        int c0 = (int)(__dp2a_lo(wA[k], T0, __dp2a_lo(wB[k], T1, 512u)) >> 10);
-        int c1 = (int)(__dp2a_hi(wA[k], T0, __dp2a_hi(wB[k], T1, 512u)) >> 10);
-        int c2 = (int)(__dp2a_lo(wA[k], U0, __dp2a_lo(wB[k], U1, 512u)) >> 10);
-        g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
+        uint32_t d0, d1, d2;
+        k1t_sample(addr[k] + boff, shf[k], wA[k], wB[k], d0, d1, d2);
+        g[k] = chain_px(T, (int)(d0 >> 10), (int)(d1 >> 10), (int)(d2 >> 10), o0[k], o1[k], o2[k]);
     }
 }
 
+// ---- sparse evaluation ------------------------------------------------------------------------------------------
+// The detector reads gray only (a) as 4x4-tile extrema for the threshold decision (a6.A1: a tile whose 3x3-dilated range is
+// below aprilTagMinWhiteBlackDiff becomes 127 and is never looked at again: 99 % of a sparse frame), (b) at the pixels of the
+// remaining tiles and their 1-pixel surroundings (threshold, gradient weights of fit_quad), (c) at the 48x48 samples of every
+// candidate quad.  So the colour chain (90 of K1t's 119 instructions per pixel) is needed on a few percent of the frame.
+// Which few percent is decided RIGOROUSLY: BoundTable[c0 >> 4][c1 >> 3][c2 >> 3] = (min, max) of the chain's gray over all
+// colours of the cell, computed by brute force over all 2^24 colours from the chain itself when the LUT is set.  K1t in MODE 1
+// samples every pixel (the remap is unchanged) and reduces the cell bounds to per-tile bounds; k_sparse_flags marks the tiles
+// whose dilated BOUND range reaches the threshold (P, a superset of the truly high-contrast tiles) plus a one-tile ring (E);
+// k_sparse_exact runs the exact chain on E (gray + exact extrema); all other tiles get the neutral extrema (255, 0), which
+// leaves every dilated range that matters untouched (every neighbour of a P tile is in E).  Results are bit-identical to the
+// dense path by construction; tests/test_gpu_sparse.py checks the table against a brute-force CPU evaluation of all 2^24 colours
+// and the detections against MODE 0.
+// packed (lo | (255 - hi) << 16) of the cell of one pixel (d = Q10 channel sums)
+__device__ __forceinline__ uint32_t bound_px(uint32_t tbl, uint32_t d0, uint32_t d1, uint32_t d2)
+{
+    const uint32_t a = ((d0 >> 3) & 0x7800u) | ((d1 >> 7) & 0x7C0u) | ((d2 >> 12) & 0x3Eu);   // 2 * (c0>>4 << 10 | c1>>3 << 5 | c2>>3)
+    uint32_t e;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(tbl + a));
+    return __byte_perm(e, 0u, 0x4140);
+}
+
 // WC: compile-time frame width (0 = run-time): row offsets of the stores become immediates for the 3840-px footage
-template <bool WANT_BGR, int NREG, int WC, bool FULL = false>   // FULL: every thread of every CTA has pixels (w % 64 == 0, h % 24 == 0)
+// MODE 1: `tables` is the bound table, `tmm` receives per-tile BOUNDS (lo | hi << 8), gray / bgr_out are not touched
+template <bool WANT_BGR, int NREG, int WC, bool FULL = false, int MODE = 0, int NSTAGES = 0>   // FULL: every thread of every CTA has pixels (w % 64 == 0, h % 24 == 0)
 __global__ void __maxnreg__(NREG)
 k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ bgr, uint8_t *__restrict__ bgr_out,
                  uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm,
-                 const float *__restrict__ mapx, const float *__restrict__ mapy, const P2Tables *__restrict__ tables, int w_rt, int h,
+                 const float *__restrict__ mapx, const float *__restrict__ mapy, const void *__restrict__ tables, int w_rt, int h,
                  int batch, int fpb)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    P2Tables *T = reinterpret_cast<P2Tables *>(smem + P2_OFF_TABLES);
-    unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC);   // full[2], empty[2]
-    int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC + 32);   // xmin, xmax, ymin, ymax
+    constexpr int NS = NSTAGES ? NSTAGES : P2_STAGES(MODE);
+    P2Tables *T = reinterpret_cast<P2Tables *>(smem + P2_OFF_TABLES_N(NS));
+    unsigned long long *mbar_p = reinterpret_cast<unsigned long long *>(smem + P2_OFF_MISC_N(MODE, NS));   // full[NS], empty[NS]
+    int *box = reinterpret_cast<int *>(smem + P2_OFF_MISC_N(MODE, NS) + 16 * NS);   // xmin, xmax, ymin, ymax
     const int w = WC ? WC : w_rt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mbar0 = smem_u32(mbar_p), raw0 = smem_u32(smem);
+    const uint32_t tbl0 = smem_u32(smem + P2_OFF_TABLES_N(NS));
 
     {   // tables -> shared memory
         const uint4 *src = reinterpret_cast<const uint4 *>(tables);
         uint4 *dst = reinterpret_cast<uint4 *>(T);
-        for (int i = tid; i < (int)(sizeof(P2Tables) / 16); i += P2_CTA_THREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < P2_TABLE_BYTES(MODE) / 16; i += P2_CTA_THREADS) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0));          // full[0]: the producer's expect_tx arrival
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8));      // full[1]
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar0 + 16), "r"(P2_THREADS / 32));   // empty[0]: one arrival per consumer warp
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar0 + 24), "r"(P2_THREADS / 32));   // empty[1]
+        for (int b = 0; b < NS; b++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar0 + 8 * b));          // full[b]: the producer's expect_tx arrival
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar0 + 8 * (NS + b)), "r"(P2_THREADS / 32));   // empty[b]: one arrival per consumer warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         box[0] = INT32_MAX; box[1] = INT32_MIN; box[2] = INT32_MAX; box[3] = INT32_MIN;
     }
@@ -483,12 +443,19 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     const int tw4 = w >> 2;
     const int c0x = (bx0 * 3) >> 2;
     // output cursors of this thread, advanced by one frame per iteration
-    uint8_t *gp = gray + (size_t)f0 * frame_px + (size_t)(valid ? y0 : 0) * w + (valid ? x : 0);
+    uint8_t *gp = MODE ? nullptr : gray + (size_t)f0 * frame_px + (size_t)(valid ? y0 : 0) * w + (valid ? x : 0);
     uint8_t *cp = WANT_BGR ? bgr_out + ((size_t)f0 * frame_px + (size_t)(valid ? y0 : 0) * w + (valid ? x : 0)) * 3 : nullptr;
     const size_t tile_stride = (size_t)(h >> 2) * tw4;
     uint16_t *tp = tmm ? tmm + (size_t)f0 * tile_stride + (size_t)((valid ? y0 : 0) >> 2) * tw4 + ((valid ? x : 0) >> 2) : nullptr;
     const bool tile_writer = valid && (lane & 3) == 0;
 
+    // 4x4-tile reduction of the packed (min | (255 - max) << 16) of this thread's column over the 4 lanes of the tile
+    auto tile_out = [&](uint32_t pk) {
+        pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 1));
+        pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 2));
+        if (tile_writer) *tp = (uint16_t)((pk & 0xffu) | ((255u - (pk >> 16)) << 8));
+        tp += tile_stride;
+    };
     // stores of one frame + the 4x4-tile extrema (this thread holds one column of a tile, 4 lanes hold its columns),
     // then advance the cursors
     auto finish = [&](const int (&g)[P2_NPX], const int (&o0)[P2_NPX], const int (&o1)[P2_NPX], const int (&o2)[P2_NPX]) {
@@ -509,14 +476,23 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                 mx = max(max(g[0], g[1]), max(g[2], g[3]));
             }
             // min and (255 - max) side by side in one register: one shuffle + one VIMNMX.U16x2 per butterfly step
-            uint32_t pk = (uint32_t)mn | ((uint32_t)(255 - mx) << 16);
-            pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 1));
-            pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 2));
-            if (tile_writer) *tp = (uint16_t)((pk & 0xffu) | ((255u - (pk >> 16)) << 8));
-            tp += tile_stride;
+            tile_out((uint32_t)mn | ((uint32_t)(255 - mx) << 16));
         }
         gp += frame_px;
         if (WANT_BGR) cp += frame_px * 3;
+    };
+    // MODE 1: cell bounds of the four pixels sampled from staging buffer `boff`, reduced to the tile
+    auto bounds_frame = [&](uint32_t boff) {
+        uint32_t pk = 0x00ff00ffu;   // (min 255, max 0)
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < P2_NPX; k++) {
+                uint32_t d0, d1, d2;
+                k1t_sample(addr[k] + boff, shf[k], wA[k], wB[k], d0, d1, d2);
+                pk = __vminu2(pk, bound_px(tbl0, d0, d1, d2));
+            }
+        }
+        return pk;
     };
     if (fast) {
         // Producer / consumer over two staging buffers with full / empty mbarriers; no CTA-wide barrier in the frame loop, so
@@ -527,37 +503,39 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         if (producer) {
             if (lane == 0) {
                 for (int i = 0; i < nf; i++) {
-                    const int b = i & 1;
-                    if (i >= 2) mbar_wait(mbar0 + 16 + b * 8, (uint32_t)((i >> 1) - 1) & 1u);
-                    tma_load_box(raw0 + b * P2_RAW_STRIDE, &tmap, c0x, by0, f0 + i, mbar0 + b * 8);
+                    const int b = i % NS;
+                    if (i >= NS) mbar_wait(mbar0 + 8 * (NS + b), (uint32_t)(i / NS - 1) & 1u);
+                    tma_load_box(raw0 + b * P2_RAW_STRIDE, &tmap, c0x, by0, f0 + i, mbar0 + 8 * b);
                 }
             }
             return;
         }
-        // two frames per trip: staging buffer and barriers of a frame are compile-time constants
-        for (int i = 0; i < nf; i += 2) {
-            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-            {
-                mbar_wait(mbar0, ph);
-                int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
-                if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, 0u, g, o0, o1, o2);
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar0 + 16) : "memory");
-                finish(g, o0, o1, o2);
-            }
-            if (i + 1 < nf) {
-                mbar_wait(mbar0 + 8, ph);
-                int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
-                if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, (uint32_t)P2_RAW_STRIDE, g, o0, o1, o2);
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar0 + 24) : "memory");
-                finish(g, o0, o1, o2);
+        // NS frames per trip: staging buffer and barriers of a frame are compile-time constants
+        for (int i = 0; i < nf; i += NS) {
+            const uint32_t ph = (uint32_t)(i / NS) & 1u;
+#pragma unroll
+            for (int b = 0; b < NS; b++) {
+                if (i + b >= nf) break;
+                mbar_wait(mbar0 + 8 * b, ph);
+                if (MODE) {
+                    const uint32_t pk = bounds_frame((uint32_t)(b * P2_RAW_STRIDE));
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar0 + 8 * (NS + b)) : "memory");
+                    tile_out(pk);
+                } else {
+                    int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
+                    if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, (uint32_t)(b * P2_RAW_STRIDE), g, o0, o1, o2);
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar0 + 8 * (NS + b)) : "memory");
+                    finish(g, o0, o1, o2);
+                }
             }
         }
     } else if (!producer) {
         // direct-gather path (source box larger than the staging buffer: folded corners of the rational model)
         for (int f = f0; f < f1; f++) {
             int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
+            uint32_t pk = 0x00ff00ffu;
             if (valid) {
                 const uint8_t *src = bgr + (size_t)f * frame_px * 3;
 #pragma unroll
@@ -565,10 +543,12 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                     size_t o = (size_t)(y0 + k) * w + x;
                     Taps t = make_taps(__ldg(mapx + o), __ldg(mapy + o), w, h, 3);
                     int c0 = sample(src, t, w * 3, 3, 0), c1 = sample(src, t, w * 3, 3, 1), c2 = sample(src, t, w * 3, 3, 2);
-                    g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
+                    if (MODE) pk = __vminu2(pk, bound_px(tbl0, (uint32_t)c0 << 10, (uint32_t)c1 << 10, (uint32_t)c2 << 10));
+                    else g[k] = chain_px(T, c0, c1, c2, o0[k], o1[k], o2[k]);
                 }
             }
-            finish(g, o0, o1, o2);
+            if (MODE) tile_out(pk);
+            else finish(g, o0, o1, o2);
         }
     }
 }
@@ -648,6 +628,271 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
     else
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 64, 0><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES, st>>>(K1T_ARGS));
 #undef K1T_ARGS
+    return APSE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sparse evaluation: bound table, tile flags, exact chain on the flagged tiles (see the comment above bound_px)
+
+// one CTA per cell of the bound table: the exact chain on the cell's 16 x 8 x 8 colours, min / max of gray
+__global__ void __launch_bounds__(256) k_build_bounds(const P2Tables *__restrict__ tables, uint16_t *__restrict__ out)
+{
+    __shared__ P2Tables T;
+    __shared__ int s_mn[8], s_mx[8];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tables);
+        uint4 *dst = reinterpret_cast<uint4 *>(&T);
+        for (int i = threadIdx.x; i < (int)(sizeof(P2Tables) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int cell = blockIdx.x, i0 = cell >> 10, i1 = (cell >> 5) & 31, i2 = cell & 31;
+    int mn = 255, mx = 0;
+    for (int j = threadIdx.x; j < 16 * 8 * 8; j += blockDim.x) {
+        int o0, o1, o2;
+        const int g = chain_px(&T, i0 * 16 + (j >> 6), i1 * 8 + ((j >> 3) & 7), i2 * 8 + (j & 7), o0, o1, o2);
+        mn = min(mn, g); mx = max(mx, g);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) { mn = min(mn, s_mn[i]); mx = max(mx, s_mx[i]); }
+        out[cell] = (uint16_t)(mn | ((255 - mx) << 8));
+    }
+}
+
+int apse_build_bound_table(apse_ctx *ctx, cudaStream_t st)
+{
+    if (!ctx->btable) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->btable, SB_ENTRIES * sizeof(uint16_t)));
+    KLAUNCH(ctx, KID_SPARSE_FLAGS, st, k_build_bounds<<<SB_ENTRIES, 256, 0, st>>>(ctx->tables2, ctx->btable));
+    return APSE_OK;
+}
+
+// P = tiles whose 3x3-dilated BOUND range reaches the threshold; E = P dilated by one tile.  E tiles go to the list of the
+// exact pass; every tile of the frame first gets the neutral extrema (min 255, max 0), the exact pass overwrites those of E.
+// One thread = 8 consecutive tiles of a tile row, walking down SFL_ROWS rows: the horizontally dilated bounds of the five rows
+// around the current one slide through registers (one new row per step), two tiles per register, 16-bit SIMD min / max
+// (VIMNMX3.U16x2), no shared memory.  Requires tw % 8 == 0.
+#define SFL_ROWS 6
+struct FlagRow { uint32_t mn[6], mx[6]; };   // horizontally dilated bounds, column pair j = (tx0 - 2 + 2j, tx0 - 1 + 2j)
+
+__device__ __forceinline__ void flag_row_load(const uint16_t *__restrict__ T, int tw, int th, int tx0, int yy, FlagRow &R)
+{
+    uint32_t wv[6] = {0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu};   // (min 255, max 0) pairs
+    if (yy >= 0 && yy < th) {
+        const uint16_t *row = T + (size_t)yy * tw;
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row + tx0));
+        wv[1] = q.x; wv[2] = q.y; wv[3] = q.z; wv[4] = q.w;
+        if (tx0 > 0) wv[0] = __ldg(reinterpret_cast<const uint32_t *>(row + tx0 - 2));
+        if (tx0 + 8 < tw) wv[5] = __ldg(reinterpret_cast<const uint32_t *>(row + tx0 + 8));
+    }
+    uint32_t mn[6], mx[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) { mn[j] = wv[j] & 0x00ff00ffu; mx[j] = __byte_perm(wv[j], 0u, 0x4341); }
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        // neighbours of pair j: (col 2j-1, col 2j) and (col 2j+1, col 2j+2); outside the 12 columns: neutral
+        const uint32_t ln = j == 0 ? __byte_perm(0x00ffu, mn[0], 0x5410) : __byte_perm(mn[j - 1], mn[j], 0x5432);
+        const uint32_t rn = j == 5 ? __byte_perm(mn[5], 0x00ffu, 0x5432) : __byte_perm(mn[j], mn[j + 1], 0x5432);
+        const uint32_t lx = j == 0 ? __byte_perm(0u, mx[0], 0x5410) : __byte_perm(mx[j - 1], mx[j], 0x5432);
+        const uint32_t rx = j == 5 ? __byte_perm(mx[5], 0u, 0x5432) : __byte_perm(mx[j], mx[j + 1], 0x5432);
+        R.mn[j] = __vimin3_u16x2(ln, mn[j], rn);
+        R.mx[j] = __vimax3_u16x2(lx, mx[j], rx);
+    }
+}
+
+// P of one tile row for the 12 columns (bit c: column tx0 - 2 + c; the outer two are incomplete and masked by the caller)
+__device__ __forceinline__ unsigned flag_row_p(const FlagRow &A, const FlagRow &B, const FlagRow &C, uint32_t kk)
+{
+    unsigned p = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const uint32_t vmn = __vimin3_u16x2(A.mn[j], B.mn[j], C.mn[j]), vmx = __vimax3_u16x2(A.mx[j], B.mx[j], C.mx[j]);
+        const uint32_t t = ((vmx | 0x80008000u) - vmn) - kk;   // bit 15 / 31: range >= diff (k_threshold_scan)
+        p |= ((t >> 15) & 1u) << (2 * j) | (t >> 31) << (2 * j + 1);
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(128) k_sparse_flags(const uint16_t *__restrict__ tb, int tw, int th, int min_wb_diff,
+                                                      uint16_t *__restrict__ tmm, uint8_t *__restrict__ eflag,
+                                                      uint32_t *__restrict__ elist, int *__restrict__ ecount)
+{
+    const int groups = tw >> 3;
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x, f = blockIdx.z, lane = threadIdx.x & 31;
+    const int tx0 = gi * 8, ty0 = blockIdx.y * SFL_ROWS, ty1 = min(th, ty0 + SFL_ROWS);
+    const uint16_t *T = tb + (size_t)f * tw * th;
+    const bool live = gi < groups;
+    const uint32_t kk = (uint32_t)min(max(min_wb_diff, 0), 256) * 0x00010001u;
+    unsigned colmask = 0x7feu;   // P is complete for columns tx0 - 1 .. tx0 + 8 = bits 1 .. 10; columns outside the image never count
+    if (tx0 == 0) colmask &= ~2u;
+    if (tx0 + 8 >= tw) colmask &= ~(1u << 10);
+    // rows ty - 2 .. ty + 1 of the first tile row; P of rows ty - 1 and ty
+    FlagRow r0, r1, r2, r3;
+    unsigned p_prev = 0, p_cur = 0;
+    if (live) {
+        flag_row_load(T, tw, th, tx0, ty0 - 2, r0);
+        flag_row_load(T, tw, th, tx0, ty0 - 1, r1);
+        flag_row_load(T, tw, th, tx0, ty0, r2);
+        flag_row_load(T, tw, th, tx0, ty0 + 1, r3);
+        if (ty0 - 1 >= 0) p_prev = flag_row_p(r0, r1, r2, kk) & colmask;
+        p_cur = flag_row_p(r1, r2, r3, kk) & colmask;
+    }
+    for (int ty = ty0; ty < ty1; ty++) {
+        unsigned e8 = 0;
+        if (live) {
+            r1 = r2; r2 = r3;                                   // r1 = row ty, r2 = row ty + 1
+            flag_row_load(T, tw, th, tx0, ty + 2, r3);
+            const unsigned p_next = ty + 1 < th ? flag_row_p(r1, r2, r3, kk) & colmask : 0u;
+            const unsigned prow = p_prev | p_cur | p_next;
+            p_prev = p_cur; p_cur = p_next;
+            e8 = ((prow >> 1) | (prow >> 2) | (prow >> 3)) & 0xffu;   // bit c: tile tx0 + c is within one tile of a P tile
+            const size_t o = (size_t)f * tw * th + (size_t)ty * tw + tx0;
+            uint2 fl;
+            fl.x = ((e8 & 1u) ? 1u : 0u) | ((e8 & 2u) ? 0x100u : 0u) | ((e8 & 4u) ? 0x10000u : 0u) | ((e8 & 8u) ? 0x1000000u : 0u);
+            fl.y = ((e8 & 16u) ? 1u : 0u) | ((e8 & 32u) ? 0x100u : 0u) | ((e8 & 64u) ? 0x10000u : 0u) | ((e8 & 128u) ? 0x1000000u : 0u);
+            *reinterpret_cast<uint2 *>(eflag + o) = fl;
+            *reinterpret_cast<uint4 *>(tmm + o) = make_uint4(0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu);
+        }
+        if (!__any_sync(0xffffffffu, e8 != 0)) continue;
+        const int cnt = __popc(e8);
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        int base = 0;
+        if (lane == 31) base = atomicAdd(ecount, inc);
+        base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            if ((e8 >> c) & 1u) elist[base++] = ATILE(f, tx0 + c, ty);
+    }
+}
+
+// exact chain on the listed tiles: 16 lanes = the 16 pixels of a tile (direct gather from the source frame), gray and the exact
+// tile extrema written.  Latency-bound (a tile is six dependent round trips: list entry, map, taps, three table levels), so
+// the kernel runs six 256-thread CTAs per SM; each loads the 9.7 KB of colour tables into shared memory once.
+__global__ void __launch_bounds__(256) k_sparse_exact(const uint8_t *__restrict__ bgr, const float *__restrict__ mapx, const float *__restrict__ mapy,
+                                                      const P2Tables *tables, int w, int h, const uint32_t *__restrict__ elist,
+                                                      const int *__restrict__ ecount, uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm)
+{
+    __shared__ P2Tables Ts;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tables);
+        uint4 *dst = reinterpret_cast<uint4 *>(&Ts);
+        for (int i = threadIdx.x; i < (int)(sizeof(P2Tables) / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    tables = &Ts;
+    const int n = *ecount, tw = w >> 2, th = h >> 2, px = threadIdx.x & 15;
+    const size_t frame_px = (size_t)w * h;
+    for (int it = blockIdx.x * 16 + (threadIdx.x >> 4); it < n; it += gridDim.x * 16) {   // a tile's 16 lanes leave the loop together
+        const uint32_t e = __ldg(elist + it);
+        const int tx = ATILE_TX(e), ty = ATILE_TY(e), f = ATILE_F(e);
+        const int x = tx * 4 + (px & 3), y = ty * 4 + (px >> 2);
+        const uint8_t *src = bgr + (size_t)f * frame_px * 3;
+        int g;
+        {
+            const size_t o = (size_t)y * w + x;
+            const int sx = q5(__ldg(mapx + o)), sy = q5(__ldg(mapy + o));
+            const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+            if (ix >= 0 && ix + 4 < w && iy >= 0 && iy + 1 < h) {
+                // interior: the 2 x 6 tap bytes through aligned 32-bit loads, funnel shift, PRMT and IDP.2A with Q10 weights, as K1t
+                // samples its staging buffer (rows of the frame are 4-byte aligned: w % 4 == 0)
+                const uint32_t wA = (uint32_t)((32 - fy) * (32 - fx)) | ((uint32_t)((32 - fy) * fx) << 16);
+                const uint32_t wB = (uint32_t)(fy * (32 - fx)) | ((uint32_t)(fy * fx) << 16);
+                const int b = ix * 3;
+                const uint32_t *r0 = reinterpret_cast<const uint32_t *>(src + (size_t)iy * w * 3 + (b & ~3));
+                const uint32_t *r1 = reinterpret_cast<const uint32_t *>(src + (size_t)(iy + 1) * w * 3 + (b & ~3));
+                const uint32_t shf = (uint32_t)(b & 3) * 8;
+                const uint32_t r00 = __ldg(r0), r01 = __ldg(r0 + 1), r02 = __ldg(r0 + 2), r10 = __ldg(r1), r11 = __ldg(r1 + 1), r12 = __ldg(r1 + 2);
+                const uint32_t X0 = __funnelshift_r(r00, r01, shf), X1 = __funnelshift_r(r01, r02, shf);
+                const uint32_t Y0 = __funnelshift_r(r10, r11, shf), Y1 = __funnelshift_r(r11, r12, shf);
+                const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);
+                const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);
+                const int c0 = (int)(__dp2a_lo(wA, T0, __dp2a_lo(wB, T1, 512u)) >> 10);
+                const int c1 = (int)(__dp2a_hi(wA, T0, __dp2a_hi(wB, T1, 512u)) >> 10);
+                const int c2 = (int)(__dp2a_lo(wA, U0, __dp2a_lo(wB, U1, 512u)) >> 10);
+                int o0, o1, o2;
+                g = chain_px(tables, c0, c1, c2, o0, o1, o2);
+            } else {
+                g = exact_gray_px(src, mapx, mapy, tables, w, h, x, y);
+            }
+        }
+        gray[(size_t)f * frame_px + (size_t)y * w + x] = (uint8_t)g;
+        uint32_t pk = (uint32_t)g | ((uint32_t)(255 - g) << 16);
+        const unsigned half = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) pk = __vminu2(pk, __shfl_xor_sync(half, pk, d));
+        if (px == 0) tmm[(size_t)f * tw * th + (size_t)ty * tw + tx] = (uint16_t)((pk & 0xffu) | ((255u - (pk >> 16)) << 8));
+    }
+}
+
+void apse_sparse_free(apse_ctx *ctx)
+{
+    cudaFree(ctx->btable);
+    for (int k = 0; k < 2; k++) { cudaFree(ctx->tbounds[k]); cudaFree(ctx->eflag[k]); cudaFree(ctx->elist[k]); cudaFree(ctx->ecount[k]); }
+}
+
+int apse_preprocess_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, uint16_t *tmm, int slot, int batch, int min_wb_diff,
+                           cudaStream_t st)
+{
+    const int w = ctx->w, h = ctx->h;
+    PFN_tmapEncodeTiled enc = get_tmap_encoder();
+    static const bool force_generic = getenv("APSE_K1_GENERIC") != nullptr;
+    const bool tma_ok = !force_generic && enc && (w % 4) == 0 && (h % 4) == 0 && ((w * 3) % 16) == 0 && w >= P2_TW && h >= P2_TH &&
+                        ((uintptr_t)bgr % 16) == 0 && ctx->tables2 && ctx->btable && batch <= 64 && (w % 32) == 0;   // k_sparse_flags: 8 tiles per thread
+    if (!tma_ok) return 1;
+    CUtensorMap tmap;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)(w * 3 / 4), (cuuint64_t)h, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)w * 3, (cuuint64_t)w * 3 * h};
+        cuuint32_t boxd[3] = {P2_BOX_WORDS, P2_BOX_H, 1}, estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)bgr, dims, strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 1;
+    }
+    const int tw = w / 4, th = h / 4;
+    const size_t ntiles = (size_t)ctx->max_batch * (ctx->max_w / 4) * (ctx->max_h / 4);
+    if (!ctx->tbounds[slot]) {
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->tbounds[slot], ntiles * sizeof(uint16_t)));
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->eflag[slot], ntiles));
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->elist[slot], ntiles * sizeof(uint32_t)));
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->ecount[slot], sizeof(int)));
+    }
+    // development knobs: registers per thread (40 leaves 15 K registers per SM to co-resident chain CTAs, 48 has no spill) and
+    // depth of the staging ring
+    static const int nreg = getenv("APSE_K1B_NREG") ? atoi(getenv("APSE_K1B_NREG")) : 40;
+    static const int nst = getenv("APSE_K1B_STAGES") ? atoi(getenv("APSE_K1B_STAGES")) : 3;
+    static bool attr_set[64] = {false};
+    if (!attr_set[ctx->device & 63]) {
+#define K1B_ATTR(NR, NST)                                                                                                                     \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, NR, 3840, true, 1, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES_N(1, NST)))
+        K1B_ATTR(48, 4); K1B_ATTR(48, 3); K1B_ATTR(48, 2); K1B_ATTR(40, 4); K1B_ATTR(40, 3); K1B_ATTR(40, 2);
+#undef K1B_ATTR
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_preprocess_tma<false, 48, 0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES_M(1)));
+        attr_set[ctx->device & 63] = true;
+    }
+    static const int fpb_max = getenv("APSE_K1_FPB") ? atoi(getenv("APSE_K1_FPB")) : 20;
+    const int nz = div_up(batch, fpb_max), fpb = div_up(batch, nz);
+    dim3 grid(div_up(w, P2_TW), div_up(h, P2_TH), nz);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->ecount[slot], 0, sizeof(int), st));
+#define K1B_ARGS tmap, bgr, nullptr, nullptr, ctx->tbounds[slot], ctx->mapx, ctx->mapy, ctx->btable, w, h, batch, fpb
+#define K1B_GO(NR, NST) KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, NR, 3840, true, 1, NST><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES_N(1, NST), st>>>(K1B_ARGS))
+    if (w == 3840 && h % P2_TH == 0) {
+        if (nreg == 40 && nst == 2) K1B_GO(40, 2);
+        else if (nreg == 40 && nst == 3) K1B_GO(40, 3);
+        else if (nreg == 40) K1B_GO(40, 4);
+        else if (nst == 2) K1B_GO(48, 2);
+        else if (nst == 3) K1B_GO(48, 3);
+        else K1B_GO(48, 4);
+    } else
+        KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 0, false, 1><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES_M(1), st>>>(K1B_ARGS));
+#undef K1B_GO
+#undef K1B_ARGS
+    KLAUNCH(ctx, KID_SPARSE_FLAGS, st, k_sparse_flags<<<dim3(div_up(tw / 8, 128), div_up(th, SFL_ROWS), batch), 128, 0, st>>>(
+                ctx->tbounds[slot], tw, th, min_wb_diff, tmm, ctx->eflag[slot], ctx->elist[slot], ctx->ecount[slot]));
+    KLAUNCH(ctx, KID_SPARSE_EXACT, st, k_sparse_exact<<<ctx->sm_count * 6, 256, 0, st>>>(bgr, ctx->mapx, ctx->mapy, ctx->tables2, w, h, ctx->elist[slot],
+                                                                                      ctx->ecount[slot], gray, tmm));
     return APSE_OK;
 }
 

@@ -269,11 +269,13 @@ class Engine:
                                                  out["tvec"].data_ptr(), self._stream()))
         return out
 
-    def preprocess_tiles(self, bgr, gray, stream=None):
-        """first half of process_frames on `stream` (torch stream or None = current): K1t -> gray + tile extrema"""
+    def preprocess_tiles(self, bgr, gray, stream=None, sparse=False):
+        """first half of process_frames on `stream` (torch stream or None = current): K1t -> gray + tile extrema.
+        sparse=True: `gray` is only a work buffer of the detect_pose_frames call that follows (apse_preprocess_tiles_sparse)."""
         B = bgr.shape[0]
         st = C.c_void_p(stream.cuda_stream) if stream is not None else self._stream()
-        self._check(self.lib.apse_preprocess_tiles(self.h, bgr.data_ptr(), gray.data_ptr(), B, st))
+        fn = self.lib.apse_preprocess_tiles_sparse if sparse else self.lib.apse_preprocess_tiles
+        self._check(fn(self.h, bgr.data_ptr(), gray.data_ptr(), B, st))
 
     def detect_pose_frames(self, gray, out, marker_length, stream=None):
         """second half of process_frames on `stream`: candidates -> decode -> pose on the gray batch of preprocess_tiles"""

@@ -151,7 +151,9 @@ class Pipeline:
                     g = self._gray[s][par][:hi - lo]
                 if self._done[s][par] is not None:
                     pre.wait_event(self._done[s][par])   # this gray / extrema buffer pair of engine s is free again
-                eng.preprocess_tiles(frames[lo:hi], g, stream=pre)
+                # the pipeline's own gray buffers are scratch of the chain that follows: sparse evaluation; a caller who
+                # asked for the gray frames gets all of them
+                eng.preprocess_tiles(frames[lo:hi], g, stream=pre, sparse=(gray_out is None and not want_gray))
                 ev = pre.record_event()
                 st.wait_event(ev)
                 if alloc is not None:

@@ -140,7 +140,8 @@ int apse_pose_frames(apse_ctx *ctx, const float *corners, const int32_t *n_marke
 /* aruco_detect.py:589-601 in one call for a batch of raw frames: preprocessFrame + BGR2GRAY + detectMarkers +
  * estimatePoseSingleMarkers (camera of apse_set_camera).  Same results as apse_preprocess -> apse_detect ->
  * apse_pose_frames; the fused kernel hands the 4x4-tile extrema of gray to the candidate stage directly.
- * bgr: [batch][h][w][3]; gray: [batch][h][w] or NULL (context scratch); rvec/tvec nullable (no pose) */
+ * bgr: [batch][h][w][3]; gray: [batch][h][w] or NULL (context scratch; the library then evaluates gray sparsely, see
+ * apse_preprocess_tiles_sparse); rvec/tvec nullable (no pose) */
 int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, apse_detections *out,
                         const float *marker_len, float marker_len_all, double *rvec, double *tvec, void *stream);
 
@@ -149,6 +150,15 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
  * decode / pose chain of batch k): apse_preprocess_tiles = aruco_detect.py:250-259,592 (+ tile extrema kept in the
  * context); apse_detect_pose_frames = :267 + :601 on that gray batch (the caller orders the two with an event). */
 int apse_preprocess_tiles(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream);
+/* Sparse evaluation of the same half (CORNER_REFINE_APRILTAG only): identical detections, but the colour chain of
+ * aruco_detect.py:255-257,592 runs only where the detector can read its result.  Every pixel is still remapped (:252) and
+ * bounded through a table of (min, max) gray per colour cell that the library computes from the exact chain over all 2^24
+ * colours when the LUT is set; tiles whose 3x3-dilated BOUND range cannot reach aprilTagMinWhiteBlackDiff (:200) are certain
+ * to become 127 in the detector's threshold image and are skipped; the others (+ a one-tile ring) and the samples of
+ * candidate quads get the exact chain.  `gray` is a work buffer afterwards: complete only on the evaluated tiles and only
+ * meaningful to the apse_detect_pose_frames call that follows on this context.  apse_process_frames(gray = NULL) takes this
+ * path as well.  Falls back to apse_preprocess_tiles for frame geometries without a TMA path.  APSE_DENSE=1 disables it. */
+int apse_preprocess_tiles_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int batch, void *stream);
 int apse_detect_pose_frames(apse_ctx *ctx, const uint8_t *gray, int batch, apse_detections *out, const float *marker_len,
                             float marker_len_all, double *rvec, double *tvec, void *stream);
 
@@ -247,6 +257,11 @@ int apse_sequence_jobs(apse_ctx *ctx, const apse_seq_job *jobs_host, int n_jobs,
 int apse_sequence_finish(int n_frames, apse_seq_row *rows, const apse_seq_job_result *results, int n_jobs);
 /* The CSV text of :131-139,146-185 (Python's str() of ints and floats); returns the number of bytes written or a negative status */
 int64_t apse_sequence_csv(const apse_seq_row *rows, int n_frames, int with_header, char *buf, int64_t cap);
+
+/* test tap of the sparse evaluation: the bound table (HOST, 16*32*32 entries min | (255 - max) << 8, cell = (c0 >> 4, c1 >> 3,
+ * c2 >> 3)), the tile flags of the last apse_preprocess_tiles_sparse batch (DEVICE, [batch][h/4][w/4], 1 = evaluated exactly)
+ * and their count; every pointer nullable */
+int apse_debug_sparse(apse_ctx *ctx, uint16_t *bound_table_host, uint8_t *eflag_dev, int batch, int *n_exact_host, void *stream);
 
 /* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
 int64_t apse_launch_count(apse_ctx *ctx);
