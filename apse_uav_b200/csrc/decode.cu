@@ -171,26 +171,20 @@ __device__ void inverse_homography(const float *src, int S, double *Mi)
     Mi[6] = (m[3] * m[7] - m[4] * m[6]) * d; Mi[7] = (m[1] * m[6] - m[0] * m[7]) * d; Mi[8] = (m[0] * m[4] - m[1] * m[3]) * d;
 }
 
-// one warp: _identifyOneCandidate.  Returns (valid, id, rot) on every lane.
+// _identifyOneCandidate, two phases.
+// (1) decode_sample: ALL threads of the CTA.  Nearest-neighbour warp (rint of the FP64 source coordinate, border 0) into img,
+//     histogram, inner-region moments.  This is the latency of the candidate (2304 dependent gathers for a 48 x 48 canonical
+//     image), so it is spread over the whole CTA.
 // SPARSE: the gray buffer holds exact values only on the tiles flagged in S.eflag; every other sample is computed on demand
 // from the source frame (same remap + colour chain as the preprocess kernels, bit-identical by construction)
 template <bool SPARSE>
-__device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, const float *corners, const DeviceParams &P,
-                                 const SparseSrc &SS, int frame,
-                                 const uint8_t *__restrict__ dict, uint8_t *img, int *hist, uint8_t *bits, bool &valid,
-                                 int &id, int &rot)
+__device__ __forceinline__ void decode_sample(const uint8_t *__restrict__ im, int w, int h, const double *Mi, const DeviceParams &P,
+                                              const SparseSrc &SS, int frame, uint8_t *img, int *hist, long long &s1, long long &s2)
 {
-    const int lane = threadIdx.x & 31;
     const int nb = P.marker_size + 2 * P.border_bits, cs = P.cell_size, S = nb * cs;
-    double Mi[9];
-    if (lane == 0) inverse_homography(corners, S, Mi);
-    for (int i = 0; i < 9; i++) Mi[i] = __shfl_sync(0xffffffffu, Mi[i], 0);
-    for (int i = lane; i < 256; i += 32) hist[i] = 0;
-    __syncwarp();
-    // nearest-neighbour warp (rint of the FP64 source coordinate, border 0) + histogram + inner-region moments
     const int c0 = cs / 2, c1 = S - cs / 2;
-    long long s1 = 0, s2 = 0;
-    for (int p = lane; p < S * S; p += 32) {
+    s1 = 0; s2 = 0;
+    for (int p = threadIdx.x; p < S * S; p += blockDim.x) {
         int y = p / S, x = p - y * S;
         double X0 = Mi[1] * y + Mi[2], Y0 = Mi[4] * y + Mi[5], W0 = Mi[7] * y + Mi[8];
         double W = W0 + Mi[6] * x;
@@ -210,8 +204,16 @@ __device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, c
         atomicAdd(&hist[v], 1);
         if (x >= c0 && x < c1 && y >= c0 && y < c1) { s1 += v; s2 += v * v; }
     }
-    for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d); }
-    __syncwarp();
+}
+
+// (2) decode_finish: ONE warp.  Otsu (sequential over the 256 bins in the dependency's order), cell majority, border check,
+//     Hamming match against the dictionary.  Returns (valid, id, rot) on every lane.
+__device__ void decode_finish(const DeviceParams &P, long long s1, long long s2, const uint8_t *__restrict__ dict, const uint8_t *img,
+                              const int *hist, uint8_t *bits, bool &valid, int &id, int &rot)
+{
+    const int lane = threadIdx.x & 31;
+    const int nb = P.marker_size + 2 * P.border_bits, cs = P.cell_size, S = nb * cs;
+    const int c0 = cs / 2, c1 = S - cs / 2;
     const int cnt = (c1 - c0) * (c1 - c0);
     double mean = (double)s1 / cnt, var = (double)s2 / cnt - mean * mean;
     double sd = sqrt(var > 0 ? var : 0);
@@ -285,24 +287,46 @@ __device__ void decode_candidate(const uint8_t *__restrict__ im, int w, int h, c
     if (packed != 0x7fffffff) { valid = true; id = packed >> 2; rot = packed & 3; }
 }
 
-// _identifyOneCandidate for every raw quad of the batch: warp per candidate, grid = (candidate groups, frames).
+// _identifyOneCandidate for every raw quad of the batch: one CTA per candidate at a time, grid = (candidate slots, frames).
 // Results (valid | rot << 1 | id << 8) are indexed like the raw quads; k_decode picks them up after its sort.
+#define DECB_THREADS 128
 template <bool SPARSE>
-__global__ void __launch_bounds__(DEC_THREADS) k_decode_bits(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
-                                                             const int32_t *__restrict__ counters, DeviceParams P,
-                                                             const uint8_t *__restrict__ dict, int32_t *__restrict__ dec_raw, SparseSrc S)
+__global__ void __launch_bounds__(DECB_THREADS) k_decode_bits(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
+                                                              const int32_t *__restrict__ counters, DeviceParams P,
+                                                              const uint8_t *__restrict__ dict, int32_t *__restrict__ dec_raw, SparseSrc S)
 {
-    __shared__ uint8_t s_img[DEC_WARPS][DEC_MAX_S * DEC_MAX_S];
-    __shared__ int s_hist[DEC_WARPS][256];
-    __shared__ uint8_t s_bits[DEC_WARPS][16 * 16];
+    __shared__ uint8_t s_img[DEC_MAX_S * DEC_MAX_S];
+    __shared__ int s_hist[256];
+    __shared__ uint8_t s_bits[16 * 16];
+    __shared__ double s_Mi[9];
+    __shared__ long long s_sum[2][DECB_THREADS / 32];
     const int f = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nq = min(counters[f * APSE_COUNTERS + 2], DEC_MAXC);
     const uint8_t *im = gray + (size_t)f * w * h;
-    for (int i = blockIdx.x * DEC_WARPS + wid; i < nq; i += gridDim.x * DEC_WARPS) {
-        bool v; int id, rot;
-        decode_candidate<SPARSE>(im, w, h, quads + ((size_t)f * APSE_MAX_QUADS + i) * 8, P, S, f, dict, s_img[wid], s_hist[wid], s_bits[wid], v, id, rot);
-        if (lane == 0) dec_raw[(size_t)f * APSE_MAX_QUADS + i] = (v ? 1 : 0) | (rot << 1) | (id << 8);
-        __syncwarp();
+    const int nbc = P.marker_size + 2 * P.border_bits;
+    for (int i = blockIdx.x; i < nq; i += gridDim.x) {
+        if (threadIdx.x == 0) {
+            double Mi[9];
+            inverse_homography(quads + ((size_t)f * APSE_MAX_QUADS + i) * 8, nbc * P.cell_size, Mi);
+            for (int k = 0; k < 9; k++) s_Mi[k] = Mi[k];
+        }
+        for (int k = threadIdx.x; k < 256; k += DECB_THREADS) s_hist[k] = 0;
+        __syncthreads();
+        double Mi[9];
+        for (int k = 0; k < 9; k++) Mi[k] = s_Mi[k];
+        long long s1, s2;
+        decode_sample<SPARSE>(im, w, h, Mi, P, S, f, s_img, s_hist, s1, s2);
+        for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d); }
+        if (lane == 0) { s_sum[0][wid] = s1; s_sum[1][wid] = s2; }
+        __syncthreads();
+        if (wid == 0) {
+            s1 = 0; s2 = 0;
+            for (int k = 0; k < DECB_THREADS / 32; k++) { s1 += s_sum[0][k]; s2 += s_sum[1][k]; }
+            bool v; int id, rot;
+            decode_finish(P, s1, s2, dict, s_img, s_hist, s_bits, v, id, rot);
+            if (lane == 0) dec_raw[(size_t)f * APSE_MAX_QUADS + i] = (v ? 1 : 0) | (rot << 1) | (id << 8);
+        }
+        __syncthreads();
     }
 }
 
@@ -607,11 +631,11 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
     int skip = (env && env[0] == '1') ? 0 : 1;
     // hierarchy scratch of the quad fit is free at this point: [batch][APSE_MAX_QUADS] decode results
     int32_t *dec_raw = reinterpret_cast<int32_t *>(ctx->errs);
-    const int cand_blocks = ctx->params.cornerRefinementMethod == 3 ? 4 : 32;   // classic path: hundreds of candidates per frame
+    const int cand_blocks = ctx->params.cornerRefinementMethod == 3 ? 64 : 128;   // CTAs per frame; a CTA without a candidate exits at once
     if (ctx->sparse_active)
-        KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<true><<<dim3(cand_blocks, batch), DEC_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, ctx->sparse_src));
+        KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<true><<<dim3(cand_blocks, batch), DECB_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, ctx->sparse_src));
     else
-        KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<false><<<dim3(cand_blocks, batch), DEC_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, SparseSrc{}));
+        KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<false><<<dim3(cand_blocks, batch), DECB_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, SparseSrc{}));
     KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem) + decode_arrays_bytes(DEC_SMEMC), st>>>(
                 gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, dec_raw, skip,
                 (unsigned char *)ctx->decode_scratch, decode_arrays_bytes(DEC_MAXC), *out));

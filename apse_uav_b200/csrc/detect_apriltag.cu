@@ -1396,7 +1396,7 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
     A.sort_keys = ctx->sort_keys; A.lfps = ctx->lfps; A.errs = ctx->errs; A.counters = ctx->counters; A.quads = ctx->quads;
     A.quad_order = ctx->quad_order; A.work_counter = ex->work_counter; A.max_nmaxima = dp.max_nmaxima;
     A.critical_rad = dp.critical_rad; A.max_line_fit_mse = dp.max_line_fit_mse; A.max_dot = dp.max_dot;
-    KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<chain_grid(ctx), FQ_THREADS, 0, st>>>(A));
+    KLAUNCH(ctx, KID_FIT_QUADS, st, k_fit_quads<<<chain_grid(ctx) * 2, FQ_THREADS, 0, st>>>(A));   // one cluster per CTA at a time: dense frames have thousands
     return APSE_OK;
 }
 

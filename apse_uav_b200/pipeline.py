@@ -15,6 +15,10 @@ from .engine import Engine
 from ._lib import ApseError
 
 
+# development knob: APSE_SKIP_CHAIN=1 runs only the preprocess half in the multi-stream path (ceiling of that half; results are empty)
+_SKIP_CHAIN = os.environ.get("APSE_SKIP_CHAIN") == "1"
+
+
 class Pipeline:
     """`streams` > 1 splits every batch into that many sub-batches, each with its own context (scratch), and runs the
     two halves of the pipeline on different CUDA streams: the fused preprocess kernel (issue / bandwidth bound, fills the
@@ -161,7 +165,8 @@ class Pipeline:
                 sl = {k: v[lo:hi] for k, v in det.items()}
                 mls = ml[lo:hi] if isinstance(ml, torch.Tensor) else ml
                 with torch.cuda.stream(st):   # (a per-frame marker-length tensor is staged on the chain's stream)
-                    eng.detect_pose_frames(g, sl, mls, stream=st)
+                    if not _SKIP_CHAIN:
+                        eng.detect_pose_frames(g, sl, mls, stream=st)
                 self._done[s][par] = st.record_event()
                 done.append(self._done[s][par])
                 grays.append(g)
