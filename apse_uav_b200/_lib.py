@@ -52,9 +52,12 @@ class SeqConfig(C.Structure):
 # numpy views of the sequence post-pass structs (apse_seq_job / apse_seq_job_result / apse_seq_row)
 SEQ_JOB_DTYPE = [("frame", "<i4"), ("kind", "<i4"), ("rvec", "<f8", 3), ("tvec", "<f8", 3), ("dim", "<f8", 4), ("src", "<f4", 2),
                  ("tgt", "<f4", 2), ("scale", "<f8"), ("led_threshold", "<i4"), ("pad_", "<i4")]
-SEQ_RESULT_DTYPE = [("dist_aruco", "<f8"), ("dist_bbox", "<f8"), ("leds", "<i4"), ("valid", "<i4")]
+SEQ_RESULT_DTYPE = [("dist_aruco", "<f8"), ("dist_bbox", "<f8"), ("leds", "<i4"), ("valid", "<i4"), ("nearest_px", "<i4", 2),
+                    ("outline_px", "<i4", (4, 2))]
+OVERLAY_PRIM_DTYPE = [("frame", "<i4"), ("kind", "<i4"), ("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4"), ("thickness", "<i4"),
+                      ("bgr", "u1", 4)]
 SEQ_ROW_DTYPE = [("frame_id", "<i4"), ("detected", "<i4", 4), ("host_fields", "<i4"), ("leds", "<i4"), ("job_led", "<i4"),
-                 ("job_dist", "<i4", 3), ("pad_", "<i4"), ("marker_length", "<f8"), ("altitude", "<f8"), ("fov_width", "<f8"),
+                 ("job_dist", "<i4", 3), ("accepted_mask", "<i4"), ("marker_length", "<f8"), ("altitude", "<f8"), ("fov_width", "<f8"),
                  ("fov_height", "<f8"), ("dist_aruco", "<f8", 3), ("dist_bbox", "<f8", 3)]
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -100,6 +103,7 @@ SIGNATURES = {
     "apse_sequence_finish": [_i, _vp, _vp, _i],
     "apse_sequence_csv": [_vp, _i, _i, _vp, _i64],
     "apse_debug_sparse": [_vp, _vp, _vp, _i, C.POINTER(C.c_int), _vp],
+    "apse_draw_overlay": [_vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "apse_launch_count": [_vp],
     "apse_kernel_count": [],
     "apse_kernel_name": [_i],

@@ -183,6 +183,7 @@ int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers
                     }
                     if ((S.detected_prev[slot] == 1 && diff < diff_max) || first) {
                         detected[slot] = 1;
+                        if (row && i < 31) row->accepted_mask |= 1 << i;
                         if (vid == 4) {                                                    // :622-624
                             S.altitude = tz;
                             S.marker_length = marker_length_correction(c, S.altitude);
@@ -447,6 +448,9 @@ __global__ void __launch_bounds__(128) k_sequence_jobs(const apse_seq_job *__res
         const double dx = (double)J.src[0] - (double)px, dy = (double)J.src[1] - (double)py;
         const double d = sqrt(dx * dx + dy * dy);
         if (d < best) { best = d; best_i = i; best_x = px; best_y = py; }   // strict <: the first minimum wins
+        // the outline corners drawContours connects (:421-425): points 0, 19, 39, 20 of the sampled outline
+        const int corner = i == 0 ? 0 : i == 19 ? 1 : i == 39 ? 2 : i == 20 ? 3 : -1;
+        if (corner >= 0) { out[ji].outline_px[corner][0] = px; out[ji].outline_px[corner][1] = py; }
     }
     for (int o = 16; o > 0; o >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -461,6 +465,7 @@ __global__ void __launch_bounds__(128) k_sequence_jobs(const apse_seq_job *__res
         const double d_bbox = sqrt(bx * bx + by * by);
         out[ji].dist_aruco = (double)d_aruco * J.scale;
         out[ji].dist_bbox = d_bbox * J.scale;
+        out[ji].nearest_px[0] = best_x; out[ji].nearest_px[1] = best_y;
         out[ji].valid = 1;
     }
 }

@@ -150,11 +150,12 @@ def _np_types(torch):
         _NP.update({torch.int32: np.int32, torch.float32: np.float32, torch.float64: np.float64, torch.uint8: np.uint8})
 
 
-def postpass_device(engine, det, start_frame=1, leds=False, leds_threshold=None, gray=None, frame0=0, exchange=None):
+def postpass_device(engine, det, start_frame=1, leds=False, leds_threshold=None, gray=None, frame0=0, exchange=None, details=False):
     """Post-pass of one sequence whose per-frame results `det` (dict of CUDA tensors n [F], ids [F,M], corners [F,M,4,2],
     rvec / tvec [F,M,3], poses computed with the nominal marker length) are on this rank's device.  Returns the rows.
     Only the first max(n) marker slots of every frame travel to the host (one packed pinned transfer per direction).
-    exchange(jobs, results) (frame-sharded runs): lets the other ranks fill the LED jobs of the frames they own."""
+    exchange(jobs, results) (frame-sharded runs): lets the other ranks fill the LED jobs of the frames they own.
+    details=True: dict(rows, jobs, results, n, ids, corners) instead of the rows alone."""
     torch = engine.torch
     _np_types(torch)
     F = int(det["n"].shape[0])
@@ -177,4 +178,7 @@ def postpass_device(engine, det, start_frame=1, leds=False, leds_threshold=None,
     results = run_jobs(engine, jobs, gray=gray if leds else None, frame0=frame0)
     if exchange is not None:
         results = exchange(jobs, results)
-    return finish(rows, results)
+    rows = finish(rows, results)
+    if details:   # what the overlay renderer needs (render.py)
+        return dict(rows=rows, jobs=jobs, results=results, n=n, ids=ids, corners=corners)
+    return rows

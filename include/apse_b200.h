@@ -223,6 +223,8 @@ typedef struct apse_seq_job_result {
     double dist_aruco, dist_bbox;                  /* kind >= 1, metres, unrounded */
     int32_t leds;                                  /* kind 0: the 8-bit LED code */
     int32_t valid;                                 /* 1 once a device has filled this result */
+    int32_t nearest_px[2];                         /* kind >= 1: the outline point closest to the host marker (:466-481), for the renderer */
+    int32_t outline_px[4][2];                      /* kind >= 1: projected outline corners in drawContours order (:421-425) */
 } apse_seq_job_result;
 
 typedef struct apse_seq_row {                      /* one CSV row (:146-185); float fields carry Python's round() */
@@ -231,7 +233,7 @@ typedef struct apse_seq_row {                      /* one CSV row (:146-185); fl
     int32_t host_fields;                           /* 1: markerLength .. fov_height are written as floats, 0: the reference writes integer zeros */
     int32_t leds;
     int32_t job_led, job_dist[3];                  /* jobs whose results this frame takes (-1: value stays stale) */
-    int32_t pad_;
+    int32_t accepted_mask;                         /* bits 0-7: marker slot i of this frame passed the track gate (:613) -- what drawMarkers draws */
     double marker_length, altitude, fov_width, fov_height;
     double dist_aruco[3], dist_bbox[3];
 } apse_seq_row;
@@ -257,6 +259,19 @@ int apse_sequence_jobs(apse_ctx *ctx, const apse_seq_job *jobs_host, int n_jobs,
 int apse_sequence_finish(int n_frames, apse_seq_row *rows, const apse_seq_job_result *results, int n_jobs);
 /* The CSV text of :131-139,146-185 (Python's str() of ints and floats); returns the number of bytes written or a negative status */
 int64_t apse_sequence_csv(const apse_seq_row *rows, int n_frames, int with_header, char *buf, int64_t cap);
+
+/* ---- annotated frames (aruco_detect.py:494-500,614-616,421-425: marker quads, vehicle outlines, distance lines, points) ---------
+ * Overlay primitives drawn straight into device-resident BGR frames: a thick segment with round caps (what cv2.line /
+ * cv2.drawContours produce up to their anti-aliasing-free edge rule) or a filled disc (cv2.circle, thickness -1).  Primitives of
+ * one frame are drawn in list order (later ones on top); the list must be sorted by frame.  prims: DEVICE pointer. */
+typedef struct apse_overlay_prim {
+    int32_t frame;
+    int32_t kind;                                  /* 0 = segment, 1 = disc */
+    int32_t x0, y0, x1, y1;                        /* segment end points; disc: centre = (x0, y0) */
+    int32_t thickness;                             /* segment: cv2 thickness; disc: radius */
+    uint8_t bgr[4];
+} apse_overlay_prim;
+int apse_draw_overlay(apse_ctx *ctx, uint8_t *bgr, int w, int h, int batch, const apse_overlay_prim *prims, int n_prims, void *stream);
 
 /* test tap of the sparse evaluation: the bound table (HOST, 16*32*32 entries min | (255 - max) << 8, cell = (c0 >> 4, c1 >> 3,
  * c2 >> 3)), the tile flags of the last apse_preprocess_tiles_sparse batch (DEVICE, [batch][h/4][w/4], 1 = evaluated exactly)
