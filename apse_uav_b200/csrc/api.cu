@@ -86,6 +86,7 @@ void apse_destroy(apse_ctx *ctx)
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
     delete[] ctx->trace;
     cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask); cudaFree(ctx->seq_jobs); cudaFree(ctx->seq_results);
+    cudaFree(ctx->quad_im); cudaFree(ctx->quad_im2); cudaFree(ctx->quad_tmp);
     delete ctx;
 }
 
@@ -182,8 +183,10 @@ int apse_set_params(apse_ctx *ctx, const apse_params *p)
     if (p->perspectiveRemovePixelPerCell <= 0 || p->perspectiveRemoveIgnoredMarginPerCell < 0 ||
         p->perspectiveRemoveIgnoredMarginPerCell > 0.5)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: perspectiveRemove* invalid");
-    if (p->aprilTagQuadDecimate > 1 || p->aprilTagQuadSigma != 0 || p->aprilTagDeglitch != 0)
-        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagQuadDecimate / QuadSigma / Deglitch are not supported");
+    if (p->aprilTagDeglitch != 0) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagDeglitch is not supported");
+    if (p->aprilTagQuadDecimate > 1 && (p->aprilTagQuadDecimate != floorf(p->aprilTagQuadDecimate) || p->aprilTagQuadDecimate > 16))
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagQuadDecimate must be an integer factor <= 16 (the frame size must be a multiple of it)");
+    if (fabsf(p->aprilTagQuadSigma) >= 8.25f) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: |aprilTagQuadSigma| must be below 8.25 (33 taps)");
     if (p->detectInvertedMarker || p->useAruco3Detection)
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: detectInvertedMarker / useAruco3Detection are not supported");
     if (p->cornerRefinementMethod == 2) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: CORNER_REFINE_CONTOUR is not supported");
@@ -285,7 +288,17 @@ static int apse_detect_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, in
     apse_fill_device_params(ctx, &dp, w, h);
     const int mode = ctx->params.cornerRefinementMethod;
     int rc;
-    if (mode == 3) {
+    if (mode == 3 && apse_quad_image_needed(ctx->params)) {
+        // aprilTagQuadDecimate / aprilTagQuadSigma: quads are found on the shrunk / blurred image and scaled back; the tile
+        // extrema of the full-size gray (if any) do not apply
+        const uint8_t *qim; int qw, qh; float qscale;
+        rc = apse_quad_image(ctx, gray, w, h, batch, &qim, &qw, &qh, &qscale, st);
+        if (rc) return rc;
+        DeviceParams dq;
+        apse_fill_device_params(ctx, &dq, qw, qh);
+        rc = apse_apriltag_quads(ctx, qim, qw, qh, batch, dq, st, false);
+        if (!rc && qscale != 1.f) rc = apse_scale_quads(ctx, batch, qscale, st);
+    } else if (mode == 3) {
         rc = apse_apriltag_quads(ctx, gray, w, h, batch, dp, st, have_tile_minmax);
     } else {
         rc = apse_decode_big_scratch(ctx);
@@ -326,7 +339,7 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
     // K1 writes the 4x4-tile extrema of gray straight into the candidate stage's tile arrays.  A caller that does not ask for
     // the gray frames gets the sparse evaluation (identical detections; gray is computed only where the detector reads it).
     int rc = 1;
-    const bool sparse = want_sparse && sparse_enabled() && ctx->params.cornerRefinementMethod == 3;
+    const bool sparse = want_sparse && sparse_enabled() && ctx->params.cornerRefinementMethod == 3 && !apse_quad_image_needed(ctx->params);
     if (sparse) {
         rc = apse_preprocess_sparse(ctx, bgr, gray, ctx->tmm, 0, batch, ctx->params.aprilTagMinWhiteBlackDiff, st);
         if (rc < 0) return rc;
@@ -358,7 +371,7 @@ static int preprocess_tiles_impl(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gra
     int rc = 1;
     ctx->tiles_sparse[slot] = false;
     for (int k = 0; k < 2; k++) if (ctx->sparse_gray[k] == gray) ctx->sparse_gray[k] = nullptr;   // the buffer is rewritten now
-    if (want_sparse && sparse_enabled() && ctx->params.cornerRefinementMethod == 3) {
+    if (want_sparse && sparse_enabled() && ctx->params.cornerRefinementMethod == 3 && !apse_quad_image_needed(ctx->params)) {
         rc = apse_preprocess_sparse(ctx, bgr, gray, ctx->tmm_buf[slot], slot, batch, ctx->params.aprilTagMinWhiteBlackDiff, (cudaStream_t)stream);
         if (rc < 0) return rc;
         if (rc == APSE_OK) { ctx->tiles_sparse[slot] = true; ctx->tiles_bgr[slot] = bgr; ctx->sparse_gray[slot] = gray; }

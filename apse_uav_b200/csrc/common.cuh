@@ -139,6 +139,9 @@ struct apse_ctx {
     const uint8_t *sparse_gray[2] = {nullptr, nullptr};   // gray buffer a sparse batch was written into (partial: only valid with its slot)
     bool sparse_active = false;       // the detect call in flight reads gray through sparse_src
     SparseSrc sparse_src;
+    // image of the quad detector when aprilTagQuadDecimate / aprilTagQuadSigma are set (quadim.cu), allocated on first use
+    uint8_t *quad_im = nullptr, *quad_im2 = nullptr;
+    uint16_t *quad_tmp = nullptr;
     bool k1_attr_set = false;         // dynamic shared-memory attribute of the K1t instantiations set on this context's device
 };
 
@@ -195,6 +198,9 @@ int apse_preprocess_ex(apse_ctx *ctx, const uint8_t *bgr, uint8_t *bgr_out, uint
 int apse_preprocess_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, uint16_t *tmm, int slot, int batch, int min_wb_diff,
                            cudaStream_t st);
 int apse_build_bound_table(apse_ctx *ctx, cudaStream_t st);
+bool apse_quad_image_needed(const apse_params &p);
+int apse_quad_image(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const uint8_t **out, int *qw, int *qh, float *scale, cudaStream_t st);
+int apse_scale_quads(apse_ctx *ctx, int batch, float f, cudaStream_t st);
 void apse_sparse_free(apse_ctx *ctx);
 int apse_detect_alloc(apse_ctx *ctx);
 void apse_detect_free(apse_ctx *ctx);

@@ -53,7 +53,7 @@ typedef struct apse_params {
     double maxErroneousBitsInBorderRate;
     double minOtsuStdDev;
     double errorCorrectionRate;
-    float aprilTagQuadDecimate, aprilTagQuadSigma;   /* must be 0 (reference leaves them disabled) */
+    float aprilTagQuadDecimate, aprilTagQuadSigma;   /* decimate: 0 / 1 (off) or an integer factor dividing the frame size; sigma: |sigma| < 8.25 */
     int aprilTagMinClusterPixels, aprilTagMaxNmaxima;
     float aprilTagCriticalRad, aprilTagMaxLineFitMse;
     int aprilTagMinWhiteBlackDiff, aprilTagDeglitch; /* deglitch must be 0 */

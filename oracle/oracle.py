@@ -107,6 +107,27 @@ def preprocess(bgr, mapx, mapy, lut):
     return out, gray
 
 
+def quad_image(gray, decimate=0.0, sigma=0.0):
+    """Image of the APRILTAG quad detector for aprilTagQuadDecimate / aprilTagQuadSigma (aruco_detect.py:203,231-233):
+    (image, corner scale).  Integer decimation factors only (frame size a multiple of the factor)."""
+    q = np.ascontiguousarray(gray)
+    scale = np.float32(1.0)
+    if decimate > 1:
+        f = int(decimate)
+        h, w = q.shape
+        if f != decimate or w % f or h % f:
+            raise ValueError("integer decimation factor dividing the frame size required")
+        out = np.empty((h // f, w // f), np.uint8)
+        lib().orc_resize_area_int(u8p(q), w, h, f, u8p(out))
+        q, scale = out, np.float32(decimate)
+    if sigma != 0:
+        out = np.empty_like(q)
+        if lib().orc_quad_sigma(u8p(q), q.shape[1], q.shape[0], C.c_float(sigma), u8p(out)) != 0:
+            raise ValueError("aprilTagQuadSigma too large")
+        q = out
+    return q, scale
+
+
 def lab_tables():
     g = np.empty(256, np.uint16)
     c = np.empty(3072, np.uint16)
@@ -242,7 +263,12 @@ def identify_candidates(gray, quads, dp, bytes_list, max_out=4096):
 
 def detect_markers_apriltag(gray, bytes_list, cvparams, marker_size=4, max_correction_bits=1):
     """aruco_detect.py:267 (APRILTAG mode) -> (corners (n,4,2) f32, ids (n,) i32, rejected (m,4,2) f32)."""
-    quads = at_quads(gray, cvparams)
+    dec, sigma = float(getattr(cvparams, "aprilTagQuadDecimate", 0.0)), float(getattr(cvparams, "aprilTagQuadSigma", 0.0))
+    if dec > 1 or sigma != 0:   # quads on the shrunk / blurred image, scaled back in float32; identification on the original
+        qim, scale = quad_image(gray, dec, sigma)
+        quads = (at_quads(qim, cvparams) * scale).astype(np.float32)
+    else:
+        quads = at_quads(gray, cvparams)
     dp = DecParams.from_cv(cvparams, marker_size, max_correction_bits)
     return identify_candidates(gray, quads, dp, bytes_list)
 

@@ -263,3 +263,75 @@ void orc_undistort(const uint8_t *src, int w, int h, int cn, const double *K, co
             }
         }
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * The image the APRILTAG quad detector works on when aprilTagQuadDecimate / aprilTagQuadSigma are set (dependency: aruco
+ * detectMarkers, APRILTAG branch; knobs documented at aruco_detect.py:203,231-233): cv2.resize(INTER_AREA) by 1/f for an
+ * integer factor f, then cv2.GaussianBlur (sigma > 0) or unsharp masking (sigma < 0) with floor(4 |sigma|) | 1 taps.
+ * Pinned against cv2.resize / cv2.GaussianBlur in tests/test_oracle_pre.py. */
+void orc_resize_area_int(const uint8_t *src, int w, int h, int f, uint8_t *dst)
+{
+    const int dw = w / f, dh = h / f;
+    const float scale = 1.f / (float)(f * f);
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            int s = 0;
+            for (int dy = 0; dy < f; dy++)
+                for (int dx = 0; dx < f; dx++) s += src[(size_t)(y * f + dy) * w + x * f + dx];
+            dst[(size_t)y * dw + x] = (uint8_t)(f == 2 ? (s + 2) >> 2 : (int)lrintf((float)s * scale));
+        }
+}
+
+/* 8.8 fixed-point Gaussian kernel with error diffusion towards the centre tap; returns the tap count (0: too many) */
+int orc_gauss_kernel_fixed(float sigma_f, int *k, int max_taps)
+{
+    const float s = fabsf(sigma_f);
+    int ksz = (int)floorf(4 * s);
+    ksz |= 1;
+    if (ksz <= 1) { k[0] = 256; return 1; }
+    if (ksz > max_taps) return 0;
+    const double sigma = (double)s, scale2x = -0.5 * 0.25 / (sigma * sigma);
+    const int n2 = (ksz - 1) / 2;
+    double vals[64], sum = 0;
+    for (int i = 0, x = 1 - ksz; i < n2; i++, x += 2) { vals[i] = exp((double)(x * x) * scale2x); sum += vals[i]; }
+    sum = sum * 2 + 1.0;
+    const double mul1 = 1.0 / sum;
+    double err = 0;
+    long long tot = 0;
+    for (int i = 0; i < n2; i++) {
+        const double adj = vals[i] * mul1 * 256.0 + err;
+        const long long v0 = llrint(adj);
+        err = adj - (double)v0;
+        k[i] = k[ksz - 1 - i] = (int)v0;
+        tot += v0;
+    }
+    k[n2] = (int)(256 - 2 * tot);
+    return ksz;
+}
+
+/* sigma > 0: blur; sigma < 0: clamp(2 * src - blur); |sigma| below 0.5: copy.  Returns 0, or -1 when the kernel is too long */
+int orc_quad_sigma(const uint8_t *src, int w, int h, float sigma, uint8_t *dst)
+{
+    int k[64];
+    const int n = orc_gauss_kernel_fixed(sigma, k, 63);
+    if (n == 0) return -1;
+    if (n == 1 || sigma == 0) { memcpy(dst, src, (size_t)w * h); return 0; }
+    const int r = n / 2;
+    uint16_t *tmp = (uint16_t *)malloc((size_t)w * h * sizeof(uint16_t));
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int s = 0;
+            for (int i = 0; i < n; i++) { int xx = x + i - r; xx = xx < 0 ? 0 : xx >= w ? w - 1 : xx; s += k[i] * src[(size_t)y * w + xx]; }
+            tmp[(size_t)y * w + x] = (uint16_t)s;
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            unsigned s = 0;
+            for (int i = 0; i < n; i++) { int yy = y + i - r; yy = yy < 0 ? 0 : yy >= h ? h - 1 : yy; s += (unsigned)k[i] * tmp[(size_t)yy * w + x]; }
+            int v = (int)((s + 32768u) >> 16);
+            if (sigma < 0) { v = 2 * src[(size_t)y * w + x] - v; v = v < 0 ? 0 : v > 255 ? 255 : v; }
+            dst[(size_t)y * w + x] = (uint8_t)v;
+        }
+    free(tmp);
+    return 0;
+}

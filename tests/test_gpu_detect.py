@@ -112,7 +112,13 @@ def test_parameter_validation_mirrors_opencv_asserts(dictionary):
     p = aruco.DetectorParameters(); p.cornerRefinementMethod = aruco.CORNER_REFINE_APRILTAG; p.markerBorderBits = 0
     with pytest.raises(ApseError):
         aruco.detectMarkers(img, dictionary, parameters=p)
-    p = aruco.DetectorParameters(); p.cornerRefinementMethod = aruco.CORNER_REFINE_APRILTAG; p.aprilTagQuadDecimate = 2.0
+    p = aruco.DetectorParameters(); p.cornerRefinementMethod = aruco.CORNER_REFINE_APRILTAG; p.aprilTagQuadDecimate = 2.5   # integer factors only
+    with pytest.raises(ApseError):
+        aruco.detectMarkers(img, dictionary, parameters=p)
+    p = aruco.DetectorParameters(); p.cornerRefinementMethod = aruco.CORNER_REFINE_APRILTAG; p.aprilTagQuadDecimate = 3.0   # 64 is not a multiple of 3
+    with pytest.raises(ApseError):
+        aruco.detectMarkers(img, dictionary, parameters=p)
+    p = aruco.DetectorParameters(); p.cornerRefinementMethod = aruco.CORNER_REFINE_APRILTAG; p.aprilTagDeglitch = 1
     with pytest.raises(ApseError):
         aruco.detectMarkers(img, dictionary, parameters=p)
     with pytest.raises(ApseError):
@@ -133,3 +139,45 @@ def test_detect_golden(dictionary, ref_params, oracle, name):
     assert np.array_equal(got, g["ids"])
     assert len(got) == 0 or np.abs(np.array(c).reshape(-1, 4, 2) - g["corners"]).max() <= CORNER_TOL
     assert len(rej) == len(g["rejected"])
+
+
+@pytest.mark.parametrize("dec,sigma", [(2.0, 0.0), (3.0, 0.0), (0.0, 0.8), (0.0, -0.8), (2.0, 0.8), (4.0, -1.3)])
+def test_quad_decimate_and_sigma(oracle, camera, lut, dictionary, ref_params, frames4k, dec, sigma):
+    """aprilTagQuadDecimate / aprilTagQuadSigma (aruco_detect.py:203,231-233) on 4K frames: ids, order, float32
+    corners and rejected count equal to the oracle (which equals cv2: tests/test_oracle_detect.py), and to cv2 itself."""
+    import copy
+    import torch
+    from apse_uav_b200 import aruco
+    from apse_uav_b200.engine import Engine
+    p = copy.copy(ref_params)
+    p.aprilTagQuadDecimate, p.aprilTagQuadSigma = dec, sigma
+    e = Engine(0, 3840, 2160, 2)
+    bl = np.ascontiguousarray(dictionary.bytesList, np.uint8)
+    e.set_dictionary(bl.reshape(bl.shape[0], -1), dictionary.markerSize, dictionary.maxCorrectionBits)
+    e.set_params(p)
+    K, D = camera
+    e.set_camera(K, D, 3840, 2160)
+    e.set_lut(lut)
+    _, g = e.preprocess(torch.from_numpy(np.stack([frames4k["sparse"], frames4k["dense"]])).cuda())   # aruco_detect.py:250-259,592
+    grays = g.cpu().numpy()
+    det = e.detect(g, max_markers=512)
+    res = {k: v.cpu().numpy() for k, v in det.items()}
+    assert (res["status"] == 0).all()
+    for f in range(2):
+        oc, oi, orj = oracle.detect_markers_apriltag(grays[f], dictionary.raw, p)
+        n = int(res["n"][f])
+        assert n == len(oi) and n >= (4 if f == 0 else 60)
+        assert np.array_equal(res["ids"][f, :n], oi)
+        assert np.array_equal(res["corners"][f, :n], oc)
+        assert int(res["n_rejected"][f]) == len(orj)
+    try:
+        import cv2
+        from conftest import cv2_params
+    except ImportError:
+        return
+    det2 = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(p))
+    cc, ci, _ = det2.detectMarkers(grays[0])
+    n = int(res["n"][0])
+    assert ci.ravel().tolist() == res["ids"][0, :n].tolist()
+    assert np.abs(np.array([c[0] for c in cc]) - res["corners"][0, :n]).max() <= 1e-3
+    e.close()

@@ -90,3 +90,24 @@ def test_detect_vs_golden(oracle, dictionary, ref_params, name):
     mx, my = oracle.init_undistort_map(g["K"], g["D"], w, h)
     _, gray = oracle.preprocess(g["frame"], mx, my, g["lut"])
     _check(oracle, gray, dictionary, ref_params, g["corners"], g["ids"], g["rejected"])
+
+
+@needs_cv2
+@pytest.mark.parametrize("dec,sigma", [(2.0, 0.0), (3.0, 0.0), (0.0, 0.8), (0.0, -0.8), (2.0, 0.8), (4.0, -1.3)])
+def test_quad_decimate_and_sigma_vs_cv2(oracle, dictionary, ref_params, dec, sigma):
+    """detectMarkers with aprilTagQuadDecimate / aprilTagQuadSigma equals cv2 (ids, order, float32 corners, rejected)."""
+    import copy
+    import cv2
+    from conftest import cv2_params
+    from tools import synth
+    p = copy.copy(ref_params)
+    p.aprilTagQuadDecimate, p.aprilTagQuadSigma = dec, sigma
+    for seed, (w, h) in ((5, (1920, 1080)), (6, (1200, 720))):
+        frame = synth.make_frame(dictionary.bytesList, seed, w, h, ids=(1, 2, 3, 4, 7, 9), side_range=(50, 110))
+        gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+        det = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(p))
+        cc, ci, cr = det.detectMarkers(gray)
+        oc, oi, orj = oracle.detect_markers_apriltag(gray, dictionary.raw, p)
+        assert len(oi) >= 4 and oi.tolist() == ci.ravel().tolist()
+        assert np.array_equal(oc, np.array([c[0] for c in cc]))
+        assert len(orj) == len(cr)

@@ -73,3 +73,23 @@ def test_undistort_equals_cv2_undistort(oracle, camera):
     g = rng.integers(0, 256, (540, 960), dtype=np.uint8)
     assert np.array_equal(oracle.undistort(g, Ks, D, newK), cv2.undistort(g, Ks, D, None, newK))
     assert np.array_equal(oracle.undistort(g, Ks, D[:5]), cv2.undistort(g, Ks, D[:5]))
+
+
+@needs_cv2
+def test_quad_image_resize_and_blur_bit_exact(oracle):
+    """aprilTagQuadDecimate / aprilTagQuadSigma (aruco_detect.py:203,231-233): the image the quad detector sees = cv2.resize(
+    INTER_AREA) by an integer factor, then cv2.GaussianBlur / unsharp masking with floor(4 |sigma|) | 1 taps."""
+    import cv2
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (360, 480), dtype=np.uint8)
+    for f in (2, 3, 4, 5, 6, 8):
+        want = cv2.resize(img, None, fx=1 / f, fy=1 / f, interpolation=cv2.INTER_AREA)
+        got, scale = oracle.quad_image(img, float(f), 0.0)
+        assert np.array_equal(got, want) and scale == np.float32(f)
+    for sigma in list(np.arange(0.3, 4.0, 0.1)) + [0.8, 1.3, 2.3, 5.0, 7.9]:
+        s = float(np.float32(sigma))
+        ksz = int(np.floor(4 * np.float32(sigma))) | 1
+        blur = cv2.GaussianBlur(img, (ksz, ksz), s, sigmaY=s, borderType=cv2.BORDER_REPLICATE) if ksz > 1 else img
+        assert np.array_equal(oracle.quad_image(img, 0.0, s)[0], blur), sigma
+        sharp = np.clip(2 * img.astype(int) - blur, 0, 255).astype(np.uint8) if ksz > 1 else img
+        assert np.array_equal(oracle.quad_image(img, 0.0, -s)[0], sharp), -sigma
