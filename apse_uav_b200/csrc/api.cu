@@ -86,7 +86,7 @@ void apse_destroy(apse_ctx *ctx)
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
     delete[] ctx->trace;
     cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask); cudaFree(ctx->seq_jobs); cudaFree(ctx->seq_results);
-    cudaFree(ctx->quad_im); cudaFree(ctx->quad_im2); cudaFree(ctx->quad_tmp);
+    cudaFree(ctx->quad_im); cudaFree(ctx->quad_im2); cudaFree(ctx->quad_tmp); cudaFree(ctx->quads_refined);
     delete ctx;
 }
 
@@ -189,7 +189,7 @@ int apse_set_params(apse_ctx *ctx, const apse_params *p)
     if (fabsf(p->aprilTagQuadSigma) >= 8.25f) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: |aprilTagQuadSigma| must be below 8.25 (33 taps)");
     if (p->detectInvertedMarker || p->useAruco3Detection)
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: detectInvertedMarker / useAruco3Detection are not supported");
-    if (p->cornerRefinementMethod == 2) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: CORNER_REFINE_CONTOUR is not supported");
+    if (p->cornerRefinementMethod < 0 || p->cornerRefinementMethod > 3) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: cornerRefinementMethod must be 0 .. 3");
     if (p->aprilTagMaxNmaxima < 4 || p->aprilTagMaxNmaxima > 16)
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagMaxNmaxima must be in [4,16]");
     ctx->tiles_gray[0] = ctx->tiles_gray[1] = nullptr;   // cached tile extrema (apse_preprocess_tiles) never survive another entry point
@@ -308,6 +308,7 @@ static int apse_detect_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, in
     rc = apse_decode_candidates(ctx, gray, w, h, batch, dp, out, st);
     if (rc) return rc;
     if (mode == 1) rc = apse_corner_subpix(ctx, gray, w, h, batch, out, st);
+    if (mode == 2) rc = apse_contour_refine(ctx, batch, out, st);
     return rc;
 }
 

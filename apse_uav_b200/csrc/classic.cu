@@ -239,11 +239,154 @@ struct ClassicArgs {
     int desc_cap;
     int32_t *counters;
     float *quads;
+    float *refined;              // nullable: CORNER_REFINE_CONTOUR corners of every candidate, parallel to quads
     unsigned long long *quad_keys;
     int quad_cap;
     int w, h, window_index;
     double accuracy_rate, min_corner_rate;
 };
+
+// CORNER_REFINE_CONTOUR of one candidate (dependency: _refineCandidateLines, _interpolate2Dline, _getCrossPoint), one warp.
+// The contour points are grouped by the corner they follow in contour order (points ahead of the first corner join the group
+// that is open at the end), one least-squares line per group, refined corner = intersection of the two lines meeting at it.
+// Arithmetic of cv2 4.13, bit for bit: exact sums (double), the 2 x 2 normal equations and their LU with partial pivoting in
+// float32, Matx22f::solve's closed form in float32 (oracle_classic.c: orc_refine_candidate_lines).  marks: >= 128 words of scratch.
+#define RC_MAX_MARKS 60
+__device__ void refine_candidate_lines(const uint32_t *__restrict__ src, int count, const float (&c)[8], float *__restrict__ out, uint32_t *marks)
+{
+    const int lane = threadIdx.x & 31;
+    // positions where the contour passes through a corner, in contour order: (position << 2 | corner)
+    int nm = 0;
+    for (int base = 0; base < count; base += 32) {
+        const int i = base + lane;
+        int hit = -1;
+        if (i < count) {
+            const uint32_t p = src[i];
+            const float x = (float)pt_x(p), y = (float)pt_y(p);
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (c[2 * j] == x && c[2 * j + 1] == y) hit = j;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit >= 0);
+        if (hit >= 0) {
+            const int k = nm + __popc(m & ((1u << lane) - 1));
+            if (k < RC_MAX_MARKS) marks[k] = ((uint32_t)i << 2) | (uint32_t)hit;
+        }
+        nm += __popc(m);
+    }
+    __syncwarp();
+    int idx[4] = {-1, -1, -1, -1};
+    const int nmk = min(nm, RC_MAX_MARKS);
+    for (int k = 0; k < nmk; k++) idx[marks[k] & 3u] = (int)(marks[k] >> 2);   // last occurrence wins
+    if (nm > RC_MAX_MARKS || idx[0] < 0 || idx[1] < 0 || idx[2] < 0 || idx[3] < 0) {   // (not seen on real contours) keep the corners
+        if (lane < 8) out[lane] = c[lane];
+        return;
+    }
+    const int last_group = (int)(marks[nmk - 1] & 3u);
+    // per group: n, sum x, sum y, sum xx, sum yy, sum xy (exact in double), extents
+    double S[4][6];
+    int mn_x[4], mx_x[4], mn_y[4], mx_y[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) { for (int k = 0; k < 6; k++) S[g][k] = 0; mn_x[g] = mn_y[g] = INT32_MAX; mx_x[g] = mx_y[g] = INT32_MIN; }
+    for (int i = lane; i < count; i += 32) {
+        // group of point i: the corner of the last mark at or before i; ahead of the first mark: the group open at the end
+        int g = last_group;
+        for (int k = 0; k < nmk; k++) { if ((int)(marks[k] >> 2) <= i) g = (int)(marks[k] & 3u); else break; }
+        const uint32_t p = src[i];
+        const int xi = pt_x(p), yi = pt_y(p);
+        const double x = xi, y = yi;
+#pragma unroll
+        for (int gg = 0; gg < 4; gg++)
+            if (gg == g) {
+                S[gg][0] += 1; S[gg][1] += x; S[gg][2] += y; S[gg][3] += x * x; S[gg][4] += y * y; S[gg][5] += x * y;
+                mn_x[gg] = min(mn_x[gg], xi); mx_x[gg] = max(mx_x[gg], xi); mn_y[gg] = min(mn_y[gg], yi); mx_y[gg] = max(mx_y[gg], yi);
+            }
+    }
+    float L[4][3];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+            for (int o = 16; o > 0; o >>= 1) S[g][k] += __shfl_xor_sync(0xffffffffu, S[g][k], o);
+        mn_x[g] = __reduce_min_sync(0xffffffffu, mn_x[g]); mx_x[g] = __reduce_max_sync(0xffffffffu, mx_x[g]);
+        mn_y[g] = __reduce_min_sync(0xffffffffu, mn_y[g]); mx_y[g] = __reduce_max_sync(0xffffffffu, mx_y[g]);
+        const bool horiz = (float)mx_x[g] - (float)mn_x[g] > (float)mx_y[g] - (float)mn_y[g];
+        float A00 = (float)(horiz ? S[g][3] : S[g][4]), A01 = (float)(horiz ? S[g][1] : S[g][2]), A10 = A01, A11 = (float)S[g][0];
+        float B0 = (float)S[g][5], B1 = (float)(horiz ? S[g][2] : S[g][1]);
+        if (fabsf(A10) > fabsf(A00)) { float t = A00; A00 = A10; A10 = t; t = A01; A01 = A11; A11 = t; t = B0; B0 = B1; B1 = t; }
+        float x0 = 0.f, x1 = 0.f;
+        if (!(fabsf(A00) < FLT_EPSILON)) {
+            const float d = __fdiv_rn(-1.f, A00), alpha = __fmul_rn(A10, d);
+            A11 = __fadd_rn(A11, __fmul_rn(alpha, A01));
+            B1 = __fadd_rn(B1, __fmul_rn(alpha, B0));
+            if (!(fabsf(A11) < FLT_EPSILON)) {
+                x1 = __fdiv_rn(B1, A11);
+                x0 = __fdiv_rn(__fsub_rn(B0, __fmul_rn(A01, x1)), A00);
+            }
+        }
+        if (horiz) { L[g][0] = x0; L[g][1] = -1.f; L[g][2] = x1; }
+        else { L[g][0] = -1.f; L[g][1] = x0; L[g][2] = x1; }
+    }
+    int inc = 1;
+    if (idx[0] > idx[1] && idx[3] > idx[0]) inc = -1;
+    if (idx[2] > idx[3] && idx[1] > idx[2]) inc = -1;
+    if (lane < 4) {
+        const int i = lane, j = inc < 0 ? (i + 1) & 3 : (i + 3) & 3;
+        float a0, a1, a2, b0_, b1_, b2;
+        // (register arrays indexed by a lane-dependent value: select explicitly)
+        a0 = i == 0 ? L[0][0] : i == 1 ? L[1][0] : i == 2 ? L[2][0] : L[3][0];
+        a1 = i == 0 ? L[0][1] : i == 1 ? L[1][1] : i == 2 ? L[2][1] : L[3][1];
+        a2 = i == 0 ? L[0][2] : i == 1 ? L[1][2] : i == 2 ? L[2][2] : L[3][2];
+        b0_ = j == 0 ? L[0][0] : j == 1 ? L[1][0] : j == 2 ? L[2][0] : L[3][0];
+        b1_ = j == 0 ? L[0][1] : j == 1 ? L[1][1] : j == 2 ? L[2][1] : L[3][1];
+        b2 = j == 0 ? L[0][2] : j == 1 ? L[1][2] : j == 2 ? L[2][2] : L[3][2];
+        const float r0 = -a2, r1 = -b2;
+        const float det = __fsub_rn(__fmul_rn(a0, b1_), __fmul_rn(a1, b0_));
+        float ox = 0.f, oy = 0.f;   // Matx::solve fails on a singular system: the zero vector comes back
+        if (det != 0.f) {
+            const float dinv = __fdiv_rn(1.f, det);
+            ox = __fmul_rn(__fsub_rn(__fmul_rn(r0, b1_), __fmul_rn(r1, a1)), dinv);
+            oy = __fmul_rn(__fsub_rn(__fmul_rn(r1, a0), __fmul_rn(r0, b0_)), dinv);
+        }
+        out[2 * i] = ox; out[2 * i + 1] = oy;
+    }
+}
+
+// after the decode stage: every accepted marker takes the refined corners of its candidate -- the first candidate in the
+// dependency's order with the same corners up to the rotation the identification applied.  One CTA per frame.
+__global__ void __launch_bounds__(256) k_contour_refine_out(const float *__restrict__ quads, const float *__restrict__ refined,
+                                                            const uint32_t *__restrict__ quad_order, const int32_t *__restrict__ counters, int quad_cap,
+                                                            apse_detections out)
+{
+    __shared__ unsigned s_best;
+    const int f = blockIdx.x;
+    const int nq = min(counters[f * APSE_COUNTERS + 2], quad_cap), nm = min(out.n_markers[f], out.max_markers);
+    const float *Q = quads + (size_t)f * quad_cap * 8, *R = refined + (size_t)f * quad_cap * 8;
+    const uint32_t *O = quad_order + (size_t)f * quad_cap;
+    for (int m = 0; m < nm; m++) {
+        float *oc = out.corners + ((size_t)f * out.max_markers + m) * 8;
+        if (threadIdx.x == 0) s_best = 0xffffffffu;
+        __syncthreads();
+        float c[8];
+        for (int k = 0; k < 8; k++) c[k] = oc[k];
+        for (int qi = threadIdx.x; qi < nq; qi += blockDim.x) {
+            const float *q = Q + 8 * qi;
+            for (int sh = 0; sh < 4; sh++) {
+                bool same = true;
+                for (int k = 0; k < 4 && same; k++) { const int s2 = (k + sh) & 3; same = q[2 * s2] == c[2 * k] && q[2 * s2 + 1] == c[2 * k + 1]; }
+                if (same) { atomicMin(&s_best, (O[qi] << 14) | ((unsigned)qi << 2) | (unsigned)sh); break; }
+            }
+        }
+        __syncthreads();
+        const unsigned best = s_best;
+        __syncthreads();
+        if (best != 0xffffffffu && threadIdx.x < 4) {
+            const int qi = (int)((best >> 2) & 0xfffu), sh = (int)(best & 3u), k = threadIdx.x, s2 = (k + sh) & 3;
+            oc[2 * k] = R[8 * qi + 2 * s2];
+            oc[2 * k + 1] = R[8 * qi + 2 * s2 + 1];
+        }
+        __syncthreads();
+    }
+}
 
 __global__ void __launch_bounds__(AQ_WARPS * 32) k_approx_quads(ClassicArgs A)
 {
@@ -343,6 +486,8 @@ __global__ void __launch_bounds__(AQ_WARPS * 32) k_approx_quads(ClassicArgs A)
         }
         if (overflow) { if (lane == 0) atomicExch(&cnt[3], APSE_ERR_CAPACITY); continue; }
         // ---- clean-up pass + filters: sequential, lane 0
+        int emitted = -1;             // index of the quad this contour produced (lane 0)
+        float ec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (lane == 0) {
             int cntv = nout, new_count = nout;
             if (cntv >= 3) {
@@ -407,7 +552,8 @@ __global__ void __launch_bounds__(AQ_WARPS * 32) k_approx_quads(ClassicArgs A)
                             for (int k = 0; k < 4; k++) { c[2 * k] = (float)qx[k]; c[2 * k + 1] = (float)qy[k]; }
                             double dx1 = c[2] - c[0], dy1 = c[3] - c[1], dx2 = c[4] - c[0], dy2 = c[5] - c[1];
                             if (dx1 * dy2 - dy1 * dx2 < 0.0) { float tx = c[2], ty = c[3]; c[2] = c[6]; c[3] = c[7]; c[6] = tx; c[7] = ty; }
-                            for (int k = 0; k < 8; k++) q[k] = c[k];
+                            for (int k = 0; k < 8; k++) { q[k] = c[k]; ec[k] = c[k]; }
+                            emitted = qi;
                             // candidate order of the dependency: window ascending, then descending trigger pixel
                             A.quad_keys[(size_t)f * A.quad_cap + qi] =
                                 ((unsigned long long)A.window_index << 32) | (unsigned long long)(0xffffffffu - cd.trigger);
@@ -416,6 +562,16 @@ __global__ void __launch_bounds__(AQ_WARPS * 32) k_approx_quads(ClassicArgs A)
                         }
                     }
                 }
+            }
+        }
+        __syncwarp();
+        // ---- CORNER_REFINE_CONTOUR: refined corners of this candidate from its contour (whole warp)
+        if (A.refined) {
+            emitted = __shfl_sync(0xffffffffu, emitted, 0);
+            if (emitted >= 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) ec[k] = __shfl_sync(0xffffffffu, ec[k], 0);
+                refine_candidate_lines(src, count, ec, A.refined + ((size_t)f * A.quad_cap + emitted) * 8, s_out[wid]);
             }
         }
         __syncwarp();
@@ -579,6 +735,11 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
         A.pts = reinterpret_cast<uint32_t *>(ctx->sorted_pts); A.pts_cap = pts_cap;
         A.descs = reinterpret_cast<ContourDesc *>(ctx->clusters); A.desc_cap = desc_cap;
         A.counters = ctx->counters; A.quads = ctx->quads; A.quad_keys = ctx->sort_keys; A.quad_cap = APSE_MAX_QUADS;
+        A.refined = nullptr;
+        if (p.cornerRefinementMethod == 2) {   // CORNER_REFINE_CONTOUR: the line fits need the contour, which only lives in this loop
+            if (!ctx->quads_refined) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->quads_refined, (size_t)ctx->max_batch * APSE_MAX_QUADS * 8 * sizeof(float)));
+            A.refined = ctx->quads_refined;
+        }
         A.w = w; A.h = h; A.window_index = s;
         A.accuracy_rate = p.polygonalApproxAccuracyRate; A.min_corner_rate = p.minCornerDistanceRate;
         KLAUNCH(ctx, KID_APPROX, st, k_approx_quads<<<dim3(ctx->sm_count, batch), AQ_WARPS * 32, 0, st>>>(A));
@@ -587,6 +748,13 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
         CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters + 5, APSE_COUNTERS * sizeof(int32_t), 0, sizeof(int32_t), batch, st));
     }
     KLAUNCH(ctx, KID_APPROX, st, k_rank_quads<<<dim3(8, batch), 256, 0, st>>>(ctx->sort_keys, ctx->counters, APSE_MAX_QUADS, ctx->quad_order));
+    return APSE_OK;
+}
+
+int apse_contour_refine(apse_ctx *ctx, int batch, apse_detections *out, cudaStream_t st)
+{
+    if (!ctx->quads_refined) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "detect: no refined candidates (CORNER_REFINE_CONTOUR)");
+    KLAUNCH(ctx, KID_SUBPIX, st, k_contour_refine_out<<<batch, 256, 0, st>>>(ctx->quads, ctx->quads_refined, ctx->quad_order, ctx->counters, APSE_MAX_QUADS, *out));
     return APSE_OK;
 }
 

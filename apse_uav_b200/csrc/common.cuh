@@ -140,6 +140,7 @@ struct apse_ctx {
     bool sparse_active = false;       // the detect call in flight reads gray through sparse_src
     SparseSrc sparse_src;
     // image of the quad detector when aprilTagQuadDecimate / aprilTagQuadSigma are set (quadim.cu), allocated on first use
+    float *quads_refined = nullptr;   // [max_batch][APSE_MAX_QUADS][8] CORNER_REFINE_CONTOUR corners of the candidates (first use)
     uint8_t *quad_im = nullptr, *quad_im2 = nullptr;
     uint16_t *quad_tmp = nullptr;
     bool k1_attr_set = false;         // dynamic shared-memory attribute of the K1t instantiations set on this context's device
@@ -213,6 +214,7 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
 int apse_decode_big_scratch(apse_ctx *ctx);
 int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out, cudaStream_t st);
 int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, cudaStream_t st);
+int apse_contour_refine(apse_ctx *ctx, int batch, apse_detections *out, cudaStream_t st);
 int apse_corner_subpix(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, cudaStream_t st);
 int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
                            apse_detections *out, cudaStream_t st);

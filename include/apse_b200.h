@@ -42,7 +42,7 @@ typedef struct apse_params {
     int minDistanceToBorder;
     double minMarkerDistanceRate;
     float minGroupDistance;
-    int cornerRefinementMethod;       /* 0 NONE, 1 SUBPIX, 2 CONTOUR (unsupported), 3 APRILTAG */
+    int cornerRefinementMethod;       /* 0 NONE, 1 SUBPIX, 2 CONTOUR, 3 APRILTAG */
     int cornerRefinementWinSize;
     float relativeCornerRefinmentWinSize;
     int cornerRefinementMaxIterations;

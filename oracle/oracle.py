@@ -378,15 +378,26 @@ def is_contour_convex(poly):
     return bool(lib().orc_is_contour_convex(i32p(p), len(p)))
 
 
-def classic_quads(gray, cvparams, max_quads=1 << 16):
-    """Candidate quads of the classic path, (n,4,2) float32, dependency order (windows ascending, contour order)."""
+def classic_quads(gray, cvparams, max_quads=1 << 16, refined=False):
+    """Candidate quads of the classic path, (n,4,2) float32, dependency order (windows ascending, contour order).
+    refined=True: also the CORNER_REFINE_CONTOUR corners of every candidate (same corner order)."""
     gray = np.ascontiguousarray(gray)
     P = cvparams if isinstance(cvparams, ClassicParams) else ClassicParams.from_cv(cvparams)
     q = np.zeros((max_quads, 8), np.float32)
-    n = lib().orc_classic_quads(u8p(gray), gray.shape[1], gray.shape[0], C.byref(P), f32p(q), max_quads)
+    r = np.zeros((max_quads, 8), np.float32) if refined else None
+    n = lib().orc_classic_quads_refined(u8p(gray), gray.shape[1], gray.shape[0], C.byref(P), f32p(q), f32p(r) if refined else None, max_quads)
     if n > max_quads:
         raise RuntimeError("oracle quad capacity exceeded")
+    if refined:
+        return q[:n].reshape(n, 4, 2).copy(), r[:n].reshape(n, 4, 2).copy()
     return q[:n].reshape(n, 4, 2).copy()
+
+
+def refine_candidate_lines(contour, corners):
+    c = np.ascontiguousarray(np.asarray(contour, np.int32).reshape(-1, 2))
+    out = np.zeros(8, np.float32)
+    rc = lib().orc_refine_candidate_lines(i32p(c), len(c), f32p(np.ascontiguousarray(corners, np.float32).ravel()), f32p(out))
+    return out.reshape(4, 2) if rc == 0 else None
 
 
 def corner_subpix(gray, corners, win, max_iter, eps):
@@ -398,10 +409,27 @@ def corner_subpix(gray, corners, win, max_iter, eps):
 
 
 def detect_markers_classic(gray, bytes_list, cvparams, marker_size=4, max_correction_bits=1):
-    """aruco_detect.py:267 with cornerRefinementMethod NONE (0) or SUBPIX (1) -> (corners, ids, rejected)."""
-    quads = classic_quads(gray, cvparams)
+    """aruco_detect.py:267 with cornerRefinementMethod NONE (0), SUBPIX (1) or CONTOUR (2) -> (corners, ids, rejected)."""
+    method = int(cvparams.cornerRefinementMethod)
+    if method == 2:
+        quads, refined = classic_quads(gray, cvparams, refined=True)
+    else:
+        quads = classic_quads(gray, cvparams)
     dp = DecParams.from_cv(cvparams, marker_size, max_correction_bits)
     corners, ids, rejected = identify_candidates(gray, quads, dp, bytes_list)
+    if method == 2:
+        # every accepted marker takes the refined corners of its candidate: the first candidate (dependency order) with the
+        # same corners up to the rotation the identification applied
+        for i in range(len(corners)):
+            done = False
+            for qi in range(len(quads)):
+                for sh in range(4):
+                    if np.array_equal(np.roll(quads[qi], -sh, axis=0), corners[i]):
+                        corners[i] = np.roll(refined[qi], -sh, axis=0)
+                        done = True
+                        break
+                if done:
+                    break
     if int(cvparams.cornerRefinementMethod) == 1 and len(corners):
         nb = marker_size + 2 * int(cvparams.markerBorderBits)
         for i in range(len(corners)):

@@ -306,8 +306,74 @@ int orc_is_contour_convex(const int32_t *p, int n)
     return 1;
 }
 
+/* ------------------------------------------------------------------------------------------------------ */
+/* CORNER_REFINE_CONTOUR (dependency: _refineCandidateLines / _interpolate2Dline / _getCrossPoint): the contour points are
+ * grouped by the corner they follow in contour order (points ahead of the first corner join the last group), one least-squares
+ * line per group (y = a x + b or x = a y + b, whichever extent is larger), refined corner = intersection of the two lines that
+ * meet at it.  Bit-exact with cv2 4.13: sums in double, the 2 x 2 normal equations and their LU in float32, the intersection with
+ * Matx22f::solve's closed form in float32.  Returns 0, or -1 when a corner is not a contour point. */
+static void interp_line(double n, double sx, double sy, double sxx, double syy, double sxy, double minx, double maxx, double miny,
+                        double maxy, float L[3])
+{
+    /* normal equations [[saa, sa], [sa, n]] (a, b)^T = (sab, sb): the sums are exact (the dependency accumulates the products of
+     * its float32 matrices in double), stored as float32, then its float32 LU with partial pivoting */
+    const int horiz = (float)maxx - (float)minx > (float)maxy - (float)miny;
+    float A00 = (float)(horiz ? sxx : syy), A01 = (float)(horiz ? sx : sy), A10 = A01, A11 = (float)n;
+    float B0 = (float)sxy, B1 = (float)(horiz ? sy : sx);
+    if (fabsf(A10) > fabsf(A00)) { float t = A00; A00 = A10; A10 = t; t = A01; A01 = A11; A11 = t; t = B0; B0 = B1; B1 = t; }
+    float x0 = 0, x1 = 0;
+    if (!(fabsf(A00) < FLT_EPSILON)) {
+        const float d = -1.f / A00, alpha = A10 * d;
+        A11 = A11 + alpha * A01;
+        B1 = B1 + alpha * B0;
+        if (!(fabsf(A11) < FLT_EPSILON)) {
+            x1 = B1 / A11;
+            x0 = (B0 - A01 * x1) / A00;
+        }
+    }
+    if (horiz) { L[0] = x0; L[1] = -1.f; L[2] = x1; }   /* y = a x + b */
+    else { L[0] = -1.f; L[1] = x0; L[2] = x1; }         /* x = a y + b */
+}
+
+int orc_refine_candidate_lines(const int32_t *cont, int n, const float *corners, float *out)
+{
+    int idx[4] = {-1, -1, -1, -1};
+    double S[5][10];
+    for (int g = 0; g < 5; g++) { for (int k = 0; k < 6; k++) S[g][k] = 0; S[g][6] = S[g][8] = 1e300; S[g][7] = S[g][9] = -1e300; }
+    int group = 4;
+    for (int i = 0; i < n; i++) {
+        double x = cont[2 * i], y = cont[2 * i + 1];
+        for (int j = 0; j < 4; j++)
+            if ((double)corners[2 * j] == x && (double)corners[2 * j + 1] == y) { idx[j] = i; group = j; }
+        double *s = S[group];
+        s[0] += 1; s[1] += x; s[2] += y; s[3] += x * x; s[4] += y * y; s[5] += x * y;
+        if (x < s[6]) s[6] = x; if (x > s[7]) s[7] = x; if (y < s[8]) s[8] = y; if (y > s[9]) s[9] = y;
+    }
+    for (int j = 0; j < 4; j++) if (idx[j] < 0) return -1;
+    if (S[4][0] > 0) {   /* points ahead of the first corner belong to the group that was open at the end */
+        double *s = S[group], *e = S[4];
+        for (int k = 0; k < 6; k++) s[k] += e[k];
+        if (e[6] < s[6]) s[6] = e[6]; if (e[7] > s[7]) s[7] = e[7]; if (e[8] < s[8]) s[8] = e[8]; if (e[9] > s[9]) s[9] = e[9];
+    }
+    int inc = 1;
+    if (idx[0] > idx[1] && idx[3] > idx[0]) inc = -1;
+    if (idx[2] > idx[3] && idx[1] > idx[2]) inc = -1;
+    float L[4][3];
+    for (int g = 0; g < 4; g++) interp_line(S[g][0], S[g][1], S[g][2], S[g][3], S[g][4], S[g][5], S[g][6], S[g][7], S[g][8], S[g][9], L[g]);
+    for (int i = 0; i < 4; i++) {
+        const float *a = L[i], *b = inc < 0 ? L[(i + 1) % 4] : L[(i + 3) % 4];
+        const float b0 = -a[2], b1 = -b[2];
+        const float det = a[0] * b[1] - a[1] * b[0];
+        if (det == 0) { out[2 * i] = 0; out[2 * i + 1] = 0; continue; }   /* Matx::solve fails: the zero vector comes back */
+        const float dinv = 1.f / det;
+        out[2 * i] = (b0 * b[1] - b1 * a[1]) * dinv;
+        out[2 * i + 1] = (b1 * a[0] - b0 * b[0]) * dinv;
+    }
+    return 0;
+}
+
 /* quads of one thresholded window in the dependency's order; returns count (may exceed max_quads) */
-static int window_quads(const uint8_t *bin, int w, int h, const orc_classic_params *P, float *quads, int have, int max_quads)
+static int window_quads(const uint8_t *bin, int w, int h, const orc_classic_params *P, float *quads, float *refined, int have, int max_quads)
 {
     long long max_pts = (long long)w * h * 2 + 16;
     int max_c = w * h / 2 + 16;
@@ -341,6 +407,8 @@ static int window_quads(const uint8_t *bin, int w, int h, const orc_classic_para
                 float tx = q[2], ty = q[3];
                 q[2] = q[6]; q[3] = q[7]; q[6] = tx; q[7] = ty;
             }
+            if (refined && orc_refine_candidate_lines(pts + 2 * off[i], (int)cnt, q, refined + (size_t)have * 8) != 0)
+                memcpy(refined + (size_t)have * 8, q, 8 * sizeof(float));
         }
         have++;
     }
@@ -349,14 +417,21 @@ static int window_quads(const uint8_t *bin, int w, int h, const orc_classic_para
 }
 
 /* a6.C1-C3: candidate quads of all windows (ascending window size), [n][8] float32.  Returns n (> max: overflow) */
+int orc_classic_quads_refined(const uint8_t *gray, int w, int h, const orc_classic_params *P, float *quads, float *refined, int max_quads);
 int orc_classic_quads(const uint8_t *gray, int w, int h, const orc_classic_params *P, float *quads, int max_quads)
+{
+    return orc_classic_quads_refined(gray, w, h, P, quads, NULL, max_quads);
+}
+
+/* as orc_classic_quads; refined (nullable) receives the CORNER_REFINE_CONTOUR corners of every candidate, same corner order */
+int orc_classic_quads_refined(const uint8_t *gray, int w, int h, const orc_classic_params *P, float *quads, float *refined, int max_quads)
 {
     int n_scales = (P->win_max - P->win_min) / P->win_step + 1;
     uint8_t *bin = (uint8_t *)malloc((size_t)w * h);
     int have = 0;
     for (int i = 0; i < n_scales; i++) {
         orc_adaptive_threshold(gray, w, h, P->win_min + i * P->win_step, P->constant, bin);
-        have = window_quads(bin, w, h, P, quads, have, max_quads);
+        have = window_quads(bin, w, h, P, quads, refined, have, max_quads);
     }
     free(bin);
     return have;

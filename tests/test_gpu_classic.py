@@ -143,3 +143,24 @@ def test_pipeline_classic_mode(camera, lut, dictionary, frames4k, oracle):
         orv, otv = oracle.estimate_pose_single_markers(oc, 0.55, K, D)
         assert np.abs(det["tvec"][b, :n] - otv[:, 0]).max() <= 1e-4 * np.abs(otv).max()
     pipe.close()
+
+
+@pytest.mark.parametrize("wins", [(3, 23, 10), (13, 13, 1)])
+def test_corner_refine_contour_dense_4k(oracle, dictionary, gray_dense, wins):
+    """CORNER_REFINE_CONTOUR on the dense 4K frame: ids, order, rejected and the refined float32 corners
+    bit-identical to the oracle (which is bit-identical to cv2 below 100 contour points per side: tests/test_oracle_classic.py);
+    against cv2 itself within 0.25 px (its BLAS-backed sums above 100 points)."""
+    from apse_uav_b200 import aruco
+    p = classic_params(aruco, 2, wins)
+    gc, gi, gr = _detect(gray_dense, dictionary, p)
+    oc, oi, orj = oracle.detect_markers_classic(gray_dense, dictionary.raw, p)
+    assert len(oi) >= 150
+    assert np.array_equal(gi, oi) and np.array_equal(gr, orj)
+    assert np.array_equal(gc, oc)
+    if has_cv2():
+        import cv2
+        c, i, r = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(p)).detectMarkers(gray_dense)
+        cvc = np.array(c, np.float32).reshape(-1, 4, 2)
+        assert np.array_equal(gi, i.ravel())
+        assert np.abs(gc - cvc).max() <= 0.25
+        assert (np.abs(gc - cvc).reshape(len(gc), -1).max(1) == 0).mean() >= 0.9

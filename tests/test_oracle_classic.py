@@ -153,3 +153,29 @@ def test_classic_golden(oracle, dictionary, name):
         assert np.array_equal(oi, g[f"ids_{tag}"])
         assert np.array_equal(orj, g[f"rejected_{tag}"])
         assert oc.shape == g[f"corners_{tag}"].shape and (len(oc) == 0 or np.abs(oc - g[f"corners_{tag}"]).max() <= 1e-3)
+
+
+@needs_cv2
+@pytest.mark.parametrize("wins", [(3, 23, 10), (13, 13, 1)])
+def test_corner_refine_contour_vs_cv2(oracle, dictionary, gray_dense, frames4k, wins):
+    """SURVEY.md 8f-4, CORNER_REFINE_CONTOUR (the only mode that reads the contour; aruco_detect.py:267 passes the camera for it):
+    ids / order / rejected equal to cv2, refined corners BIT-IDENTICAL wherever every side of the marker has fewer than 100
+    contour points; from 100 points on cv2's gemm hands the 2 x N product of the normal equations to BLAS sgemm (float32
+    accumulation in an implementation-defined order) and agrees with the exact sums only to a few hundredths of a pixel."""
+    import cv2
+    from apse_uav_b200 import aruco
+    p = classic_params(aruco, 2, wins)
+    n_exact = 0
+    for gray in (gray_dense, cv2.cvtColor(frames4k["sparse"], cv2.COLOR_BGR2GRAY)):
+        rc, ri, rr = _detect_cv2(gray, p)
+        oc, oi, orj = oracle.detect_markers_classic(gray, dictionary.raw, p)
+        assert np.array_equal(oi, ri) and np.array_equal(orj, rr)
+        p0 = classic_params(aruco, 0, wins)
+        ic, _, _ = oracle.detect_markers_classic(gray, dictionary.raw, p0)     # integer corners of the same markers
+        assert np.median(np.abs(oc - ic)) < 1.0 and not np.array_equal(oc, ic)  # refined (occluded sides move a corner by many pixels)
+        side = np.abs(ic - np.roll(ic, -1, axis=1)).sum(-1).max(-1)            # L1 side length bounds the contour points of a side
+        small = side < 70
+        n_exact += int(small.sum())
+        assert np.array_equal(oc[small], rc[small])
+        assert np.abs(oc - rc).max() <= 0.25
+    assert n_exact >= 50
