@@ -86,7 +86,7 @@ void apse_destroy(apse_ctx *ctx)
     for (int i = 0; i < ctx->ev_created; i++) { cudaEventDestroy(ctx->ev_start[i]); cudaEventDestroy(ctx->ev_stop[i]); }
     delete[] ctx->trace;
     cudaFree(ctx->mapx); cudaFree(ctx->mapy); cudaFree(ctx->tables); cudaFree(ctx->tables_id); cudaFree(ctx->tables2); cudaFree(ctx->dict); cudaFree(ctx->gray_scratch); cudaFree(ctx->nbr_mask); cudaFree(ctx->seq_jobs); cudaFree(ctx->seq_results);
-    cudaFree(ctx->quad_im); cudaFree(ctx->quad_im2); cudaFree(ctx->quad_tmp); cudaFree(ctx->quads_refined);
+    cudaFree(ctx->quad_im); cudaFree(ctx->quad_im2); cudaFree(ctx->quad_tmp); cudaFree(ctx->quads_refined); cudaFree(ctx->area_tab);
     delete ctx;
 }
 
@@ -184,8 +184,7 @@ int apse_set_params(apse_ctx *ctx, const apse_params *p)
         p->perspectiveRemoveIgnoredMarginPerCell > 0.5)
         CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: perspectiveRemove* invalid");
     if (p->aprilTagDeglitch != 0) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagDeglitch is not supported");
-    if (p->aprilTagQuadDecimate > 1 && (p->aprilTagQuadDecimate != floorf(p->aprilTagQuadDecimate) || p->aprilTagQuadDecimate > 16))
-        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagQuadDecimate must be an integer factor <= 16 (the frame size must be a multiple of it)");
+    if (p->aprilTagQuadDecimate > 64) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagQuadDecimate above 64 is not supported");
     if (fabsf(p->aprilTagQuadSigma) >= 8.25f) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: |aprilTagQuadSigma| must be below 8.25 (33 taps)");
     if (p->detectInvertedMarker || p->useAruco3Detection)
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: detectInvertedMarker / useAruco3Detection are not supported");

@@ -143,6 +143,10 @@ struct apse_ctx {
     float *quads_refined = nullptr;   // [max_batch][APSE_MAX_QUADS][8] CORNER_REFINE_CONTOUR corners of the candidates (first use)
     uint8_t *quad_im = nullptr, *quad_im2 = nullptr;
     uint16_t *quad_tmp = nullptr;
+    void *area_tab = nullptr;         // tap tables of the non-integer INTER_AREA filter for (area_w, area_h, area_dec)
+    size_t area_ofs[4] = {0, 0, 0, 0};
+    int area_w = 0, area_h = 0;
+    float area_dec = 0;
     bool k1_attr_set = false;         // dynamic shared-memory attribute of the K1t instantiations set on this context's device
 };
 

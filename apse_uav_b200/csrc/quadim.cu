@@ -4,11 +4,16 @@
 // with a (floor(4 |sigma|) | 1)-tap Gaussian, finds the quads on that image and scales their corners back by `decimate`;
 // identification then samples the ORIGINAL frame.  Arithmetic restated from the dependency's 8-bit paths and pinned against
 // cv2.resize / cv2.GaussianBlur (oracle/oracle_pre.c, tests/test_oracle_pre.py):
-//   INTER_AREA, integer factor f: block sum, f == 2: (s + 2) >> 2, else rint(float(s) * (1.f / (f * f))) (float32, half to even)
+//   INTER_AREA, integer factor f: block sum, f == 2: (s + 2) >> 2, else rint(float(s) * (1.f / (f * f))) (float32, half to even),
+//   partial blocks at the right / bottom edge: rint(float(s) / count); any other factor (the reference's example is 1.5): the
+//   dependency's table-driven area filter, sum_rows beta * (sum_cols alpha * src) in float32 in table order, scale = 1 / fx with
+//   fx = 1.f / decimate
 //   GaussianBlur 8-bit: 8.8 fixed-point kernel with error diffusion towards the centre tap (sum exactly 256), horizontal pass
 //   exact in 16 bits, vertical pass in 32 bits, (v + 32768) >> 16, BORDER_REPLICATE.
 #include "common.cuh"
 #include <math.h>
+#include <string.h>
+#include <vector>
 
 #define QI_MAX_TAPS 33
 
@@ -47,11 +52,55 @@ __global__ void k_decimate(const uint8_t *__restrict__ src, int w, int h, int f,
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, fr = blockIdx.z;
     if (x >= dw || y >= dh) return;
     const uint8_t *p = src + (size_t)fr * w * h + (size_t)y * f * w + x * f;
-    int s = 0;
-    for (int dy = 0; dy < f; dy++)
-        for (int dx = 0; dx < f; dx++) s += p[(size_t)dy * w + dx];
-    const int v = f == 2 ? (s + 2) >> 2 : __float2int_rn(__fmul_rn((float)s, scale));
+    int s = 0, cnt = 0;
+    for (int dy = 0; dy < f && y * f + dy < h; dy++)
+        for (int dx = 0; dx < f && x * f + dx < w; dx++) { s += p[(size_t)dy * w + dx]; cnt++; }
+    int v;
+    if (cnt == f * f) v = f == 2 ? (s + 2) >> 2 : __float2int_rn(__fmul_rn((float)s, scale));
+    else v = cnt ? __float2int_rn(__fdiv_rn((float)s, (float)cnt)) : 0;
     dst[(size_t)fr * dw * dh + (size_t)y * dw + x] = (uint8_t)v;
+}
+
+// non-integer factor: taps of destination column x = xt[xo[x] .. xo[x + 1]), of destination row y = yt[yo[y] .. yo[y + 1])
+struct AreaTap { int si; float alpha; };
+__global__ void k_resize_area(const uint8_t *__restrict__ src, int w, int h, const int *__restrict__ xo, const AreaTap *__restrict__ xt,
+                              const int *__restrict__ yo, const AreaTap *__restrict__ yt, uint8_t *__restrict__ dst, int dw, int dh)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, fr = blockIdx.z;
+    if (x >= dw || y >= dh) return;
+    const uint8_t *im = src + (size_t)fr * w * h;
+    const int x0 = xo[x], x1 = xo[x + 1], y0 = yo[y], y1 = yo[y + 1];
+    float sum = 0.f;
+    for (int j = y0; j < y1; j++) {
+        const uint8_t *S = im + (size_t)yt[j].si * w;
+        float buf = 0.f;
+        for (int k = x0; k < x1; k++) buf = __fadd_rn(buf, __fmul_rn((float)S[xt[k].si], xt[k].alpha));
+        sum = __fadd_rn(sum, __fmul_rn(yt[j].alpha, buf));
+    }
+    dst[(size_t)fr * dw * dh + (size_t)y * dw + x] = (uint8_t)min(max(__float2int_rn(sum), 0), 255);
+}
+
+// host: the dependency's tap table of one axis (computeResizeAreaTab)
+static void area_tab(int ssize, int dsize, double scale, std::vector<int> &ofs, std::vector<AreaTap> &tab)
+{
+    ofs.assign(dsize + 1, 0);
+    tab.clear();
+    for (int dx = 0; dx < dsize; dx++) {
+        ofs[dx] = (int)tab.size();
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale, cell = scale < ssize - fsx1 ? scale : ssize - fsx1;
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        if (sx2 > ssize - 1) sx2 = ssize - 1;
+        if (sx1 > sx2) sx1 = sx2;
+        if (sx1 - fsx1 > 1e-3) tab.push_back(AreaTap{sx1 - 1, (float)((sx1 - fsx1) / cell)});
+        for (int sx = sx1; sx < sx2; sx++) tab.push_back(AreaTap{sx, (float)(1.0 / cell)});
+        if (fsx2 - sx2 > 1e-3) {
+            double a = fsx2 - sx2;
+            if (a > 1.) a = 1.;
+            if (a > cell) a = cell;
+            tab.push_back(AreaTap{sx2, (float)(a / cell)});
+        }
+    }
+    ofs[dsize] = (int)tab.size();
 }
 
 __global__ void k_gauss_h(const uint8_t *__restrict__ src, int w, int h, GaussKernel K, uint16_t *__restrict__ tmp)
@@ -104,9 +153,13 @@ int apse_quad_image(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch,
                     cudaStream_t st)
 {
     const apse_params &p = ctx->params;
-    const int f = p.aprilTagQuadDecimate > 1 ? (int)p.aprilTagQuadDecimate : 1;
-    if (p.aprilTagQuadDecimate > 1 && ((float)f != p.aprilTagQuadDecimate || w % f || h % f))
-        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: aprilTagQuadDecimate %.3f needs an integer factor that divides the %dx%d frame", p.aprilTagQuadDecimate, w, h);
+    const bool dec = p.aprilTagQuadDecimate > 1;
+    // cv2.resize(src, None, fx = fy = 1.f / decimate): destination size = cvRound(size * fx), filter scale = 1 / fx
+    const double fx = (double)(1.f / (dec ? p.aprilTagQuadDecimate : 1.f)), fscale = 1.0 / fx;
+    const int dw = dec ? (int)lrint(w * fx) : w, dh = dec ? (int)lrint(h * fx) : h;
+    const int f = (int)lrint(fscale);
+    const bool integer_factor = fabs(fscale - f) < 2.220446049250313e-16;
+    if (dec && (dw < 8 || dh < 8)) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "detect: aprilTagQuadDecimate %.3f leaves a %dx%d image", p.aprilTagQuadDecimate, dw, dh);
     GaussKernel K;
     if (!make_gauss_kernel(p.aprilTagQuadSigma, K)) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: aprilTagQuadSigma %.3f needs more than %d taps", p.aprilTagQuadSigma, QI_MAX_TAPS);
     const bool blur = p.aprilTagQuadSigma != 0 && K.n > 1;
@@ -116,10 +169,35 @@ int apse_quad_image(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch,
         CUDA_TRY(ctx, cudaMalloc((void **)&ctx->quad_im2, npx));
         CUDA_TRY(ctx, cudaMalloc((void **)&ctx->quad_tmp, npx * sizeof(uint16_t)));
     }
-    const int dw = w / f, dh = h / f;
+    if (dec && !integer_factor && (ctx->area_w != w || ctx->area_h != h || ctx->area_dec != p.aprilTagQuadDecimate)) {
+        // tap tables of the area filter for this geometry (rebuilt when the frame size or the factor changes)
+        std::vector<int> xo, yo;
+        std::vector<AreaTap> xt, yt;
+        area_tab(w, dw, fscale, xo, xt);
+        area_tab(h, dh, fscale, yo, yt);
+        const size_t bytes = (xo.size() + yo.size()) * sizeof(int) + (xt.size() + yt.size()) * sizeof(AreaTap);
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        cudaFree(ctx->area_tab);
+        ctx->area_tab = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&ctx->area_tab, bytes));
+        std::vector<unsigned char> blob(bytes);
+        size_t o = 0;
+        ctx->area_ofs[0] = o; memcpy(blob.data() + o, xo.data(), xo.size() * sizeof(int)); o += xo.size() * sizeof(int);
+        ctx->area_ofs[1] = o; memcpy(blob.data() + o, yo.data(), yo.size() * sizeof(int)); o += yo.size() * sizeof(int);
+        ctx->area_ofs[2] = o; memcpy(blob.data() + o, xt.data(), xt.size() * sizeof(AreaTap)); o += xt.size() * sizeof(AreaTap);
+        ctx->area_ofs[3] = o; memcpy(blob.data() + o, yt.data(), yt.size() * sizeof(AreaTap));
+        CUDA_TRY(ctx, cudaMemcpy(ctx->area_tab, blob.data(), bytes, cudaMemcpyHostToDevice));
+        ctx->area_w = w; ctx->area_h = h; ctx->area_dec = p.aprilTagQuadDecimate;
+    }
     const uint8_t *cur = gray;
-    if (f > 1) {
+    if (dec && integer_factor) {
         KLAUNCH(ctx, KID_TILE_MINMAX, st, k_decimate<<<dim3(div_up(dw, 256), dh, batch), 256, 0, st>>>(gray, w, h, f, 1.f / (float)(f * f), ctx->quad_im, dw, dh));
+        cur = ctx->quad_im;
+    } else if (dec) {
+        const unsigned char *t = (const unsigned char *)ctx->area_tab;
+        KLAUNCH(ctx, KID_TILE_MINMAX, st, k_resize_area<<<dim3(div_up(dw, 256), dh, batch), 256, 0, st>>>(
+                    gray, w, h, (const int *)(t + ctx->area_ofs[0]), (const AreaTap *)(t + ctx->area_ofs[2]), (const int *)(t + ctx->area_ofs[1]),
+                    (const AreaTap *)(t + ctx->area_ofs[3]), ctx->quad_im, dw, dh));
         cur = ctx->quad_im;
     }
     if (blur) {
@@ -128,7 +206,7 @@ int apse_quad_image(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch,
         KLAUNCH(ctx, KID_TILE_MINMAX, st, k_gauss_v<<<dim3(div_up(dw, 256), dh, batch), 256, 0, st>>>(ctx->quad_tmp, dw, dh, K, cur, p.aprilTagQuadSigma < 0 ? 1 : 0, dst));
         cur = dst;
     }
-    *out = cur; *qw = dw; *qh = dh; *scale = p.aprilTagQuadDecimate > 1 ? p.aprilTagQuadDecimate : 1.f;
+    *out = cur; *qw = dw; *qh = dh; *scale = dec ? p.aprilTagQuadDecimate : 1.f;
     return APSE_OK;
 }
 

@@ -53,7 +53,7 @@ typedef struct apse_params {
     double maxErroneousBitsInBorderRate;
     double minOtsuStdDev;
     double errorCorrectionRate;
-    float aprilTagQuadDecimate, aprilTagQuadSigma;   /* decimate: 0 / 1 (off) or an integer factor dividing the frame size; sigma: |sigma| < 8.25 */
+    float aprilTagQuadDecimate, aprilTagQuadSigma;   /* decimate: 0 / 1 (off) or any factor > 1 (the reference's example: 1.5); sigma: |sigma| < 8.25 */
     int aprilTagMinClusterPixels, aprilTagMaxNmaxima;
     float aprilTagCriticalRad, aprilTagMaxLineFitMse;
     int aprilTagMinWhiteBlackDiff, aprilTagDeglitch; /* deglitch must be 0 */

@@ -109,16 +109,20 @@ def preprocess(bgr, mapx, mapy, lut):
 
 def quad_image(gray, decimate=0.0, sigma=0.0):
     """Image of the APRILTAG quad detector for aprilTagQuadDecimate / aprilTagQuadSigma (aruco_detect.py:203,231-233):
-    (image, corner scale).  Integer decimation factors only (frame size a multiple of the factor)."""
+    (image, corner scale)."""
     q = np.ascontiguousarray(gray)
     scale = np.float32(1.0)
     if decimate > 1:
-        f = int(decimate)
         h, w = q.shape
-        if f != decimate or w % f or h % f:
-            raise ValueError("integer decimation factor dividing the frame size required")
-        out = np.empty((h // f, w // f), np.uint8)
-        lib().orc_resize_area_int(u8p(q), w, h, f, u8p(out))
+        dw, dh = C.c_int(0), C.c_int(0)
+        lib().orc_resize_area_dsize(w, h, C.c_float(decimate), C.byref(dw), C.byref(dh))
+        dw, dh = dw.value, dh.value
+        out = np.empty((dh, dw), np.uint8)
+        scale_f = 1.0 / float(np.float32(1.0) / np.float32(decimate))   # 1 / fx, fx = 1.f / decimate in float32
+        if abs(scale_f - round(scale_f)) < 2.220446049250313e-16:    # integer factor: the dependency's block-average fast path
+            lib().orc_resize_area_int(u8p(q), w, h, int(round(scale_f)), dw, dh, u8p(out))
+        else:
+            lib().orc_resize_area(u8p(q), w, h, dw, dh, C.c_double(scale_f), u8p(out))
         q, scale = out, np.float32(decimate)
     if sigma != 0:
         out = np.empty_like(q)

@@ -269,17 +269,87 @@ void orc_undistort(const uint8_t *src, int w, int h, int cn, const double *K, co
  * detectMarkers, APRILTAG branch; knobs documented at aruco_detect.py:203,231-233): cv2.resize(INTER_AREA) by 1/f for an
  * integer factor f, then cv2.GaussianBlur (sigma > 0) or unsharp masking (sigma < 0) with floor(4 |sigma|) | 1 taps.
  * Pinned against cv2.resize / cv2.GaussianBlur in tests/test_oracle_pre.py. */
-void orc_resize_area_int(const uint8_t *src, int w, int h, int f, uint8_t *dst)
+void orc_resize_area_int(const uint8_t *src, int w, int h, int f, int dw, int dh, uint8_t *dst)
 {
-    const int dw = w / f, dh = h / f;
     const float scale = 1.f / (float)(f * f);
     for (int y = 0; y < dh; y++)
         for (int x = 0; x < dw; x++) {
-            int s = 0;
-            for (int dy = 0; dy < f; dy++)
-                for (int dx = 0; dx < f; dx++) s += src[(size_t)(y * f + dy) * w + x * f + dx];
-            dst[(size_t)y * dw + x] = (uint8_t)(f == 2 ? (s + 2) >> 2 : (int)lrintf((float)s * scale));
+            int s = 0, cnt = 0;
+            for (int dy = 0; dy < f && y * f + dy < h; dy++)
+                for (int dx = 0; dx < f && x * f + dx < w; dx++) { s += src[(size_t)(y * f + dy) * w + x * f + dx]; cnt++; }
+            int v;
+            if (cnt == f * f) v = f == 2 ? (s + 2) >> 2 : (int)lrintf((float)s * scale);
+            else v = cnt ? (int)lrintf((float)s / (float)cnt) : 0;   /* partial block at the right / bottom edge: mean of what is there */
+            dst[(size_t)y * dw + x] = (uint8_t)v;
         }
+}
+
+/* cv2.resize(INTER_AREA) for a non-integer shrink factor (the reference's own example is aprilTagQuadDecimate = 1.5,
+ * aruco_detect.py:203): the dependency's table-driven area filter in float32.  Tap table of one axis: for every destination
+ * index the source pixels it covers with weights coverage / cell width; a destination pixel is
+ * sum_rows beta * (sum_cols alpha * src), accumulated in float32 in table order, then rounded half to even. */
+typedef struct { int si, di; float alpha; } orc_area_tap;
+
+int orc_area_tab(int ssize, int dsize, double scale, orc_area_tap *tab)
+{
+    int k = 0;
+    for (int dx = 0; dx < dsize; dx++) {
+        double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        double cell = scale < ssize - fsx1 ? scale : ssize - fsx1;
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        if (sx2 > ssize - 1) sx2 = ssize - 1;
+        if (sx1 > sx2) sx1 = sx2;
+        if (sx1 - fsx1 > 1e-3) { tab[k].di = dx; tab[k].si = sx1 - 1; tab[k++].alpha = (float)((sx1 - fsx1) / cell); }
+        for (int sx = sx1; sx < sx2; sx++) { tab[k].di = dx; tab[k].si = sx; tab[k++].alpha = (float)(1.0 / cell); }
+        if (fsx2 - sx2 > 1e-3) {
+            double a = fsx2 - sx2;
+            if (a > 1.) a = 1.;
+            if (a > cell) a = cell;
+            tab[k].di = dx; tab[k].si = sx2; tab[k++].alpha = (float)(a / cell);
+        }
+    }
+    return k;
+}
+
+/* destination size of cv2.resize(src, None, fx = 1 / decimate (float32 division), fy = ...): cvRound of the product */
+void orc_resize_area_dsize(int w, int h, float decimate, int *dw, int *dh)
+{
+    const double inv = (double)(1.f / decimate);
+    *dw = (int)lrint(w * inv); *dh = (int)lrint(h * inv);
+}
+
+/* scale: the dependency keeps 1 / fx (fx = 1.f / decimate in float32) as the filter scale even where the rounded destination
+ * size would imply a slightly different one */
+void orc_resize_area(const uint8_t *src, int w, int h, int dw, int dh, double scale, uint8_t *dst)
+{
+    const double sx = scale, sy = scale;
+    orc_area_tap *xt = (orc_area_tap *)malloc(sizeof(orc_area_tap) * (size_t)w * 2), *yt = (orc_area_tap *)malloc(sizeof(orc_area_tap) * (size_t)h * 2);
+    const int nx = orc_area_tab(w, dw, sx, xt), ny = orc_area_tab(h, dh, sy, yt);
+    float *buf = (float *)malloc(sizeof(float) * dw), *sum = (float *)malloc(sizeof(float) * dw);
+    int prev_dy = ny > 0 ? yt[0].di : 0;
+    for (int x = 0; x < dw; x++) sum[x] = 0;
+    for (int j = 0; j < ny; j++) {
+        const float beta = yt[j].alpha;
+        const int dy = yt[j].di;
+        const uint8_t *S = src + (size_t)yt[j].si * w;
+        for (int x = 0; x < dw; x++) buf[x] = 0;
+        for (int k = 0; k < nx; k++) buf[xt[k].di] += S[xt[k].si] * xt[k].alpha;
+        if (dy != prev_dy) {
+            for (int x = 0; x < dw; x++) {
+                long v = lrintf(sum[x]);
+                dst[(size_t)prev_dy * dw + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                sum[x] = beta * buf[x];
+            }
+            prev_dy = dy;
+        } else {
+            for (int x = 0; x < dw; x++) sum[x] += beta * buf[x];
+        }
+    }
+    for (int x = 0; x < dw; x++) {
+        long v = lrintf(sum[x]);
+        dst[(size_t)prev_dy * dw + x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+    }
+    free(buf); free(sum); free(xt); free(yt);
 }
 
 /* 8.8 fixed-point Gaussian kernel with error diffusion towards the centre tap; returns the tap count (0: too many) */

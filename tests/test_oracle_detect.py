@@ -93,7 +93,7 @@ def test_detect_vs_golden(oracle, dictionary, ref_params, name):
 
 
 @needs_cv2
-@pytest.mark.parametrize("dec,sigma", [(2.0, 0.0), (3.0, 0.0), (0.0, 0.8), (0.0, -0.8), (2.0, 0.8), (4.0, -1.3)])
+@pytest.mark.parametrize("dec,sigma", [(1.5, 0.0), (2.0, 0.0), (3.0, 0.0), (0.0, 0.8), (0.0, -0.8), (2.0, 0.8), (4.0, -1.3), (2.5, 1.3)])
 def test_quad_decimate_and_sigma_vs_cv2(oracle, dictionary, ref_params, dec, sigma):
     """detectMarkers with aprilTagQuadDecimate / aprilTagQuadSigma equals cv2 (ids, order, float32 corners, rejected)."""
     import copy
@@ -102,7 +102,7 @@ def test_quad_decimate_and_sigma_vs_cv2(oracle, dictionary, ref_params, dec, sig
     from tools import synth
     p = copy.copy(ref_params)
     p.aprilTagQuadDecimate, p.aprilTagQuadSigma = dec, sigma
-    for seed, (w, h) in ((5, (1920, 1080)), (6, (1200, 720))):
+    for seed, (w, h) in ((5, (1920, 1080)), (6, (1200, 720)), (7, (1922, 1083))):
         frame = synth.make_frame(dictionary.bytesList, seed, w, h, ids=(1, 2, 3, 4, 7, 9), side_range=(50, 110))
         gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
         det = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(p))

@@ -82,10 +82,14 @@ def test_quad_image_resize_and_blur_bit_exact(oracle):
     import cv2
     rng = np.random.default_rng(1)
     img = rng.integers(0, 256, (360, 480), dtype=np.uint8)
-    for f in (2, 3, 4, 5, 6, 8):
-        want = cv2.resize(img, None, fx=1 / f, fy=1 / f, interpolation=cv2.INTER_AREA)
-        got, scale = oracle.quad_image(img, float(f), 0.0)
-        assert np.array_equal(got, want) and scale == np.float32(f)
+    for shape in ((360, 480), (361, 483), (725, 1283)):
+        im = rng.integers(0, 256, shape, dtype=np.uint8)
+        for f in (1.5, 2, 2.5, 3, 1.3, 4, 5, 6, 8, 1.1, 3.7):     # aruco_detect.py:203 names 1.5
+            fx = float(np.float32(1) / np.float32(f))                # the dependency divides in float32
+            want = cv2.resize(im, None, fx=fx, fy=fx, interpolation=cv2.INTER_AREA)
+            got, scale = oracle.quad_image(im, float(f), 0.0)
+            assert got.shape == want.shape and np.array_equal(got, want), (shape, f)
+            assert scale == np.float32(f)
     for sigma in list(np.arange(0.3, 4.0, 0.1)) + [0.8, 1.3, 2.3, 5.0, 7.9]:
         s = float(np.float32(sigma))
         ksz = int(np.floor(4 * np.float32(sigma))) | 1
