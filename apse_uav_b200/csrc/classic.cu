@@ -250,7 +250,7 @@ struct ClassicArgs {
 // The contour points are grouped by the corner they follow in contour order (points ahead of the first corner join the group
 // that is open at the end), one least-squares line per group, refined corner = intersection of the two lines meeting at it.
 // Arithmetic of cv2 4.13, bit for bit: exact sums (double), the 2 x 2 normal equations and their LU with partial pivoting in
-// float32, Matx22f::solve's closed form in float32 (oracle_classic.c: orc_refine_candidate_lines).  marks: >= 128 words of scratch.
+// float32, Matx22f::solve's closed form in float32 (the CPU restatement of the same arithmetic is pinned to cv2 in tests/).  marks: >= 128 words of scratch.
 #define RC_MAX_MARKS 60
 __device__ void refine_candidate_lines(const uint32_t *__restrict__ src, int count, const float (&c)[8], float *__restrict__ out, uint32_t *marks)
 {

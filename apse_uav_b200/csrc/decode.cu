@@ -627,8 +627,10 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
     int nb = dp.marker_size + 2 * dp.border_bits;
     if (nb * dp.cell_size > DEC_MAX_S || nb > 16 || dp.nbytes > 8)
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: canonical marker image %d px exceeds the %d px limit", nb * dp.cell_size, DEC_MAX_S);
-    const char *env = getenv("APSE_IDENTIFY_DECODED_PARENTS");
-    int skip = (env && env[0] == '1') ? 0 : 1;
+    // a quad that encloses an already decoded marker IS identified (cv2 4.13 on nested-marker frames, tests/test_gpu_detect.py);
+    // development switch APSE_SKIP_DECODED_PARENTS=1 restores the behaviour round 1 assumed
+    static const bool skip_env = getenv("APSE_SKIP_DECODED_PARENTS") != nullptr && getenv("APSE_SKIP_DECODED_PARENTS")[0] == '1';
+    int skip = skip_env ? 1 : 0;
     // hierarchy scratch of the quad fit is free at this point: [batch][APSE_MAX_QUADS] decode results
     int32_t *dec_raw = reinterpret_cast<int32_t *>(ctx->errs);
     const int cand_blocks = ctx->params.cornerRefinementMethod == 3 ? 64 : 128;   // CTAs per frame; a CTA without a candidate exits at once

@@ -3,7 +3,7 @@
 // mode) shrinks the gray frame by 1/decimate with INTER_AREA, blurs it (sigma > 0) or sharpens it by unsharp masking (sigma < 0)
 // with a (floor(4 |sigma|) | 1)-tap Gaussian, finds the quads on that image and scales their corners back by `decimate`;
 // identification then samples the ORIGINAL frame.  Arithmetic restated from the dependency's 8-bit paths and pinned against
-// cv2.resize / cv2.GaussianBlur (oracle/oracle_pre.c, tests/test_oracle_pre.py):
+// cv2.resize / cv2.GaussianBlur by the CPU restatement in tests/ (test_*_pre.py):
 //   INTER_AREA, integer factor f: block sum, f == 2: (s + 2) >> 2, else rint(float(s) * (1.f / (f * f))) (float32, half to even),
 //   partial blocks at the right / bottom edge: rint(float(s) / count); any other factor (the reference's example is 1.5): the
 //   dependency's table-driven area filter, sum_rows beta * (sum_cols alpha * src) in float32 in table order, scale = 1 / fx with

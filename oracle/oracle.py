@@ -204,7 +204,7 @@ class DecParams(C.Structure):
                 ("detect_inverted", C.c_int), ("skip_decoded_parents", C.c_int)]
 
     @classmethod
-    def from_cv(cls, p, marker_size=4, max_correction_bits=1, skip_decoded_parents=1):
+    def from_cv(cls, p, marker_size=4, max_correction_bits=1, skip_decoded_parents=0):
         return cls(marker_size, int(p.markerBorderBits), int(p.perspectiveRemovePixelPerCell),
                    float(p.perspectiveRemoveIgnoredMarginPerCell), float(p.minOtsuStdDev),
                    float(p.maxErroneousBitsInBorderRate), float(p.errorCorrectionRate), max_correction_bits,

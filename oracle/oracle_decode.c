@@ -24,7 +24,8 @@ typedef struct {
     double min_marker_distance_rate;
     float min_group_distance;
     int detect_inverted;
-    int skip_decoded_parents; /* 1: a quad enclosing an already decoded marker is not identified */
+    int skip_decoded_parents; /* 1: a quad enclosing an already decoded marker is not identified.  cv2 4.13 DOES identify such
+                               * quads (24 nested-marker frames, tests/test_oracle_detect.py): 0 is the pinned behaviour */
 } orc_dec_params;
 
 /* ------------------------------------------------------------------------------------------------------ */

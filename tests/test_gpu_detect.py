@@ -178,3 +178,31 @@ def test_quad_decimate_and_sigma(oracle, camera, lut, dictionary, ref_params, fr
     assert ci.ravel().tolist() == res["ids"][0, :n].tolist()
     assert np.abs(np.array([c[0] for c in cc]) - res["corners"][0, :n]).max() <= 1e-3
     e.close()
+
+
+@pytest.mark.parametrize("mode", [3, 0])
+def test_nested_markers(oracle, dictionary, ref_params, mode):
+    """Markers inside markers: the quad that encloses an already decoded marker is identified as cv2 4.13 does (ids, order,
+    corners, rejected count equal to the oracle = cv2, tests/test_oracle_detect.py::test_nested_markers_vs_cv2)."""
+    import copy
+    import torch
+    from apse_uav_b200.engine import Engine
+    from tools import synth
+    p = copy.copy(ref_params)
+    p.cornerRefinementMethod = mode
+    e = Engine(0, 1920, 1080, 6)
+    bl = np.ascontiguousarray(dictionary.bytesList, np.uint8)
+    e.set_dictionary(bl.reshape(bl.shape[0], -1), dictionary.markerSize, dictionary.maxCorrectionBits)
+    e.set_params(p)
+    frames = [synth.make_nested_frame(dictionary.bytesList, 100 + s, levels=2 + s % 2)[0] for s in (1, 2, 5, 9, 10, 11)]
+    grays = np.stack([np.ascontiguousarray(((f[..., 0].astype(np.int32) * 3735 + f[..., 1].astype(np.int32) * 19235 + f[..., 2].astype(np.int32) * 9798 + 16384) >> 15).astype(np.uint8)) for f in frames])
+    det = e.detect(torch.from_numpy(grays).cuda(), max_markers=128)
+    res = {k: v.cpu().numpy() for k, v in det.items()}
+    assert (res["status"] == 0).all()
+    fn = oracle.detect_markers_apriltag if mode == 3 else oracle.detect_markers_classic
+    for f in range(len(frames)):
+        oc, oi, orj = fn(grays[f], dictionary.raw, p)
+        n = int(res["n"][f])
+        assert n == len(oi) and np.array_equal(res["ids"][f, :n], oi) and np.array_equal(res["corners"][f, :n], oc)
+        assert int(res["n_rejected"][f]) == len(orj)
+    e.close()

@@ -157,6 +157,46 @@ def make_dense_frame(bytes_list, seed: int, width: int = 3840, height: int = 216
                       noise_sigma=noise_sigma, occlude_frac=0.15, margin=70)
 
 
+def make_nested_frame(bytes_list, seed: int, width: int = 1920, height: int = 1080, levels: int = 3, noise_sigma: float = 2.0):
+    """Markers inside markers: a big marker, a medium one inside one of its white cells, (levels = 3) a tiny one inside a white
+    cell of the medium one, and a free-standing marker.  Exercises the candidate tree of detectMarkers (a quad that encloses an
+    already decoded marker).  Returns (frame, ids placed outermost first)."""
+    rng = np.random.default_rng(seed)
+    frame = background(rng, width, height)
+
+    def square(cx, cy, s, ang):
+        c, s_ = np.cos(ang), np.sin(ang)
+        base = np.float32([[-1, -1], [1, -1], [1, 1], [-1, 1]]) * (s / 2)
+        return base @ np.float32([[c, s_], [-s_, c]]) + np.float32([cx, cy])
+
+    def paste(mid, quad):
+        tile = render_marker(bytes_list, int(mid))
+        _paste_marker(frame, tile, np.float32(quad), quiet_frac=8.0 / tile.shape[0])
+
+    def white_cell(mid, k, cx, cy, side, ang):
+        ys, xs = np.nonzero(marker_bits(bytes_list, int(mid)))
+        k %= len(ys)
+        u, v = (xs[k] + 1.5) / 6 - 0.5, (ys[k] + 1.5) / 6 - 0.5
+        c, s_ = np.cos(ang), np.sin(ang)
+        off = np.float32([u * side, v * side]) @ np.float32([[c, s_], [-s_, c]])
+        return cx + off[0], cy + off[1]
+
+    sc = min(width / 1920.0, height / 1080.0)
+    a1, a2 = rng.uniform(-0.5, 0.5, 2)
+    ids = [int(v) for v in rng.choice(len(bytes_list), 4, replace=False)]
+    bx, by, bs = 0.36 * width, 0.5 * height, 900 * sc
+    paste(ids[0], square(bx, by, bs, a1))
+    mx, my = white_cell(ids[0], int(rng.integers(0, 16)), bx, by, bs, a1)
+    paste(ids[1], square(mx, my, 100 * sc, a2))
+    if levels >= 3:
+        tx, ty = white_cell(ids[1], int(rng.integers(0, 16)), mx, my, 100 * sc, a2)
+        paste(ids[2], square(tx, ty, 11 * sc, rng.uniform(-0.5, 0.5)))
+    paste(ids[3], square(0.83 * width, 0.28 * height, 150 * sc, 0.3))
+    if noise_sigma > 0:
+        frame = np.clip(np.rint(frame.astype(np.float32) + rng.normal(0, noise_sigma, frame.shape)), 0, 255).astype(np.uint8)
+    return frame, ids
+
+
 def make_sequence(bytes_list, base_seed: int, n_frames: int, width: int = 3840, height: int = 2160,
                   noise_sigma: float = 3.0, leds=None, events=None):
     """Sparse sequence (ids 1,2,3 = vehicles, 4 = host) with slow drift so that the track gating of
