@@ -103,6 +103,7 @@ SIGNATURES = {
     "apse_sequence_finish": [_i, _vp, _vp, _i],
     "apse_sequence_csv": [_vp, _i, _i, _vp, _i64],
     "apse_debug_sparse": [_vp, _vp, _vp, _i, C.POINTER(C.c_int), _vp],
+    "apse_debug_decode": [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],
     "apse_draw_overlay": [_vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "apse_launch_count": [_vp],
     "apse_kernel_count": [],

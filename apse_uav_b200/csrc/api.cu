@@ -451,6 +451,15 @@ int apse_debug_classic(apse_ctx *ctx, const uint8_t *gray, int w, int h, float *
     return APSE_OK;
 }
 
+int apse_debug_decode(apse_ctx *ctx, const uint8_t *gray, int w, int h, const float *corners, int n, uint8_t *img, uint8_t *bits, int32_t *result, void *stream)
+{
+    if (!ctx || !gray || !corners || !img || !bits || !result || n <= 0) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "debug_decode: bad argument");
+    if (!ctx->has_dict) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "debug_decode: set_dictionary first");
+    DeviceParams dp;
+    apse_fill_device_params(ctx, &dp, w, h);
+    return apse_decode_tap(ctx, gray, w, h, corners, n, dp, img, bits, result, (cudaStream_t)stream);
+}
+
 int apse_debug_sparse(apse_ctx *ctx, uint16_t *bound_table_host, uint8_t *eflag_dev, int batch, int *n_exact_host, void *stream)
 {
     if (!ctx) return APSE_ERR_INVALID_ARG;

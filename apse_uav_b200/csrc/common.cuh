@@ -220,5 +220,7 @@ int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int 
 int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, cudaStream_t st);
 int apse_contour_refine(apse_ctx *ctx, int batch, apse_detections *out, cudaStream_t st);
 int apse_corner_subpix(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, apse_detections *out, cudaStream_t st);
+int apse_decode_tap(apse_ctx *ctx, const uint8_t *gray, int w, int h, const float *corners, int n, const DeviceParams &dp, uint8_t *img_out,
+                    uint8_t *bits_out, int32_t *res_out, cudaStream_t st);
 int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const DeviceParams &dp,
                            apse_detections *out, cudaStream_t st);

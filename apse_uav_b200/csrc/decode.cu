@@ -209,7 +209,7 @@ __device__ __forceinline__ void decode_sample(const uint8_t *__restrict__ im, in
 // (2) decode_finish: ONE warp.  Otsu (sequential over the 256 bins in the dependency's order), cell majority, border check,
 //     Hamming match against the dictionary.  Returns (valid, id, rot) on every lane.
 __device__ void decode_finish(const DeviceParams &P, long long s1, long long s2, const uint8_t *__restrict__ dict, const uint8_t *img,
-                              const int *hist, uint8_t *bits, bool &valid, int &id, int &rot)
+                              const int *hist, uint8_t *bits, bool &valid, int &id, int &rot, int *thr_out = nullptr)
 {
     const int lane = threadIdx.x & 31;
     const int nb = P.marker_size + 2 * P.border_bits, cs = P.cell_size, S = nb * cs;
@@ -219,6 +219,7 @@ __device__ void decode_finish(const DeviceParams &P, long long s1, long long s2,
     double sd = sqrt(var > 0 ? var : 0);
     if (sd < P.min_otsu_stddev) {
         for (int i = lane; i < nb * nb; i += 32) bits[i] = mean > 127 ? 1 : 0;
+        if (thr_out && lane == 0) *thr_out = -1;   // flat candidate: no Otsu threshold
     } else {
         int thr = 0;
         if (lane == 0) {  // Otsu, sequential over the 256 bins in the dependency's order
@@ -239,6 +240,7 @@ __device__ void decode_finish(const DeviceParams &P, long long s1, long long s2,
             }
         }
         thr = __shfl_sync(0xffffffffu, thr, 0);
+        if (thr_out && lane == 0) *thr_out = thr;
         const int margin = P.cell_margin_px, inner = cs - 2 * margin;
         for (int cell = lane; cell < nb * nb; cell += 32) {
             int cy = cell / nb, cx = cell - cy * nb, nz = 0;
@@ -328,6 +330,57 @@ __global__ void __launch_bounds__(DECB_THREADS) k_decode_bits(const uint8_t *__r
         }
         __syncthreads();
     }
+}
+
+// test tap (a6.A6 / a6.A7 in isolation): one candidate -> canonical image, Otsu threshold, cell bits, identification
+__global__ void __launch_bounds__(DECB_THREADS) k_decode_tap(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ corners, int n,
+                                                             DeviceParams P, const uint8_t *__restrict__ dict, uint8_t *__restrict__ img_out,
+                                                             uint8_t *__restrict__ bits_out, int32_t *__restrict__ res_out)
+{
+    __shared__ uint8_t s_img[DEC_MAX_S * DEC_MAX_S];
+    __shared__ int s_hist[256];
+    __shared__ uint8_t s_bits[16 * 16];
+    __shared__ double s_Mi[9];
+    __shared__ long long s_sum[2][DECB_THREADS / 32];
+    __shared__ int s_thr;
+    const int i = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (i >= n) return;
+    const int nbc = P.marker_size + 2 * P.border_bits, S = nbc * P.cell_size;
+    if (threadIdx.x == 0) {
+        double Mi[9];
+        inverse_homography(corners + 8 * i, S, Mi);
+        for (int k = 0; k < 9; k++) s_Mi[k] = Mi[k];
+        s_thr = -2;
+    }
+    for (int k = threadIdx.x; k < 256; k += DECB_THREADS) s_hist[k] = 0;
+    __syncthreads();
+    double Mi[9];
+    for (int k = 0; k < 9; k++) Mi[k] = s_Mi[k];
+    long long s1, s2;
+    decode_sample<false>(gray, w, h, Mi, P, SparseSrc{}, 0, s_img, s_hist, s1, s2);
+    for (int d = 16; d > 0; d >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, d); s2 += __shfl_xor_sync(0xffffffffu, s2, d); }
+    if (lane == 0) { s_sum[0][wid] = s1; s_sum[1][wid] = s2; }
+    __syncthreads();
+    if (wid == 0) {
+        s1 = 0; s2 = 0;
+        for (int k = 0; k < DECB_THREADS / 32; k++) { s1 += s_sum[0][k]; s2 += s_sum[1][k]; }
+        bool v; int id, rot;
+        decode_finish(P, s1, s2, dict, s_img, s_hist, s_bits, v, id, rot, &s_thr);
+        __syncwarp();
+        if (lane == 0) { res_out[4 * i] = v ? 1 : 0; res_out[4 * i + 1] = id; res_out[4 * i + 2] = rot; res_out[4 * i + 3] = s_thr; }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < S * S; k += DECB_THREADS) img_out[(size_t)i * DEC_MAX_S * DEC_MAX_S + k] = s_img[k];
+    for (int k = threadIdx.x; k < nbc * nbc; k += DECB_THREADS) bits_out[(size_t)i * 256 + k] = s_bits[k];
+}
+
+int apse_decode_tap(apse_ctx *ctx, const uint8_t *gray, int w, int h, const float *corners, int n, const DeviceParams &dp, uint8_t *img_out,
+                    uint8_t *bits_out, int32_t *res_out, cudaStream_t st)
+{
+    int nb = dp.marker_size + 2 * dp.border_bits;
+    if (nb * dp.cell_size > DEC_MAX_S || nb > 16 || dp.nbytes > 8) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "decode tap: canonical marker image too large");
+    KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_tap<<<n, DECB_THREADS, 0, st>>>(gray, w, h, corners, n, dp, ctx->dict, img_out, bits_out, res_out));
+    return APSE_OK;
 }
 
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,

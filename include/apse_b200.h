@@ -273,6 +273,13 @@ typedef struct apse_overlay_prim {
 } apse_overlay_prim;
 int apse_draw_overlay(apse_ctx *ctx, uint8_t *bgr, int w, int h, int batch, const apse_overlay_prim *prims, int n_prims, void *stream);
 
+/* test tap of the identification stage in isolation (_extractBits + Dictionary::identify of ONE gray frame): for each of the n
+ * candidate quads (corners [n][4][2] float32) the canonical image (img [n][64*64], the first S*S bytes, S = (markerSize + 2
+ * border) * perspectiveRemovePixelPerCell), the cell bits (bits [n][256], first (markerSize + 2 border)^2) and result [n][4] =
+ * {valid, id, rotation, Otsu threshold (-1: flat candidate, decided by its mean)}.  All pointers DEVICE. */
+int apse_debug_decode(apse_ctx *ctx, const uint8_t *gray, int w, int h, const float *corners, int n, uint8_t *img, uint8_t *bits,
+                      int32_t *result, void *stream);
+
 /* test tap of the sparse evaluation: the bound table (HOST, 16*32*32 entries min | (255 - max) << 8, cell = (c0 >> 4, c1 >> 3,
  * c2 >> 3)), the tile flags of the last apse_preprocess_tiles_sparse batch (DEVICE, [batch][h/4][w/4], 1 = evaluated exactly)
  * and their count; every pointer nullable */

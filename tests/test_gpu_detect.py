@@ -206,3 +206,57 @@ def test_nested_markers(oracle, dictionary, ref_params, mode):
         assert n == len(oi) and np.array_equal(res["ids"][f, :n], oi) and np.array_equal(res["corners"][f, :n], oc)
         assert int(res["n_rejected"][f]) == len(orj)
     e.close()
+
+
+def test_identification_stage_in_isolation(oracle, camera, lut, dictionary, ref_params, frames4k):
+    """a6.A6 (_extractBits) and a6.A7 (Dictionary::identify) on their own (apse_debug_decode): for every raw quad of the dense 4K
+    frame and for random / degenerate quads, the 48 x 48 canonical image (nearest-neighbour warp), the Otsu threshold, the 36 cell
+    bits and (valid, id, rotation) equal the CPU restatement -- a decode error that cancels end to end would show up here."""
+    import ctypes as C
+    import torch
+    from apse_uav_b200.engine import Engine
+    K, D = camera
+    e = Engine(0, 3840, 2160, 1)
+    bl = np.ascontiguousarray(dictionary.bytesList, np.uint8)
+    e.set_dictionary(bl.reshape(bl.shape[0], -1), dictionary.markerSize, dictionary.maxCorrectionBits)
+    e.set_params(ref_params)
+    e.set_camera(K, D, 3840, 2160)
+    e.set_lut(lut)
+    _, g = e.preprocess(torch.from_numpy(frames4k["dense"][None]).cuda())
+    gray = g[0].cpu().numpy()
+    quads = oracle.at_quads(gray, ref_params)
+    rng = np.random.default_rng(9)
+    extra = []
+    for _ in range(40):   # random convex-ish quads anywhere, partly outside the frame, some tiny
+        c = rng.uniform([-40, -40], [3880, 2200]); s = rng.uniform(3, 200); a = rng.uniform(0, 6.28)
+        base = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]]) * s / 2 + rng.uniform(-0.2 * s, 0.2 * s, (4, 2))
+        extra.append(base @ np.array([[np.cos(a), np.sin(a)], [-np.sin(a), np.cos(a)]]) + c)
+    quads = np.concatenate([quads, np.float32(extra)]).astype(np.float32)
+    n = len(quads)
+    assert n >= 150
+    dq = torch.from_numpy(quads.reshape(n, 8).copy()).cuda()
+    img = torch.zeros((n, 64 * 64), dtype=torch.uint8, device="cuda")
+    bits = torch.zeros((n, 256), dtype=torch.uint8, device="cuda")
+    res = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    e._check(e.lib.apse_debug_decode(e.h, g.data_ptr(), 3840, 2160, dq.data_ptr(), n, img.data_ptr(), bits.data_ptr(), res.data_ptr(), e._stream()))
+    img, bits, res = img.cpu().numpy(), bits.cpu().numpy(), res.cpu().numpy()
+    dp = oracle.DecParams.from_cv(ref_params)
+    nb, S = 6, 48
+    n_valid = n_otsu = 0
+    for i in range(n):
+        assert np.array_equal(img[i, :S * S].reshape(S, S), oracle.warp_nearest(gray, quads[i], S)), i
+        obits, othr = oracle.extract_bits(gray, quads[i], dp)
+        assert int(res[i, 3]) == othr, (i, res[i, 3], othr)
+        assert np.array_equal(bits[i, :nb * nb].reshape(nb, nb), obits), i
+        n_otsu += othr >= 0
+        # identification = the end-to-end oracle on this single candidate
+        oc, oi, _ = oracle.identify_candidates(gray, quads[i:i + 1], oracle.DecParams.from_cv(ref_params, ), dictionary.raw)
+        border_ok = bool(np.all((quads[i] >= 3) & (quads[i] < [3840 - 3, 2160 - 3])))   # minDistanceToBorder is applied later, not by the tap
+        if border_ok:
+            assert bool(res[i, 0]) == (len(oi) == 1), i
+            if len(oi) == 1:
+                assert int(res[i, 1]) == int(oi[0])
+                assert np.array_equal(np.roll(quads[i], int(res[i, 2]), axis=0), oc[0])
+                n_valid += 1
+    assert n_valid >= 100 and n_otsu >= 150
+    e.close()
