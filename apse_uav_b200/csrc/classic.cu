@@ -23,57 +23,92 @@
 #include <float.h>
 
 // ---------------------------------------------------------------------------------------------------------
-// C1: adaptive threshold.  Tile 64 x 32 outputs, 256 threads; halo r = win / 2 (win <= 65).
+// C1: adaptive threshold, ALL windows of the sweep from one staged tile.  Tile 64 x 32 outputs, 256 threads; the gray tile
+// with the halo of the LARGEST window is staged once (replicated border) as row prefix sums in dynamic shared memory (warp
+// per row, shuffle scan); every window then takes its horizontal box sums as prefix differences and slides them down the
+// columns.  Prefix sums are kept modulo 2^16: a difference is exact while win * 255 < 2^16, i.e. for every window up to 255.
 #define AT_TW 64
 #define AT_TH 32
-#define AT_RMAX 32
-#define AT_SW (AT_TW + 2 * AT_RMAX)   // 128
-#define AT_SH (AT_TH + 2 * AT_RMAX)   // 96
+#define AT_MAX_WINDOWS 16
+#define AT_MAX_WIN 255
+struct AtWindows { int n; int win[AT_MAX_WINDOWS]; };
 
-__global__ void __launch_bounds__(256) k_adaptive_threshold(const uint8_t *__restrict__ gray, int w, int h, int win, int idelta,
-                                                            uint8_t *__restrict__ out)
+static inline size_t at_smem_bytes(int rmax) { return (size_t)(AT_TH + 2 * rmax) * (size_t)(AT_TW + 2 * rmax + 2) * sizeof(uint16_t); }
+
+__global__ void __launch_bounds__(256) k_adaptive_threshold(const uint8_t *__restrict__ gray, int w, int h, AtWindows W, int rmax, int idelta,
+                                                            uint8_t *__restrict__ out, size_t window_stride)
 {
-    __shared__ uint16_t P[AT_SH][AT_SW + 2];   // inclusive row prefix sums of the staged tile (<= 128 * 255 fits 16 bits)
-    const int r = win >> 1, sw = AT_TW + 2 * r, sh = AT_TH + 2 * r;
+    extern __shared__ uint16_t at_P[];   // [sh][pitch] inclusive row prefix sums (mod 2^16), column 0 = 0
+    const int sw = AT_TW + 2 * rmax, sh = AT_TH + 2 * rmax, pitch = sw + 2;
     const int f = blockIdx.z, x0 = blockIdx.x * AT_TW, y0 = blockIdx.y * AT_TH;
     const uint8_t *g = gray + (size_t)f * w * h;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // stage rows (replicated border) and turn each into prefix sums: one warp per row, 4 columns per lane
+    // stage rows and turn each into prefix sums: one warp per row, chunks of 128 columns (4 per lane) with a running carry
     for (int ry = warp; ry < sh; ry += 8) {
-        const int gy = min(max(y0 - r + ry, 0), h - 1);
+        const int gy = min(max(y0 - rmax + ry, 0), h - 1);
         const uint8_t *row = g + (size_t)gy * w;
-        int v[4], s = 0;
+        uint16_t *P = at_P + (size_t)ry * pitch;
+        int carry = 0;
+        for (int c0 = 0; c0 < sw; c0 += 128) {
+            int v[4], s = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int cx = lane * 4 + k;
-            int gx = min(max(x0 - r + cx, 0), w - 1);
-            v[k] = cx < sw ? (int)__ldg(row + gx) : 0;
-            s += v[k];
+            for (int k = 0; k < 4; k++) {
+                const int cx = c0 + lane * 4 + k;
+                const int gx = min(max(x0 - rmax + cx, 0), w - 1);
+                v[k] = cx < sw ? (int)__ldg(row + gx) : 0;
+                s += v[k];
+            }
+            int inc = s;
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            int run = carry + inc - s;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { run += v[k]; const int cx = c0 + lane * 4 + k; if (cx < sw) P[cx + 1] = (uint16_t)run; }
+            carry += __shfl_sync(0xffffffffu, inc, 31);
         }
-        int inc = s;
-        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-        int run = inc - s;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { run += v[k]; P[ry][lane * 4 + k + 1] = (uint16_t)run; }
-        if (lane == 0) P[ry][0] = 0;
+        if (lane == 0) P[0] = 0;
     }
     __syncthreads();
-    // column sums of the horizontal box sums: thread = (column, group of 8 output rows), sliding along y
+    // per window: column sums of the horizontal box sums: thread = (column, group of 8 output rows), sliding along y
     const int cx = tid & 63, yg = tid >> 6;
     const int x = x0 + cx;
-    const int area = win * win;
-    int s = 0;
-    for (int k = 0; k < win; k++) s += (int)P[yg * 8 + k][cx + win] - (int)P[yg * 8 + k][cx];
+    for (int wi = 0; wi < W.n; wi++) {
+        const int win = W.win[wi], r = win >> 1, off = rmax - r;   // this window's box starts `off` inside the staged halo
+        const int area = win * win;
+        const uint16_t *Q = at_P + (size_t)off * pitch + off + cx;  // row 0 / left edge of the box of output (cx, 0)
+        auto hbox = [&](int row) { return (int)(uint16_t)(Q[(size_t)row * pitch + win] - Q[(size_t)row * pitch]); };
+        int s = 0;
+        for (int k = 0; k < win; k++) s += hbox(yg * 8 + k);
+        uint8_t *o = out + (size_t)wi * window_stride + (size_t)f * w * h;
 #pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-        const int oy = yg * 8 + j, y = y0 + oy;
-        if (j > 0) s += ((int)P[oy + win - 1][cx + win] - (int)P[oy + win - 1][cx]) - ((int)P[oy - 1][cx + win] - (int)P[oy - 1][cx]);
-        if (x < w && y < h) {
-            // mean = round-half-even(s / area); area is odd, so no ties exist and floor((2s + area) / (2 area)) is exact
-            int mean = (2 * s + area) / (2 * area);
-            out[(size_t)f * w * h + (size_t)y * w + x] = ((int)g[(size_t)y * w + x] - mean <= -idelta) ? 255 : 0;
+        for (int j = 0; j < 8; j++) {
+            const int oy = yg * 8 + j, y = y0 + oy;
+            if (j > 0) s += hbox(oy + win - 1) - hbox(oy - 1);
+            if (x < w && y < h) {
+                // mean = round-half-even(s / area); area is odd, so no ties exist and floor((2s + area) / (2 area)) is exact
+                const int mean = (2 * s + area) / (2 * area);
+                o[(size_t)y * w + x] = ((int)g[(size_t)y * w + x] - mean <= -idelta) ? 255 : 0;
+            }
         }
     }
+}
+
+// all windows of a sweep (ascending, odd) for a batch: out[wi] = out + wi * window_stride
+static int launch_adaptive(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, const AtWindows &W, int idelta, uint8_t *out,
+                           size_t window_stride, cudaStream_t st)
+{
+    int wmax = 0;
+    for (int i = 0; i < W.n; i++) wmax = W.win[i] > wmax ? W.win[i] : wmax;
+    if (wmax > AT_MAX_WIN) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "adaptiveThreshold: block size %d exceeds the supported %d", wmax, AT_MAX_WIN);
+    const int rmax = wmax >> 1;
+    const size_t smem = at_smem_bytes(rmax);
+    static size_t attr_bytes[64] = {0};
+    if (smem > 48 * 1024 && smem > attr_bytes[ctx->device & 63]) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_adaptive_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_bytes[ctx->device & 63] = smem;
+    }
+    dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), batch);
+    KLAUNCH(ctx, KID_ADAPTIVE, st, k_adaptive_threshold<<<grid, 256, smem, st>>>(gray, w, h, W, rmax, idelta, out, window_stride));
+    return APSE_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -694,10 +729,9 @@ int apse_ccl_binary(apse_ctx *ctx, const uint8_t *bin, int w, int h, int batch, 
 int apse_adaptive_threshold_impl(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, int win, double c, uint8_t *out, cudaStream_t st)
 {
     if (win % 2 == 0) win++;
-    if (win > 2 * AT_RMAX + 1) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "adaptiveThreshold: block size %d exceeds the supported %d", win, 2 * AT_RMAX + 1);
-    dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), batch);
-    KLAUNCH(ctx, KID_ADAPTIVE, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, (int)floor(c), out));
-    return APSE_OK;
+    AtWindows W;
+    W.n = 1; W.win[0] = win;
+    return launch_adaptive(ctx, gray, w, h, batch, W, (int)floor(c), out, 0, st);
 }
 
 int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int batch, cudaStream_t st)
@@ -717,17 +751,31 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
     const int job_cap = APSE_MAX_POINTS * 4, pts_cap = APSE_MAX_POINTS * 2, desc_cap = APSE_MAX_CLUSTERS;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
     if (!ctx->nbr_mask) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->nbr_mask, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h));
-    for (int s = 0; s < n_scales; s++) {
-        int win = p.adaptiveThreshWinSizeMin + s * p.adaptiveThreshWinSizeStep;
-        if (win % 2 == 0) win++;
-        if (win > 2 * AT_RMAX + 1) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: adaptiveThreshWinSize %d exceeds the supported %d", win, 2 * AT_RMAX + 1);
-        dim3 grid(div_up(w, AT_TW), div_up(h, AT_TH), batch);
-        KLAUNCH(ctx, KID_ADAPTIVE, st, k_adaptive_threshold<<<grid, 256, 0, st>>>(gray, w, h, win, idelta, ctx->thresh));
-        int rc = apse_ccl_binary(ctx, ctx->thresh, w, h, batch, st);
+    // all binaries of the sweep from one staged gray tile (north_star stage 2): bin_all[window][batch][h][w]
+    if (n_scales > AT_MAX_WINDOWS) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: %d threshold windows exceed the supported %d", n_scales, AT_MAX_WINDOWS);
+    const size_t win_stride = (size_t)batch * w * h;
+    if (ctx->bin_all_bytes < (size_t)n_scales * win_stride) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        cudaFree(ctx->bin_all);
+        ctx->bin_all = nullptr; ctx->bin_all_bytes = 0;
+        const size_t want = (size_t)n_scales * (size_t)ctx->max_batch * ctx->max_w * ctx->max_h;
+        CUDA_TRY(ctx, cudaMalloc((void **)&ctx->bin_all, want));
+        ctx->bin_all_bytes = want;
+    }
+    {
+        AtWindows W;
+        W.n = n_scales;
+        for (int s = 0; s < n_scales; s++) { int win = p.adaptiveThreshWinSizeMin + s * p.adaptiveThreshWinSizeStep; W.win[s] = win % 2 == 0 ? win + 1 : win; }
+        int rc = launch_adaptive(ctx, gray, w, h, batch, W, idelta, ctx->bin_all, win_stride, st);
         if (rc) return rc;
-        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_mark_outside<<<div_up(2 * (w + h) * batch, 256), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, batch));
+    }
+    for (int s = 0; s < n_scales; s++) {
+        const uint8_t *bin = ctx->bin_all + (size_t)s * win_stride;
+        int rc = apse_ccl_binary(ctx, bin, w, h, batch, st);
+        if (rc) return rc;
+        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_mark_outside<<<div_up(2 * (w + h) * batch, 256), 256, 0, st>>>(bin, w, h, ctx->labels, batch));
         // per window: reset the job / border / point counters, keep quads and status
-        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_border_jobs<<<dim3(ctx->sm_count * 2, batch), 256, 0, st>>>(ctx->thresh, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, ctx->nbr_mask));
+        KLAUNCH(ctx, KID_BORDER_JOBS, st, k_border_jobs<<<dim3(ctx->sm_count * 2, batch), 256, 0, st>>>(bin, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, ctx->nbr_mask));
         KLAUNCH(ctx, KID_TRACE, st, k_trace_borders<<<dim3(ctx->sm_count, batch), 128, 0, st>>>(ctx->nbr_mask, w, h, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, min_px,
                                                                                 max_px, reinterpret_cast<uint32_t *>(ctx->sorted_pts), pts_cap,
                                                                                 reinterpret_cast<ContourDesc *>(ctx->clusters), desc_cap, batch));

@@ -22,7 +22,7 @@ def gray_dense(oracle, camera, lut, frames4k):
     return oracle.preprocess(frames4k["dense"], mx, my, lut)[1]
 
 
-@pytest.mark.parametrize("win,c", [(3, 7), (13, 7), (23, 7), (53, 7), (65, 7), (4, 7), (5, 3.5), (7, -2.5)])
+@pytest.mark.parametrize("win,c", [(3, 7), (13, 7), (23, 7), (53, 7), (65, 7), (129, 7), (255, 7), (4, 7), (5, 3.5), (7, -2.5)])
 def test_adaptive_threshold_4k_bit_exact(eng, oracle, gray_dense, win, c):
     out = eng.adaptive_threshold(gray_dense, win, c).cpu().numpy()
     assert np.array_equal(out, oracle.adaptive_threshold(gray_dense, win, c))

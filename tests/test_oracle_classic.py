@@ -14,7 +14,7 @@ def gray_dense(frames4k):
 
 
 @needs_cv2
-@pytest.mark.parametrize("win,c", [(3, 7), (13, 7), (23, 7), (43, 7), (53, 7), (4, 7), (5, 3.5), (7, -2.5), (23, 0)])
+@pytest.mark.parametrize("win,c", [(3, 7), (13, 7), (23, 7), (43, 7), (53, 7), (129, 7), (255, 7), (4, 7), (5, 3.5), (7, -2.5), (23, 0)])
 def test_adaptive_threshold_vs_cv2(oracle, gray_dense, win, c):
     import cv2
     g = gray_dense[:1080, :1920]
