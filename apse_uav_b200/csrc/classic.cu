@@ -186,6 +186,9 @@ __global__ void __launch_bounds__(256) k_border_jobs(const uint8_t *__restrict__
 __device__ __constant__ int8_t c_dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 __device__ __constant__ int8_t c_dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
 __device__ __forceinline__ unsigned rotr8(unsigned m, int r) { return ((m >> r) | (m << (8 - r))) & 0xffu; }
+// c_dx / c_dy without the dependent constant-memory load: (d + 1) packed two bits per direction
+__device__ __forceinline__ int dir_dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }   // {1, 1, 0, -1, -1, -1, 0, 1} + 1 = {2, 2, 1, 0, 0, 0, 1, 2}
+__device__ __forceinline__ int dir_dy(int s) { return (int)((0xA901u >> (2 * s)) & 3u) - 1; }   // {0, -1, -1, -1, 0, 1, 1, 1} + 1 = {1, 0, 0, 0, 1, 2, 2, 2}
 
 template <bool STORE>
 __device__ int trace_border(const uint8_t *__restrict__ M, int w, int x0, int y0, bool hole, int max_n, uint32_t *out)
@@ -198,13 +201,13 @@ __device__ int trace_border(const uint8_t *__restrict__ M, int w, int x0, int y0
     }
     // first neighbour clockwise from s0 - 1: candidate k <-> direction (s0 - 1 - k) & 7
     int s = (s0 - 1 - (__ffs(rotr8(__brev(m) >> 24, (8 - s0) & 7)) - 1)) & 7;
-    const int x1 = x0 + c_dx[s], y1 = y0 + c_dy[s];
+    const int x1 = x0 + dir_dx(s), y1 = y0 + dir_dy(s);
     int cx = x0, cy = y0, n = 0;
     for (;;) {
         // next neighbour counter-clockwise from s + 1: candidate k <-> direction (s + 1 + k) & 7
         const int base = (s + 1) & 7;
         s = (base + __ffs(rotr8(m, base)) - 1) & 7;
-        const int nx = cx + c_dx[s], ny = cy + c_dy[s];
+        const int nx = cx + dir_dx(s), ny = cy + dir_dy(s);
         if (STORE) out[n] = (uint32_t)cx | ((uint32_t)cy << 16);
         n++;
         if (nx == x0 && ny == y0 && cx == x1 && cy == y1) break;
@@ -218,32 +221,154 @@ __device__ int trace_border(const uint8_t *__restrict__ M, int w, int x0, int y0
 
 struct ContourDesc { uint32_t offset, count, trigger, hole; };   // same footprint as ClusterDesc (scratch is shared)
 
+// Borders are followed in two kernels.  k_trace_borders: one thread per border, for the ~10^5 short borders of a noisy frame; a
+// border that is still open after TRACE_SHORT steps is handed to k_trace_long: one WARP per border, lane 0 follows it while all
+// lanes keep the mask bytes around the current position in L1 (prefetch of the 32 rows x 2 lines around it every TRACE_PF
+// steps).  A step is one dependent load; from L2 that is ~340 cycles, and the longest border of a frame (up to the perimeter
+// limit, 15 360 steps at 4K) used to set the duration of the whole stage.
+#define TRACE_SHORT 256
+#define TRACE_PF 12
+#define TRACE_LONG_CAP (1 << 16)
+#define TW_W 64                       // shared-memory window of k_trace_long
+#define TW_H 32
+
+__device__ __forceinline__ void store_border(const uint8_t *I, int w, uint32_t e, int n, int32_t *cnt, uint32_t *P, int pts_cap, ContourDesc *D,
+                                             int desc_cap, int max_px)
+{
+    const bool hole = (e >> 31) != 0;
+    const uint32_t trig = e & 0x7fffffffu;
+    const int ty = trig / w, tx = trig - ty * w;
+    const int x0 = hole ? tx - 1 : tx, y0 = ty;
+    const int di = atomicAdd(&cnt[1], 1);
+    const int off = atomicAdd(&cnt[5], n);
+    if (di >= desc_cap || off + n > pts_cap) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); return; }
+    trace_border<true>(I, w, x0, y0, hole, max_px, P + off);
+    D[di] = ContourDesc{(uint32_t)off, (uint32_t)n, trig, hole ? 1u : 0u};
+}
+
 __global__ void __launch_bounds__(128) k_trace_borders(const uint8_t *__restrict__ bin, int w, int h, const uint32_t *__restrict__ jobs,
                                                        int job_cap, int32_t *__restrict__ counters, int min_px, int max_px,
                                                        uint32_t *__restrict__ pts, int pts_cap, ContourDesc *__restrict__ descs,
-                                                       int desc_cap, int batch)
+                                                       int desc_cap, int batch, uint32_t *__restrict__ long_jobs)
 {
     const int f = blockIdx.y;
-    const int32_t *cnt_r = counters + f * APSE_COUNTERS;
     int32_t *cnt = counters + f * APSE_COUNTERS;
-    const int njobs = min(cnt_r[0], job_cap);
+    const int njobs = min(cnt[0], job_cap);
     const uint8_t *I = bin + (size_t)f * w * h;   // neighbour masks
     const uint32_t *J = jobs + (size_t)f * job_cap;
     uint32_t *P = pts + (size_t)f * pts_cap;
     ContourDesc *D = descs + (size_t)f * desc_cap;
+    const int short_max = (w % 16 == 0 && w >= TW_W && h >= TW_H) ? min(max_px, TRACE_SHORT) : max_px;   // else: every border in this kernel
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < njobs; j += gridDim.x * blockDim.x) {
         uint32_t e = J[j];
         bool hole = (e >> 31) != 0;
         uint32_t trig = e & 0x7fffffffu;
         int ty = trig / w, tx = trig - ty * w;
         int x0 = hole ? tx - 1 : tx, y0 = ty;
-        int n = trace_border<false>(I, w, x0, y0, hole, max_px, nullptr);
+        int n = trace_border<false>(I, w, x0, y0, hole, short_max, nullptr);
+        if (n > short_max) {
+            if (short_max < max_px) {   // still open: a long border
+                const int k = atomicAdd(&cnt[6], 1);
+                if (k < TRACE_LONG_CAP) long_jobs[(size_t)f * TRACE_LONG_CAP + k] = e;
+                else atomicExch(&cnt[3], APSE_ERR_CAPACITY);
+            }
+            continue;
+        }
+        if (n < min_px) continue;
+        store_border(I, w, e, n, cnt, P, pts_cap, D, desc_cap, max_px);
+    }
+}
+
+// lane 0 follows the border ONCE, writing the points to this warp's temporary strip.  The neighbour masks around the current
+// position live in a per-warp shared-memory window (TW_W x TW_H bytes, loaded by the whole warp with 16-byte loads and re-centred
+// whenever the walker leaves it), and the next direction comes from a 2 KB table indexed by (mask, incoming direction): a step is
+// two shared-memory look-ups and a handful of integer instructions instead of a dependent global load.  Needs w % 16 == 0.
+// Returns the length (> max_n: over the perimeter limit).
+__device__ int trace_border_warp(const uint8_t *__restrict__ M, int w, int h, int x0, int y0, bool hole, int max_n, uint32_t *tmp,
+                                 uint8_t *win /* [TW_H][TW_W] */, const uint8_t *next_dir /* [256][8] */)
+{
+    const int lane = threadIdx.x & 31;
+    const int s0 = hole ? 0 : 4;
+    unsigned m = M[(size_t)y0 * w + x0];
+    int s = (s0 - 1 - (__ffs(rotr8(__brev(m) >> 24, (8 - s0) & 7)) - 1)) & 7;
+    const int x1 = x0 + dir_dx(s), y1 = y0 + dir_dy(s);
+    int cx = x0, cy = y0, n = 0;
+    bool done = false;
+    while (!done) {
+        // re-centre the window on (cx, cy): lane = window row, four 16-byte loads per lane
+        const int wx0 = min(max((cx - TW_W / 2) & ~15, 0), w - TW_W), wy0 = min(max(cy - TW_H / 2, 0), h - TW_H);
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(M + (size_t)(wy0 + lane) * w + wx0);
+            uint4 *dst = reinterpret_cast<uint4 *>(win + lane * TW_W);
+#pragma unroll
+            for (int k = 0; k < TW_W / 16; k++) dst[k] = __ldg(src + k);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int lx = cx - wx0, ly = cy - wy0;
+            for (;;) {
+                s = next_dir[m * 8 + s];                                   // next neighbour counter-clockwise from s + 1
+                const int dx = dir_dx(s), dy = dir_dy(s);
+                const int nx = cx + dx, ny = cy + dy;
+                tmp[n] = (uint32_t)cx | ((uint32_t)cy << 16);
+                n++;
+                if (nx == x0 && ny == y0 && cx == x1 && cy == y1) { done = true; break; }
+                if (n > max_n) { done = true; break; }
+                cx = nx; cy = ny; lx += dx; ly += dy;
+                s = (s + 4) & 7;
+                if ((unsigned)lx >= (unsigned)TW_W || (unsigned)ly >= (unsigned)TW_H) { m = 0x100u; break; }   // left the window
+                m = win[ly * TW_W + lx];
+            }
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        cx = __shfl_sync(0xffffffffu, cx, 0);
+        cy = __shfl_sync(0xffffffffu, cy, 0);
+        if (!done && lane == 0) m = M[(size_t)cy * w + cx];   // (the mask of the pixel the walker stands on, from the new window's centre)
+        __syncwarp();
+    }
+    return __shfl_sync(0xffffffffu, n, 0);
+}
+
+__global__ void __launch_bounds__(128) k_trace_long(const uint8_t *__restrict__ bin, int w, int h, const uint32_t *__restrict__ long_jobs,
+                                                    int32_t *__restrict__ counters, int min_px, int max_px, uint32_t *__restrict__ pts, int pts_cap,
+                                                    ContourDesc *__restrict__ descs, int desc_cap, uint32_t *__restrict__ strips)
+{
+    __shared__ __align__(16) uint8_t s_win[4][TW_H * TW_W];
+    __shared__ uint8_t s_next[256 * 8];
+    // next direction for (neighbour mask m, incoming direction s): first neighbour counter-clockwise from s + 1
+    for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+        const unsigned m = (unsigned)i >> 3;
+        const int base = ((i & 7) + 1) & 7;
+        s_next[i] = m ? (uint8_t)((base + __ffs(rotr8(m, base)) - 1) & 7) : 0;
+    }
+    __syncthreads();
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    int32_t *cnt = counters + f * APSE_COUNTERS;
+    const int njobs = min(cnt[6], TRACE_LONG_CAP);
+    const uint8_t *I = bin + (size_t)f * w * h;
+    uint32_t *P = pts + (size_t)f * pts_cap;
+    ContourDesc *D = descs + (size_t)f * desc_cap;
+    const int warps = blockDim.x >> 5;
+    uint32_t *tmp = strips + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * warps + (threadIdx.x >> 5)) * (size_t)(max_px + 2);
+    for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < njobs; j += gridDim.x * warps) {
+        const uint32_t e = long_jobs[(size_t)f * TRACE_LONG_CAP + j];
+        const bool hole = (e >> 31) != 0;
+        const uint32_t trig = e & 0x7fffffffu;
+        const int ty = trig / w, tx = trig - ty * w;
+        const int x0 = hole ? tx - 1 : tx, y0 = ty;
+        const int n = trace_border_warp(I, w, h, x0, y0, hole, max_px, tmp, s_win[threadIdx.x >> 5], s_next);
+#ifdef TRACE_DEBUG
+        if (lane == 0 && (n > 3000)) printf("long border f=%d j=%d x0=%d y0=%d hole=%d n=%d njobs=%d\n", f, j, x0, y0, (int)hole, n, njobs);
+#endif
         if (n < min_px || n > max_px) continue;
-        int di = atomicAdd(&cnt[1], 1);
-        int off = atomicAdd(&cnt[5], n);
-        if (di >= desc_cap || off + n > pts_cap) { atomicExch(&cnt[3], APSE_ERR_CAPACITY); continue; }
-        trace_border<true>(I, w, x0, y0, hole, max_px, P + off);
-        D[di] = ContourDesc{(uint32_t)off, (uint32_t)n, trig, hole ? 1u : 0u};
+        int di = 0, off = 0;
+        if (lane == 0) { di = atomicAdd(&cnt[1], 1); off = atomicAdd(&cnt[5], n); }
+        di = __shfl_sync(0xffffffffu, di, 0); off = __shfl_sync(0xffffffffu, off, 0);
+        if (di >= desc_cap || off + n > pts_cap) { if (lane == 0) atomicExch(&cnt[3], APSE_ERR_CAPACITY); continue; }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) P[off + i] = tmp[i];   // (lane 0's stores are visible to the warp after the barrier)
+        if (lane == 0) D[di] = ContourDesc{(uint32_t)off, (uint32_t)n, trig, hole ? 1u : 0u};
+        __syncwarp();
     }
 }
 
@@ -751,6 +876,18 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
     const int job_cap = APSE_MAX_POINTS * 4, pts_cap = APSE_MAX_POINTS * 2, desc_cap = APSE_MAX_CLUSTERS;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters, 0, (size_t)batch * APSE_COUNTERS * sizeof(int32_t), st));
     if (!ctx->nbr_mask) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->nbr_mask, (size_t)ctx->max_batch * ctx->max_w * ctx->max_h));
+    if (!ctx->long_jobs) CUDA_TRY(ctx, cudaMalloc((void **)&ctx->long_jobs, (size_t)ctx->max_batch * TRACE_LONG_CAP * sizeof(uint32_t)));
+    if (max_px > (1 << 18)) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: maxMarkerPerimeterRate allows borders of %d points, more than the supported %d", max_px, 1 << 18);
+    {   // one temporary strip of max_px + 2 points per resident warp of k_trace_long
+        const size_t want = (size_t)ctx->max_batch * ctx->sm_count * 4 * (size_t)(max_px + 2) * sizeof(uint32_t);
+        if (ctx->trace_strips_bytes < want) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            cudaFree(ctx->trace_strips);
+            ctx->trace_strips = nullptr; ctx->trace_strips_bytes = 0;
+            CUDA_TRY(ctx, cudaMalloc((void **)&ctx->trace_strips, want));
+            ctx->trace_strips_bytes = want;
+        }
+    }
     // all binaries of the sweep from one staged gray tile (north_star stage 2): bin_all[window][batch][h][w]
     if (n_scales > AT_MAX_WINDOWS) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "detect: %d threshold windows exceed the supported %d", n_scales, AT_MAX_WINDOWS);
     const size_t win_stride = (size_t)batch * w * h;
@@ -778,7 +915,10 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
         KLAUNCH(ctx, KID_BORDER_JOBS, st, k_border_jobs<<<dim3(ctx->sm_count * 2, batch), 256, 0, st>>>(bin, w, h, ctx->labels, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, ctx->nbr_mask));
         KLAUNCH(ctx, KID_TRACE, st, k_trace_borders<<<dim3(ctx->sm_count, batch), 128, 0, st>>>(ctx->nbr_mask, w, h, reinterpret_cast<uint32_t *>(ctx->points), job_cap, ctx->counters, min_px,
                                                                                 max_px, reinterpret_cast<uint32_t *>(ctx->sorted_pts), pts_cap,
-                                                                                reinterpret_cast<ContourDesc *>(ctx->clusters), desc_cap, batch));
+                                                                                reinterpret_cast<ContourDesc *>(ctx->clusters), desc_cap, batch, ctx->long_jobs));
+        KLAUNCH(ctx, KID_TRACE, st, k_trace_long<<<dim3(ctx->sm_count, batch), 128, 0, st>>>(ctx->nbr_mask, w, h, ctx->long_jobs, ctx->counters, min_px, max_px,
+                                                                             reinterpret_cast<uint32_t *>(ctx->sorted_pts), pts_cap,
+                                                                             reinterpret_cast<ContourDesc *>(ctx->clusters), desc_cap, ctx->trace_strips));
         ClassicArgs A;
         A.pts = reinterpret_cast<uint32_t *>(ctx->sorted_pts); A.pts_cap = pts_cap;
         A.descs = reinterpret_cast<ContourDesc *>(ctx->clusters); A.desc_cap = desc_cap;
@@ -793,7 +933,7 @@ int apse_classic_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int bat
         KLAUNCH(ctx, KID_APPROX, st, k_approx_quads<<<dim3(ctx->sm_count, batch), AQ_WARPS * 32, 0, st>>>(A));
         // counters [0] (jobs), [1] (borders), [5] (points) restart for the next window
         CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters, APSE_COUNTERS * sizeof(int32_t), 0, 2 * sizeof(int32_t), batch, st));
-        CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters + 5, APSE_COUNTERS * sizeof(int32_t), 0, sizeof(int32_t), batch, st));
+        CUDA_TRY(ctx, cudaMemset2DAsync(ctx->counters + 5, APSE_COUNTERS * sizeof(int32_t), 0, 2 * sizeof(int32_t), batch, st));   // [5] points, [6] long borders
     }
     KLAUNCH(ctx, KID_APPROX, st, k_rank_quads<<<dim3(8, batch), 256, 0, st>>>(ctx->sort_keys, ctx->counters, APSE_MAX_QUADS, ctx->quad_order));
     return APSE_OK;

@@ -140,6 +140,9 @@ struct apse_ctx {
     bool sparse_active = false;       // the detect call in flight reads gray through sparse_src
     SparseSrc sparse_src;
     // image of the quad detector when aprilTagQuadDecimate / aprilTagQuadSigma are set (quadim.cu), allocated on first use
+    uint32_t *trace_strips = nullptr; // classic path: per-warp temporary point strips of k_trace_long
+    size_t trace_strips_bytes = 0;
+    uint32_t *long_jobs = nullptr;    // classic path: borders handed to the warp-per-border kernel [max_batch][2^16]
     uint8_t *bin_all = nullptr;       // classic path: the binaries of all threshold windows [window][batch][h][w] (first use)
     size_t bin_all_bytes = 0;
     float *quads_refined = nullptr;   // [max_batch][APSE_MAX_QUADS][8] CORNER_REFINE_CONTOUR corners of the candidates (first use)

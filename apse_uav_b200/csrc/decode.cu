@@ -12,7 +12,7 @@
 #include <math.h>
 #include <float.h>
 
-#define DEC_THREADS 256
+#define DEC_THREADS 1024
 #define DEC_WARPS (DEC_THREADS / 32)
 #define DEC_MAX_S 64                      // canonical image side limit ((markerSize + 2*border) * cellSize)
 #define DEC_SMEMC 512                     // candidates per frame handled entirely in shared memory
@@ -686,7 +686,7 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
     int skip = skip_env ? 1 : 0;
     // hierarchy scratch of the quad fit is free at this point: [batch][APSE_MAX_QUADS] decode results
     int32_t *dec_raw = reinterpret_cast<int32_t *>(ctx->errs);
-    const int cand_blocks = ctx->params.cornerRefinementMethod == 3 ? 64 : 128;   // CTAs per frame; a CTA without a candidate exits at once
+    const int cand_blocks = ctx->params.cornerRefinementMethod == 3 ? 64 : 512;   // CTAs per frame; a CTA without a candidate exits at once
     if (ctx->sparse_active)
         KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<true><<<dim3(cand_blocks, batch), DECB_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, ctx->sparse_src));
     else

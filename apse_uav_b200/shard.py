@@ -86,25 +86,43 @@ def final_scan(records, project, start_frame=1, led_mean_for_frame=None, led_sum
 
 def gather_detections(det, n_local, rank=0, world=1, group=None):
     """Per-frame results of every rank's block on rank 0, in frame order, as one dict of tensors (device tensors over
-    NCCL, CPU tensors over gloo).  This is the only data-path exchange of a frame-sharded run: ~5 KB per frame."""
+    NCCL, CPU tensors over gloo).  This is the only data-path exchange of a frame-sharded run: two collectives -- the block
+    sizes and the number of marker slots in use, then ONE packed byte buffer per rank holding only those slots
+    (8 + 84 bytes per frame and used slot instead of 5.4 KB per frame)."""
     keys = ("n", "ids", "corners", "rvec", "tvec", "status")
     if world == 1:
         return {k: det[k] for k in keys}, [n_local]
     import torch
     import torch.distributed as dist
-    sizes = [None] * world
-    dist.all_gather_object(sizes, int(n_local), group=group)
-    cap = max(max(sizes), 1)
+    dev = det["n"].device
+    M = int(det["ids"].shape[1])
+    hdr = torch.zeros(2, dtype=torch.int64, device=dev)
+    hdr[0] = n_local
+    if n_local:
+        hdr[1] = det["n"][:n_local].max()
+    all_hdr = torch.empty((world, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_hdr, hdr, group=group) if dev.type == "cuda" else dist.all_gather(list(all_hdr.unbind(0)), hdr, group=group)
+    all_hdr = all_hdr.cpu()
+    sizes = [int(v) for v in all_hdr[:, 0]]
+    cap, m = max(max(sizes), 1), max(1, min(M, int(all_hdr[:, 1].max())))
+    # packed layout of one rank: n [cap] i32 | status [cap] i32 | ids [cap, m] i32 | corners [cap, m, 8] f32 | rvec [cap, m, 3] f64 | tvec
+    fields = (("n", torch.int32, ()), ("status", torch.int32, ()), ("ids", torch.int32, (m,)), ("corners", torch.float32, (m, 4, 2)),
+              ("rvec", torch.float64, (m, 3)), ("tvec", torch.float64, (m, 3)))
+    sizes_b = [cap * int(np.prod(shape, dtype=np.int64)) * torch.empty((), dtype=dt).element_size() for _, dt, shape in fields]
+    offs = np.concatenate([[0], np.cumsum([(b + 15) // 16 * 16 for b in sizes_b])]).astype(np.int64)   # 16-byte aligned fields
+    buf = torch.zeros(int(offs[-1]), dtype=torch.uint8, device=dev)
+    for (k, dt, shape), o, sb in zip(fields, offs, sizes_b):
+        dst = buf[int(o):int(o) + sb].view(dt).reshape((cap,) + shape)
+        src = det[k][:n_local]
+        dst[:n_local] = src[:, :m] if len(shape) else src
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, parts, dst=0, group=group)
+    if rank != 0:
+        return None, sizes
     out = {}
-    for k in keys:
-        t = det[k]
-        pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:n_local] = t[:n_local]
-        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, parts, dst=0, group=group)
-        if rank == 0:
-            out[k] = torch.cat([p_[:sz] for p_, sz in zip(parts, sizes)], 0)
-    return (out if rank == 0 else None), sizes
+    for (k, dt, shape), o, sb in zip(fields, offs, sizes_b):
+        out[k] = torch.cat([p_[int(o):int(o) + sb].view(dt).reshape((cap,) + shape)[:sz] for p_, sz in zip(parts, sizes)], 0)
+    return out, sizes
 
 
 def _exchange_led_jobs(engine, gray, frame0, rank, world, group):
