@@ -346,6 +346,7 @@ int apse_process_frames(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int ba
         if (rc == APSE_OK) {
             ctx->sparse_active = true;
             ctx->sparse_src = SparseSrc{bgr, ctx->mapx, ctx->mapy, ctx->tables2, ctx->eflag[0], w / 4, h / 4};
+            ctx->sparse_elist = ctx->elist[0]; ctx->sparse_ecount = ctx->ecount[0];
         }
     }
     if (rc == 1) rc = apse_preprocess_ex(ctx, bgr, nullptr, gray, ctx->tmm, batch, st);
@@ -407,6 +408,7 @@ int apse_detect_pose_frames(apse_ctx *ctx, const uint8_t *gray, int batch, apse_
             if (ctx->tiles_sparse[slot]) {
                 ctx->sparse_active = true;
                 ctx->sparse_src = SparseSrc{ctx->tiles_bgr[slot], ctx->mapx, ctx->mapy, ctx->tables2, ctx->eflag[slot], ctx->w / 4, ctx->h / 4};
+                ctx->sparse_elist = ctx->elist[slot]; ctx->sparse_ecount = ctx->ecount[slot];
                 ctx->tiles_sparse[slot] = false;
                 ctx->sparse_gray[slot] = nullptr;
             }

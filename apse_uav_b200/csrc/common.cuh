@@ -139,6 +139,8 @@ struct apse_ctx {
     const uint8_t *sparse_gray[2] = {nullptr, nullptr};   // gray buffer a sparse batch was written into (partial: only valid with its slot)
     bool sparse_active = false;       // the detect call in flight reads gray through sparse_src
     SparseSrc sparse_src;
+    const uint32_t *sparse_elist = nullptr;   // tiles of that batch that carry exact extrema (k_threshold_scan_list)
+    const int *sparse_ecount = nullptr;
     // image of the quad detector when aprilTagQuadDecimate / aprilTagQuadSigma are set (quadim.cu), allocated on first use
     uint32_t *trace_strips = nullptr; // classic path: per-warp temporary point strips of k_trace_long
     size_t trace_strips_bytes = 0;

@@ -188,6 +188,42 @@ __global__ void __launch_bounds__(128) k_threshold_scan(int w, int h, int tw, in
     }
 }
 
+// Sparse evaluation: only the tiles of the E-list carry real extrema (every other tile is neutral and cannot be high-contrast), so
+// the threshold decision runs over that list (7 % of the tiles of a sparse frame) instead of over all tiles: one thread per
+// listed tile, 3x3 dilation of the extrema, high-contrast tiles appended to the A-list (one atomic per warp).
+__global__ void __launch_bounds__(256) k_threshold_scan_list(int tw, int th, const uint16_t *__restrict__ tmm, const uint32_t *__restrict__ elist,
+                                                             const int *__restrict__ ecount, int min_wb_diff, uint32_t *__restrict__ alist,
+                                                             uint8_t *__restrict__ alist_thr, int *__restrict__ acount, int acap,
+                                                             uint8_t *__restrict__ tile_active, int ctw, int cth)
+{
+    const int n = *ecount, lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {   // whole warps stay in the loop together
+        const int i = base + threadIdx.x;
+        bool on = false;
+        uint32_t e = 0;
+        int thr = 0;
+        if (i < n) {
+            e = __ldg(elist + i);
+            const int tx = ATILE_TX(e), ty = ATILE_TY(e), f = ATILE_F(e);
+            int mn, mx;
+            dilated_minmax(tmm + (size_t)f * tw * th, tw, th, tx, ty, mn, mx);
+            on = mx - mn >= min_wb_diff;
+            thr = mn + (mx - mn) / 2;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (m) {
+            int b0 = 0;
+            if (lane == 0) b0 = atomicAdd(acount, __popc(m));
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            if (on) {
+                const int k = b0 + __popc(m & ((1u << lane) - 1));
+                if (k < acap) { alist[k] = e; alist_thr[k] = (uint8_t)thr; }
+                tile_active[((size_t)ATILE_F(e) * cth + (ATILE_TY(e) * 4) / CCL_TH) * ctw + (ATILE_TX(e) * 4) / CCL_TW] = 1;
+            }
+        }
+    }
+}
+
 // ternary pixels of the listed tiles: one thread per tile row (a 32-bit word of gray in, a word of {0, 255} out)
 __global__ void __launch_bounds__(256) k_threshold_apply(const uint8_t *__restrict__ gray, int w, int h, int tw, int th,
                                                          const uint32_t *__restrict__ alist, const uint8_t *__restrict__ alist_thr,
@@ -1351,9 +1387,15 @@ int apse_apriltag_quads(apse_ctx *ctx, const uint8_t *gray, int w, int h, int ba
         dim3 block(32, 8), grid(div_up(tw, 32), div_up(th, 8), batch);
         if (!have_tile_minmax)
             KLAUNCH(ctx, KID_TILE_MINMAX, st, k_tile_minmax<<<grid, block, 0, st>>>(gray, w, h, tw, th, ctx->tmm));
-        dim3 tgrid(div_up(div_up(tw, THR_TPT), 128), th, batch);
-        KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_scan<<<tgrid, 128, 0, st>>>(w, h, tw, th, ctx->tmm, dp.min_white_black_diff, ex->alist[cur],
-                                                                               ex->alist_thr[cur], acount, ex->acap, ex->tile_active, ctw, cth));
+        if (have_tile_minmax && ctx->sparse_active && ctx->sparse_elist && tw * 4 == w && th * 4 == h) {
+            KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_scan_list<<<chain_grid(ctx), 256, 0, st>>>(tw, th, ctx->tmm, ctx->sparse_elist, ctx->sparse_ecount,
+                                                                                             dp.min_white_black_diff, ex->alist[cur], ex->alist_thr[cur], acount,
+                                                                                             ex->acap, ex->tile_active, ctw, cth));
+        } else {
+            dim3 tgrid(div_up(div_up(tw, THR_TPT), 128), th, batch);
+            KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_scan<<<tgrid, 128, 0, st>>>(w, h, tw, th, ctx->tmm, dp.min_white_black_diff, ex->alist[cur],
+                                                                                   ex->alist_thr[cur], acount, ex->acap, ex->tile_active, ctw, cth));
+        }
         if (tw * 4 != w || th * 4 != h) {
             KLAUNCH(ctx, KID_THRESHOLD, st, k_threshold_edges<<<dim3(64, 1, batch), 256, 0, st>>>(gray, w, h, tw, th, ctx->tmm, ctx->thresh,
                                                                                      ex->tile_active, ctw, cth, ex->alist[cur], ex->alist_thr[cur],
