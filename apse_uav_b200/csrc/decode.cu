@@ -2,7 +2,8 @@
 // aruco.detectMarkers (aruco_detect.py:267, dictionary aruco_detect.py:263); SURVEY.md rows a6.A5-a6.A7,
 // cv2 4.13 semantics.  One CTA per frame:
 //   * quads ordered deterministically, border filter, stable sort by perimeter (descending)
-//   * "too close" predicate for all pairs in parallel (bit matrix), sequential grouping walk on one thread
+//   * "too close" predicate for all pairs in parallel (centroid pre-test -> pair list -> exact test); the dependency's
+//     order-dependent grouping walk restated as "first partner per candidate" (atomicMin) + chains to a mutual first pair
 //   * every candidate decoded by one warp: FP64 homography, 48x48 nearest-neighbour gather, Otsu on a
 //     shared-memory histogram, per-cell majority, border check, Hamming match against the dictionary
 //   * nesting hierarchy + depth-ordered acceptance, corner rotation, output
@@ -16,6 +17,7 @@
 #define DEC_WARPS (DEC_THREADS / 32)
 #define DEC_MAX_S 64                      // canonical image side limit ((markerSize + 2*border) * cellSize)
 #define DEC_SMEMC 512                     // candidates per frame handled entirely in shared memory
+#define DEC_MIDC 1920                     // ... with everything but the too-close bit matrix in shared memory (classic path)
 #define DEC_MAXC APSE_MAX_QUADS           // candidates per frame (beyond DEC_SMEMC the arrays live in global scratch)
 
 // per-frame candidate arrays, carved out of shared memory (n <= DEC_SMEMC) or of a global scratch block
@@ -23,9 +25,9 @@ struct DecodeArrays {
     float (*c)[8];                        // candidate corners, sorted by perimeter (descending, stable)
     float *perim;
     uint32_t *key;                        // ordering key (cluster index) / scratch
-    uint32_t *close_bits;                 // [cap][cap / 32] too-close predicate, bit (i, j)
-    uint32_t *pairs;                      // [cap * 8] too-close pairs (i << 16 | j) in row-major order
-    float *cxy;                           // [cap][2] candidate centroids (cheap rejection in the pair matrix)
+    uint32_t *close_bits;                 // [cap][cap / 32] words of scratch (centroid-test operands, bounding boxes; once a bit matrix)
+    uint32_t *pairs;                      // [cap * 8] pairs (i << 16 | j) that pass the centroid pre-test, unordered
+    float *cxy;                           // [cap][2] scratch: perimeters before the sort, group member lists, nesting heights
     short *group_id, *next_in_group, *close_next, *parent, *depth, *sel, *sel_of, *dec_id, *use_c, *group_head, *group_tail;
     uint8_t *dec_valid, *dec_rot, *selected, *was, *valid;
     int cap;
@@ -36,14 +38,22 @@ __host__ __device__ inline size_t decode_arrays_bytes(int cap)
     return (size_t)cap * (8 * 4 + 4 + 4 + (cap / 32) * 4 + 8 * 4 + 2 * 4 + 11 * 2 + 5) + 64;
 }
 
-__device__ inline void decode_arrays_carve(DecodeArrays &A, unsigned char *base, int cap)
+// bytes of everything but the too-close bit matrix (the middle tier keeps that matrix in global memory)
+__host__ __device__ inline size_t decode_arrays_small_bytes(int cap)
+{
+    return (size_t)cap * (8 * 4 + 4 + 4 + 8 * 4 + 2 * 4 + 11 * 2 + 5) + 64;
+}
+
+// close_bits_ext != nullptr: the bit matrix lives there instead of behind `key`
+__device__ inline void decode_arrays_carve(DecodeArrays &A, unsigned char *base, int cap, uint32_t *close_bits_ext = nullptr)
 {
     A.cap = cap;
     unsigned char *p = base;
     A.c = reinterpret_cast<float(*)[8]>(p); p += (size_t)cap * 32;
     A.perim = reinterpret_cast<float *>(p); p += (size_t)cap * 4;
     A.key = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4;
-    A.close_bits = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * (cap / 32) * 4;
+    if (close_bits_ext) A.close_bits = close_bits_ext;
+    else { A.close_bits = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * (cap / 32) * 4; }
     A.pairs = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 32;
     A.cxy = reinterpret_cast<float *>(p); p += (size_t)cap * 8;
     short **sp[11] = {&A.group_id, &A.next_in_group, &A.close_next, &A.parent, &A.depth, &A.sel, &A.sel_of, &A.dec_id, &A.use_c,
@@ -52,6 +62,33 @@ __device__ inline void decode_arrays_carve(DecodeArrays &A, unsigned char *base,
     uint8_t **bp[5] = {&A.dec_valid, &A.dec_rot, &A.selected, &A.was, &A.valid};
     for (int i = 0; i < 5; i++) { *bp[i] = p; p += cap; }
 }
+
+// Top tier (up to DEC_MAXC candidates): the three big arrays -- corners, pair list, bit matrix -- in global scratch, every array the
+// single-thread walks and the O(n^2) loops index per element (perimeters, centroids, group / nesting bookkeeping) in shared memory
+__host__ __device__ inline size_t decode_arrays_top_bytes(int cap) { return (size_t)cap * (4 + 4 + 2 * 4 + 11 * 2 + 5) + 64; }
+__device__ inline void decode_arrays_carve_top(DecodeArrays &A, unsigned char *smem, unsigned char *global, int cap)
+{
+    A.cap = cap;
+    unsigned char *g = global, *p = smem;
+    A.c = reinterpret_cast<float(*)[8]>(g); g += (size_t)cap * 32;
+    A.close_bits = reinterpret_cast<uint32_t *>(g); g += (size_t)cap * (cap / 32) * 4;
+    A.pairs = reinterpret_cast<uint32_t *>(g);
+    A.perim = reinterpret_cast<float *>(p); p += (size_t)cap * 4;
+    A.key = reinterpret_cast<uint32_t *>(p); p += (size_t)cap * 4;
+    A.cxy = reinterpret_cast<float *>(p); p += (size_t)cap * 8;
+    short **sp[11] = {&A.group_id, &A.next_in_group, &A.close_next, &A.parent, &A.depth, &A.sel, &A.sel_of, &A.dec_id, &A.use_c,
+                      &A.group_head, &A.group_tail};
+    for (int i = 0; i < 11; i++) { *sp[i] = reinterpret_cast<short *>(p); p += (size_t)cap * 2; }
+    uint8_t **bp[5] = {&A.dec_valid, &A.dec_rot, &A.selected, &A.was, &A.valid};
+    for (int i = 0; i < 5; i++) { *bp[i] = p; p += cap; }
+}
+
+// development aid (-DAPSE_DEC_PROFILE): cycles between the phases of k_decode, printed by frame 0
+#ifdef APSE_DEC_PROFILE
+#define DEC_T(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) dbg_t[i] = clock64(); } while (0)
+#else
+#define DEC_T(i) do { } while (0)
+#endif
 
 struct DecodeSmem {
     int n, ns, ngroups;
@@ -383,14 +420,39 @@ int apse_decode_tap(apse_ctx *ctx, const uint8_t *gray, int w, int h, const floa
     return APSE_OK;
 }
 
+// exclusive prefix sum of one int per thread over the CTA; s_scan[DEC_WARPS] = total.  s_scan is reusable after the call's barriers.
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_scan)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    __syncthreads();   // previous readers of s_scan are done
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < DEC_WARPS ? s_scan[lane] : 0, winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= d) winc += t; }
+        if (lane < DEC_WARPS) s_scan[lane] = winc - w;
+        if (lane == 31) s_scan[DEC_WARPS] = winc;
+    }
+    __syncthreads();
+    return s_scan[warp] + inc - v;
+}
+
 __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restrict__ gray, int w, int h, const float *__restrict__ quads,
                                                         const uint32_t *__restrict__ quad_order, int32_t *__restrict__ counters,
                                                         DeviceParams P, const int32_t *__restrict__ dec_raw, int skip_decoded_parents,
-                                                        unsigned char *__restrict__ big_scratch, size_t big_stride, apse_detections out)
+                                                        unsigned char *__restrict__ big_scratch, size_t big_stride, int mid_tier, apse_detections out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeSmem &S = *reinterpret_cast<DecodeSmem *>(smem_raw);
     __shared__ DecodeArrays A;
+#ifdef APSE_DEC_PROFILE
+    __shared__ long long dbg_t[24];
+    DEC_T(0);
+#endif
     const int f = blockIdx.x, tid = threadIdx.x;
     int32_t *cnt = counters + f * APSE_COUNTERS;
     const int nq = min(cnt[2], DEC_MAXC);
@@ -401,265 +463,319 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
         return;
     }
     if (tid == 0) {
+        // three tiers: everything in shared memory; the sequentially walked arrays in shared memory and the O(n^2) bit matrix in
+        // global memory (the classic path's ~10^3 candidates per frame: its single-thread grouping walk is a chain of dependent
+        // loads); everything in global memory
         if (nq <= DEC_SMEMC) decode_arrays_carve(A, smem_raw + sizeof(DecodeSmem), DEC_SMEMC);
+        else if (nq <= DEC_MIDC && mid_tier) decode_arrays_carve(A, smem_raw + sizeof(DecodeSmem), DEC_MIDC, reinterpret_cast<uint32_t *>(big_scratch + (size_t)f * big_stride));
+        else if (mid_tier) decode_arrays_carve_top(A, smem_raw + sizeof(DecodeSmem), big_scratch + (size_t)f * big_stride, DEC_MAXC);
         else decode_arrays_carve(A, big_scratch + (size_t)f * big_stride, DEC_MAXC);
     }
     __syncthreads();
-    const int rw = A.cap / 32;   // words per close_bits row
+    DEC_T(1);
 
-    // ---- deterministic order (candidate key), perimeter, stable sort (descending).  n = nq: the border-distance test
-    // comes AFTER the grouping (4.13: a border-touching quad still groups and, as a group main, takes its group with it)
-    for (int i = tid; i < nq; i += DEC_THREADS) A.key[i] = qo[i];
-    __syncthreads();
-    for (int i = tid; i < nq; i += DEC_THREADS) {
-        uint32_t k = A.key[i];
-        int r = 0;
-        for (int j = 0; j < nq; j++) r += A.key[j] < k;
-        A.sel[i] = (short)r;  // rank in candidate order
-    }
-    __syncthreads();
+    // ---- candidates sorted by perimeter (descending), ties in the deterministic candidate order (key).  n = nq: the
+    // border-distance test comes AFTER the grouping (4.13: a border-touching quad still groups and, as a group main, takes its
+    // group with it).  One rank pass over (perimeter, key), then one scatter straight from the quad list.
     const int n = nq;
     const int32_t *dr = dec_raw + (size_t)f * APSE_MAX_QUADS;
-    for (int i = tid; i < nq; i += DEC_THREADS) {
-        int r = A.sel[i];
-        for (int k = 0; k < 8; k++) A.c[r][k] = q[8 * i + k];
-        A.group_id[r] = (short)(dr[i] & 0xff);      // decode result rides along through the two permutations
-        A.next_in_group[r] = (short)(dr[i] >> 8);
-    }
+    float *perim0 = A.cxy;   // perimeters in quad-list order (the centroids are computed after the scatter)
+    for (int i = tid; i < n; i += DEC_THREADS) { A.key[i] = qo[i]; perim0[i] = perimeter_of(q + 8 * i); }
     __syncthreads();
-    for (int i = tid; i < n; i += DEC_THREADS) A.perim[i] = perimeter_of(A.c[i]);
-    __syncthreads();
-    // stable descending rank; permute through the key / close_bits scratch (ranks first, then a copy pass)
+    DEC_T(2);
     for (int i = tid; i < n; i += DEC_THREADS) {
-        float p = A.perim[i];
-        int r = 0;
-        for (int j = 0; j < n; j++) { float pj = A.perim[j]; r += (pj > p) || (pj == p && j < i); }
+        const float p = perim0[i];
+        const uint32_t k = A.key[i];
+        int r = 0, j = 0;
+        for (; j + 4 <= n; j += 4) {
+            const float4 pj = *reinterpret_cast<const float4 *>(perim0 + j);
+            const uint4 kj = *reinterpret_cast<const uint4 *>(A.key + j);
+            r += (pj.x > p) || (pj.x == p && kj.x < k);
+            r += (pj.y > p) || (pj.y == p && kj.y < k);
+            r += (pj.z > p) || (pj.z == p && kj.z < k);
+            r += (pj.w > p) || (pj.w == p && kj.w < k);
+        }
+        for (; j < n; j++) r += (perim0[j] > p) || (perim0[j] == p && A.key[j] < k);
         A.sel_of[i] = (short)r;
     }
     __syncthreads();
-    {
-        float *tmp = reinterpret_cast<float *>(A.close_bits);   // >= 9 floats per candidate (cap / 32 >= 16 words per row)
-        for (int i = tid; i < n; i += DEC_THREADS) {
-            for (int k = 0; k < 8; k++) tmp[9 * i + k] = A.c[i][k];
-            tmp[9 * i + 8] = A.perim[i];
-        }
-        __syncthreads();
-        for (int i = tid; i < n; i += DEC_THREADS) {
-            int r = A.sel_of[i];
-            for (int k = 0; k < 8; k++) A.c[r][k] = tmp[9 * i + k];
-            A.perim[r] = tmp[9 * i + 8];
-            int flags = A.group_id[i];
-            A.dec_valid[r] = (uint8_t)(flags & 1); A.dec_rot[r] = (uint8_t)((flags >> 1) & 3); A.dec_id[r] = A.next_in_group[i];
-        }
+    DEC_T(3);
+    for (int i = tid; i < n; i += DEC_THREADS) {
+        const int r = A.sel_of[i];
+        for (int k = 0; k < 8; k++) A.c[r][k] = q[8 * i + k];
+        A.perim[r] = perim0[i];
+        const int flags = dr[i] & 0xff;   // result of k_decode_bits for this quad
+        A.dec_valid[r] = (uint8_t)(flags & 1); A.dec_rot[r] = (uint8_t)((flags >> 1) & 3); A.dec_id[r] = (short)(dr[i] >> 8);
     }
     __syncthreads();
+    DEC_T(4);
 
-    // ---- too-close predicate matrix: bit (i,j), i < j, set when avgDist(i,j) < perimeter[j] * rate.
+    // ---- too-close predicate, avgDist(i,j) < perimeter[j] * rate for i < j, and the grouping it drives.
+    // The dependency walks the close pairs in row-major order: both ungrouped -> new group; one grouped -> the other joins; both
+    // grouped -> nothing.  A candidate is therefore assigned at the FIRST pair (in that order) it takes part in -- it is still
+    // ungrouped there, and either its partner already has a group (it joins) or the partner is ungrouped too, which makes this the
+    // partner's first pair as well (a new group).  The first pair of v is (i_min, v) with the smallest close i < v if there is one
+    // (rows before row v), else (v, j_min).  So: first partner per candidate by atomicMin while the predicate is evaluated (no bit
+    // matrix, no pair list, no sequential walk); groups = chains of first partners, ending in a mutual pair whose smaller index --
+    // the smallest index of the whole group, the group's head -- labels the group.
     // avgDist^2 is a mean of squared corner distances, so it is never below the squared centroid distance (Jensen):
     // pairs whose centroids are clearly farther apart than the threshold are skipped without the 4-shift evaluation.
-    const int words = (n + 31) / 32;
-    for (int i = tid; i < n; i += DEC_THREADS) {
-        const float *c = A.c[i];
-        A.cxy[2 * i] = 0.25f * (c[0] + c[2] + c[4] + c[6]);
-        A.cxy[2 * i + 1] = 0.25f * (c[1] + c[3] + c[5] + c[7]);
+    const int lane = tid & 31, warp = tid >> 5;
+    // centroid test operands, one array each (unit-stride reads), padded so that a row's last 128 columns need no bounds test
+    const int sstride = A.cap + 128;
+    float *thr2 = reinterpret_cast<float *>(A.close_bits), *cxs = thr2 + sstride, *cys = cxs + sstride;
+    int *list_head = reinterpret_cast<int *>(A.cxy);   // per group (indexed by its head): unordered member list
+    for (int i = tid; i < n + 128; i += DEC_THREADS) {
+        if (i < n) {
+            const float *c = A.c[i];
+            cxs[i] = 0.25f * (c[0] + c[2] + c[4] + c[6]);
+            cys[i] = 0.25f * (c[1] + c[3] + c[5] + c[7]);
+            const float thr = A.perim[i] * P.min_marker_distance_rate;
+            thr2[i] = thr * thr * 1.02f + 4.f;   // conservative: float rounding of the centroids
+            A.key[i] = 0xffffffffu;   // first partner: u < v as u, u > v as 0x10000 + u (any smaller index wins over any larger one)
+            list_head[i] = -1;
+        } else { cxs[i] = 0.f; cys[i] = 0.f; thr2[i] = -1.f; }
     }
+    if (tid == 0) S.n = 0;
     __syncthreads();
-    for (int p = tid; p < n * words; p += DEC_THREADS) {
-        int i = p / words, wj = p - i * words;
-        uint32_t bitsw = 0;
-        if (wj * 32 + 31 > i) {
-            const float cxi = A.cxy[2 * i], cyi = A.cxy[2 * i + 1];
-            for (int b = 0; b < 32; b++) {
-                int j = wj * 32 + b;
-                if (j > i && j < n) {
-                    const float thr = A.perim[j] * P.min_marker_distance_rate;
-                    const float dx = A.cxy[2 * j] - cxi, dy = A.cxy[2 * j + 1] - cyi;
-                    if (dx * dx + dy * dy > thr * thr * 1.02f + 4.f) continue;   // conservative: float rounding of the centroids
-                    float md = average_distance(A.c[i], A.c[j]);
-                    if (md < thr) bitsw |= 1u << b;
+    DEC_T(5);
+    // pass 1, warp per row i, lane = column: the pairs the centroid test cannot exclude go to a list (a few per candidate)
+    const int pair_cap = A.cap * 8;
+    for (int i = warp; i < n; i += DEC_WARPS) {
+        const float cxi = cxs[i], cyi = cys[i];
+        for (int jb = i & ~31; jb < n; jb += 128) {
+            uint32_t m[4];
+            bool cand[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = jb + 32 * u + lane;
+                const float dx = cxs[j] - cxi, dy = cys[j] - cyi;
+                cand[u] = j > i && !(dx * dx + dy * dy > thr2[j]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) m[u] = __ballot_sync(0xffffffffu, cand[u]);
+            if (m[0] | m[1] | m[2] | m[3]) {
+                const int total = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.n, total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int o = base + __popc(m[u] & ((1u << lane) - 1));
+                    if (cand[u] && o < pair_cap) A.pairs[o] = ((uint32_t)i << 16) | (uint32_t)(jb + 32 * u + lane);
+                    base += __popc(m[u]);
                 }
             }
         }
-        A.close_bits[(size_t)i * rw + wj] = bitsw;
     }
     __syncthreads();
-    // compact the set bits into a row-major pair list: per-row counts, block scan, scatter
+    DEC_T(6);
+    // pass 2, thread per listed pair: the exact predicate
     {
-        __shared__ int s_part[DEC_THREADS];
-        const int chunk = (n + DEC_THREADS - 1) / DEC_THREADS, r0 = tid * chunk, r1 = min(n, r0 + chunk);
-        int local = 0;
-        for (int i = r0; i < r1; i++) {
-            int c = 0;
-            for (int wj = i / 32; wj < words; wj++) c += __popc(A.close_bits[(size_t)i * rw + wj]);
-            A.key[i] = (uint32_t)c;
-            local += c;
-        }
-        s_part[tid] = local;
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int t = 0; t < DEC_THREADS; t++) { int v = s_part[t]; s_part[t] = acc; acc += v; }
-            S.n = acc;   // total number of too-close pairs
-        }
-        __syncthreads();
-        int off = s_part[tid];
-        const int pair_cap = A.cap * 8;
-        for (int i = r0; i < r1; i++) {
-            if (!A.key[i]) continue;
-            for (int wj = i / 32; wj < words; wj++) {
-                uint32_t m = A.close_bits[(size_t)i * rw + wj];
-                while (m) {
-                    int j = wj * 32 + __ffs(m) - 1;
-                    m &= m - 1;
-                    if (off < pair_cap) A.pairs[off] = ((uint32_t)i << 16) | (uint32_t)j;
-                    off++;
-                }
-            }
-        }
-    }
-    for (int i = tid; i < n; i += DEC_THREADS) {
-        A.group_id[i] = -1; A.selected[i] = 1; A.next_in_group[i] = -1; A.close_next[i] = -1;
-        A.parent[i] = -1; A.depth[i] = 0; A.was[i] = 0; A.valid[i] = 0; A.use_c[i] = (short)i;
-    }
-    __syncthreads();
-
-    // ---- sequential grouping walk over the pair list (order-dependent by definition)
-    if (tid == 0) {
-        int ngroups = 0;
-        const int npairs = S.n;
-        if (npairs > A.cap * 8) cnt[3] = APSE_ERR_CAPACITY;   // reported through status; never truncated silently
-        for (int k = 0; k < min(npairs, A.cap * 8); k++) {
+        const int np = S.n;
+        if (np > pair_cap && tid == 0) cnt[3] = APSE_ERR_CAPACITY;   // reported through status; never truncated silently
+        for (int k = tid; k < min(np, pair_cap); k += DEC_THREADS) {
             const uint32_t pr = A.pairs[k];
             const int i = pr >> 16, j = pr & 0xffff;
-            A.selected[i] = 0; A.selected[j] = 0;
-            if (A.group_id[i] < 0 && A.group_id[j] < 0) { A.group_id[i] = A.group_id[j] = (short)ngroups++; }
-            else if (A.group_id[i] > -1 && A.group_id[j] == -1) A.group_id[j] = A.group_id[i];
-            else if (A.group_id[j] > -1 && A.group_id[i] == -1) A.group_id[i] = A.group_id[j];
-        }
-        // members of each group in ascending index order (= largest perimeter first)
-        for (int g = 0; g < ngroups; g++) { A.group_head[g] = -1; A.group_tail[g] = -1; }
-        for (int i = 0; i < n; i++) {
-            int g = A.group_id[i];
-            if (g < 0) continue;
-            if (A.group_head[g] < 0) A.group_head[g] = (short)i; else A.next_in_group[A.group_tail[g]] = (short)i;
-            A.group_tail[g] = (short)i;
-        }
-        for (int g = 0; g < ngroups; g++) {
-            int head = A.group_head[g], cur = head, tail_close = -1;
-            A.selected[head] = 1;
-            for (int id = A.next_in_group[head]; id >= 0; id = A.next_in_group[id]) {
-                float dist = average_distance(A.c[id], A.c[cur]);
-                float msz = average_module_size(A.c[id], P.marker_size, P.border_bits);
-                if (dist > P.min_group_distance * msz) {
-                    cur = id;
-                    if (tail_close < 0) A.close_next[head] = (short)id; else A.close_next[tail_close] = (short)id;
-                    tail_close = id;
-                }
+            if (average_distance(A.c[i], A.c[j]) < A.perim[j] * P.min_marker_distance_rate) {
+                atomicMin(&A.key[j], (uint32_t)i);
+                atomicMin(&A.key[i], 0x10000u + (uint32_t)j);
             }
         }
-        // NB close_next chains start at the group's head; members never head a chain themselves.
-        // Border-distance test on the selected (main) candidates only: a main too near the edge is dropped with its group.
+    }
+    __syncthreads();
+    DEC_T(7);
+    for (int v = tid; v < n; v += DEC_THREADS) {
+        const uint32_t k = A.key[v];
+        int label = -1;
+        if (k != 0xffffffffu) {
+            int r = v, q1 = (int)(k & 0xffffu);
+            for (int it = 0; it < n; it++) {   // the first-pair order strictly decreases along the chain
+                const int q2 = (int)(A.key[q1] & 0xffffu);
+                if (q2 == r) { label = min(r, q1); break; }
+                r = q1; q1 = q2;
+            }
+        }
+        A.group_id[v] = (short)label; A.selected[v] = label < 0 || label == v;
+        A.close_next[v] = -1; A.parent[v] = -1; A.valid[v] = 0; A.use_c[v] = (short)v;
+        A.next_in_group[v] = label >= 0 && label != v ? (short)atomicExch(&list_head[label], v) : (short)-1;
+    }
+    __syncthreads();
+    DEC_T(8);
+    // thread per group head: its members in ascending index order (= largest perimeter first; the next one is picked from the
+    // unordered list each time -- groups are a handful of candidates); kept: the chain of members far enough from the previous one
+    for (int head = tid; head < n; head += DEC_THREADS) {
+        if (A.group_id[head] != head) continue;
+        int cur = head, tail_close = -1, last = head;
+        for (;;) {
+            int id = 0x7fffffff;
+            for (int m = list_head[head]; m >= 0; m = A.next_in_group[m]) if (m > last && m < id) id = m;
+            if (id == 0x7fffffff) break;
+            last = id;
+            float dist = average_distance(A.c[id], A.c[cur]);
+            float msz = average_module_size(A.c[id], P.marker_size, P.border_bits);
+            if (dist > P.min_group_distance * msz) {
+                cur = id;
+                if (tail_close < 0) A.close_next[head] = (short)id; else A.close_next[tail_close] = (short)id;
+                tail_close = id;
+            }
+        }
+    }
+    DEC_T(9);
+    // NB close_next chains start at the group's head; members never head a chain themselves.
+    // Border-distance test on the selected (main) candidates only: a main too near the edge is dropped with its group.
+    __shared__ int s_scan[DEC_WARPS + 1];
+    const int chunk = (n + DEC_THREADS - 1) / DEC_THREADS, r0 = min(n, tid * chunk), r1 = min(n, r0 + chunk);
+    {
         const float d = (float)P.min_distance_to_border;
-        int ns = 0;
-        for (int i = 0; i < n; i++) {
+        uint32_t keep = 0;
+        for (int i = r0; i < r1; i++) {
             if (!A.selected[i]) continue;
             const float *c = A.c[i];
             bool near = false;
             for (int j = 0; j < 4; j++) near |= c[2 * j] < d || c[2 * j + 1] < d || c[2 * j] > w - 1 - d || c[2 * j + 1] > h - 1 - d;
-            if (near) continue;
-            A.sel[ns] = (short)i; A.sel_of[i] = (short)ns; ns++;
+            if (!near) keep |= 1u << (i - r0);
         }
-        S.ns = ns;
-        S.ngroups = ngroups;
+        int off = block_exclusive_scan(__popc(keep), s_scan);
+        for (int i = r0; i < r1; i++)
+            if (keep >> (i - r0) & 1) { A.sel[off] = (short)i; A.sel_of[i] = (short)off; off++; }
+        if (tid == 0) S.ns = s_scan[DEC_WARPS];
     }
     __syncthreads();
+    DEC_T(10);
     const int ns = S.ns;
 
     // ---- nesting hierarchy among the selected candidates: parent = nearest smaller index that contains all 4 corners
+    // (a point strictly inside a quad lies inside the quad's bounding box: the box test rejects almost every pair before the four
+    // exact point-in-polygon tests; with ~10^3 candidates per frame on the classic path the plain O(n^2) loop was 0.8 ms per frame)
+    float4 *box = reinterpret_cast<float4 *>(A.close_bits);   // bounding boxes (x0, x1, y0, y1) of the selected candidates
     for (int v = tid; v < ns; v += DEC_THREADS) {
         const float *a = A.c[A.sel[v]];
+        box[v] = make_float4(fminf(fminf(a[0], a[2]), fminf(a[4], a[6])), fmaxf(fmaxf(a[0], a[2]), fmaxf(a[4], a[6])),
+                             fminf(fminf(a[1], a[3]), fminf(a[5], a[7])), fmaxf(fmaxf(a[1], a[3]), fmaxf(a[5], a[7])));
+    }
+    __syncthreads();
+    for (int v = tid; v < ns; v += DEC_THREADS) {
+        const float *a = A.c[A.sel[v]];
+        const float4 ba = box[v];
         int par = -1;
         for (int j = v - 1; j >= 0; j--) {
+            const float4 bb = box[j];
+            if (ba.x < bb.x || ba.y > bb.y || ba.z < bb.z || ba.w > bb.w) continue;
             const float *b = A.c[A.sel[j]];
             if (strictly_inside(b, a[0], a[1]) && strictly_inside(b, a[2], a[3]) && strictly_inside(b, a[4], a[5]) &&
                 strictly_inside(b, a[6], a[7])) { par = j; break; }
         }
         A.parent[v] = (short)par;
     }
+    // height of every node of the nesting forest (the dependency's "depth": longest chain of nested candidates below it) and the
+    // "seen" marks of the acceptance loop, in the centroid scratch (no longer needed)
+    DEC_T(11);
+    int *hgt = reinterpret_cast<int *>(A.cxy);   // [2 v] height, [2 v + 1] seen
+    __shared__ int s_lvl[2];                      // [0] number of candidates accounted for, [1] largest height
+    for (int v = tid; v < ns; v += DEC_THREADS) { hgt[2 * v] = 0; hgt[2 * v + 1] = 0; }
+    if (tid == 0) { s_lvl[0] = 0; s_lvl[1] = 0; }
     __syncthreads();
-    if (tid == 0) {
-        int max_depth = 0;
-        for (int v = ns - 1; v >= 0; v--) {
-            int p = A.parent[v];
-            if (p >= 0 && A.depth[v] + 1 > A.depth[p]) A.depth[p] = (short)(A.depth[v] + 1);
+    for (int v = tid; v < ns; v += DEC_THREADS) {
+        // a node that finds an ancestor already as high as it would make it stops: whoever raised that ancestor carries on upwards
+        // (a frame-sized outer candidate is an ancestor of everything: without the test every thread would hit its counter)
+        int k = 0;
+        for (int p = A.parent[v]; p >= 0; p = A.parent[p]) {
+            ++k;
+            if (*reinterpret_cast<volatile int *>(&hgt[2 * p]) >= k) break;
+            atomicMax(&hgt[2 * p], k);
+            if (*reinterpret_cast<volatile int *>(&s_lvl[1]) < k) atomicMax(&s_lvl[1], k);
         }
-        for (int v = 0; v < ns; v++) max_depth = max(max_depth, (int)A.depth[v]);
-        int counter = 0;
-        for (int dep = 0; dep <= max_depth && counter < ns; dep++) {
-            for (int v = 0; v < ns; v++) {
-                if (A.depth[v] != dep) continue;
-                if (skip_decoded_parents && A.was[v]) continue;
-                A.was[v] = 1;
-                int head = A.sel[v];
-                int use = -1;
-                if (A.dec_valid[head]) use = head;
-                else
-                    for (int c = A.close_next[head]; c >= 0; c = A.close_next[c])
-                        if (A.dec_valid[c]) { use = c; break; }
-                if (use >= 0) { A.valid[v] = 1; A.use_c[v] = (short)use; }
-            }
-            for (int v = 0; v < ns; v++) {
-                if (A.depth[v] != dep) continue;
-                if (A.valid[v]) {
-                    int p = A.parent[v];
-                    while (p != -1) {
-                        if (!A.was[p]) { A.was[p] = 1; counter++; }
-                        p = A.parent[p];
-                    }
-                }
-                counter++;
-            }
+    }
+    __syncthreads();
+    DEC_T(12);
+    // Acceptance, level by level from the innermost candidates outwards, as the dependency does it: a level's candidates are tried
+    // (the group's main first, then its far-enough members); every accepted one marks its not yet seen ancestors, and each mark
+    // counts as a processed candidate -- as does, again, the ancestor itself when its own level comes.  The loop ends when the count
+    // reaches the number of candidates, so outer candidates of a frame with nested markers may never be tried (and end up rejected);
+    // with skip_decoded_parents a marked ancestor is not tried at all.  Ancestors are strictly higher than their descendants, so
+    // the candidates of one level are independent of each other.
+    const int max_depth = s_lvl[1];
+    for (int dep = 0; dep <= max_depth; dep++) {
+        if (s_lvl[0] >= ns) break;
+        __syncthreads();
+        int mine = 0;
+        for (int v = tid; v < ns; v += DEC_THREADS) {
+            if (hgt[2 * v] != dep) continue;
+            mine++;
+            if (skip_decoded_parents && hgt[2 * v + 1]) continue;
+            const int head = A.sel[v];
+            int use = -1;
+            if (A.dec_valid[head]) use = head;
+            else
+                for (int c = A.close_next[head]; c >= 0; c = A.close_next[c])
+                    if (A.dec_valid[c]) { use = c; break; }
+            if (use < 0) continue;
+            A.valid[v] = 1; A.use_c[v] = (short)use;
+            for (int p = A.parent[v]; p >= 0; p = A.parent[p])
+                if (atomicExch(&hgt[2 * p + 1], 1) == 0) mine++;
         }
-        // ---- output
-        int na = 0, nr = 0;
+        if (mine) atomicAdd(&s_lvl[0], mine);
+        __syncthreads();
+    }
+    __syncthreads();
+    DEC_T(13);
+
+    // ---- output: accepted markers (corners rotated to the dictionary's orientation) and rejected candidates, in candidate order
+    {
         const int cap = out.max_markers;
         float *oc = out.corners + (size_t)f * cap * 8;
         int32_t *oi = out.ids + (size_t)f * cap;
         float *orj = out.rejected ? out.rejected + (size_t)f * cap * 8 : nullptr;
-        int status = cnt[3];
-        for (int v = 0; v < ns; v++) {
+        const int ochunk = (ns + DEC_THREADS - 1) / DEC_THREADS, v0 = min(ns, tid * ochunk), v1 = min(ns, v0 + ochunk);
+        int nv = 0;
+        for (int v = v0; v < v1; v++) nv += A.valid[v];
+        int na = block_exclusive_scan(nv, s_scan);
+        const int na_total = s_scan[DEC_WARPS];
+        int nr = v0 - na;
+        for (int v = v0; v < v1; v++) {
             if (A.valid[v]) {
-                int u = A.use_c[v];
+                const int u = A.use_c[v];
                 const float *c = A.c[u];
                 if (na < cap) {
-                    int r = A.dec_rot[u];
+                    const int r = A.dec_rot[u];
                     for (int k = 0; k < 4; k++) {
-                        int s = (k + 4 - r) % 4;
+                        const int s = (k + 4 - r) % 4;
                         oc[8 * na + 2 * k] = c[2 * s];
                         oc[8 * na + 2 * k + 1] = c[2 * s + 1];
                     }
                     oi[na] = A.dec_id[u];
-                } else status = APSE_ERR_CAPACITY;
+                }
                 na++;
             } else {
                 const float *c = A.c[A.sel[v]];
-                if (orj) {
-                    if (nr < cap) for (int k = 0; k < 8; k++) orj[8 * nr + k] = c[k];
-                    else status = APSE_ERR_CAPACITY;
-                }
+                if (orj && nr < cap) for (int k = 0; k < 8; k++) orj[8 * nr + k] = c[k];
                 nr++;
             }
         }
-        out.n_markers[f] = min(na, cap);
-        if (out.n_rejected) out.n_rejected[f] = min(nr, cap);
-        out.status[f] = status;
+        if (tid == 0) {
+            const int nr_total = ns - na_total;
+            int status = cnt[3];
+            if (na_total > cap || (orj && nr_total > cap)) status = APSE_ERR_CAPACITY;
+            out.n_markers[f] = min(na_total, cap);
+            if (out.n_rejected) out.n_rejected[f] = min(nr_total, cap);
+            out.status[f] = status;
+#ifdef APSE_DEC_PROFILE
+            if (blockIdx.x == 0) {
+                const long long t_end = clock64();
+                const char *names[14] = {"carve", "perimeters", "rank", "scatter", "centroids", "pairs: centroid test", "pairs: exact", "labels", "groups", "border + scan", "nesting", "heights", "levels", "output"};
+                for (int i = 1; i <= 13; i++) printf("%-22s %8lld cycles\n", names[i - 1], dbg_t[i] - dbg_t[i - 1]);
+                printf("%-22s %8lld cycles; nq %d ns %d listed pairs %d\n", names[13], t_end - dbg_t[13], nq, ns, S.n);
+            }
+#endif
+        }
     }
 }
 
 int apse_decode_alloc(apse_ctx *ctx)
 {
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(sizeof(DecodeSmem) + decode_arrays_bytes(DEC_SMEMC))));
+                                       (int)(sizeof(DecodeSmem) + decode_arrays_small_bytes(DEC_MIDC))));
     return APSE_OK;
 }
 void apse_decode_free(apse_ctx *ctx) { cudaFree(ctx->decode_scratch); ctx->decode_scratch = nullptr; }
@@ -691,8 +807,12 @@ int apse_decode_candidates(apse_ctx *ctx, const uint8_t *gray, int w, int h, int
         KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<true><<<dim3(cand_blocks, batch), DECB_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, ctx->sparse_src));
     else
         KLAUNCH(ctx, KID_DECODE_BITS, st, k_decode_bits<false><<<dim3(cand_blocks, batch), DECB_THREADS, 0, st>>>(gray, w, h, ctx->quads, ctx->counters, dp, ctx->dict, dec_raw, SparseSrc{}));
-    KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, sizeof(DecodeSmem) + decode_arrays_bytes(DEC_SMEMC), st>>>(
+    // the classic path (hundreds of candidates per frame) launches with the shared memory of the middle tier; the APRILTAG path keeps
+    // the small footprint (its decode CTAs share SMs with the preprocess kernels of the next sub-batch)
+    const int mid_tier = ctx->params.cornerRefinementMethod != 3 && ctx->decode_scratch ? 1 : 0;
+    const size_t dec_smem = sizeof(DecodeSmem) + (mid_tier ? decode_arrays_small_bytes(DEC_MIDC) : decode_arrays_bytes(DEC_SMEMC));
+    KLAUNCH(ctx, KID_DECODE, st, k_decode<<<batch, DEC_THREADS, dec_smem, st>>>(
                 gray, w, h, ctx->quads, ctx->quad_order, ctx->counters, dp, dec_raw, skip,
-                (unsigned char *)ctx->decode_scratch, decode_arrays_bytes(DEC_MAXC), *out));
+                (unsigned char *)ctx->decode_scratch, decode_arrays_bytes(DEC_MAXC), mid_tier, *out));
     return APSE_OK;
 }
