@@ -186,8 +186,8 @@ int apse_set_params(apse_ctx *ctx, const apse_params *p)
     if (p->aprilTagDeglitch != 0) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagDeglitch is not supported");
     if (p->aprilTagQuadDecimate > 64) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagQuadDecimate above 64 is not supported");
     if (fabsf(p->aprilTagQuadSigma) >= 8.25f) CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: |aprilTagQuadSigma| must be below 8.25 (33 taps)");
-    if (p->detectInvertedMarker || p->useAruco3Detection)
-        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: detectInvertedMarker / useAruco3Detection are not supported");
+    if (p->useAruco3Detection)
+        CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: useAruco3Detection is not supported");
     if (p->cornerRefinementMethod < 0 || p->cornerRefinementMethod > 3) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "set_params: cornerRefinementMethod must be 0 .. 3");
     if (p->aprilTagMaxNmaxima < 4 || p->aprilTagMaxNmaxima > 16)
         CTX_FAIL(ctx, APSE_ERR_UNSUPPORTED, "set_params: aprilTagMaxNmaxima must be in [4,16]");
@@ -262,6 +262,7 @@ int apse_fill_device_params(apse_ctx *ctx, DeviceParams *dp, int w, int h)
     dp->cell_size = p.perspectiveRemovePixelPerCell;
     dp->cell_margin_px = (int)(p.perspectiveRemoveIgnoredMarginPerCell * p.perspectiveRemovePixelPerCell);
     dp->max_border_errors = (int)(ctx->marker_size * ctx->marker_size * p.maxErroneousBitsInBorderRate);
+    dp->detect_inverted = p.detectInvertedMarker ? 1 : 0;
     dp->max_correction = (int)((double)ctx->max_corr_bits * p.errorCorrectionRate);
     dp->min_otsu_stddev = p.minOtsuStdDev;
     dp->min_distance_to_border = p.minDistanceToBorder;

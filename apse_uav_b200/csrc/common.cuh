@@ -61,6 +61,7 @@ struct DeviceParams {  // what the detection kernels need of apse_params (+ deri
     int min_distance_to_border;
     float min_marker_distance_rate, min_group_distance;
     int n_markers, nbytes;
+    int detect_inverted;   // detectInvertedMarker
 };
 
 enum KernelId {

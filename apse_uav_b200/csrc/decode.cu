@@ -296,6 +296,15 @@ __device__ void decode_finish(const DeviceParams &P, long long s1, long long s2,
     }
     for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xffffffffu, e, d);
     valid = false; id = -1; rot = 0;
+    if (P.detect_inverted) {
+        // detectInvertedMarker: a white marker is read through the inverted bits when its border fits better that way
+        const int n_border = nb * nb - P.marker_size * P.marker_size;
+        if (n_border - e < e) {
+            for (int cell = lane; cell < nb * nb; cell += 32) bits[cell] = !bits[cell];
+            e = n_border - e;
+            __syncwarp();
+        }
+    }
     if (e > P.max_border_errors) return;
     // candidate bytes (MSB first, rows of inner bits)
     const int ms = P.marker_size, nbits = ms * ms, nbytes = P.nbytes;
@@ -596,21 +605,27 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
                 r = q1; q1 = q2;
             }
         }
-        A.group_id[v] = (short)label; A.selected[v] = label < 0 || label == v;
+        A.group_id[v] = (short)label; A.selected[v] = label < 0;   // (a group's main is selected by its head thread below)
         A.close_next[v] = -1; A.parent[v] = -1; A.valid[v] = 0; A.use_c[v] = (short)v;
         A.next_in_group[v] = label >= 0 && label != v ? (short)atomicExch(&list_head[label], v) : (short)-1;
     }
     __syncthreads();
     DEC_T(8);
-    // thread per group head: its members in ascending index order (= largest perimeter first; the next one is picked from the
-    // unordered list each time -- groups are a handful of candidates); kept: the chain of members far enough from the previous one
-    for (int head = tid; head < n; head += DEC_THREADS) {
-        if (A.group_id[head] != head) continue;
+    // thread per group (its label = smallest index): the members in ascending index order (= largest perimeter first; with
+    // detectInvertedMarker descending: the dependency then makes the SMALLEST candidate the group's main), the next one picked from
+    // the unordered list each time -- groups are a handful of candidates; kept: the chain of members far enough from the previous one
+    const bool desc = P.detect_inverted != 0;
+    for (int g = tid; g < n; g += DEC_THREADS) {
+        if (A.group_id[g] != g) continue;
+        int head = g;
+        if (desc) for (int m = list_head[g]; m >= 0; m = A.next_in_group[m]) head = max(head, m);
+        A.selected[head] = 1;
         int cur = head, tail_close = -1, last = head;
         for (;;) {
-            int id = 0x7fffffff;
-            for (int m = list_head[head]; m >= 0; m = A.next_in_group[m]) if (m > last && m < id) id = m;
-            if (id == 0x7fffffff) break;
+            int id = desc ? -1 : 0x7fffffff;
+            for (int m = list_head[g]; m >= 0; m = A.next_in_group[m]) if (desc ? (m < last && m > id) : (m > last && m < id)) id = m;
+            if (desc && id < 0 && g < last) id = g;   // the label itself is the group's smallest index: last in descending order
+            if (id < 0 || id == 0x7fffffff) break;
             last = id;
             float dist = average_distance(A.c[id], A.c[cur]);
             float msz = average_module_size(A.c[id], P.marker_size, P.border_bits);
@@ -621,6 +636,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decode(const uint8_t *__restric
             }
         }
     }
+    __syncthreads();   // selected[] of the group mains
     DEC_T(9);
     // NB close_next chains start at the group's head; members never head a chain themselves.
     // Border-distance test on the selected (main) candidates only: a main too near the edge is dropped with its group.

@@ -292,6 +292,29 @@ static char *py_float_str(char *p, char *end, double x)
 {
     if (x == 0) { const char *z = signbit(x) ? "-0.0" : "0.0"; size_t n = strlen(z); if (p + n <= end) { memcpy(p, z, n); p += n; } return p; }
     const double a = fabs(x);
+    if (a >= 1e-4 && a < 1e9 && end - p >= 32) {
+        // the CSV columns are round(value, <= 5): x is the double nearest to a decimal q / 10^nd with few digits.  A decimal of at most
+        // 15 significant digits that converts to x IS Python's shortest round-trip repr of x (two different such decimals never share
+        // a double), so the smallest nd with (double)q / 10^nd == x -- one correctly rounded division of exact integers -- gives the
+        // text without a general shortest-digits search.  Anything else falls through to std::to_chars.
+        static const double P10[7] = {1, 10, 100, 1000, 10000, 100000, 1000000};
+        for (int nd = 0; nd <= 6; nd++) {
+            const double sc = a * P10[nd];
+            const unsigned long long q = (unsigned long long)(sc + 0.5);
+            if ((double)q / P10[nd] != a) continue;
+            if (x < 0) *p++ = '-';
+            char tmp[24];
+            int len = 0;
+            unsigned long long v = q;
+            do { tmp[len++] = (char)('0' + v % 10); v /= 10; } while (v);
+            while (len <= nd) tmp[len++] = '0';            // at least one digit before the point
+            for (int i = len - 1; i >= nd; i--) *p++ = tmp[i];
+            *p++ = '.';
+            if (nd == 0) *p++ = '0';
+            for (int i = nd - 1; i >= 0; i--) *p++ = tmp[i];
+            return p;
+        }
+    }
     if (a >= 1e-4 && a < 1e16) {
         auto r = std::to_chars(p, end, x, std::chars_format::fixed);
         bool dot = false;

@@ -94,11 +94,11 @@ def rows_to_csv(rows, header=True) -> str:
     """The text aruco_detect.py:131-139,146-185 writes for these rows."""
     rows = np.ascontiguousarray(rows)
     cap = 512 * (len(rows) + 2)
-    buf = C.create_string_buffer(cap)
-    nb = _lib.load().apse_sequence_csv(_ptr(rows), len(rows), 1 if header else 0, buf, cap)
+    buf = np.empty(cap, np.uint8)   # uninitialised: only the bytes the library reports are read
+    nb = _lib.load().apse_sequence_csv(_ptr(rows), len(rows), 1 if header else 0, _ptr(buf), cap)
     if nb < 0:
         raise ApseError(int(nb), "apse_sequence_csv failed")
-    return buf.raw[:nb].decode()
+    return buf[:nb].tobytes().decode("ascii")
 
 
 def rows_to_dicts(rows):

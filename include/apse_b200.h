@@ -57,7 +57,7 @@ typedef struct apse_params {
     int aprilTagMinClusterPixels, aprilTagMaxNmaxima;
     float aprilTagCriticalRad, aprilTagMaxLineFitMse;
     int aprilTagMinWhiteBlackDiff, aprilTagDeglitch; /* deglitch must be 0 */
-    int detectInvertedMarker;                        /* must be 0 */
+    int detectInvertedMarker;                        /* white markers: inverted bits tried when the border fits better; smallest candidate of a group is its main */
     int useAruco3Detection;                          /* must be 0 */
     int minSideLengthCanonicalImg;
     float minMarkerLengthRatioOriginalImg;

@@ -234,7 +234,14 @@ static int identify_one(const uint8_t *im, int w, int h, const float *corners, c
     uint8_t bits[32 * 32];
     orc_extract_bits(im, w, h, corners, P, bits, NULL, NULL);
     int max_border = (int)(P->marker_size * P->marker_size * P->max_border_err_rate);
-    if (border_errors(bits, P->marker_size, P->border_bits) > max_border) return 0;
+    int berr = border_errors(bits, P->marker_size, P->border_bits);
+    if (P->detect_inverted) {   /* detectInvertedMarker: a white marker is read through the inverted bits when its border fits better */
+        uint8_t inv[32 * 32];
+        for (int i = 0; i < n * n; i++) inv[i] = (uint8_t)!bits[i];
+        int ierr = border_errors(inv, P->marker_size, P->border_bits);
+        if (ierr < berr) { berr = ierr; memcpy(bits, inv, (size_t)n * n); }
+    }
+    if (berr > max_border) return 0;
     uint8_t inner[32 * 32];
     for (int y = 0; y < P->marker_size; y++)
         for (int x = 0; x < P->marker_size; x++)

@@ -260,3 +260,36 @@ def test_identification_stage_in_isolation(oracle, camera, lut, dictionary, ref_
                 n_valid += 1
     assert n_valid >= 100 and n_otsu >= 150
     e.close()
+
+
+@pytest.mark.parametrize("mode", [3, 0])
+def test_inverted_markers(oracle, dictionary, ref_params, mode):
+    """detectInvertedMarker on the GPU: ids, order, corners and rejected count equal to the oracle (= cv2 4.13,
+    tests/test_oracle_detect.py::test_inverted_markers_vs_cv2) on frames where every other marker is white on black -- the
+    inverted-bits branch of the identification and the descending member order of the too-close groups."""
+    import copy
+    import torch
+    from apse_uav_b200.engine import Engine
+    from tools import synth
+    p = copy.copy(ref_params)
+    p.cornerRefinementMethod = mode
+    p.detectInvertedMarker = True
+    e = Engine(0, 1920, 1080, 6)
+    bl = np.ascontiguousarray(dictionary.bytesList, np.uint8)
+    e.set_dictionary(bl.reshape(bl.shape[0], -1), dictionary.markerSize, dictionary.maxCorrectionBits)
+    e.set_params(p)
+    frames = [synth.make_inverted_frame(dictionary.bytesList, 500 + s, n_markers=40 if s % 2 else 6) for s in range(6)]
+    grays = np.stack([np.ascontiguousarray(((f[..., 0].astype(np.int32) * 3735 + f[..., 1].astype(np.int32) * 19235 + f[..., 2].astype(np.int32) * 9798 + 16384) >> 15).astype(np.uint8)) for f in frames])
+    det = e.detect(torch.from_numpy(grays).cuda(), max_markers=256)
+    res = {k: v.cpu().numpy() for k, v in det.items()}
+    assert (res["status"] == 0).all()
+    fn = oracle.detect_markers_apriltag if mode == 3 else oracle.detect_markers_classic
+    total = 0
+    for f in range(len(frames)):
+        oc, oi, orj = fn(grays[f], dictionary.raw, p)
+        n = int(res["n"][f])
+        assert n == len(oi) and np.array_equal(res["ids"][f, :n], oi) and np.array_equal(res["corners"][f, :n], oc)
+        assert int(res["n_rejected"][f]) == len(orj)
+        total += n
+    assert total > 50
+    e.close()

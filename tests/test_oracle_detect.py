@@ -138,3 +138,33 @@ def test_nested_markers_vs_cv2(oracle, dictionary, ref_params, mode):
         parents += int((placed[0] in got and placed[1] in got) or (seed % 2 == 1 and placed[1] in got and placed[2] in got))
     if mode == 0:                # (the APRILTAG quad detector rarely yields the enclosing quad with the reference's parameters)
         assert parents >= 3      # frames in which BOTH an enclosing marker and the marker inside it were identified
+
+
+@pytest.mark.parametrize("mode", [3, 0])
+def test_inverted_markers_vs_cv2(oracle, dictionary, ref_params, mode):
+    """detectInvertedMarker (DetectorParameters): white markers on black are read through the inverted bits when
+    their border fits better, and the smallest candidate of a too-close group becomes its main.  ids, order, corners and the
+    rejected count equal cv2 4.13 on frames where every other marker is inverted, with the switch on and off.  (The APRILTAG
+    quad detector drops white quads before identification -- black must be inside --, so only the classic path finds them.)"""
+    import copy
+    import cv2
+    from conftest import cv2_params
+    from tools import synth
+    found = {True: 0, False: 0}
+    for inv in (True, False):
+        p = copy.copy(ref_params)
+        p.cornerRefinementMethod = mode
+        p.detectInvertedMarker = inv
+        for seed in range(6):
+            frame = synth.make_inverted_frame(dictionary.bytesList, 500 + seed, n_markers=40 if seed % 2 else 6)
+            gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+            cc, ci, cr = cv2.aruco.ArucoDetector(cv2.aruco.getPredefinedDictionary(cv2.aruco.DICT_4X4_50), cv2_params(p)).detectMarkers(gray)
+            det = oracle.detect_markers_apriltag if mode == 3 else oracle.detect_markers_classic
+            oc, oi, orj = det(gray, dictionary.raw, p)
+            want = [] if ci is None else ci.ravel().tolist()
+            assert oi.tolist() == want and len(orj) == len(cr)
+            if want:
+                assert np.array_equal(oc, np.array([c[0] for c in cc]))
+            found[inv] += len(want)
+    if mode == 0:
+        assert found[True] > 1.4 * found[False]   # the white markers are only found with the switch on

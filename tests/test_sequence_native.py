@@ -145,3 +145,25 @@ def test_py_round_equals_python_round():
     for nd in (0, 2, 3, 5):
         for v in vals:
             assert f(float(v), nd) == round(float(v), nd), (v, nd)
+
+
+def test_csv_float_fast_path_equals_python_str():
+    """apse_sequence_csv prints round(value, n) columns from the integer q of q / 10^n (sequence.cu, py_float_str): equal to
+    Python's str() on rounded values of every column width, on values that are NOT short decimals (general path), on
+    negative values, tiny values (scientific notation) and integers."""
+    rng = np.random.default_rng(11)
+    vals = []
+    for nd in (0, 1, 2, 3, 5, 6):
+        vals += [round(float(v), nd) for v in rng.uniform(-5000, 5000, 3000)]
+        vals += [round(float(v), nd) for v in rng.uniform(-1, 1, 1000)]
+    vals += [float(v) for v in rng.uniform(-100, 100, 2000)]                      # not short decimals
+    vals += [1e-05, 5e-05, 9.9e-05, 0.0001, 0.00011, 1e8, 999999999.0, 1e9, 1234567890.12, 1e15, 1e16, 0.1 + 0.2, 1 / 3, 2.675, 1e-9]
+    rows = np.zeros(len(vals), sequence.SEQ_ROW_DTYPE)
+    rows["frame_id"] = np.arange(len(vals)) + 1
+    rows["detected"][:, 3] = 1
+    rows["host_fields"] = 1
+    rows["marker_length"] = vals
+    text = sequence.rows_to_csv(rows, header=False).splitlines()
+    assert len(text) == len(vals)
+    for v, line in zip(vals, text):
+        assert line.split(",")[2] == str(v), (v, line)

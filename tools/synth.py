@@ -220,3 +220,27 @@ def make_sequence(bytes_list, base_seed: int, n_frames: int, width: int = 3840, 
         yield make_frame(bytes_list, base_seed + k, width, height, ids=tuple(all_ids[i] for i in keep), side_range=(64, 66),
                          jitter=0.01, noise_sigma=noise_sigma, centers=[centers[i].tolist() for i in keep],
                          angles=[float(ang[i]) for i in keep], leds=None if leds is None else leds[k % len(leds)])
+
+
+def make_inverted_frame(bytes_list, seed: int, width: int = 1920, height: int = 1080, n_markers: int = 6, noise_sigma: float = 3.0):
+    """Every other marker as a WHITE marker on a black quiet zone (detectInvertedMarker of cv2's DetectorParameters): random ids,
+    side 40-100 px, rotation + corner jitter, Gaussian noise.  Returns the frame."""
+    rng = np.random.default_rng(seed)
+    frame = background(rng, width, height)
+    placed = []
+    for k in range(n_markers):
+        side = float(rng.uniform(40, 100))
+        for _ in range(200):
+            cx, cy = float(rng.uniform(90, width - 90)), float(rng.uniform(90, height - 90))
+            if all((cx - px) ** 2 + (cy - py) ** 2 > (1.1 * (side + ps)) ** 2 for px, py, ps in placed):
+                break
+        else:
+            continue
+        placed.append((cx, cy, side))
+        quad = _random_quad(rng, cx, cy, side, 0.06)
+        tile = render_marker(bytes_list, int(rng.integers(0, 50)))
+        if k % 2 == 0:
+            tile = 255 - tile
+        _paste_marker(frame, tile, quad, quiet_frac=8.0 / tile.shape[0])
+    noise = rng.normal(0.0, noise_sigma, size=frame.shape).astype(np.float32)
+    return np.clip(np.rint(frame.astype(np.float32) + noise), 0, 255).astype(np.uint8)
