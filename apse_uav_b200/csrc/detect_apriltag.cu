@@ -466,15 +466,30 @@ __global__ void k_ccl_merge(const uint8_t *__restrict__ thresh, int w, int h, ui
         if (v == 127) continue;
         const uint32_t o = (uint32_t)(y * w + x);
         const bool has_s = y + 1 < h, has_e = x + 1 < w, has_w = x >= 1;   // always true inside the AprilTag ranges
+        // A union is skipped when other unions already join the same two components: pixels that are neighbours in a row (or a
+        // column) of ONE tile with equal values were joined by k_ccl_local, so only the first pixel of a run that continues across
+        // the boundary does the (global, latency-bound) union, and a diagonal crossing is only needed where the straight one is
+        // not there.  The unions relied upon must lie inside the AprilTag ranges (initiators x in [1, w-2], y in [0, h-2]); next
+        // to the image frame the plain rule stays.
         if (kind == 0) {
-            if (has_s && t[o + w] == v) uf_union_gmem(L, o, o + w);
-            if (v == 255 && has_s) {
+            const bool s_eq = has_s && t[o + w] == v;
+            const bool dedupe = full || (x >= 2 && y + 1 <= h - 2);
+            if (s_eq) {
+                const bool left_pair = dedupe && k > 0 && has_w && t[o - 1] == v && t[o + w - 1] == v;
+                if (!left_pair) uf_union_gmem(L, o, o + w);
+            }
+            if (v == 255 && has_s && !(s_eq && dedupe)) {
                 if (has_w && t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
                 if (has_e && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
             }
         } else if (kind == 1) {
-            if (has_e && t[o + 1] == v) uf_union_gmem(L, o, o + 1);
-            if (v == 255 && has_e && has_s && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
+            const bool e_eq = has_e && t[o + 1] == v;
+            const bool dedupe = full || x + 1 <= w - 2;
+            if (e_eq) {
+                const bool up_pair = dedupe && k > 32 && t[o - w] == v && t[o - w + 1] == v;
+                if (!up_pair) uf_union_gmem(L, o, o + 1);
+            }
+            if (v == 255 && has_e && has_s && !(e_eq && dedupe) && t[o + w + 1] == v) uf_union_gmem(L, o, o + w + 1);
         } else {
             if (v == 255 && has_w && has_s && t[o + w - 1] == v) uf_union_gmem(L, o, o + w - 1);
         }
