@@ -101,6 +101,8 @@ SIGNATURES = {
     "apse_sequence_scan": [C.POINTER(SeqConfig), _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(C.c_int)],
     "apse_sequence_jobs": [_vp, _vp, _i, _vp, _i, _i, _i, _i, _dp, _dp, _vp, _vp],
     "apse_sequence_finish": [_i, _vp, _vp, _i],
+    "apse_sequence_scan_chunk": [C.POINTER(SeqConfig), _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, C.POINTER(C.c_int)],
+    "apse_sequence_finish_chunk": [_vp, _i, _vp, _vp, _i],
     "apse_sequence_csv": [_vp, _i, _i, _vp, _i64],
     "apse_debug_sparse": [_vp, _vp, _vp, _i, C.POINTER(C.c_int), _vp],
     "apse_debug_decode": [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp],

@@ -71,7 +71,12 @@ struct SeqState {   // module globals of the reference that survive from frame t
     double msp[5], size_corr[5];
     bool have_msp[5];
     double altitude;
+    // values apse_sequence_finish leaves stale between frames
+    int leds;
+    double dist[3][2];
+    int initialised;
 };
+static_assert(sizeof(SeqState) <= sizeof(apse_seq_state), "apse_seq_state too small");
 
 static double marker_length_correction(const apse_seq_config &c, double altitude)
 {
@@ -111,18 +116,32 @@ int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers
                        const float *corners, const double *rvec, const double *tvec, int rescale_tvec, double *lengths,
                        apse_seq_row *rows, apse_seq_job *jobs, int job_cap, int *n_jobs)
 {
-    if (!cfg || n_frames < 0 || max_markers <= 0 || !n_markers || !ids || !corners || !rvec || !tvec) return APSE_ERR_INVALID_ARG;
+    apse_seq_state st;
+    memset(&st, 0, sizeof st);
+    return apse_sequence_scan_chunk(cfg, &st, 0, n_frames, max_markers, n_markers, ids, corners, rvec, tvec, rescale_tvec, lengths, rows, jobs,
+                                    job_cap, n_jobs);
+}
+
+int apse_sequence_scan_chunk(const apse_seq_config *cfg, apse_seq_state *state, int frame0, int n_frames, int max_markers,
+                             const int32_t *n_markers, const int32_t *ids, const float *corners, const double *rvec, const double *tvec,
+                             int rescale_tvec, double *lengths, apse_seq_row *rows, apse_seq_job *jobs, int job_cap, int *n_jobs)
+{
+    if (!cfg || !state || frame0 < 0 || n_frames < 0 || max_markers <= 0) return APSE_ERR_INVALID_ARG;
+    if (n_frames > 0 && (!n_markers || !ids || !corners || !rvec || !tvec)) return APSE_ERR_INVALID_ARG;
     if ((rows || jobs) && (!rows || !jobs || !n_jobs || job_cap < 0)) return APSE_ERR_INVALID_ARG;
     const apse_seq_config &c = *cfg;
     const double diff_max = 2.0 / 3 * c.step_frame * 2;                                    // :524
-    SeqState S;
-    memset(&S, 0, sizeof S);
-    S.marker_length = c.marker_length_org;                                                 // :521
+    SeqState &S = *reinterpret_cast<SeqState *>(state);
+    if (!S.initialised) {
+        memset(&S, 0, sizeof S);
+        S.marker_length = c.marker_length_org;                                             // :521
+        S.initialised = 1;
+    }
     int nj = 0;
     std::vector<int32_t> idl((size_t)max_markers);
     for (int fr = 0; fr < n_frames; fr++) {
-        const int k = c.start_frame + fr * c.step_frame;
-        const bool first = fr == 0;
+        const int k = c.start_frame + (frame0 + fr) * c.step_frame;
+        const bool first = frame0 + fr == 0;
         if (lengths) lengths[fr] = S.marker_length;    // the marker length estimatePoseSingleMarkers sees in this frame (:601)
         const double tscale = rescale_tvec ? S.marker_length / c.marker_length_org : 1.0;   // tvec is linear in the marker length
         const int n = n_markers[fr] < max_markers ? n_markers[fr] : max_markers;
@@ -200,7 +219,7 @@ int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers
                             if (nj >= job_cap) return APSE_ERR_CAPACITY;
                             apse_seq_job &J = jobs[nj];
                             memset(&J, 0, sizeof J);
-                            J.frame = fr; J.kind = 0;
+                            J.frame = frame0 + fr; J.kind = 0;
                             for (int a = 0; a < 3; a++) { J.rvec[a] = frv[3 * i + a]; J.tvec[a] = tv[a] / size_corr; }
                             int thr = c.leds_threshold;
                             if (thr < 0) { thr = 190 + (int)(tv[2] / c.marker_div); if (thr < 240) thr = 240; }   // max(190 + int(..), 240)
@@ -232,7 +251,7 @@ int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers
                         if (nj >= job_cap) return APSE_ERR_CAPACITY;
                         apse_seq_job &J = jobs[nj];
                         memset(&J, 0, sizeof J);
-                        J.frame = fr; J.kind = v;
+                        J.frame = frame0 + fr; J.kind = v;
                         for (int a = 0; a < 3; a++) {
                             J.rvec[a] = frv[3 * j + a];
                             J.tvec[a] = ftv[3 * j + a] * tscale / S.size_corr[v];
@@ -265,9 +284,18 @@ int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers
 
 int apse_sequence_finish(int n_frames, apse_seq_row *rows, const apse_seq_job_result *results, int n_jobs)
 {
-    if (n_frames < 0 || !rows || (n_jobs > 0 && !results)) return APSE_ERR_INVALID_ARG;
-    int leds = 0;
-    double dist[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    apse_seq_state st;
+    memset(&st, 0, sizeof st);
+    reinterpret_cast<SeqState *>(&st)->initialised = 1;
+    return apse_sequence_finish_chunk(&st, n_frames, rows, results, n_jobs);
+}
+
+int apse_sequence_finish_chunk(apse_seq_state *state, int n_frames, apse_seq_row *rows, const apse_seq_job_result *results, int n_jobs)
+{
+    if (!state || n_frames < 0 || (n_frames > 0 && !rows) || (n_jobs > 0 && !results)) return APSE_ERR_INVALID_ARG;
+    SeqState &S = *reinterpret_cast<SeqState *>(state);
+    int &leds = S.leds;
+    double (&dist)[3][2] = S.dist;
     for (int fr = 0; fr < n_frames; fr++) {
         apse_seq_row &r = rows[fr];
         if (r.job_led >= 0 && r.job_led < n_jobs) leds = results[r.job_led].leds;

@@ -32,10 +32,19 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def scan(cfg: SeqConfig, n, ids, corners, rvec, tvec, rescale_tvec=False, want_rows=True):
+def new_state():
+    """State of one pass of a chunked scan (apse_seq_state: the reference's module globals, zeroed)."""
+    return np.zeros(512, np.uint8)
+
+
+def scan(cfg: SeqConfig, n, ids, corners, rvec, tvec, rescale_tvec=False, want_rows=True, state=None, frame0=0):
     """apse_sequence_scan on host arrays n [F], ids [F,M], corners [F,M,4,2], rvec / tvec [F,M,3].
-    Returns (lengths [F] float64, rows | None, jobs | None)."""
+    Returns (lengths [F] float64, rows | None, jobs | None).
+    state (new_state()) + frame0: these are frames frame0 .. frame0 + F - 1 of a sequence scanned chunk by chunk
+    (apse_sequence_scan_chunk); a job-list overflow is retried from a copy of the state."""
     lib = _lib.load()
+    if state is not None:
+        return _scan_chunk(lib, cfg, state, int(frame0), n, ids, corners, rvec, tvec, rescale_tvec, want_rows)
     n = np.ascontiguousarray(n, np.int32)
     F = int(n.shape[0])
     ids = np.ascontiguousarray(ids, np.int32).reshape(F, -1)
@@ -63,6 +72,46 @@ def scan(cfg: SeqConfig, n, ids, corners, rvec, tvec, rescale_tvec=False, want_r
     if rc != 0:
         raise ApseError(rc, "apse_sequence_scan failed")
     return lengths, rows, jobs
+
+
+def _scan_chunk(lib, cfg, state, frame0, n, ids, corners, rvec, tvec, rescale_tvec, want_rows):
+    n = np.ascontiguousarray(n, np.int32)
+    F = int(n.shape[0])
+    ids = np.ascontiguousarray(ids, np.int32).reshape(F, -1)
+    M = int(ids.shape[1]) if F else 1
+    corners = np.ascontiguousarray(corners, np.float32).reshape(F, M, 4, 2)
+    rvec = np.ascontiguousarray(rvec, np.float64).reshape(F, M, 3)
+    tvec = np.ascontiguousarray(tvec, np.float64).reshape(F, M, 3)
+    lengths = np.empty(F, np.float64)
+    args = (F, M, _ptr(n), _ptr(ids), _ptr(corners), _ptr(rvec), _ptr(tvec), 1 if rescale_tvec else 0, _ptr(lengths))
+    if not want_rows:
+        rc = lib.apse_sequence_scan_chunk(C.byref(cfg), _ptr(state), frame0, *args, None, None, 0, None)
+        if rc != 0:
+            raise ApseError(rc, "apse_sequence_scan_chunk failed")
+        return lengths, None, None
+    rows = np.zeros(F, SEQ_ROW_DTYPE)
+    nj = C.c_int(0)
+    cap = 4 * F + 64
+    entry = state.copy()
+    while True:
+        jobs = np.empty(cap, SEQ_JOB_DTYPE)   # (the library clears every job it emits)
+        rc = lib.apse_sequence_scan_chunk(C.byref(cfg), _ptr(state), frame0, *args, _ptr(rows), _ptr(jobs), cap, C.byref(nj))
+        if rc != -4:
+            break
+        state[:] = entry   # duplicated marker ids: again from the chunk's entry state with a larger job list
+        cap *= 4
+    if rc != 0:
+        raise ApseError(rc, "apse_sequence_scan_chunk failed")
+    return lengths, rows, jobs[:nj.value]
+
+
+def finish_chunk(state, rows, results):
+    """apse_sequence_finish_chunk: the stale distance / LED values travel in the second pass's state."""
+    rc = _lib.load().apse_sequence_finish_chunk(_ptr(state), len(rows), _ptr(rows) if len(rows) else None,
+                                                _ptr(results) if len(results) else None, len(results))
+    if rc != 0:
+        raise ApseError(rc, "apse_sequence_finish_chunk failed")
+    return rows
 
 
 def run_jobs(engine, jobs, gray=None, frame0=0, results=None):
@@ -182,3 +231,46 @@ def postpass_device(engine, det, start_frame=1, leds=False, leds_threshold=None,
     if details:   # what the overlay renderer needs (render.py)
         return dict(rows=rows, jobs=jobs, results=results, n=n, ids=ids, corners=corners)
     return rows
+
+
+class SequenceStream:
+    """The post-pass of postpass_device for a sequence whose per-frame results arrive in chunks (frame order): every push runs
+    both scans, the exact-pose launch and the projection jobs for its frames only, carrying the reference's globals in two
+    apse_seq_state blocks -- the rows equal those of one postpass_device call over the whole sequence (tests/test_sequence_native.py,
+    tests/test_gpu_pipeline.py).  The GPU work of a push goes to a high-priority stream of its own, so it does not queue behind
+    pipeline batches that are still running.  LED read-out is not streamed (shard.run_sequence handles it)."""
+
+    def __init__(self, engine, start_frame=1):
+        self.engine = engine
+        torch = engine.torch
+        _np_types(torch)
+        w, h = engine.size
+        self.cfg = seq_config(start_frame, 1, False, None, w, h)
+        self.s1, self.s2 = new_state(), new_state()
+        self.frames = 0
+        self.rows = []
+        self.stream = torch.cuda.Stream(device=engine.tdev, priority=-1)
+
+    def push(self, n, ids, corners, rvec, tvec, corners_dev, n_dev, ready=None):
+        """Host arrays n [F], ids [F,M], corners [F,M,4,2], rvec / tvec [F,M,3] (nominal marker length) of the next F frames and the
+        same corners / counts on the device ([F,M,4,2] float32, [F] int32, contiguous); ready: event the device copies wait for."""
+        e = self.engine
+        torch = e.torch
+        F = int(len(n))
+        if F == 0:
+            return
+        f0 = self.frames
+        lengths, _, _ = scan(self.cfg, n, ids, corners, rvec, tvec, rescale_tvec=True, want_rows=False, state=self.s1, frame0=f0)
+        with torch.cuda.stream(self.stream):
+            if ready is not None:
+                self.stream.wait_event(ready)
+            ml = torch.from_numpy(lengths.astype(np.float32)).to(e.tdev)
+            rv2, tv2 = e.pose_frames(corners_dev, n_dev, ml)
+            rv2h, tv2h = _host_copy(e, [rv2, tv2])
+            _, rows, jobs = scan(self.cfg, n, ids, corners, rv2h, tv2h, state=self.s2, frame0=f0)
+            results = run_jobs(e, jobs)
+        self.rows.append(finish_chunk(self.s2, rows, results))
+        self.frames += F
+
+    def result(self):
+        return np.concatenate(self.rows) if self.rows else np.zeros(0, SEQ_ROW_DTYPE)

@@ -254,6 +254,154 @@ def _finish_sequence(pipe, det, gray, n_local, rank, world, group, start_frame, 
     return rows if as_rows else sequence.rows_to_dicts(rows)
 
 
+def round_plan(n_frames: int, world: int, batch: int, tail: int = 0):
+    """Round-robin sharding for a streamed run: the sequence is cut into rounds of at most world * batch consecutive frames and
+    every round into `world` consecutive parts (rank r takes part r), all as equal as possible.  Round k is complete as soon as
+    every rank has finished its k-th batch, so rank 0 can run the sequential post-pass of round k while all ranks work on round
+    k + 1 -- with contiguous blocks (shard_bounds) nothing could start before the very end.  tail > 0: a last, short round of
+    about `tail` frames per rank keeps the part of the post-pass that nothing overlaps small.
+    Returns [[(lo, hi) for each rank] for each round]."""
+    world, batch = max(1, int(world)), max(1, int(batch))
+    cuts = [0]
+    tail_frames = min(n_frames, max(0, int(tail)) * world)
+    if tail_frames and n_frames - tail_frames < world * batch:
+        tail_frames = 0
+    body = n_frames - tail_frames
+    nr = max(1, -(-body // (world * batch))) if body else 0
+    for k in range(nr):
+        cuts.append((body * (k + 1)) // nr)
+    if tail_frames:
+        cuts.append(n_frames)
+    return [[(a + lo, a + hi) for lo, hi in shard_bounds(b - a, world)] for a, b in zip(cuts[:-1], cuts[1:])]
+
+
+def _packed_fields(torch, cap, m):
+    """Layout of the packed per-round results of one rank: n | status | ids | corners | rvec | tvec, 16-byte aligned fields."""
+    fields = (("n", torch.int32, ()), ("status", torch.int32, ()), ("ids", torch.int32, (m,)), ("corners", torch.float32, (m, 4, 2)),
+              ("rvec", torch.float64, (m, 3)), ("tvec", torch.float64, (m, 3)))
+    sizes_b = [cap * int(np.prod(shape, dtype=np.int64)) * torch.empty((), dtype=dt).element_size() for _, dt, shape in fields]
+    offs = np.concatenate([[0], np.cumsum([(b + 15) // 16 * 16 for b in sizes_b])]).astype(np.int64)
+    return fields, sizes_b, offs
+
+
+def run_sequence_streamed(pipe, frames, plan, rank=0, world=1, group=None, start_frame=1, as_rows=False, chunk_frames=240):
+    """aruco_detect.py:571-810 for a sequence sharded by round_plan, with the post-pass streamed behind the pipeline.
+    frames: this rank's parts of all rounds, concatenated ([n_local,H,W,3] uint8 CUDA tensor); plan: round_plan(...) of the whole
+    sequence (the same on every rank).  Per round every rank enqueues its batch (no host synchronisation), packs the batch's
+    results on a side stream and -- world > 1 -- sends them to rank 0 (one NCCL gather per round, off the pipeline's streams);
+    rank 0 copies the round to pinned memory and, between its own enqueues, feeds every completed round to a
+    sequence.SequenceStream (both scans, exact poses, projection jobs for those frames).  What is left after the last batch is
+    the post-pass of the last round.  Rows equal run_sequence's (tests/test_gpu_pipeline.py).  No LED read-out (run_sequence)."""
+    from . import sequence
+    from ._lib import ApseError
+    e = pipe.engine
+    torch = e.torch
+    dev = e.tdev
+    M = pipe.max_markers
+    nr = len(plan)
+    cap = max(1, max((hi - lo for rnd in plan for lo, hi in rnd), default=0))
+    if cap > pipe.max_batch:
+        raise ApseError(-1, f"round_plan parts of {cap} frames exceed the pipeline's max_batch {pipe.max_batch}")
+    fields, sizes_b, offs = _packed_fields(torch, cap, M)
+    nbytes = int(offs[-1])
+    n_local = sum(rnd[rank][1] - rnd[rank][0] for rnd in plan)
+    if int(frames.shape[0]) != n_local:
+        raise ValueError(f"rank {rank} holds {int(frames.shape[0])} frames, the plan gives it {n_local}")
+    key = (nr, world, nbytes, n_local)
+    st = getattr(pipe, "_stream_bufs", None)
+    if st is None or st["key"] != key:
+        st = pipe._stream_bufs = dict(key=key, comm=torch.cuda.Stream(device=dev, priority=-1),
+                                      send=torch.zeros((nr, nbytes), dtype=torch.uint8, device=dev),
+                                      recv=torch.zeros((nr, world, nbytes), dtype=torch.uint8, device=dev) if rank == 0 else None,
+                                      pin=torch.zeros((nr, world, nbytes), dtype=torch.uint8).pin_memory() if rank == 0 else None,
+                                      det=e.alloc_detections(max(n_local, 1), M, False, pose=True))
+        torch.cuda.current_stream(dev).synchronize()
+    comm, det = st["comm"], st["det"]
+    cur = torch.cuda.current_stream(dev)
+    filled = cur.record_event()
+    for s_ in pipe.streams or ():
+        s_.wait_event(filled)
+    comm.wait_event(filled)
+    seq = sequence.SequenceStream(e, start_frame) if rank == 0 else None
+    arrived = []          # rank 0: (round, event) of rounds whose results are on their way to pinned memory
+    done_upto = 0
+
+    def process(upto):
+        # rounds [done_upto, upto) are in pinned memory: one push
+        nonlocal done_upto
+        if upto <= done_upto:
+            return
+        host = st["pin"].numpy()
+        parts = {k: [] for k, _, _ in fields}
+        dev_c, dev_n = [], []
+        for r in range(done_upto, upto):
+            for q in range(world):
+                sz = plan[r][q][1] - plan[r][q][0]
+                if sz == 0:
+                    continue
+                for (k, dt, shape), o, sb in zip(fields, offs, sizes_b):
+                    parts[k].append(host[r, q, int(o):int(o) + sb].view(sequence._NP[dt]).reshape((cap,) + shape)[:sz])
+                    if k in ("corners", "n"):
+                        (dev_c if k == "corners" else dev_n).append(st["recv"][r, q, int(o):int(o) + sb].view(dt).reshape((cap,) + shape)[:sz])
+        if not parts["n"]:
+            done_upto = upto
+            return
+        h = {k: (v[0] if len(v) == 1 else np.concatenate(v)) for k, v in parts.items()}
+        bad = np.nonzero(h["status"])[0]
+        if len(bad):
+            raise ApseError(int(h["status"][bad[0]]), f"work-buffer capacity exceeded in frames {(seq.frames + bad[:8]).tolist()}")
+        with torch.cuda.stream(seq.stream):
+            seq.stream.wait_event(arrived[upto - 1][1])
+            cd = dev_c[0].contiguous() if len(dev_c) == 1 else torch.cat(dev_c, 0)
+            nd = dev_n[0].contiguous() if len(dev_n) == 1 else torch.cat(dev_n, 0)
+        seq.push(h["n"], h["ids"], h["corners"], h["rvec"], h["tvec"], cd, nd)
+        done_upto = upto
+
+    lo = 0
+    for r in range(nr):
+        a, b = plan[r][rank]
+        sz = b - a
+        done = []
+        if sz:
+            sl = {k: v[lo:lo + sz] for k, v in det.items()}
+            res = pipe.run_batch(frames[lo:lo + sz], sync=False, input_ready=False, out=sl)
+            done = list(res.get("_done", ())) or [cur.record_event()]
+        with torch.cuda.stream(comm):
+            for ev in done:
+                comm.wait_event(ev)
+            buf = st["send"][r] if world > 1 or rank != 0 else st["recv"][r, 0]
+            if sz:
+                for (k, dt, shape), o, sb in zip(fields, offs, sizes_b):
+                    buf[int(o):int(o) + sb].view(dt).reshape((cap,) + shape)[:sz] = det[k][lo:lo + sz]
+            if world > 1:
+                import torch.distributed as dist
+                dist.gather(buf, list(st["recv"][r].unbind(0)) if rank == 0 else None, dst=0, group=group)
+            if rank == 0:
+                st["pin"][r].copy_(st["recv"][r], non_blocking=True)
+                arrived.append((r, comm.record_event()))
+        lo += sz
+        if rank == 0:
+            # completed rounds, once enough frames have piled up (every push costs a few host round trips)
+            ready = done_upto
+            while ready < len(arrived) and arrived[ready][1].query():
+                ready += 1
+            pending = sum(hi_ - lo_ for rr in range(done_upto, ready) for lo_, hi_ in plan[rr])
+            if pending >= chunk_frames:
+                process(ready)
+    if rank != 0:
+        comm.synchronize()
+        return None
+    # what is left: first everything but the last round (its batch may still be running), then the last round
+    if nr - done_upto > 1:
+        arrived[nr - 2][1].synchronize()
+        process(nr - 1)
+    if nr:
+        arrived[nr - 1][1].synchronize()
+        process(nr)
+    rows = seq.result()
+    return rows if as_rows else sequence.rows_to_dicts(rows)
+
+
 def run_sequence_python(pipe, frames, start_frame=1, leds=False):
     """Single-process run with the per-frame Python mirror of the reference's loop (postpass.SequencePostPass) instead of the
     native post-pass: every cv2.projectPoints of the reference becomes one kernel launch.  Kept for the parity tests (the

@@ -10,8 +10,11 @@ Default workload = BASELINE.json configs[2] (N = 1) / configs[3] (N > 1): ONE ST
     batched GPU pipeline (undistort + gamma + gray -> detectMarkers -> estimatePoseSingleMarkers) per rank
     -> per-frame results gathered on rank 0 -> native sequence post-pass (marker-length recurrence, gating, second exact
     pose pass, vehicle distances) -> the CSV text of aruco_detect.py:146-185, to its last row.
-For N > 1 the SAME sequence is frame-sharded (contiguous blocks, shard.shard_bounds): strong scaling, the gather and the
-post-pass on rank 0 are inside the timed region, no collective on the hot path.
+For N > 1 the SAME sequence is frame-sharded: strong scaling, the gather and the post-pass on rank 0 are inside the timed
+region, no collective on the pipeline's streams.  Default: the frames are dealt out in rounds (shard.round_plan; round k = N
+consecutive batches, one per rank) and the post-pass is STREAMED (shard.run_sequence_streamed): the results of round k travel
+to rank 0 on a side stream and are post-processed there while all ranks compute round k + 1, so only the short last round's
+post-pass is left after the pipeline.  --no-stream: contiguous blocks (shard.shard_bounds), one gather and one post-pass at the end.
 Timed region: barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks.
 `value`        : frames resident in HBM -> last CSV row (every step streams 44.8 GB, far beyond the 126 MB L2).
 `pipeline_only`: the same frames through the GPU pipeline alone (no gather / post-pass): what `roofline` explains.
@@ -237,8 +240,11 @@ def workload_config(args, frames_per_step, world):
                 "step": "one step = the whole sequence, first enqueue to last CSV row",
                 "l2": "every step streams the whole HBM-resident sequence (44.8 GB at 1800 frames; L2 is 126 MB)",
                 "batch": args.batch, "streams_per_gpu": args.streams,
-                "parallelism": f"same sequence frame-sharded x{world} (contiguous blocks), no collective on the hot path; "
-                               "per-frame results gathered on rank 0 for the sequential post-pass"}
+                "parallelism": (f"same sequence frame-sharded x{world} in rounds of {world} batches (round-robin), no collective on the "
+                                "pipeline's streams; per-round results sent to rank 0 on a side stream, sequential post-pass streamed "
+                                "behind the pipeline" if args.stream else
+                                f"same sequence frame-sharded x{world} (contiguous blocks), no collective on the hot path; "
+                                "per-frame results gathered on rank 0 for the sequential post-pass")}
     if args.workload == "preprocess64":
         return {"workload": "configs[1]: undistort (cam_params.json) + gamma correction (+ gray) on a batch of 64 synthetic 4K frames, "
                             "corrected BGR and gray written", "frames_per_step": frames_per_step, "frame": [W, H, 3],
@@ -400,20 +406,30 @@ def run_sequence_workload(args, rank, world, local_rank):
     dev = c.dev
     pipe = make_pipeline(args, local_rank)
     n_seq = args.sequence_frames
-    lo, hi = shard.shard_bounds(n_seq, world)[rank]
-    n_local = hi - lo
-    # ---- this rank's block of the synthetic sequence, resident in HBM
+    # ---- this rank's frames of the synthetic sequence, resident in HBM.  Streamed run (default): the sequence is dealt out in
+    # rounds (shard.round_plan: round k = world consecutive batches, rank r takes the r-th), so that rank 0 runs the sequential
+    # post-pass of round k while all ranks compute round k + 1; --no-stream: contiguous blocks, post-pass after the gather
+    if args.stream:
+        rounds = shard.round_plan(n_seq, world, args.batch, tail=args.tail_frames)
+        local_idx = [g for rnd in rounds for g in range(*rnd[rank])]
+    else:
+        rounds = None
+        local_idx = list(range(*shard.shard_bounds(n_seq, world)[rank]))
+    n_local = len(local_idx)
     base = torch.from_numpy(base_sequence(args.base_frames)).to(dev)
     plan = sequence_plan(n_seq, args.base_frames)
     frames = torch.empty((n_local, H, W, 3), dtype=torch.uint8, device=dev)
-    for j in range(n_local):
-        p, dy, dx = plan[lo + j]
+    for j, g in enumerate(local_idx):
+        p, dy, dx = plan[g]
         frames[j] = torch.roll(base[p], shifts=(dy, dx), dims=(0, 1))
     torch.cuda.synchronize()
     state = {}
 
     def step(_i):
-        rows = shard.run_sequence(pipe, frames, rank, world, as_rows=True)
+        if args.stream:
+            rows = shard.run_sequence_streamed(pipe, frames, rounds, rank, world, as_rows=True)
+        else:
+            rows = shard.run_sequence(pipe, frames, rank, world, as_rows=True)
         if rank == 0:
             state["rows"] = rows
             state["csv"] = sequence.rows_to_csv(rows)          # the text aruco_detect.py:131-185 writes, to its last row
@@ -436,7 +452,10 @@ def run_sequence_workload(args, rank, world, local_rank):
     markers = int(state["det"]["n"].sum().item())
     # ---- post-pass alone (rank 0; everything after the pipeline of a one-GPU run), for the split in the report
     post_ms = None
+    stream_check = None
     if world == 1:
+        if args.stream:   # the streamed rows are the rows of the plain run (gather at the end, one post-pass)
+            stream_check = bool(sequence.rows_to_csv(shard.run_sequence(pipe, frames, 0, 1, as_rows=True)) == state["csv"])
         det = state["det"]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -519,6 +538,11 @@ def run_sequence_workload(args, rank, world, local_rank):
             "pipeline_only": {"value": pipe_value, "unit": "frames/s", "ms_per_step": ms_pipe / args.steps,
                               "note": "GPU pipeline alone (undistort+gamma+gray -> detect -> pose), no gather / post-pass / CSV"},
             "postpass_ms_per_step": post_ms,
+            "postpass": ({"mode": "streamed", "rounds": len(rounds), "frames_in_last_round": sum(b - a for a, b in rounds[-1]) if rounds else 0,
+                          "equals_unstreamed_csv": stream_check,
+                          "note": "post-pass of round k on rank 0 while all ranks compute round k+1 (shard.run_sequence_streamed); "
+                                  "postpass_ms_per_step = the same post-pass run in one piece after the pipeline"}
+                         if args.stream else {"mode": "after the gather"}),
             "pipeline_roofline": {"algorithmic_bytes_per_frame": ALG_BYTES["pipeline"],
                                   "achieved_gbs_per_gpu": ALG_BYTES["pipeline"] * pipe_value / world / 1e9,
                                   "frac_of_hbm_peak": ALG_BYTES["pipeline"] * pipe_value / world / 1e9 / peak,
@@ -722,6 +746,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10, help="timed steps; one step = the whole sequence (default workload)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-stream", dest="stream", action="store_false", help="sequence workload: contiguous blocks, post-pass after the gather")
+    ap.add_argument("--tail-frames", type=int, default=8, help="streamed sequence: frames per rank in the short last round")
     ap.add_argument("--workload", default="sequence", choices=["sequence", "preprocess64", "dense-apriltag", "dense-classic"])
     ap.add_argument("--sequence-frames", type=int, default=SEQUENCE_FRAMES, help="frames of the sequence (configs[2]: 1800)")
     ap.add_argument("--batch", type=int, default=60, help="frames per pipeline batch")

@@ -250,6 +250,16 @@ double apse_py_round(double x, int ndigits);
 int apse_sequence_scan(const apse_seq_config *cfg, int n_frames, int max_markers, const int32_t *n_markers, const int32_t *ids,
                        const float *corners, const double *rvec, const double *tvec, int rescale_tvec, double *lengths,
                        apse_seq_row *rows, apse_seq_job *jobs, int job_cap, int *n_jobs);
+/* The same scan for a sequence that arrives in chunks (frames frame0 .. frame0 + n_frames - 1 of the sequence, chunks in order):
+ * `state` carries the reference's module globals (:519-524, :782) from chunk to chunk; zero it before the first chunk.  Use one
+ * state per pass (rescale_tvec = 1 / = 0).  Job and row indices are local to the chunk. */
+typedef struct apse_seq_state { unsigned char opaque[512]; } apse_seq_state;
+int apse_sequence_scan_chunk(const apse_seq_config *cfg, apse_seq_state *state, int frame0, int n_frames, int max_markers,
+                             const int32_t *n_markers, const int32_t *ids, const float *corners, const double *rvec, const double *tvec,
+                             int rescale_tvec, double *lengths, apse_seq_row *rows, apse_seq_job *jobs, int job_cap, int *n_jobs);
+/* apse_sequence_finish for one chunk; the stale values (:729-780 leave the last distance / LED code in place) travel in the
+ * state of the SECOND pass (the one apse_sequence_scan_chunk produced these rows with) */
+int apse_sequence_finish_chunk(apse_seq_state *state, int n_frames, apse_seq_row *rows, const apse_seq_job_result *results, int n_jobs);
 /* Evaluates the jobs on the device (one warp per job) and copies the results back; synchronous on `stream`.
  * gray (DEVICE, nullable): corrected gray frames [n_gray_frames][h][w] of the sequence frames frame0 .. frame0 + n_gray_frames - 1;
  * LED jobs of other frames are left with valid = 0 (frame-sharded runs: every rank fills the LED jobs of its own frames). */

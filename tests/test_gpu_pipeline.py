@@ -139,6 +139,7 @@ def test_sharded_sequence_world2(dictionary, tmp_path):
     import json
     res = json.load(open(out))
     assert res["sharded"] == res["single"]
+    assert res["rounds"] >= 5 and res["streamed"] == res["single_noleds"]
     from conftest import assert_csv_rows_match, golden_csv
     assert_csv_rows_match(res["sharded"], golden_csv("sequence_4k_events.json")[1])
 
@@ -163,12 +164,38 @@ frames = np.stack(list(synth.make_sequence(d.bytesList, g["base_seed"], g["n_fra
 pipe = A.Pipeline(K, D, (3840, 2160), G.gamma_lut(), d, G.reference_parameters(aruco), max_batch=6, device=lr, max_markers=64, streams=3)
 lo, hi = shard.shard_bounds(len(frames), world)[rank]
 rows = shard.run_sequence(pipe, torch.from_numpy(frames[lo:hi]).cuda(), rank, world, leds=True)
+# the streamed run: frames dealt out in rounds, post-pass of round k on rank 0 while both ranks compute round k + 1
+plan = shard.round_plan(len(frames), world, 6, tail=2)
+mine = np.concatenate([frames[a:b] for rnd in plan for a, b in [rnd[rank]]])
+streamed = None
+for _ in range(2):   # twice: the second run reuses the cached buffers
+    streamed = shard.run_sequence_streamed(pipe, torch.from_numpy(mine).cuda(), plan, rank, world, chunk_frames=12)
 if rank == 0:
     single = shard.run_sequence(pipe, torch.from_numpy(frames).cuda(), 0, 1, leds=True)
-    json.dump({"sharded": rows, "single": single}, open(sys.argv[2], "w"))
+    single_noleds = shard.run_sequence(pipe, torch.from_numpy(frames).cuda(), 0, 1)
+    json.dump({"sharded": rows, "single": single, "streamed": streamed, "single_noleds": single_noleds, "rounds": len(plan)}, open(sys.argv[2], "w"))
 dist.barrier()
 dist.destroy_process_group()
 """
+
+
+@pytest.mark.parametrize("streams", [0, 3])
+def test_streamed_sequence_equals_plain(camera, lut, dictionary, ref_params, streams):
+    """shard.run_sequence_streamed (frames dealt out in rounds, post-pass fed chunk by chunk behind the pipeline: what bench.py
+    times) gives the rows and the CSV text of shard.run_sequence on the 64-frame events sequence, for several round / chunk sizes."""
+    pytest.importorskip("cv2")
+    import torch
+    import apse_uav_b200 as A
+    from apse_uav_b200 import shard, sequence
+    K, D = camera
+    pipe = A.Pipeline(K, D, (3840, 2160), lut, dictionary, ref_params, max_batch=6, max_markers=64, streams=streams)
+    g, ref, frames = _golden_frames(dictionary, "sequence_4k_events.json")
+    want = sequence.rows_to_csv(shard.run_sequence(pipe, frames, as_rows=True))
+    for batch, tail, chunk in ((6, 2, 12), (6, 0, 1), (5, 1, 1000), (6, 2, 12)):
+        plan = shard.round_plan(len(frames), 1, batch, tail=tail)
+        rows = shard.run_sequence_streamed(pipe, frames, plan, as_rows=True, chunk_frames=chunk)
+        assert len(rows) == len(frames) and sequence.rows_to_csv(rows) == want
+    pipe.close()
 
 
 def test_multi_stream_equals_single_stream(pipe, camera, lut, dictionary, ref_params, frames4k):

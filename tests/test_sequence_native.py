@@ -167,3 +167,32 @@ def test_csv_float_fast_path_equals_python_str():
     assert len(text) == len(vals)
     for v, line in zip(vals, text):
         assert line.split(",")[2] == str(v), (v, line)
+
+
+@pytest.mark.parametrize("chunks", [[60], [7, 1, 30, 22], [1] * 60, [59, 1]])
+def test_chunked_scan_equals_whole_sequence(oracle, camera, chunks):
+    """apse_sequence_scan_chunk / _finish_chunk (a sequence that arrives in pieces: shard.run_sequence_streamed): lengths, rows
+    and jobs of both passes, and the finished rows with their stale values, equal the single-call scan for any chunking."""
+    K, D = camera
+    n, ids, corners, rvec, tvec = fabricate(oracle, K, D, F=60, seed=9)
+    project = lambda obj, r, t: oracle.project_points(obj, r, t, K, D)
+    cfg = sequence.seq_config()
+    len1, _, _ = sequence.scan(cfg, n, ids, corners, rvec, tvec, rescale_tvec=True, want_rows=False)
+    len2, rows, jobs = sequence.scan(cfg, n, ids, corners, rvec, tvec)
+    want = sequence.finish(rows, eval_jobs_numpy(jobs, project))
+    s1, s2 = sequence.new_state(), sequence.new_state()
+    got_rows, got_len1, got_len2, lo = [], [], [], 0
+    for c in chunks:
+        sl = slice(lo, lo + c)
+        l1, _, _ = sequence.scan(cfg, n[sl], ids[sl], corners[sl], rvec[sl], tvec[sl], rescale_tvec=True, want_rows=False, state=s1, frame0=lo)
+        l2, r, j = sequence.scan(cfg, n[sl], ids[sl], corners[sl], rvec[sl], tvec[sl], state=s2, frame0=lo)
+        assert (j["frame"] >= lo).all() and (j["frame"] < lo + c).all()
+        got_rows.append(sequence.finish_chunk(s2, r, eval_jobs_numpy(j, project)))
+        got_len1.append(l1); got_len2.append(l2)
+        lo += c
+    assert np.array_equal(np.concatenate(got_len1), len1) and np.array_equal(np.concatenate(got_len2), len2)
+    got = np.concatenate(got_rows)
+    for f in ("frame_id", "detected", "host_fields", "leds", "accepted_mask", "marker_length", "altitude", "fov_width", "fov_height",
+              "dist_aruco", "dist_bbox"):
+        assert np.array_equal(got[f], want[f]), f
+    assert sequence.rows_to_csv(got) == sequence.rows_to_csv(want)

@@ -17,6 +17,27 @@ def test_shard_bounds_cover_everything():
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
 
 
+def test_round_plan_deals_the_sequence_out_in_order():
+    """shard.round_plan (streamed runs): rounds and parts are consecutive, cover the sequence once, stay within the batch size,
+    are balanced over the ranks, and the optional last round is short."""
+    from apse_uav_b200.shard import round_plan
+    for n in (0, 1, 7, 130, 1800, 1801):
+        for w in (1, 2, 3, 8):
+            for batch, tail in ((60, 0), (60, 8), (6, 2)):
+                plan = round_plan(n, w, batch, tail)
+                flat = [p for rnd in plan for p in rnd]
+                assert all(len(rnd) == w for rnd in plan)
+                assert sum(hi - lo for lo, hi in flat) == n
+                if flat:
+                    assert flat[0][0] == 0 and flat[-1][1] == n and all(flat[i][1] == flat[i + 1][0] for i in range(len(flat) - 1))
+                    assert max(hi - lo for lo, hi in flat) <= batch
+                for rnd in plan:
+                    sizes = [hi - lo for lo, hi in rnd]
+                    assert max(sizes) - min(sizes) <= 1
+                if tail and n >= 2 * w * batch:
+                    assert sum(hi - lo for lo, hi in plan[-1]) == tail * w
+
+
 WORKER = r'''
 import os, pickle, sys
 sys.path.insert(0, sys.argv[1])
