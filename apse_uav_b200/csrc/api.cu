@@ -482,6 +482,16 @@ int apse_debug_sparse(apse_ctx *ctx, uint16_t *bound_table_host, uint8_t *eflag_
     return APSE_OK;
 }
 
+int apse_debug_tile_bounds(apse_ctx *ctx, uint16_t *bounds_dev, int batch, void *stream)
+{
+    if (!ctx || !bounds_dev || batch <= 0 || batch > ctx->max_batch) CTX_FAIL(ctx, APSE_ERR_INVALID_ARG, "debug_tile_bounds: bad argument");
+    const int slot = ctx->tiles_slot ^ 1;   // the slot the last apse_preprocess_tiles[_sparse] call used
+    if (!ctx->tbounds[slot]) CTX_FAIL(ctx, APSE_ERR_NOT_CONFIGURED, "debug_tile_bounds: no sparse batch was preprocessed on this context");
+    CUDA_TRY(ctx, cudaMemcpyAsync(bounds_dev, ctx->tbounds[slot], (size_t)batch * (ctx->w / 4) * (ctx->h / 4) * sizeof(uint16_t),
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return APSE_OK;
+}
+
 int apse_debug_apriltag(apse_ctx *ctx, const uint8_t *gray, int w, int h, uint8_t *thresh, uint32_t *labels, float *quads,
                         int max_quads, int64_t *stats_host, void *stream)
 {

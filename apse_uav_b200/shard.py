@@ -284,14 +284,14 @@ def _packed_fields(torch, cap, m):
     return fields, sizes_b, offs
 
 
-def run_sequence_streamed(pipe, frames, plan, rank=0, world=1, group=None, start_frame=1, as_rows=False, chunk_frames=240):
+def run_sequence_streamed(pipe, frames, plan, rank=0, world=1, group=None, start_frame=1, as_rows=False, chunk_frames=240, post_thread=None):
     """aruco_detect.py:571-810 for a sequence sharded by round_plan, with the post-pass streamed behind the pipeline.
     frames: this rank's parts of all rounds, concatenated ([n_local,H,W,3] uint8 CUDA tensor); plan: round_plan(...) of the whole
     sequence (the same on every rank).  Per round every rank enqueues its batch (no host synchronisation), packs the batch's
     results on a side stream and -- world > 1 -- sends them to rank 0 (one NCCL gather per round, off the pipeline's streams);
-    rank 0 copies the round to pinned memory and, between its own enqueues, feeds every completed round to a
-    sequence.SequenceStream (both scans, exact poses, projection jobs for those frames).  What is left after the last batch is
-    the post-pass of the last round.  Rows equal run_sequence's (tests/test_gpu_pipeline.py).  No LED read-out (run_sequence)."""
+    rank 0 copies the round to pinned memory and a worker thread feeds every completed round to a sequence.SequenceStream
+    (both scans, exact poses, projection jobs for those frames) while the calling thread keeps enqueueing.  What is left after
+    the last batch is the post-pass of the last round.  Rows equal run_sequence's (tests/test_gpu_pipeline.py).  No LED read-out (run_sequence)."""
     from . import sequence
     from ._lib import ApseError
     e = pipe.engine
@@ -357,47 +357,103 @@ def run_sequence_streamed(pipe, frames, plan, rank=0, world=1, group=None, start
         seq.push(h["n"], h["ids"], h["corners"], h["rvec"], h["tvec"], cd, nd)
         done_upto = upto
 
-    lo = 0
-    for r in range(nr):
-        a, b = plan[r][rank]
-        sz = b - a
-        done = []
-        if sz:
-            sl = {k: v[lo:lo + sz] for k, v in det.items()}
-            res = pipe.run_batch(frames[lo:lo + sz], sync=False, input_ready=False, out=sl)
-            done = list(res.get("_done", ())) or [cur.record_event()]
-        with torch.cuda.stream(comm):
-            for ev in done:
-                comm.wait_event(ev)
-            buf = st["send"][r] if world > 1 or rank != 0 else st["recv"][r, 0]
+    # rank 0: the post-pass runs on a worker thread of its own (every push blocks on two small device round trips; on the
+    # enqueueing thread each of them would let the pipeline's launch queue run dry).  The worker waits for the rounds in order
+    # and pushes them once chunk_frames frames have piled up; ctypes calls and stream synchronisation release the GIL.
+    import os
+    import queue
+    import sys
+    import threading
+    import time
+    if post_thread is None:
+        post_thread = os.environ.get("APSE_POST_THREAD", "1") != "0"
+    poll = os.environ.get("APSE_POST_POLL", "1") != "0"
+    todo = queue.Queue()
+    failure = []
+
+    def worker():
+        try:
+            torch.cuda.set_device(dev)
+            sequence.POLL_WAIT = poll
+            for _ in range(nr):
+                r_, ev_ = todo.get()
+                if ev_ is None:
+                    return
+                if poll:
+                    while not ev_.query():
+                        time.sleep(5e-5)
+                else:
+                    ev_.synchronize()
+                pending = sum(hi_ - lo_ for rr in range(done_upto, r_ + 1) for lo_, hi_ in plan[rr])
+                if pending >= chunk_frames or r_ + 1 >= nr - 1:   # the last two rounds go one by one: nothing hides the very last push
+                    process(r_ + 1)
+        except BaseException as exc:   # re-raised on the calling thread
+            failure.append(exc)
+        finally:
+            sequence.POLL_WAIT = False
+
+    th = None
+    switch = sys.getswitchinterval()
+    if rank == 0 and nr and post_thread:
+        th = threading.Thread(target=worker, name="apse-postpass", daemon=True)
+        if os.environ.get("APSE_POST_SWITCH"):
+            sys.setswitchinterval(float(os.environ["APSE_POST_SWITCH"]))
+        th.start()
+    try:
+        lo = 0
+        for r in range(nr):
+            a, b = plan[r][rank]
+            sz = b - a
+            done = []
             if sz:
-                for (k, dt, shape), o, sb in zip(fields, offs, sizes_b):
-                    buf[int(o):int(o) + sb].view(dt).reshape((cap,) + shape)[:sz] = det[k][lo:lo + sz]
-            if world > 1:
-                import torch.distributed as dist
-                dist.gather(buf, list(st["recv"][r].unbind(0)) if rank == 0 else None, dst=0, group=group)
-            if rank == 0:
-                st["pin"][r].copy_(st["recv"][r], non_blocking=True)
-                arrived.append((r, comm.record_event()))
-        lo += sz
-        if rank == 0:
-            # completed rounds, once enough frames have piled up (every push costs a few host round trips)
-            ready = done_upto
-            while ready < len(arrived) and arrived[ready][1].query():
-                ready += 1
-            pending = sum(hi_ - lo_ for rr in range(done_upto, ready) for lo_, hi_ in plan[rr])
-            if pending >= chunk_frames:
-                process(ready)
+                sl = {k: v[lo:lo + sz] for k, v in det.items()}
+                res = pipe.run_batch(frames[lo:lo + sz], sync=False, input_ready=False, out=sl)
+                done = list(res.get("_done", ())) or [cur.record_event()]
+            with torch.cuda.stream(comm):
+                for ev in done:
+                    comm.wait_event(ev)
+                buf = st["send"][r] if world > 1 or rank != 0 else st["recv"][r, 0]
+                if sz:
+                    for (k, dt, shape), o, sb in zip(fields, offs, sizes_b):
+                        buf[int(o):int(o) + sb].view(dt).reshape((cap,) + shape)[:sz] = det[k][lo:lo + sz]
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.gather(buf, list(st["recv"][r].unbind(0)) if rank == 0 else None, dst=0, group=group)
+                if rank == 0:
+                    st["pin"][r].copy_(st["recv"][r], non_blocking=True)
+                    arrived.append((r, comm.record_event()))
+                    if th is not None:
+                        todo.put(arrived[-1])
+            lo += sz
+            if failure:
+                break
+            if rank == 0 and th is None:
+                # no worker thread: completed rounds between the enqueues, once enough frames have piled up
+                ready = done_upto
+                while ready < len(arrived) and arrived[ready][1].query():
+                    ready += 1
+                if sum(hi_ - lo_ for rr in range(done_upto, ready) for lo_, hi_ in plan[rr]) >= chunk_frames:
+                    process(ready)
+    except BaseException:
+        if th is not None:
+            todo.put((nr, None))
+        raise
+    finally:
+        if th is not None:
+            th.join()
+            sys.setswitchinterval(switch)
+    if failure:
+        raise failure[0]
     if rank != 0:
         comm.synchronize()
         return None
-    # what is left: first everything but the last round (its batch may still be running), then the last round
-    if nr - done_upto > 1:
-        arrived[nr - 2][1].synchronize()
-        process(nr - 1)
-    if nr:
-        arrived[nr - 1][1].synchronize()
-        process(nr)
+    if th is None:   # what is left: everything but the last round (its batch may still be running), then the last round
+        if nr - done_upto > 1:
+            arrived[nr - 2][1].synchronize()
+            process(nr - 1)
+        if nr:
+            arrived[nr - 1][1].synchronize()
+            process(nr)
     rows = seq.result()
     return rows if as_rows else sequence.rows_to_dicts(rows)
 

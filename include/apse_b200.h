@@ -295,6 +295,11 @@ int apse_debug_decode(apse_ctx *ctx, const uint8_t *gray, int w, int h, const fl
  * and their count; every pointer nullable */
 int apse_debug_sparse(apse_ctx *ctx, uint16_t *bound_table_host, uint8_t *eflag_dev, int batch, int *n_exact_host, void *stream);
 
+/* test tap of the bounds pass of the last apse_preprocess_tiles_sparse batch: per-tile bounds of gray (DEVICE,
+ * [batch][h/4][w/4], lo | hi << 8; every gray value the preprocess of aruco_detect.py:250-259,592 can produce inside the
+ * tile lies in [lo, hi]) */
+int apse_debug_tile_bounds(apse_ctx *ctx, uint16_t *bounds_dev, int batch, void *stream);
+
 /* number of kernel launches issued through this context since creation (bench.py's gpu_launches) */
 int64_t apse_launch_count(apse_ctx *ctx);
 

@@ -88,6 +88,52 @@ def test_flagged_tiles_cover_the_threshold_and_hold_exact_gray(camera, lut, dict
     e.close()
 
 
+def _hard_frames(w=3840, h=2160):
+    """Content that stresses the bounds: saturated colour blocks, full-range colour noise, a colour ramp, black / white stripes
+    one pixel wide, and a frame of uniform mid gray."""
+    rng = np.random.default_rng(11)
+    a = np.zeros((h, w, 3), np.uint8)
+    for by in range(0, h, 120):
+        for bx in range(0, w, 120):
+            a[by:by + 120, bx:bx + 120] = rng.integers(0, 2, 3) * 255 if (bx // 120 + by // 120) % 3 else rng.integers(0, 256, 3)
+    b = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    c = np.zeros((h, w, 3), np.uint8)
+    c[..., 0] = (np.arange(w) * 255 // (w - 1))[None, :]
+    c[..., 1] = (np.arange(h) * 255 // (h - 1))[:, None]
+    c[..., 2] = ((np.arange(w)[None, :] + np.arange(h)[:, None]) % 512 // 2).astype(np.uint8)
+    c[:, ::7] = 255
+    c[::5, :] = 0
+    d = np.full((h, w, 3), 128, np.uint8)
+    d += rng.integers(0, 4, (h, w, 3), dtype=np.uint8)
+    return np.stack([a, b, c, d])
+
+
+def test_tile_bounds_contain_the_dense_gray(camera, lut, dictionary, ref_params, frames4k):
+    """The bounds pass (k_preprocess_tma MODE 1: every pixel remapped, its colour cell looked up in the (min, max) table of the
+    chain) is rigorous: for EVERY tile of every frame [lo, hi] contains the gray the dense kernel computes
+    (aruco_detect.py:250-259,592) -- markers, saturated colours, full-range noise, one-pixel stripes, the black margin the
+    undistortion leaves at the frame border."""
+    import torch
+    e = _engine(camera, lut, dictionary, ref_params, batch=3)
+    hard = _hard_frames()
+    for frames in (np.stack([frames4k["sparse"], frames4k["dense"], hard[0]]), hard[1:]):
+        ft = torch.from_numpy(frames).cuda()
+        _, dense = e.preprocess(ft)
+        gray = torch.empty_like(dense)
+        e.preprocess_tiles(ft, gray, sparse=True)
+        tb = torch.zeros((len(frames), 540, 960), dtype=torch.int16, device="cuda")
+        e._check(e.lib.apse_debug_tile_bounds(e.h, tb.data_ptr(), len(frames), e._stream()))
+        torch.cuda.synchronize()
+        tb = tb.cpu().numpy().view(np.uint16)
+        lo, hi = (tb & 255).astype(int), (tb >> 8).astype(int)
+        t = dense.cpu().numpy().reshape(len(frames), 540, 4, 960, 4)
+        tmin, tmax = t.min((2, 4)).astype(int), t.max((2, 4)).astype(int)
+        assert (lo <= tmin).all(), f"lower bound above the exact minimum in {(lo > tmin).sum()} tiles"
+        assert (hi >= tmax).all(), f"upper bound below the exact maximum in {(hi < tmax).sum()} tiles"
+        print("mean bound slack (lo, hi) per frame:", (tmin - lo).mean((1, 2)), (hi - tmax).mean((1, 2)))
+    e.close()
+
+
 def _both(e, frames, max_markers=256):
     import torch
     outs = []
