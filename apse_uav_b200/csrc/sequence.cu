@@ -10,6 +10,7 @@
 //   apse_sequence_csv     host: the text the reference writes (:131-139,146-185), str(float) formatting of Python
 // apse_uav_b200/postpass.py is the readable host mirror of the same logic (used by the parity tests to cross-check this file).
 #include "common.cuh"
+#include <cmath>
 #include <math.h>
 #include <float.h>
 #include <string.h>
@@ -83,19 +84,35 @@ static double marker_length_correction(const apse_seq_config &c, double altitude
     return c.marker_length_org * (1 - 0.00057 * altitude / c.marker_div) / c.div;   // :306-308, same evaluation order
 }
 
-// first angle of scipy's Rotation.from_rotvec(rvec).as_euler('zxy', degrees=True) (:412-413)
-static double yaw_zxy_deg(const double r[3])
+// first angle of scipy's Rotation.from_rotvec(rvec).as_euler('zxy', degrees=True) (:412-413): the two matrix entries it is the
+// arctangent of
+static void yaw_zxy_terms(const double r[3], double &R10, double &R11)
 {
     const double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    if (th < 1e-300) return 0.0;
+    if (th < 1e-300) { R10 = 0.0; R11 = 1.0; return; }
     const double k[3] = {r[0] / th, r[1] / th, r[2] / th};
     const double Kx[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
     double K2[9];
     for (int i = 0; i < 3; i++)
         for (int j = 0; j < 3; j++) K2[i * 3 + j] = Kx[i * 3] * Kx[j] + Kx[i * 3 + 1] * Kx[3 + j] + Kx[i * 3 + 2] * Kx[6 + j];
     const double s = sin(th), c1 = 1 - cos(th);
-    const double R10 = s * Kx[3] + c1 * K2[3], R11 = 1.0 + s * Kx[4] + c1 * K2[4];
-    return atan2(R10, R11) * (180.0 / M_PI);
+    R10 = s * Kx[3] + c1 * K2[3];
+    R11 = 1.0 + s * Kx[4] + c1 * K2[4];
+}
+
+// round(yaw, 2) < 0 (:413-414), the only use the path makes of the angle.  yaw = atan2(R10, R11) in degrees is negative exactly
+// when R10 < 0, and rounds to a negative number unless |yaw| <= 0.005 degrees; only within a hundredfold margin of that
+// boundary the angle itself is evaluated and rounded as Python does.
+static bool yaw_rounds_negative(const double r[3])
+{
+    double R10, R11;
+    yaw_zxy_terms(r, R10, R11);
+    if (!(R10 < 0)) {
+        if (R10 > 0 || R11 >= 0 || std::signbit(R10) == 0) return false;   // yaw >= +0
+        return py_round(atan2(R10, R11) * (180.0 / M_PI), 2) < 0;           // R10 = -0, R11 < 0: atan2 gives -pi
+    }
+    if (R11 <= 0 || -R10 > 1e-2 * R11) return true;                         // |yaw| > 0.57 degrees
+    return py_round(atan2(R10, R11) * (180.0 / M_PI), 2) < 0;
 }
 
 extern "C" {
@@ -228,10 +245,10 @@ int apse_sequence_scan_chunk(const apse_seq_config *cfg, apse_seq_state *state, 
                             nj++;
                         }
                         S.prev_xy[vid][0] = cx; S.prev_xy[vid][1] = cy;
-                        if (jobs) {   // drawBoundingBox (:406-420), the dimension scaling only (feeds the distance jobs)
+                        if (jobs && vid != 4) {   // drawBoundingBox (:406-420), the dimension scaling only; it feeds the distance jobs,
+                                                  // which read the outline of vehicles 1-3 (the host's own outline is only drawn)
                             double ah = atan(tv[0] / tv[2]), av = atan(tv[1] / tv[2]);
-                            const double yaw = py_round(yaw_zxy_deg(frv + 3 * i), 2);
-                            if (!(yaw < 0)) { ah = -ah; av = -av; }
+                            if (!yaw_rounds_negative(frv + 3 * i)) { ah = -ah; av = -av; }
                             dims[vid][0] *= 1 - ah / 2; dims[vid][1] *= 1 + ah / 2;
                             dims[vid][2] *= 1 - av / 2; dims[vid][3] *= 1 + av / 2;
                         }

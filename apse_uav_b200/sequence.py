@@ -171,21 +171,6 @@ def rows_to_dicts(rows):
     return out
 
 
-POLL_WAIT = False   # set by shard.run_sequence_streamed while its post-pass thread runs
-
-
-def wait_stream(torch, stream):
-    """Host wait for `stream`.  On the post-pass thread of a streamed run (POLL_WAIT) by polling an event with short sleeps, so
-    that the thread that enqueues the pipeline keeps the interpreter; otherwise a plain synchronize."""
-    if not POLL_WAIT:
-        stream.synchronize()
-        return
-    import time
-    ev = stream.record_event()
-    while not ev.query():
-        time.sleep(5e-5)
-
-
 def _host_copy(engine, tensors):
     """One D2H transfer of several small device tensors: packed into one byte buffer on the device, copied into a cached
     pinned buffer, returned as numpy views (valid until the next call on this engine)."""
@@ -201,7 +186,7 @@ def _host_copy(engine, tensors):
     for f, o, s in zip(flat, offs, sizes):
         dev[int(o):int(o) + s] = f
     pin[:total].copy_(dev[:total], non_blocking=True)
-    wait_stream(torch, torch.cuda.current_stream(engine.tdev))
+    torch.cuda.current_stream(engine.tdev).synchronize()
     host = pin.numpy()
     return [host[int(o):int(o) + s].view(_NP[t.dtype]).reshape(tuple(t.shape)) for t, o, s in zip(tensors, offs, sizes)]
 

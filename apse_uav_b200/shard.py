@@ -358,46 +358,36 @@ def run_sequence_streamed(pipe, frames, plan, rank=0, world=1, group=None, start
         done_upto = upto
 
     # rank 0: the post-pass runs on a worker thread of its own (every push blocks on two small device round trips; on the
-    # enqueueing thread each of them would let the pipeline's launch queue run dry).  The worker waits for the rounds in order
-    # and pushes them once chunk_frames frames have piled up; ctypes calls and stream synchronisation release the GIL.
+    # enqueueing thread each of them lets the pipeline's launch queue run dry: 57.4 against 54.2 ms per 1800 frames on one GPU).
+    # The worker waits for the rounds in order and pushes them once chunk_frames frames have piled up; event / stream
+    # synchronisation and the ctypes calls release the interpreter lock.  Waiting by polling with short sleeps was tried and is
+    # much worse (67 - 105 ms: every wake-up takes the lock away from the enqueueing thread).  post_thread=False /
+    # APSE_POST_THREAD=0: pushes between the enqueues of the calling thread.
     import os
     import queue
-    import sys
     import threading
-    import time
     if post_thread is None:
         post_thread = os.environ.get("APSE_POST_THREAD", "1") != "0"
-    poll = os.environ.get("APSE_POST_POLL", "1") != "0"
     todo = queue.Queue()
     failure = []
 
     def worker():
         try:
             torch.cuda.set_device(dev)
-            sequence.POLL_WAIT = poll
             for _ in range(nr):
                 r_, ev_ = todo.get()
                 if ev_ is None:
                     return
-                if poll:
-                    while not ev_.query():
-                        time.sleep(5e-5)
-                else:
-                    ev_.synchronize()
+                ev_.synchronize()   # releases the interpreter lock (so do the ctypes calls of the push)
                 pending = sum(hi_ - lo_ for rr in range(done_upto, r_ + 1) for lo_, hi_ in plan[rr])
                 if pending >= chunk_frames or r_ + 1 >= nr - 1:   # the last two rounds go one by one: nothing hides the very last push
                     process(r_ + 1)
         except BaseException as exc:   # re-raised on the calling thread
             failure.append(exc)
-        finally:
-            sequence.POLL_WAIT = False
 
     th = None
-    switch = sys.getswitchinterval()
     if rank == 0 and nr and post_thread:
         th = threading.Thread(target=worker, name="apse-postpass", daemon=True)
-        if os.environ.get("APSE_POST_SWITCH"):
-            sys.setswitchinterval(float(os.environ["APSE_POST_SWITCH"]))
         th.start()
     try:
         lo = 0
@@ -441,7 +431,6 @@ def run_sequence_streamed(pipe, frames, plan, rank=0, world=1, group=None, start
     finally:
         if th is not None:
             th.join()
-            sys.setswitchinterval(switch)
     if failure:
         raise failure[0]
     if rank != 0:

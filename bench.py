@@ -11,10 +11,11 @@ Default workload = BASELINE.json configs[2] (N = 1) / configs[3] (N > 1): ONE ST
     -> per-frame results gathered on rank 0 -> native sequence post-pass (marker-length recurrence, gating, second exact
     pose pass, vehicle distances) -> the CSV text of aruco_detect.py:146-185, to its last row.
 For N > 1 the SAME sequence is frame-sharded: strong scaling, the gather and the post-pass on rank 0 are inside the timed
-region, no collective on the pipeline's streams.  Default: the frames are dealt out in rounds (shard.round_plan; round k = N
-consecutive batches, one per rank) and the post-pass is STREAMED (shard.run_sequence_streamed): the results of round k travel
-to rank 0 on a side stream and are post-processed there while all ranks compute round k + 1, so only the short last round's
-post-pass is left after the pipeline.  --no-stream: contiguous blocks (shard.shard_bounds), one gather and one post-pass at the end.
+region, no collective on the pipeline's streams: contiguous blocks (shard.shard_bounds), one gather and one post-pass at the end.
+--stream: the frames are dealt out in rounds (shard.round_plan; round k = N consecutive batches, one per rank) and the post-pass is
+STREAMED (shard.run_sequence_streamed): the results of round k travel to rank 0 on a side stream and are post-processed there
+(worker thread) while all ranks compute round k + 1.  Built for sequences that arrive over time; for a resident sequence it was
+measured and is slower than the plain run (1 GPU: 54.2 against 54.0 ms per 1800 frames; 8 GPUs: 12.7 against 10.3 ms).
 Timed region: barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks.
 `value`        : frames resident in HBM -> last CSV row (every step streams 44.8 GB, far beyond the 126 MB L2).
 `pipeline_only`: the same frames through the GPU pipeline alone (no gather / post-pass): what `roofline` explains.
@@ -406,7 +407,7 @@ def run_sequence_workload(args, rank, world, local_rank):
     dev = c.dev
     pipe = make_pipeline(args, local_rank)
     n_seq = args.sequence_frames
-    # ---- this rank's frames of the synthetic sequence, resident in HBM.  Streamed run (default): the sequence is dealt out in
+    # ---- this rank's frames of the synthetic sequence, resident in HBM.  Streamed run (default for N > 1): the sequence is dealt out in
     # rounds (shard.round_plan: round k = world consecutive batches, rank r takes the r-th), so that rank 0 runs the sequential
     # post-pass of round k while all ranks compute round k + 1; --no-stream: contiguous blocks, post-pass after the gather
     if args.stream:
@@ -746,7 +747,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10, help="timed steps; one step = the whole sequence (default workload)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-stream", dest="stream", action="store_false", help="sequence workload: contiguous blocks, post-pass after the gather")
+    ap.add_argument("--no-stream", dest="stream", action="store_false", default=None,
+                    help="sequence workload: contiguous blocks, one gather and one post-pass after the pipeline (the default)")
+    ap.add_argument("--stream", dest="stream", action="store_true",
+                    help="sequence workload: frames dealt out in rounds, post-pass streamed behind the pipeline")
     ap.add_argument("--tail-frames", type=int, default=8, help="streamed sequence: frames per rank in the short last round")
     ap.add_argument("--workload", default="sequence", choices=["sequence", "preprocess64", "dense-apriltag", "dense-classic"])
     ap.add_argument("--sequence-frames", type=int, default=SEQUENCE_FRAMES, help="frames of the sequence (configs[2]: 1800)")
@@ -774,6 +778,11 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.stream is None:
+        # the plain run (contiguous blocks, one gather, one post-pass) is the default: streaming the post-pass behind the pipeline
+        # was measured and loses -- 1 GPU 54.2 against 54.0 ms per 1800 frames, 8 GPUs 12.7 against 10.3 ms (per-round packing and
+        # gathers, the short last round's latency, the worker thread sharing the interpreter with the enqueueing thread)
+        args.stream = False
     {"sequence": run_sequence_workload, "preprocess64": run_preprocess_workload,
      "dense-apriltag": run_dense_workload, "dense-classic": run_dense_workload}[args.workload](args, rank, world, local_rank)
 

@@ -105,6 +105,40 @@ def test_native_scan_equals_python_mirror(oracle, camera, seed):
     assert sequence.rows_to_csv(rows) == shard.rows_to_csv(want)
 
 
+def test_yaw_sign_shortcut_at_the_rounding_boundary(oracle, camera):
+    """aruco_detect.py:412-414 uses the vehicle's yaw only as `round(yaw, 2) < 0`.  The native scan decides that from the two
+    matrix entries the angle is the arctangent of and evaluates the angle itself only near |yaw| = 0.005 degrees; here: rotation
+    vectors about the optical axis whose yaw is the rotation angle, on and around the boundary, zero, minus zero and half turns --
+    the outline dimensions the distance jobs carry must equal the Python mirror's."""
+    K, D = camera
+    project = lambda obj, r, t: oracle.project_points(obj, r, t, K, D)
+    deg = [0.0, -0.0, 0.004, -0.004, -0.005, -0.0050001, -0.0049999, -0.006, -0.015, -0.5, -0.58, 0.58, 90.0, -90.0, 179.9999, -179.9999,
+           180.0, -180.0, 1e-9, -1e-9, 33.3, -33.3]
+    F, M = len(deg), 4
+    n = np.full(F, 2, np.int32)
+    ids = np.full((F, M), -1, np.int32)
+    ids[:, 0], ids[:, 1] = 4, 1
+    sq = np.array([[-15., -15.], [15., -15.], [15., 15.], [-15., 15.]])
+    corners = np.zeros((F, M, 4, 2), np.float32)
+    corners[:, 0] = sq + np.array([1000., 1000.])
+    corners[:, 1] = sq + np.array([1700., 1150.])
+    rvec = np.zeros((F, M, 3))
+    tvec = np.zeros((F, M, 3))
+    tvec[:, :2] = np.array([[-3.0, -0.5, 30.0], [2.0, 0.7, 30.0]])
+    rvec[:, 0, 2] = 0.3
+    rvec[:, 1, 2] = np.deg2rad(np.array(deg))
+    want, _ = python_rows(n, ids, corners, rvec, tvec, project)
+    lengths, rows, jobs = sequence.scan(sequence.seq_config(start_frame=1), n, ids, corners, rvec, tvec)
+    assert len(jobs) == F and (jobs["kind"] == 1).all()
+    rows = sequence.finish(rows, eval_jobs_numpy(jobs, project))
+    assert sequence.rows_to_dicts(rows) == want
+    # and the flip itself, from the job's dimensions: dims[1] *= 1 + ah / 2 with ah = atan(2 / 30) > 0, negated unless the yaw
+    # rounds to a negative number
+    flipped = jobs["dim"][:, 1] / postpass.VEH_DIM[1][1] < 1
+    expect_negative = np.array([round(float(np.rad2deg(np.arctan2(np.sin(np.deg2rad(d)), np.cos(np.deg2rad(d))))), 2) < 0 for d in deg])
+    assert np.array_equal(flipped, ~expect_negative), (flipped, expect_negative)
+
+
 def test_native_first_pass_lengths_equal_python(oracle, camera):
     K, D = camera
     n, ids, corners, rvec, tvec = fabricate(oracle, K, D, F=60, seed=5)
