@@ -327,6 +327,18 @@ __device__ __forceinline__ void k1t_sample(uint32_t a, uint32_t shf, uint32_t wA
     d2 = __dp2a_lo(wA, U0, __dp2a_lo(wB, U1, 512u));
 }
 
+// the packed tap pairs of ONE staged row at byte address a: T = (c0, c0', c1, c1'), U = (c2, c2', ..)
+__device__ __forceinline__ void k1t_row(uint32_t a, uint32_t shf, uint32_t &T, uint32_t &U)
+{
+    uint32_t r0, r1, r2;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r0) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r1) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r2) : "r"(a));
+    const uint32_t X0 = __funnelshift_r(r0, r1, shf), X1 = __funnelshift_r(r1, r2, shf);
+    T = __byte_perm(X0, X1, 0x4130);
+    U = __byte_perm(X0, X1, 0x5252);
+}
+
 // one thread, one frame: the four pixels of the thread's column sampled from staging buffer `boff` and pushed through the
 // colour chain
 template <bool WANT_BGR>
@@ -437,6 +449,15 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         addr[k] = raw0 + (uint32_t)(r * (P2_BOX_WORDS * 4) + (b & ~3));
         shf[k] = (uint32_t)(b & 3) * 8;
     }
+    // MODE 1: where the four pixels of every thread of the warp sit in one source column on consecutive rows (most of an
+    // undistortion map), the bottom tap row of pixel k is the top tap row of pixel k + 1: five staged rows instead of eight
+    bool vshare = false;
+    if (MODE) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k + 1 < P2_NPX; k++) ok = ok && addr[k + 1] == addr[k] + P2_BOX_WORDS * 4 && shf[k + 1] == shf[k];
+        vshare = __all_sync(0xffffffffu, ok || !valid);
+    }
 
     const size_t frame_px = (size_t)w * h;
     const int f0 = blockIdx.z * fpb, f1 = min(batch, f0 + fpb);
@@ -484,7 +505,22 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     // MODE 1: cell bounds of the four pixels sampled from staging buffer `boff`, reduced to the tile
     auto bounds_frame = [&](uint32_t boff) {
         uint32_t pk = 0x00ff00ffu;   // (min 255, max 0)
-        if (valid) {
+        if (vshare) {   // warp-uniform
+            if (valid) {
+                uint32_t Tp, Up;
+                k1t_row(addr[0] + boff, shf[0], Tp, Up);
+#pragma unroll
+                for (int k = 0; k < P2_NPX; k++) {
+                    uint32_t Tn, Un;
+                    k1t_row(addr[0] + boff + (uint32_t)((k + 1) * P2_BOX_WORDS * 4), shf[0], Tn, Un);
+                    const uint32_t d0 = __dp2a_lo(wA[k], Tp, __dp2a_lo(wB[k], Tn, 512u));
+                    const uint32_t d1 = __dp2a_hi(wA[k], Tp, __dp2a_hi(wB[k], Tn, 512u));
+                    const uint32_t d2 = __dp2a_lo(wA[k], Up, __dp2a_lo(wB[k], Un, 512u));
+                    pk = __vminu2(pk, bound_px(tbl0, d0, d1, d2));
+                    Tp = Tn; Up = Un;
+                }
+            }
+        } else if (valid) {
 #pragma unroll
             for (int k = 0; k < P2_NPX; k++) {
                 uint32_t d0, d1, d2;
