@@ -307,27 +307,9 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap *tm
         : "memory");
 }
 
-// bilinear sample of pixel k of this thread from staging buffer `boff`: the three channel sums, Q10 (value = sum >> 10)
-__device__ __forceinline__ void k1t_sample(uint32_t a, uint32_t shf, uint32_t wA, uint32_t wB, uint32_t &d0, uint32_t &d1, uint32_t &d2)
-{
-    uint32_t r00, r01, r02, r10, r11, r12;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r00) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r01) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r02) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+256];" : "=r"(r10) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+260];" : "=r"(r11) : "r"(a));
-    asm volatile("ld.shared.u32 %0, [%1+264];" : "=r"(r12) : "r"(a));
-    // bytes b .. b+5 of each row: (c0 c1 c2 of tap ix, c0 c1 c2 of tap ix+1)
-    const uint32_t X0 = __funnelshift_r(r00, r01, shf), X1 = __funnelshift_r(r01, r02, shf);
-    const uint32_t Y0 = __funnelshift_r(r10, r11, shf), Y1 = __funnelshift_r(r11, r12, shf);
-    const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);   // (c0, c0', c1, c1')
-    const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);   // (c2, c2', ..)
-    d0 = __dp2a_lo(wA, T0, __dp2a_lo(wB, T1, 512u));
-    d1 = __dp2a_hi(wA, T0, __dp2a_hi(wB, T1, 512u));
-    d2 = __dp2a_lo(wA, U0, __dp2a_lo(wB, U1, 512u));
-}
-
-// the packed tap pairs of ONE staged row at byte address a: T = (c0, c0', c1, c1'), U = (c2, c2', ..)
+// the packed tap pairs of ONE staged row at byte address a (the aligned word holding the first tap byte; shf brings that byte to
+// bit 0): bytes b .. b+5 of the row are (c0 c1 c2 of tap ix, c0 c1 c2 of tap ix+1) -> T = (c0, c0', c1, c1'), U = (c2, c2', ..).
+// A pixel's three channel sums (Q10) are IDP.2A of its two rows' pairs with the packed weights wA (top row) and wB (bottom row).
 __device__ __forceinline__ void k1t_row(uint32_t a, uint32_t shf, uint32_t &T, uint32_t &U)
 {
     uint32_t r0, r1, r2;
@@ -343,14 +325,20 @@ __device__ __forceinline__ void k1t_row(uint32_t a, uint32_t shf, uint32_t &T, u
 // colour chain
 template <bool WANT_BGR>
 __device__ __forceinline__ void k1t_pixels(const P2Tables *T, const uint32_t (&addr)[P2_NPX], const uint32_t (&shf)[P2_NPX],
-                                           const uint32_t (&wA)[P2_NPX], const uint32_t (&wB)[P2_NPX], uint32_t boff,
+                                           const uint32_t (&wA)[P2_NPX], const uint32_t (&wB)[P2_NPX], uint32_t boff, unsigned brk,
                                            int (&g)[P2_NPX], int (&o0)[P2_NPX], int (&o1)[P2_NPX], int (&o2)[P2_NPX])
 {
+    uint32_t Tp = 0, Up = 0;
 #pragma unroll
     for (int k = 0; k < P2_NPX; k++) {
-        uint32_t d0, d1, d2;
-        k1t_sample(addr[k] + boff, shf[k], wA[k], wB[k], d0, d1, d2);
+        if (k == 0 || ((brk >> (k - 1)) & 1u)) k1t_row(addr[k] + boff, shf[k], Tp, Up);   // warp-uniform (see brk)
+        uint32_t Tn, Un;
+        k1t_row(addr[k] + boff + (uint32_t)(P2_BOX_WORDS * 4), shf[k], Tn, Un);
+        const uint32_t d0 = __dp2a_lo(wA[k], Tp, __dp2a_lo(wB[k], Tn, 512u));
+        const uint32_t d1 = __dp2a_hi(wA[k], Tp, __dp2a_hi(wB[k], Tn, 512u));
+        const uint32_t d2 = __dp2a_lo(wA[k], Up, __dp2a_lo(wB[k], Un, 512u));
         g[k] = chain_px(T, (int)(d0 >> 10), (int)(d1 >> 10), (int)(d2 >> 10), o0[k], o1[k], o2[k]);
+        Tp = Tn; Up = Un;
     }
 }
 
@@ -449,14 +437,18 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
         addr[k] = raw0 + (uint32_t)(r * (P2_BOX_WORDS * 4) + (b & ~3));
         shf[k] = (uint32_t)(b & 3) * 8;
     }
-    // MODE 1: where the four pixels of every thread of the warp sit in one source column on consecutive rows (most of an
-    // undistortion map), the bottom tap row of pixel k is the top tap row of pixel k + 1: five staged rows instead of eight
-    bool vshare = false;
+    // Where pixel k + 1 of every thread of the warp sits in the source column of pixel k, one row further down (most of an
+    // undistortion map), the bottom tap row of pixel k is the top tap row of pixel k + 1 and is staged once.  brk: bit k set =
+    // somewhere in the warp that does not hold between pixels k and k + 1 (warp-uniform, so the branches below do not diverge)
+    // MODE 0 stages all eight rows (measured: sharing does not pay there -- the dense kernel runs out of shared-memory
+    // wavefronts in the colour chain, config 1 went from 26.6 k to 26.2 k frames/s)
+    unsigned brk = MODE ? 0u : 7u;
     if (MODE) {
-        bool ok = true;
 #pragma unroll
-        for (int k = 0; k + 1 < P2_NPX; k++) ok = ok && addr[k + 1] == addr[k] + P2_BOX_WORDS * 4 && shf[k + 1] == shf[k];
-        vshare = __all_sync(0xffffffffu, ok || !valid);
+        for (int k = 0; k + 1 < P2_NPX; k++) {
+            const bool same = addr[k + 1] == addr[k] + P2_BOX_WORDS * 4 && shf[k + 1] == shf[k];
+            if (__any_sync(0xffffffffu, valid && !same)) brk |= 1u << k;
+        }
     }
 
     const size_t frame_px = (size_t)w * h;
@@ -505,27 +497,18 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
     // MODE 1: cell bounds of the four pixels sampled from staging buffer `boff`, reduced to the tile
     auto bounds_frame = [&](uint32_t boff) {
         uint32_t pk = 0x00ff00ffu;   // (min 255, max 0)
-        if (vshare) {   // warp-uniform
-            if (valid) {
-                uint32_t Tp, Up;
-                k1t_row(addr[0] + boff, shf[0], Tp, Up);
-#pragma unroll
-                for (int k = 0; k < P2_NPX; k++) {
-                    uint32_t Tn, Un;
-                    k1t_row(addr[0] + boff + (uint32_t)((k + 1) * P2_BOX_WORDS * 4), shf[0], Tn, Un);
-                    const uint32_t d0 = __dp2a_lo(wA[k], Tp, __dp2a_lo(wB[k], Tn, 512u));
-                    const uint32_t d1 = __dp2a_hi(wA[k], Tp, __dp2a_hi(wB[k], Tn, 512u));
-                    const uint32_t d2 = __dp2a_lo(wA[k], Up, __dp2a_lo(wB[k], Un, 512u));
-                    pk = __vminu2(pk, bound_px(tbl0, d0, d1, d2));
-                    Tp = Tn; Up = Un;
-                }
-            }
-        } else if (valid) {
+        if (valid) {
+            uint32_t Tp = 0, Up = 0;
 #pragma unroll
             for (int k = 0; k < P2_NPX; k++) {
-                uint32_t d0, d1, d2;
-                k1t_sample(addr[k] + boff, shf[k], wA[k], wB[k], d0, d1, d2);
+                if (k == 0 || ((brk >> (k - 1)) & 1u)) k1t_row(addr[k] + boff, shf[k], Tp, Up);   // warp-uniform
+                uint32_t Tn, Un;
+                k1t_row(addr[k] + boff + (uint32_t)(P2_BOX_WORDS * 4), shf[k], Tn, Un);
+                const uint32_t d0 = __dp2a_lo(wA[k], Tp, __dp2a_lo(wB[k], Tn, 512u));
+                const uint32_t d1 = __dp2a_hi(wA[k], Tp, __dp2a_hi(wB[k], Tn, 512u));
+                const uint32_t d2 = __dp2a_lo(wA[k], Up, __dp2a_lo(wB[k], Un, 512u));
                 pk = __vminu2(pk, bound_px(tbl0, d0, d1, d2));
+                Tp = Tn; Up = Un;
             }
         }
         return pk;
@@ -560,7 +543,7 @@ k_preprocess_tma(const __grid_constant__ CUtensorMap tmap, const uint8_t *__rest
                     tile_out(pk);
                 } else {
                     int g[P2_NPX], o0[P2_NPX], o1[P2_NPX], o2[P2_NPX];
-                    if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, (uint32_t)(b * P2_RAW_STRIDE), g, o0, o1, o2);
+                    if (valid) k1t_pixels<WANT_BGR>(T, addr, shf, wA, wB, (uint32_t)(b * P2_RAW_STRIDE), brk, g, o0, o1, o2);
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar0 + 8 * (NS + b)) : "memory");
                     finish(g, o0, o1, o2);
@@ -804,9 +787,21 @@ __global__ void __launch_bounds__(128) k_sparse_flags(const uint16_t *__restrict
     }
 }
 
-// exact chain on the listed tiles: 16 lanes = the 16 pixels of a tile (direct gather from the source frame), gray and the exact
-// tile extrema written.  Latency-bound (a tile is six dependent round trips: list entry, map, taps, three table levels), so
-// the kernel runs six 256-thread CTAs per SM; each loads the 9.7 KB of colour tables into shared memory once.
+// exact chain on the listed tiles: 4 lanes per tile, a lane = one column of the tile (4 pixels), so that the list entry, the
+// frame base and the tile reduction are paid once per 4 pixels and the tap rows of vertically adjacent pixels are shared where
+// the map allows (as in K1t): 5 gathered rows instead of 8.  Interior taps through aligned 32-bit loads + funnel shift + PRMT +
+// IDP.2A with Q10 weights (rows of the frame are 4-byte aligned: w % 4 == 0); a column with a tap on or beyond the frame border
+// takes the general sampler.  The gray bytes of a tile are transposed over its 4 lanes (2 shuffles) and leave as one 32-bit
+// store per row.  Each 256-thread CTA loads the 9.7 KB of colour tables into shared memory once.
+__device__ __forceinline__ void gather_row(const uint8_t *__restrict__ p, uint32_t shf, uint32_t &T, uint32_t &U)
+{
+    const uint32_t *r = reinterpret_cast<const uint32_t *>(p);
+    const uint32_t r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+    const uint32_t X0 = __funnelshift_r(r0, r1, shf), X1 = __funnelshift_r(r1, r2, shf);
+    T = __byte_perm(X0, X1, 0x4130);
+    U = __byte_perm(X0, X1, 0x5252);
+}
+
 __global__ void __launch_bounds__(256) k_sparse_exact(const uint8_t *__restrict__ bgr, const float *__restrict__ mapx, const float *__restrict__ mapy,
                                                       const P2Tables *tables, int w, int h, const uint32_t *__restrict__ elist,
                                                       const int *__restrict__ ecount, uint8_t *__restrict__ gray, uint16_t *__restrict__ tmm)
@@ -819,47 +814,67 @@ __global__ void __launch_bounds__(256) k_sparse_exact(const uint8_t *__restrict_
     }
     __syncthreads();
     tables = &Ts;
-    const int n = *ecount, tw = w >> 2, th = h >> 2, px = threadIdx.x & 15;
+    const int n = *ecount, tw = w >> 2, th = h >> 2, col = threadIdx.x & 3;
     const size_t frame_px = (size_t)w * h;
-    for (int it = blockIdx.x * 16 + (threadIdx.x >> 4); it < n; it += gridDim.x * 16) {   // a tile's 16 lanes leave the loop together
-        const uint32_t e = __ldg(elist + it);
+    const uint32_t rowb = (uint32_t)w * 3u;
+    for (int base = blockIdx.x * 64; base < n; base += gridDim.x * 64) {   // whole warps iterate together (shuffles below)
+        const int it = base + (threadIdx.x >> 2);
+        const bool live = it < n;
+        const uint32_t e = live ? __ldg(elist + it) : 0u;
         const int tx = ATILE_TX(e), ty = ATILE_TY(e), f = ATILE_F(e);
-        const int x = tx * 4 + (px & 3), y = ty * 4 + (px >> 2);
+        const int x = tx * 4 + col, y0 = ty * 4;
         const uint8_t *src = bgr + (size_t)f * frame_px * 3;
-        int g;
-        {
-            const size_t o = (size_t)y * w + x;
-            const int sx = q5(__ldg(mapx + o)), sy = q5(__ldg(mapy + o));
-            const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
-            if (ix >= 0 && ix + 4 < w && iy >= 0 && iy + 1 < h) {
-                // interior: the 2 x 6 tap bytes through aligned 32-bit loads, funnel shift, PRMT and IDP.2A with Q10 weights, as K1t
-                // samples its staging buffer (rows of the frame are 4-byte aligned: w % 4 == 0)
-                const uint32_t wA = (uint32_t)((32 - fy) * (32 - fx)) | ((uint32_t)((32 - fy) * fx) << 16);
-                const uint32_t wB = (uint32_t)(fy * (32 - fx)) | ((uint32_t)(fy * fx) << 16);
-                const int b = ix * 3;
-                const uint32_t *r0 = reinterpret_cast<const uint32_t *>(src + (size_t)iy * w * 3 + (b & ~3));
-                const uint32_t *r1 = reinterpret_cast<const uint32_t *>(src + (size_t)(iy + 1) * w * 3 + (b & ~3));
-                const uint32_t shf = (uint32_t)(b & 3) * 8;
-                const uint32_t r00 = __ldg(r0), r01 = __ldg(r0 + 1), r02 = __ldg(r0 + 2), r10 = __ldg(r1), r11 = __ldg(r1 + 1), r12 = __ldg(r1 + 2);
-                const uint32_t X0 = __funnelshift_r(r00, r01, shf), X1 = __funnelshift_r(r01, r02, shf);
-                const uint32_t Y0 = __funnelshift_r(r10, r11, shf), Y1 = __funnelshift_r(r11, r12, shf);
-                const uint32_t T0 = __byte_perm(X0, X1, 0x4130), T1 = __byte_perm(Y0, Y1, 0x4130);
-                const uint32_t U0 = __byte_perm(X0, X1, 0x5252), U1 = __byte_perm(Y0, Y1, 0x5252);
-                const int c0 = (int)(__dp2a_lo(wA, T0, __dp2a_lo(wB, T1, 512u)) >> 10);
-                const int c1 = (int)(__dp2a_hi(wA, T0, __dp2a_hi(wB, T1, 512u)) >> 10);
-                const int c2 = (int)(__dp2a_lo(wA, U0, __dp2a_lo(wB, U1, 512u)) >> 10);
-                int o0, o1, o2;
-                g = chain_px(tables, c0, c1, c2, o0, o1, o2);
+        int g[4] = {0, 0, 0, 0};
+        if (live) {
+            int sx[4], sy[4];
+            bool interior = true;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t o = (uint32_t)(y0 + k) * (uint32_t)w + (uint32_t)x;
+                sx[k] = q5(__ldg(mapx + o)); sy[k] = q5(__ldg(mapy + o));
+                const int ix = sx[k] >> 5, iy = sy[k] >> 5;
+                interior = interior && ix >= 0 && ix + 4 < w && iy >= 0 && iy + 1 < h;
+            }
+            if (interior) {
+                uint32_t Tp = 0, Up = 0;
+                int pix = 0, piy = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int ix = sx[k] >> 5, iy = sy[k] >> 5, fx = sx[k] & 31, fy = sy[k] & 31;
+                    const uint32_t wA = (uint32_t)((32 - fy) * (32 - fx)) | ((uint32_t)((32 - fy) * fx) << 16);
+                    const uint32_t wB = (uint32_t)(fy * (32 - fx)) | ((uint32_t)(fy * fx) << 16);
+                    const uint32_t b = (uint32_t)ix * 3u, shf = (b & 3u) * 8u;
+                    const uint8_t *r0 = src + (size_t)((uint32_t)iy * rowb + (b & ~3u));
+                    if (k == 0 || ix != pix || iy != piy + 1) gather_row(r0, shf, Tp, Up);   // else: the previous pixel's bottom row
+                    uint32_t Tn, Un;
+                    gather_row(r0 + rowb, shf, Tn, Un);
+                    const int c0 = (int)(__dp2a_lo(wA, Tp, __dp2a_lo(wB, Tn, 512u)) >> 10);
+                    const int c1 = (int)(__dp2a_hi(wA, Tp, __dp2a_hi(wB, Tn, 512u)) >> 10);
+                    const int c2 = (int)(__dp2a_lo(wA, Up, __dp2a_lo(wB, Un, 512u)) >> 10);
+                    int o0, o1, o2;
+                    g[k] = chain_px(tables, c0, c1, c2, o0, o1, o2);
+                    Tp = Tn; Up = Un; pix = ix; piy = iy;
+                }
             } else {
-                g = exact_gray_px(src, mapx, mapy, tables, w, h, x, y);
+#pragma unroll
+                for (int k = 0; k < 4; k++) g[k] = exact_gray_px(src, mapx, mapy, tables, w, h, x, y0 + k);
             }
         }
-        gray[(size_t)f * frame_px + (size_t)y * w + x] = (uint8_t)g;
-        uint32_t pk = (uint32_t)g | ((uint32_t)(255 - g) << 16);
-        const unsigned half = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
-#pragma unroll
-        for (int d = 1; d < 16; d <<= 1) pk = __vminu2(pk, __shfl_xor_sync(half, pk, d));
-        if (px == 0) tmm[(size_t)f * tw * th + (size_t)ty * tw + tx] = (uint16_t)((pk & 0xffu) | ((255u - (pk >> 16)) << 8));
+        // tile extrema over the 4 lanes, min and (255 - max) side by side
+        const int mn = min(min(g[0], g[1]), min(g[2], g[3])), mx = max(max(g[0], g[1]), max(g[2], g[3]));
+        uint32_t pk = (uint32_t)mn | ((uint32_t)(255 - mx) << 16);
+        pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 1));
+        pk = __vminu2(pk, __shfl_xor_sync(0xffffffffu, pk, 2));
+        // 4 x 4 byte transpose over the 4 lanes: this lane's column (bytes = rows) -> row `col` of the tile (bytes = columns)
+        uint32_t G = (uint32_t)g[0] | ((uint32_t)g[1] << 8) | ((uint32_t)g[2] << 16) | ((uint32_t)g[3] << 24);
+        uint32_t P = __shfl_xor_sync(0xffffffffu, G, 1);
+        G = __byte_perm(G, P, (col & 1) ? 0x3715 : 0x6240);
+        P = __shfl_xor_sync(0xffffffffu, G, 2);
+        G = __byte_perm(G, P, (col & 2) ? 0x3276 : 0x5410);
+        if (live) {
+            *reinterpret_cast<uint32_t *>(gray + (size_t)f * frame_px + (size_t)(y0 + col) * w + (size_t)tx * 4) = G;
+            if (col == 0) tmm[(size_t)f * tw * th + (size_t)ty * tw + tx] = (uint16_t)((pk & 0xffu) | ((255u - (pk >> 16)) << 8));
+        }
     }
 }
 
@@ -876,7 +891,8 @@ int apse_preprocess_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, uin
     PFN_tmapEncodeTiled enc = get_tmap_encoder();
     static const bool force_generic = getenv("APSE_K1_GENERIC") != nullptr;
     const bool tma_ok = !force_generic && enc && (w % 4) == 0 && (h % 4) == 0 && ((w * 3) % 16) == 0 && w >= P2_TW && h >= P2_TH &&
-                        ((uintptr_t)bgr % 16) == 0 && ctx->tables2 && ctx->btable && batch <= 64 && (w % 32) == 0;   // k_sparse_flags: 8 tiles per thread
+                        ((uintptr_t)bgr % 16) == 0 && ctx->tables2 && ctx->btable && batch <= 64 && (w % 32) == 0 &&   // k_sparse_flags: 8 tiles per thread
+                        ((uintptr_t)gray % 4) == 0;                                                                  // k_sparse_exact: 32-bit stores
     if (!tma_ok) return 1;
     CUtensorMap tmap;
     {
@@ -925,9 +941,10 @@ int apse_preprocess_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, uin
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 0, false, 1><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES_M(1), st>>>(K1B_ARGS));
 #undef K1B_GO
 #undef K1B_ARGS
+    static const int exact_ctas = getenv("APSE_EXACT_CTAS") ? atoi(getenv("APSE_EXACT_CTAS")) : 4;   // CTAs per SM of k_sparse_exact
     KLAUNCH(ctx, KID_SPARSE_FLAGS, st, k_sparse_flags<<<dim3(div_up(tw / 8, 128), div_up(th, SFL_ROWS), batch), 128, 0, st>>>(
                 ctx->tbounds[slot], tw, th, min_wb_diff, tmm, ctx->eflag[slot], ctx->elist[slot], ctx->ecount[slot]));
-    KLAUNCH(ctx, KID_SPARSE_EXACT, st, k_sparse_exact<<<ctx->sm_count * 6, 256, 0, st>>>(bgr, ctx->mapx, ctx->mapy, ctx->tables2, w, h, ctx->elist[slot],
+    KLAUNCH(ctx, KID_SPARSE_EXACT, st, k_sparse_exact<<<ctx->sm_count * exact_ctas, 256, 0, st>>>(bgr, ctx->mapx, ctx->mapy, ctx->tables2, w, h, ctx->elist[slot],
                                                                                       ctx->ecount[slot], gray, tmm));
     return APSE_OK;
 }
