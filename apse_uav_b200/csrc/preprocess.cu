@@ -358,9 +358,13 @@ __device__ __forceinline__ void k1t_pixels(const P2Tables *T, const uint32_t (&a
 // packed (lo | (255 - hi) << 16) of the cell of one pixel (d = Q10 channel sums)
 __device__ __forceinline__ uint32_t bound_px(uint32_t tbl, uint32_t d0, uint32_t d1, uint32_t d2)
 {
-    const uint32_t a = ((d0 >> 3) & 0x7800u) | ((d1 >> 7) & 0x7C0u) | ((d2 >> 12) & 0x3Eu);   // 2 * (c0>>4 << 10 | c1>>3 << 5 | c2>>3)
+    // 2 * (c0>>4 << 10 | c1>>3 << 5 | c2>>3) + tbl; the sums are below 2^18, so the shifts leave clean fields, and the fields are
+    // merged by two multiply-adds on the FMA pipe (the kernel is bound by the ALU pipe: shifts, PRMT, LOP3, VIMNMX)
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 64, %2;" : "=r"(a) : "r"(d1 >> 13), "r"((d2 >> 13) << 1));
+    asm("mad.lo.u32 %0, %1, 2048, %2;" : "=r"(a) : "r"(d0 >> 14), "r"(a + tbl));
     uint32_t e;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(tbl + a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(a));
     return __byte_perm(e, 0u, 0x4140);
 }
 
@@ -941,7 +945,7 @@ int apse_preprocess_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, uin
         KLAUNCH(ctx, KID_PREPROCESS, st, k_preprocess_tma<false, 48, 0, false, 1><<<grid, P2_CTA_THREADS, P2_SMEM_BYTES_M(1), st>>>(K1B_ARGS));
 #undef K1B_GO
 #undef K1B_ARGS
-    static const int exact_ctas = getenv("APSE_EXACT_CTAS") ? atoi(getenv("APSE_EXACT_CTAS")) : 4;   // CTAs per SM of k_sparse_exact
+    static const int exact_ctas = getenv("APSE_EXACT_CTAS") ? atoi(getenv("APSE_EXACT_CTAS")) : 6;   // CTAs per SM of k_sparse_exact
     KLAUNCH(ctx, KID_SPARSE_FLAGS, st, k_sparse_flags<<<dim3(div_up(tw / 8, 128), div_up(th, SFL_ROWS), batch), 128, 0, st>>>(
                 ctx->tbounds[slot], tw, th, min_wb_diff, tmm, ctx->eflag[slot], ctx->elist[slot], ctx->ecount[slot]));
     KLAUNCH(ctx, KID_SPARSE_EXACT, st, k_sparse_exact<<<ctx->sm_count * exact_ctas, 256, 0, st>>>(bgr, ctx->mapx, ctx->mapy, ctx->tables2, w, h, ctx->elist[slot],
