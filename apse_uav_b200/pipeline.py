@@ -49,9 +49,11 @@ class Pipeline:
             # development knobs: stream priorities of the two halves (default: chain above preprocess)
             pre_prio = int(os.environ.get("APSE_PRE_PRIO", "0"))
             chain_prio = int(os.environ.get("APSE_CHAIN_PRIO", "-1"))
-            # consecutive preprocess launches are independent (different frames, different contexts): alternating between
-            # two streams lets the next launch fill the SMs while the last wave of the previous one drains
-            n_pre = max(1, int(os.environ.get("APSE_PRE_STREAMS", "2")))
+            # consecutive preprocess launches are independent (different frames, different contexts): rotating over
+            # several streams lets the next launch fill the SMs while the last wave of the previous one drains, and lets the
+            # short flag / exact kernels of one sub-batch run beside the bounds pass of the next (measured per 1800 frames:
+            # 1 stream 52.7 ms, 2: 47.7, 3: 45.6, 4: 45.7, 6: 45.9)
+            n_pre = max(1, int(os.environ.get("APSE_PRE_STREAMS", "3")))
             self.pre_streams = [torch.cuda.Stream(device=dev, priority=pre_prio) for _ in range(n_pre)]
             self.pre_stream = self.pre_streams[0]
             self._pre_pos = 0
