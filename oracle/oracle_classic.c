@@ -347,13 +347,19 @@ int orc_refine_candidate_lines(const int32_t *cont, int n, const float *corners,
             if ((double)corners[2 * j] == x && (double)corners[2 * j + 1] == y) { idx[j] = i; group = j; }
         double *s = S[group];
         s[0] += 1; s[1] += x; s[2] += y; s[3] += x * x; s[4] += y * y; s[5] += x * y;
-        if (x < s[6]) s[6] = x; if (x > s[7]) s[7] = x; if (y < s[8]) s[8] = y; if (y > s[9]) s[9] = y;
+        if (x < s[6]) s[6] = x;
+        if (x > s[7]) s[7] = x;
+        if (y < s[8]) s[8] = y;
+        if (y > s[9]) s[9] = y;
     }
     for (int j = 0; j < 4; j++) if (idx[j] < 0) return -1;
     if (S[4][0] > 0) {   /* points ahead of the first corner belong to the group that was open at the end */
         double *s = S[group], *e = S[4];
         for (int k = 0; k < 6; k++) s[k] += e[k];
-        if (e[6] < s[6]) s[6] = e[6]; if (e[7] > s[7]) s[7] = e[7]; if (e[8] < s[8]) s[8] = e[8]; if (e[9] > s[9]) s[9] = e[9];
+        if (e[6] < s[6]) s[6] = e[6];
+        if (e[7] > s[7]) s[7] = e[7];
+        if (e[8] < s[8]) s[8] = e[8];
+        if (e[9] > s[9]) s[9] = e[9];
     }
     int inc = 1;
     if (idx[0] > idx[1] && idx[3] > idx[0]) inc = -1;
