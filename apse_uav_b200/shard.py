@@ -414,9 +414,7 @@ def run_sequence_streamed(pipe, frames, plan, rank=0, world=1, group=None, start
                     arrived.append((r, comm.record_event()))
                     if th is not None:
                         todo.put(arrived[-1])
-            lo += sz
-            if failure:
-                break
+            lo += sz   # (after a failure of the worker the remaining rounds are still enqueued: the other ranks wait in their gathers)
             if rank == 0 and th is None:
                 # no worker thread: completed rounds between the enqueues, once enough frames have piled up
                 ready = done_upto
