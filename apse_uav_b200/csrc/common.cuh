@@ -131,6 +131,8 @@ struct apse_ctx {
     int seq_cap = 0;
     // sparse evaluation (apse_preprocess_tiles_sparse / apse_process_frames without a gray output), one set per tiles slot
     uint16_t *btable = nullptr;       // [SB_ENTRIES] bound table: min | (255 - max) << 8 of gray over the colours of a cell
+    cudaStream_t aux_stream = nullptr;   // high-priority stream of the flag / exact kernels of a sparse batch (first use)
+    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     uint16_t *tbounds[2] = {nullptr, nullptr};   // [max_batch][h/4][w/4] per-tile bounds of gray (lo | hi << 8)
     uint8_t *eflag[2] = {nullptr, nullptr};      // [max_batch][h/4][w/4] 1 = tile evaluated exactly
     uint32_t *elist[2] = {nullptr, nullptr};     // tiles to evaluate exactly (ATILE entries), capacity = every tile of the batch

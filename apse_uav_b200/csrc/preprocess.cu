@@ -885,6 +885,7 @@ __global__ void __launch_bounds__(256) k_sparse_exact(const uint8_t *__restrict_
 void apse_sparse_free(apse_ctx *ctx)
 {
     cudaFree(ctx->btable);
+    if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_ev[0]); cudaEventDestroy(ctx->aux_ev[1]); }
     for (int k = 0; k < 2; k++) { cudaFree(ctx->tbounds[k]); cudaFree(ctx->eflag[k]); cudaFree(ctx->elist[k]); cudaFree(ctx->ecount[k]); }
 }
 
@@ -946,10 +947,32 @@ int apse_preprocess_sparse(apse_ctx *ctx, const uint8_t *bgr, uint8_t *gray, uin
 #undef K1B_GO
 #undef K1B_ARGS
     static const int exact_ctas = getenv("APSE_EXACT_CTAS") ? atoi(getenv("APSE_EXACT_CTAS")) : 6;   // CTAs per SM of k_sparse_exact
-    KLAUNCH(ctx, KID_SPARSE_FLAGS, st, k_sparse_flags<<<dim3(div_up(tw / 8, 128), div_up(th, SFL_ROWS), batch), 128, 0, st>>>(
+    // The two short kernels that follow gate the detector chain of this batch.  In a multi-stream pipeline they would share the
+    // GPU with the bounds pass of the NEXT batch at its priority (0.2 - 0.6 ms instead of 0.04 + 0.10 ms, profiles/r02d_timeline.txt),
+    // so they go to a high-priority stream of the context, fenced by two events: `st` sees them as if they had run on it.
+    // APSE_SPARSE_AUX=0: everything on `st`.
+    static const bool use_aux = !(getenv("APSE_SPARSE_AUX") && atoi(getenv("APSE_SPARSE_AUX")) == 0);
+    cudaStream_t sx = st;
+    if (use_aux) {
+        if (!ctx->aux_stream) {
+            int lo_prio = 0, hi_prio = 0;
+            CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi_prio));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[0], cudaEventDisableTiming));
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[1], cudaEventDisableTiming));
+        }
+        sx = ctx->aux_stream;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->aux_ev[0], st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(sx, ctx->aux_ev[0], 0));
+    }
+    KLAUNCH(ctx, KID_SPARSE_FLAGS, sx, k_sparse_flags<<<dim3(div_up(tw / 8, 128), div_up(th, SFL_ROWS), batch), 128, 0, sx>>>(
                 ctx->tbounds[slot], tw, th, min_wb_diff, tmm, ctx->eflag[slot], ctx->elist[slot], ctx->ecount[slot]));
-    KLAUNCH(ctx, KID_SPARSE_EXACT, st, k_sparse_exact<<<ctx->sm_count * exact_ctas, 256, 0, st>>>(bgr, ctx->mapx, ctx->mapy, ctx->tables2, w, h, ctx->elist[slot],
+    KLAUNCH(ctx, KID_SPARSE_EXACT, sx, k_sparse_exact<<<ctx->sm_count * exact_ctas, 256, 0, sx>>>(bgr, ctx->mapx, ctx->mapy, ctx->tables2, w, h, ctx->elist[slot],
                                                                                       ctx->ecount[slot], gray, tmm));
+    if (use_aux) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->aux_ev[1], sx));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[1], 0));
+    }
     return APSE_OK;
 }
 
