@@ -55,6 +55,13 @@ ALG_BYTES = {
     "pipeline": 132_710_400,
     "classic_window": 91_238_400,        # per threshold window of the classic path
 }
+# the library times its launches per kernel ID; what the IDs that can dominate stand for
+KERNEL_NOTES = {
+    "k_preprocess_fused": "kernel id of the preprocess launches: k_preprocess_tma<MODE 1> (bounds pass of the sparse evaluation: every pixel "
+                          "remapped through TMA-staged tiles and bounded) when no gray output is asked for, k_preprocess_tma<MODE 0> "
+                          "(dense colour chain) otherwise",
+    "k_sparse_exact": "exact colour chain on the tiles the bounds pass could not rule out",
+}
 METRIC = "4K frames/s (undistort+ArUco detect+pose)"
 
 
@@ -332,7 +339,8 @@ def roofline_of(ktimes, frames_timed, alg_override=None):
             "traffic": None if tpf is None else tpf * frames_per_launch, "peak_source": peak_src, "traffic_source": tsrc,
             "share_of_kernel_time": kms / ksum if ksum else None, "algorithmic_bytes_per_frame": per_frame,
             "algorithmic_bytes_per_launch": alg, "frames_per_launch": frames_per_launch, "launches": kcount,
-            "avg_ms": kms / max(kcount, 1)}
+            "avg_ms": kms / max(kcount, 1),
+            "kernel_note": KERNEL_NOTES.get(name)}
 
 
 def collect_ktimes(engines):
