@@ -45,6 +45,19 @@ static double py_round(double x, int nd)
     static const double P10[6] = {1, 10, 100, 1000, 10000, 100000};
     const double a = fabs(x);
     if (nd < 0 || nd > 5 || a * P10[nd] >= 4.0e15 || a < 1e-300) return py_round_slow(x, nd);
+    {
+        // fast path: y = a * 10^nd carries a relative error of 2^-53, i.e. less than 1e-6 absolute below 2^32; away from a tie by
+        // more than that the nearest integer of y is the nearest integer of the exact product, and the result is the same
+        // correctly rounded quotient the exact path returns
+        const double y = a * P10[nd];
+        if (y < 4294967296.0) {
+            const double fl = floor(y), fr = y - fl;
+            if (fabs(fr - 0.5) > 1e-6) {
+                const double r = (fr > 0.5 ? fl + 1.0 : fl) / P10[nd];
+                return x < 0 ? -r : r;
+            }
+        }
+    }
     int e;
     const double fr = frexp(a, &e);                                   // a = fr * 2^e, fr in [0.5, 1)
     const unsigned long long m = (unsigned long long)ldexp(fr, 53);   // 53-bit integer mantissa, a = m * 2^(e - 53)
